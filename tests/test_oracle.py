@@ -1,0 +1,99 @@
+"""Pins the oracle (oracle/pointpath_oracle.py + oracle/voxel_oracle.c) against the golden vectors the
+UNMODIFIED reference produced (tests/golden/make_golden.py), and against the live reference where
+/root/reference exists. CPU only."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mvxnet_makise_b200 import synth
+from oracle import pointpath_oracle as O
+from oracle import refshim
+
+G = synth.KITTI_GRID
+
+
+def sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def small_maps(seed, shapes=((13, 42), (7, 21), (4, 11))):
+    rng = np.random.default_rng(seed)
+    return [rng.standard_normal((1, 256, h, w), dtype=np.float32) for (h, w) in shapes]
+
+
+@pytest.mark.parametrize('tag', ['vox_a', 'vox_b'])
+def test_voxelizer_oracle_matches_reference_golden(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + '.npz'))
+    pcd4 = g['pcd4']
+    idx = O.cell_index(pcd4, G.velorange, G.voxelsize)
+    assert np.array_equal(idx, g['idx'])                                  # fp64 index math, bit-exact
+    assert np.array_equal(O.cell_index_numpy(pcd4, G.velorange, G.voxelsize), g['idx'])
+    vox7, (x, y, z), cnt = O.cpp_group(pcd4, idx, G.T)
+    assert vox7.dtype == np.float32 and np.array_equal(vox7, g['vox7'])
+    assert np.array_equal(np.stack([x, y, z], 1), g['uidx7']) and np.array_equal(cnt, g['cnt7'])
+    pcd6 = O.points_with_proj(pcd4, synth.kitti_calib())
+    assert np.array_equal(pcd6[:, [5, 4]], g['proj_uv'])                  # lidar2Img, bit-exact on the same CPU libs
+    vox9, uidx9 = O.group(pcd6, G.velorange, G.voxelsize, G.T)
+    assert vox9.dtype == np.float64 and np.array_equal(uidx9, g['uidx9'])
+    assert np.array_equal(vox9[..., [0, 1, 2, 6, 7, 8]], g['vox9'][..., [0, 1, 2, 6, 7, 8]])
+    # centroid offsets: fp64, summation order may differ by an ulp of the fp64 sum
+    np.testing.assert_allclose(vox9[..., 3:6], g['vox9'][..., 3:6], rtol=0, atol=1e-12)
+    assert np.array_equal(vox9.astype(np.float32), g['vox9'].astype(np.float32))   # what reaches the GPU (train.py:125)
+
+
+@pytest.mark.parametrize('tag', ['path_a', 'path_b'])
+def test_path_oracle_matches_reference_golden(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + '.npz'))
+    maps = small_maps(int(g['map_seed']))
+    sd = synth.make_weights(int(g['weight_seed']))
+    assert sha(*maps) == str(g['maps_sha']), 'numpy RNG stream changed: regenerate tests/golden'
+    assert sha(*[sd[k] for k in sorted(sd)]) == str(g['weights_sha'])
+    with torch.no_grad():
+        r = O.forward_frame(g['pcd4'], synth.kitti_calib(), maps, sd, G, synth.KITTI_IMSIZE_HW)
+    assert np.array_equal(r['voxels9'].numpy(), g['voxels9_after'])      # incl. in-place pad zeroing
+    assert np.array_equal(r['idx'].numpy(), g['idx'])
+    im768 = r['im768'].reshape(-1, 768)
+    assert np.array_equal(im768[g['im768_rows']].numpy(), g['im768_sample'])
+    np.testing.assert_allclose(im768.double().sum(0).numpy(), g['im768_colsum'], rtol=1e-12)
+    # same torch build, same ops: expect bit-equality; tolerate accumulation-order noise only
+    np.testing.assert_allclose(r['im16'].numpy(), g['im16'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(r['vfeat'].numpy(), g['vfeat'], rtol=1e-5, atol=1e-5)
+    grid = r['grid'].numpy()
+    assert tuple(grid.shape) == tuple(g['grid_shape'])
+    assert int((grid != 0).sum()) == int(g['grid_nonzero'])
+    if np.array_equal(r['vfeat'].numpy(), g['vfeat']):
+        assert sha(grid) == str(g['grid_sha'])
+
+
+@pytest.mark.skipif(not refshim.available(), reason='/root/reference absent (GPU box)')
+def test_oracle_matches_live_reference():
+    m = refshim.load()
+    pcd4 = synth.make_points(21, 3000)
+    idx = O.cell_index(pcd4, G.velorange, G.voxelsize)
+    v_ref, u_ref, c_ref = m.cpp._group(pcd4, idx, G.T)
+    v, u, c = O.cpp_group(pcd4, idx, G.T)
+    assert np.array_equal(v, v_ref) and np.array_equal(c, c_ref)
+    assert all(np.array_equal(a, b) for a, b in zip(u, u_ref))
+    calib = {k: torch.Tensor(x) for k, x in synth.kitti_calib().items()}
+    assert torch.equal(O.lidar2img(torch.Tensor(pcd4), calib), m.calib.lidar2Img(torch.Tensor(pcd4), calib, True))
+    # one CRB block vs the reference FCN module
+    torch.manual_seed(1)
+    fcn = m.layers.FCN(24, 16)
+    x = torch.randn(1, 50, 35, 24)
+    with torch.no_grad():
+        assert torch.allclose(fcn(x), O.crb(x, fcn.fc.weight, fcn.fc.bias), rtol=1e-6, atol=1e-6)
+
+
+def test_oracle_empty_and_single_point():
+    idx = np.zeros((0, 3), dtype=np.int32)
+    vox, (x, y, z), cnt = O.cpp_group(np.zeros((0, 4), np.float32), idx, 35)
+    assert vox.shape == (0, 35, 7) and cnt.shape == (0,)
+    p = np.array([[1.0, 2.0, -1.0, 0.5]], np.float32)
+    vox, (x, y, z), cnt = O.cpp_group(p, O.cell_index(p, G.velorange, G.voxelsize), 35)
+    assert vox.shape == (1, 35, 7) and cnt[0] == 1 and (x[0], y[0], z[0]) == (5, 210, 5)
