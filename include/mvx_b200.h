@@ -1,0 +1,164 @@
+/*
+ * mvx_b200 — C-ABI of the B200-native (sm_100a) point-side hot path of MVXNet.
+ *
+ * Drop-in boundary: every entry point takes plain device/host pointers, extents and a
+ * cudaStream_t (passed as void*), never throws, never allocates its outputs (caller-owned buffers; the
+ * *_bytes / *_layout queries size them) and returns 0 or a negative MVX_E* code. There is NO CPU
+ * fallback: without a CUDA device every compute entry point returns MVX_ECUDA.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference tree).
+ */
+#ifndef MVX_B200_H_
+#define MVX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVX_OK 0
+#define MVX_EINVAL (-1)   /* bad argument (null pointer, bad extent, unsupported channel count) */
+#define MVX_ECUDA (-2)    /* CUDA runtime error; mvx_last_error() has the text */
+#define MVX_ESPACE (-3)   /* workspace or capacity too small */
+#define MVX_ERANGE (-4)   /* a point fell outside the voxel grid / key range (device-detected) */
+
+#define MVX_NUM_LAYERS 8  /* fcn1 conv1 fcn2 conv2 fcn3 | vfe1 vfe2 | fcn    */
+#define MVX_NUM_LEVELS 3  /* FPN levels '0','1','2' (modules/imhead/Pipe.py:20) */
+
+/* config.yml:3-13,21 + modules/config/Config.py:7 (voxelsize is the python double (hi-lo)/shape) */
+typedef struct {
+    double range_lo[3];   /* velorange[0:3] */
+    double voxel_size[3]; /* cfg.voxelsize */
+    int32_t shape[3];     /* cfg.voxelshape = (nx, ny, nz); dense grid is (C, nz, nx, ny) */
+    int32_t T;            /* cfg.samplenum */
+} mvx_grid_t;
+
+const char *mvx_last_error(void);
+int mvx_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t mvx_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1 — voxelization.  Replaces cpp/voxelutil.cpp:325-360 (`_group`) and the grouping loop of
+ * modules/data/Preprocessing.py:75-116 (`group`).  Deterministic: voxel order = first occurrence in
+ * input order, kept points = first T occurrences (SURVEY.md trap 2).
+ *
+ * Batched over B frames whose points are concatenated; pt_off_host[B+1] are HOST offsets (in points).
+ * `cap` = per-frame capacity (>= max points per frame, multiple of 128).
+ * Either `cell_idx` (device int32 (P,3), the caller-computed idx of `_group`) is given, or it is NULL and
+ * the cell index is computed from the grid in fp64: trunc(((double)x - lo) / size) (trap 1); then points
+ * outside the grid are counted in counts[f][2] and skipped.
+ * Outputs (device, per frame f at stride cap): see mvx_voxel_out_t.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t *counts;     /* [B][4]   : N_f voxels, K_f kept rows, #invalid points, max points in one voxel */
+    int32_t *vox_coord;  /* [B][cap][4] : ix, iy, iz, linear cell (iz*nx+ix)*ny+iy (or -1 without grid) */
+    int32_t *vox_cnt;    /* [B][cap]    : min(#points, T) */
+    int32_t *vox_row0;   /* [B][cap+1]  : first compact row of voxel v (exclusive scan of vox_cnt) */
+    int32_t *row_point;  /* [B][cap]    : frame-local point index of compact row r (voxel-major, slot order) */
+    int32_t *row_vox;    /* [B][cap]    : voxel of compact row r */
+    int32_t *cell2vid;   /* [B][G] or NULL : dense cell -> voxel id map (-1 empty), needs a grid */
+} mvx_voxel_out_t;
+
+int mvx_voxelize_workspace_bytes(int32_t B, int32_t cap, size_t *bytes);
+int mvx_voxelize(const mvx_grid_t *grid, int32_t B, int32_t cap, const float *points, int32_t point_stride,
+                 const int32_t *pt_off_host, const int32_t *cell_idx, int32_t T, const mvx_voxel_out_t *out,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* `_group` result layout for ONE frame (voxelutil.cpp:344-359): voxel (V,T,7) fp32 zero-filled, cols 0-2 xyz,
+ * col 6 = pcd[:,3]; x,y,z,cnt int64[V].  V comes from counts[0] (read it back first). */
+int mvx_group_emit7(const float *points, int32_t point_stride, int32_t V, int32_t T, const int32_t *vox_coord,
+                    const int32_t *vox_cnt, const int32_t *vox_row0, const int32_t *row_point, float *voxel,
+                    int64_t *x, int64_t *y, int64_t *z, int64_t *cnt, void *stream);
+/* numba `group` result layout (Preprocessing.py:103-115): voxel (V,T,9) [x,y,z,dx,dy,dz,r,row,col], centroid in
+ * fp64 over the kept points; written as fp64 (out_f64) and/or fp32 (= torch.Tensor(voxel), train.py:125).
+ * points are (P,6) rows [x,y,z,r,row,col] (train.py:32-35). uidx (V,3) fp64 optional. */
+int mvx_group_emit9(const float *points, int32_t point_stride, int32_t V, int32_t T, const int32_t *vox_coord,
+                    const int32_t *vox_cnt, const int32_t *vox_row0, const int32_t *row_point, double *out_f64,
+                    float *out_f32, double *uidx_f64, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2a — projection.  Replaces modules/utils/Calib.py:47-70 (`lidar2Img(pcd, calib, True)`).
+ * calib32 (device, 32 floats): M = R0_rect @ Tr_velo_to_cam (row-major 4x4, host-multiplied like the
+ * reference does) followed by P2.  out_uv (P,2) = (u,v) = (width, height) coordinates.
+ * ------------------------------------------------------------------------------------------------ */
+int mvx_lidar2img(const float *points, int32_t point_stride, int64_t P, const float *calib32, float *out_uv,
+                  void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2b — PointFusion gather.  Replaces modules/imhead/Pipe.py:23-82 (`featureMaping`) for one frame.
+ * maps: 3 device pointers to NCHW fp32 maps (C, Hf, Wf) of this frame (NOT padded: the +1 row/col zero pad of
+ * Pipe.py:47-48 is a bounds predicate here).  nhwc_ws: scratch of mvx_maps_nhwc_bytes().
+ * voxels (R,9) fp32 is updated IN PLACE like the reference (pad rows, x==y==z==0, are zeroed; Pipe.py:53-59).
+ * out (R, 3*C) fp32.  Inverted "bilinear" weights and index math exactly as Pipe.py:62-75 (traps 9, 10).
+ * ------------------------------------------------------------------------------------------------ */
+int mvx_maps_nhwc_bytes(const int32_t *map_h, const int32_t *map_w, int32_t C, size_t *bytes);
+int mvx_feature_mapping(float *voxels, int64_t R, const float *const *maps, const int32_t *map_h,
+                        const int32_t *map_w, int32_t C, float imsize_h, float imsize_w, float eps, float *out,
+                        void *nhwc_ws, size_t nhwc_ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 3 — one layer primitive.  Replaces modules/layers/Blocks.py:5-18 (FCN) and :31-40 (CRB2d, k=1):
+ * y = BatchNorm(relu(x W^T + b)), batch statistics over all R rows, biased variance, no affine.
+ * x (R,Cin) fp32 row-major (Cin multiple of 4, <= 768), wt (Cin,Cout) = W^T, bias (Cout), y (R,Cout).
+ * stats_ws: >= 2*Cout doubles of scratch.  mvx_vfe_forward additionally appends the per-voxel max over each
+ * group of T rows: y (R, 2*Cout) = [pointwise | max] (modules/voxelnet/Pipe.py:12-18).
+ * mvx_fcn_max_forward returns only the per-voxel max (R/T, Cout) (VoxelNet.py:28-32).
+ * ------------------------------------------------------------------------------------------------ */
+int mvx_fcn_forward(const float *x, int64_t R, int32_t Cin, const float *wt, const float *bias, int32_t Cout,
+                    double eps, float *y, void *stats_ws, void *stream);
+int mvx_vfe_forward(const float *x, int64_t R, int32_t T, int32_t Cin, const float *wt, const float *bias,
+                    int32_t Cout, double eps, float *y, void *stats_ws, void *vmax_ws, void *stream);
+int mvx_fcn_max_forward(const float *x, int64_t R, int32_t T, int32_t Cin, const float *wt, const float *bias,
+                        int32_t Cout, double eps, float *y_max, void *stats_ws, void *vmax_ws, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 4 — scatter into the dense middle-layer grid.  Replaces modules/voxelnet/VoxelNet.py:16-22
+ * (`reindex`): out (1,C,nz,nx,ny) fp32 fully written (zeros + features) in ONE streaming pass.
+ * idx (N,4) int64 [batch, ix, iy, iz] (train.py:119,126).  map_ws: nz*nx*ny int32 scratch.
+ * ------------------------------------------------------------------------------------------------ */
+int mvx_scatter_dense(const float *feat, const int64_t *idx, int64_t N, int32_t C, int32_t nx, int32_t ny,
+                      int32_t nz, float *out, int32_t *map_ws, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The fused batched path: stages 1-4 for B frames in one stream-ordered sequence with no host sync
+ * (MVXNet.forward up to the CML input: MVXNet.py:21-27, modules/imhead/Head.py:14-22,
+ * modules/voxelnet/VoxelNet.py:24-34, with train.py:26-49's CPU half moved onto the GPU).
+ * BatchNorm statistics stay per frame (the reference is batch-1; SURVEY.md §7 hard part 6).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    mvx_grid_t grid;
+    int32_t B;                 /* frames in this call */
+    int32_t cap;               /* per-frame capacity, multiple of 128, >= max points per frame */
+    const float *points;       /* device, concatenated (sum P, point_stride) fp32 rows [x,y,z,r,...] */
+    int32_t point_stride;      /* floats per point row (>= 4) */
+    const int32_t *pt_off_host;/* HOST [B+1] point offsets */
+    const float *calib32;      /* device [B][32]: (R0@Tr, P2) per frame */
+    const float *maps[MVX_NUM_LEVELS]; /* device NCHW (B, C, Hf, Wf) fp32 */
+    int32_t map_h[MVX_NUM_LEVELS], map_w[MVX_NUM_LEVELS];
+    int32_t map_c;             /* 256 */
+    float imsize_h, imsize_w;  /* cfg.imsize (370, 1224) */
+    float gather_eps;          /* cfg.eps as fp32 (Pipe.py:62) */
+    double bn_eps;             /* cfg.eps (Blocks.py:10) */
+    const float *wt[MVX_NUM_LAYERS];   /* device W^T (Cin_pad, Cout) fp32; Cin_pad: 768,768,128,128,16,32,32,128 */
+    const float *bias[MVX_NUM_LAYERS]; /* device (Cout) */
+    float *grid_out;           /* device (B, 128, nz, nx, ny) fp32, fully overwritten; may be NULL (skip stage 4) */
+    int32_t *counts;           /* device [B][4]: N_f, K_f, #invalid points, max points per voxel */
+    void *workspace;
+    size_t workspace_bytes;
+    void *stream;
+} mvx_pointpath_args_t;
+
+/* byte offsets of named workspace regions, for tests/diagnostics (names in mvx_pointpath_layout_name) */
+#define MVX_WS_REGIONS 40
+int mvx_pointpath_workspace_bytes(const mvx_pointpath_args_t *args, size_t *bytes);
+int mvx_pointpath_layout(const mvx_pointpath_args_t *args, int64_t *offsets /* [MVX_WS_REGIONS] */);
+const char *mvx_pointpath_layout_name(int32_t region);
+int mvx_pointpath_forward(const mvx_pointpath_args_t *args);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVX_B200_H_ */

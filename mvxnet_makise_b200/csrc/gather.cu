@@ -1,0 +1,273 @@
+// Stage 2 — calibrated projection (modules/utils/Calib.py:47-70) and the PointFusion gather
+// (modules/imhead/Pipe.py:23-82).  The FPN maps are re-laid out channels-last once per call so that every
+// corner read is a contiguous, coalesced run of channels (NCHW would cost one 32-byte sector per channel).
+#include "gather.cuh"
+
+namespace mvx {
+
+namespace {
+
+// ---- NCHW -> NHWC ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int C,
+                                                           int HW) {
+    __shared__ float tile[32][33];
+    const size_t fb = (size_t)blockIdx.z * C * HW;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + k * 8, p = p0 + tx;
+        tile[ty + k * 8][tx] = (c < C && p < HW) ? __ldg(in + fb + (size_t)c * HW + p) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int p = p0 + ty + k * 8, c = c0 + tx;
+        if (c < C && p < HW) out[fb + (size_t)p * C + c] = tile[tx][ty + k * 8];
+    }
+}
+
+// ---- projection: (R0@Tr) @ [x y z 1], then P2 @ ., then divide (Calib.py:65-70) -----------------------
+// Accumulation order = sequential FMA over k (what torch's CPU sgemm does for a 4x4 operand; pinned by
+// tests/test_gpu_parity.py on the reference-generated golden projections).
+__device__ __forceinline__ void project_point(const float *__restrict__ c32, float x, float y, float z, float &u,
+                                              float &v) {
+    float cam[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float a = __fmul_rn(c32[i * 4 + 0], x);
+        a = __fmaf_rn(c32[i * 4 + 1], y, a);
+        a = __fmaf_rn(c32[i * 4 + 2], z, a);
+        a = __fmaf_rn(c32[i * 4 + 3], 1.0f, a);
+        cam[i] = a;
+    }
+    float img[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float a = __fmul_rn(c32[16 + i * 4 + 0], cam[0]);
+        a = __fmaf_rn(c32[16 + i * 4 + 1], cam[1], a);
+        a = __fmaf_rn(c32[16 + i * 4 + 2], cam[2], a);
+        a = __fmaf_rn(c32[16 + i * 4 + 3], cam[3], a);
+        img[i] = a;
+    }
+    u = __fdiv_rn(img[0], img[2]);
+    v = __fdiv_rn(img[1], img[2]);
+}
+
+__global__ void __launch_bounds__(256) lidar2img_kernel(const float *__restrict__ pts, int stride, long long P,
+                                                        const float *__restrict__ calib32, float *__restrict__ out_uv) {
+    __shared__ float c32[32];
+    if (threadIdx.x < 32) c32[threadIdx.x] = calib32[threadIdx.x];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float *q = pts + (size_t)i * stride;
+    float u, v;
+    project_point(c32, q[0], q[1], q[2], u, v);
+    reinterpret_cast<float2 *>(out_uv)[i] = make_float2(u, v);
+}
+
+// ---- the 4-corner weighted gather of one row, one warp, all levels ------------------------------------
+// Index math and the (inverted) weights are those of Pipe.py:62-75, evaluated in the same fp32 order with no
+// FMA contraction, so the result is bit-identical to the reference's eager ops for the same `proj`.
+template <bool kStreaming>
+__device__ __forceinline__ void gather_row_warp(const MapSet &m, int f, float prow, float pcol, float eps, int lane,
+                                                float *__restrict__ out_row) {
+#pragma unroll
+    for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+        const float q0 = __fsub_rn(__fdiv_rn(prow, m.rs_h[l]), eps);
+        const float q1 = __fsub_rn(__fdiv_rn(pcol, m.rs_w[l]), eps);
+        const int i0 = (int)q0, i1 = (int)q1;  // .long(): truncation toward zero
+        const float a = __fsub_rn(q0, (float)i0), b = __fsub_rn(q1, (float)i1);
+        const float a_ = __fsub_rn(1.0f, a), b_ = __fsub_rn(1.0f, b);
+        const int H = m.h[l], W = m.w[l], C = m.C;
+        const float *base = m.nhwc[l] + (size_t)f * m.frame_stride[l];
+        // corner validity: row H / column W are the zero pad of Pipe.py:47-48
+        const bool r0 = i0 >= 0 && i0 < H, r1 = i0 + 1 >= 0 && i0 + 1 < H;
+        const bool c0 = i1 >= 0 && i1 < W, c1 = i1 + 1 >= 0 && i1 + 1 < W;
+        const float4 *p00 = reinterpret_cast<const float4 *>(base + ((size_t)i0 * W + i1) * C);
+        const float4 *p10 = reinterpret_cast<const float4 *>(base + ((size_t)(i0 + 1) * W + i1) * C);
+        const float4 *p01 = reinterpret_cast<const float4 *>(base + ((size_t)i0 * W + i1 + 1) * C);
+        const float4 *p11 = reinterpret_cast<const float4 *>(base + ((size_t)(i0 + 1) * W + i1 + 1) * C);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c4 = lane; c4 < C / 4; c4 += 32) {
+            const float4 f00 = (r0 && c0) ? __ldg(p00 + c4) : z4;
+            const float4 f10 = (r1 && c0) ? __ldg(p10 + c4) : z4;
+            const float4 f01 = (r0 && c1) ? __ldg(p01 + c4) : z4;
+            const float4 f11 = (r1 && c1) ? __ldg(p11 + c4) : z4;
+            float4 g;
+#define MVX_CORNERS(e)                                                     \
+    g.e = __fmul_rn(__fmul_rn(f00.e, a), b);                               \
+    g.e = __fadd_rn(g.e, __fmul_rn(__fmul_rn(f10.e, a_), b));              \
+    g.e = __fadd_rn(g.e, __fmul_rn(__fmul_rn(f01.e, a), b_));              \
+    g.e = __fadd_rn(g.e, __fmul_rn(__fmul_rn(f11.e, a_), b_));
+            MVX_CORNERS(x) MVX_CORNERS(y) MVX_CORNERS(z) MVX_CORNERS(w)
+#undef MVX_CORNERS
+            float4 *dst = reinterpret_cast<float4 *>(out_row + (size_t)l * C) + c4;
+            if (kStreaming) st_cs_f4(dst, g); else *dst = g;
+        }
+    }
+}
+
+template <bool kStreaming>
+__device__ __forceinline__ void zero_row_warp(int C3, int lane, float *__restrict__ out_row) {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c4 = lane; c4 < C3 / 4; c4 += 32) {
+        float4 *dst = reinterpret_cast<float4 *>(out_row) + c4;
+        if (kStreaming) st_cs_f4(dst, z4); else *dst = z4;
+    }
+}
+
+// ---- featureMaping drop-in: dense (R,9) voxel rows in/out, (R,3C) out ----------------------------------
+__global__ void __launch_bounds__(256) feature_mapping_kernel(float *__restrict__ voxels, long long R, MapSet m, float eps,
+                                                              float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= R) return;
+    float *vrow = voxels + (size_t)r * 9;
+    const float mine = lane < 9 ? vrow[lane] : 0.f;
+    const float x = __shfl_sync(0xffffffffu, mine, 0), y = __shfl_sync(0xffffffffu, mine, 1),
+                z = __shfl_sync(0xffffffffu, mine, 2);
+    const float prow = __shfl_sync(0xffffffffu, mine, 7), pcol = __shfl_sync(0xffffffffu, mine, 8);
+    float *orow = out + (size_t)r * 3 * m.C;
+    if (x == 0.f && y == 0.f && z == 0.f) {  // Pipe.py:53-59,80: pad slot -> zero the voxel row and its features
+        if (lane < 9) vrow[lane] = 0.f;
+        zero_row_warp<true>(3 * m.C, lane, orow);
+    } else {
+        gather_row_warp<true>(m, 0, prow, pcol, eps, lane, orow);
+    }
+}
+
+// ---- fused path: per compact row, voxel features + projection -------------------------------------------
+__global__ void __launch_bounds__(256) rows_build_kernel(RowsParams p) {
+    __shared__ float c32[32];
+    const int f = blockIdx.y;
+    if (threadIdx.x < 32) c32[threadIdx.x] = p.calib32[f * 32 + threadIdx.x];
+    __syncthreads();
+    const int N = p.counts[f * 4 + 0], K = p.counts[f * 4 + 1];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > K) return;
+    const size_t ro = (size_t)f * p.capA + r;
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    float2 pr = make_float2(0.f, 0.f);
+    float w;
+    if (r == K) {
+        w = (float)((long long)N * p.T - K);  // the pad slots of this frame, all identical rows (SURVEY.md §7 hard part 4)
+    } else {
+        w = 1.f;
+        const float *pts = p.points + (size_t)p.off[f] * p.point_stride;
+        const int v = p.row_vox[(size_t)f * p.cap + r];
+        const int r0 = p.vox_row0[(size_t)f * (p.cap + 1) + v], n = p.vox_cnt[(size_t)f * p.cap + v];
+        double sx = 0, sy = 0, sz = 0;  // fp64 centroid over the kept points in slot order (Preprocessing.py:112-113)
+        for (int k = 0; k < n; ++k) {
+            const float *q = pts + (size_t)p.row_point[(size_t)f * p.cap + r0 + k] * p.point_stride;
+            sx += (double)q[0], sy += (double)q[1], sz += (double)q[2];
+        }
+        const float *q = pts + (size_t)p.row_point[(size_t)f * p.cap + r] * p.point_stride;
+        const float x = q[0], y = q[1], z = q[2], refl = q[3];
+        if (!(x == 0.f && y == 0.f && z == 0.f)) {  // a real point at the exact origin is treated as a pad slot (Pipe.py:53-59)
+            lo = make_float4(x, y, z, (float)((double)x - sx / (double)n));
+            hi = make_float4((float)((double)y - sy / (double)n), (float)((double)z - sz / (double)n), refl, 0.f);
+            float u, vv;
+            project_point(c32, x, y, z, u, vv);
+            pr = make_float2(vv, u);  // (row, col) = lidar2Img(...)[:, [1, 0]]  (train.py:33)
+        }
+    }
+    float4 *dst = reinterpret_cast<float4 *>(p.vox8 + ro * 8);
+    dst[0] = lo;
+    dst[1] = hi;
+    reinterpret_cast<float2 *>(p.proj)[ro] = pr;
+    p.rowA_w[ro] = w;
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(MapSet m, int capA, const int *__restrict__ counts,
+                                                          const float *__restrict__ vox8, const float *__restrict__ proj,
+                                                          float eps, float *__restrict__ A1) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int K = counts[f * 4 + 1];
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r > K) return;
+    const size_t ro = (size_t)f * capA + r;
+    const float4 xyz = *reinterpret_cast<const float4 *>(vox8 + ro * 8);
+    float *orow = A1 + ro * 3 * m.C;
+    if (xyz.x == 0.f && xyz.y == 0.f && xyz.z == 0.f) {
+        zero_row_warp<false>(3 * m.C, lane, orow);
+    } else {
+        const float2 pr = reinterpret_cast<const float2 *>(proj)[ro];
+        gather_row_warp<false>(m, f, pr.x, pr.y, eps, lane, orow);
+    }
+}
+
+}  // namespace
+
+int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, cudaStream_t st) {
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(in, out, C, HW);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+int launch_rows_build(const RowsParams &p, cudaStream_t st) {
+    dim3 grid((p.cap + 1 + 255) / 256, p.B);
+    rows_build_kernel<<<grid, 256, 0, st>>>(p);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+int launch_gather_rows(const MapSet &m, int B, int capA, const int *counts, const float *vox8, const float *proj, float eps,
+                       float *A1, cudaStream_t st) {
+    dim3 grid((capA + 7) / 8, B);
+    gather_rows_kernel<<<grid, 256, 0, st>>>(m, capA, counts, vox8, proj, eps, A1);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+}  // namespace mvx
+
+// ---- C ABI ---------------------------------------------------------------------------------------------
+extern "C" int mvx_lidar2img(const float *points, int32_t point_stride, int64_t P, const float *calib32, float *out_uv,
+                             void *stream) {
+    if (P == 0) return MVX_OK;
+    MVX_REQUIRE(points && calib32 && out_uv && P > 0 && point_stride >= 3, MVX_EINVAL, "bad lidar2img argument");
+    mvx::lidar2img_kernel<<<(unsigned)((P + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(points, point_stride, P,
+                                                                                                     calib32, out_uv);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+extern "C" int mvx_maps_nhwc_bytes(const int32_t *map_h, const int32_t *map_w, int32_t C, size_t *bytes) {
+    if (!map_h || !map_w || !bytes || C <= 0) return MVX_EINVAL;
+    size_t n = 0;
+    for (int l = 0; l < MVX_NUM_LEVELS; ++l) n += (size_t)map_h[l] * map_w[l] * C * sizeof(float);
+    *bytes = n;
+    return MVX_OK;
+}
+
+extern "C" int mvx_feature_mapping(float *voxels, int64_t R, const float *const *maps, const int32_t *map_h,
+                                   const int32_t *map_w, int32_t C, float imsize_h, float imsize_w, float eps, float *out,
+                                   void *nhwc_ws, size_t nhwc_ws_bytes, void *stream) {
+    MVX_REQUIRE(voxels && maps && map_h && map_w && out && nhwc_ws, MVX_EINVAL, "null pointer");
+    MVX_REQUIRE(C > 0 && C % 4 == 0, MVX_EINVAL, "C must be a multiple of 4");
+    size_t need = 0;
+    mvx_maps_nhwc_bytes(map_h, map_w, C, &need);
+    MVX_REQUIRE(nhwc_ws_bytes >= need, MVX_ESPACE, "nhwc workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    mvx::MapSet m{};
+    m.C = C;
+    float *ws = static_cast<float *>(nhwc_ws);
+    for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+        MVX_REQUIRE(maps[l] && map_h[l] > 0 && map_w[l] > 0, MVX_EINVAL, "bad map");
+        m.h[l] = map_h[l], m.w[l] = map_w[l];
+        m.rs_h[l] = imsize_h / (float)map_h[l];
+        m.rs_w[l] = imsize_w / (float)map_w[l];
+        m.nhwc[l] = ws;
+        m.frame_stride[l] = 0;
+        int rc = mvx::launch_nchw_to_nhwc(maps[l], ws, 1, C, map_h[l] * map_w[l], st);
+        if (rc) return rc;
+        ws += (size_t)map_h[l] * map_w[l] * C;
+    }
+    if (R == 0) return MVX_OK;
+    mvx::feature_mapping_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(voxels, R, m, eps, out);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}

@@ -1,0 +1,36 @@
+// Internal interface of stage 2 (projection + PointFusion gather), shared with the fused path.
+#pragma once
+#include "common.cuh"
+
+namespace mvx {
+
+struct MapSet {
+    const float *nhwc[MVX_NUM_LEVELS];  // channels-last copies (per frame stride = frame_stride[l] floats)
+    size_t frame_stride[MVX_NUM_LEVELS];
+    int h[MVX_NUM_LEVELS], w[MVX_NUM_LEVELS];
+    float rs_h[MVX_NUM_LEVELS], rs_w[MVX_NUM_LEVELS];  // regionSize = imsize / (Hf, Wf) in fp32 (Pipe.py:41-45)
+    int C;
+};
+
+// NCHW (B,C,H,W) -> NHWC (B,H,W,C)
+int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, cudaStream_t st);
+
+struct RowsParams {
+    int B, cap, capA, T;
+    const float *points;
+    int point_stride;
+    int off[33];
+    const float *calib32;   // [B][32]
+    const int *counts;      // [B][4]
+    const int *vox_cnt, *vox_row0, *row_point, *row_vox;
+    float *vox8;            // [B][capA][8]  x,y,z,dx,dy,dz,r,0   (pad row K_f = zeros)
+    float *proj;            // [B][capA][2]  (row, col) image coordinates
+    float *rowA_w;          // [B][capA]     BN multiplicity of each compact row
+};
+int launch_rows_build(const RowsParams &p, cudaStream_t st);
+
+// compact gather: A1[f][r][0:3C] for r <= K_f (row K_f is the all-zero pad row)
+int launch_gather_rows(const MapSet &m, int B, int capA, const int *counts, const float *vox8, const float *proj,
+                       float eps, float *A1, cudaStream_t st);
+
+}  // namespace mvx

@@ -1,0 +1,449 @@
+// Stage 3 — the layer primitive of the path: relu(Linear) followed by batch-statistic BatchNorm
+// (modules/layers/Blocks.py:5-18 FCN, :31-40 CRB2d with k=1), the VFE max/concat glue
+// (modules/voxelnet/Pipe.py:12-18) and the final FCN + max (modules/voxelnet/VoxelNet.py:27-32).
+//
+// BatchNorm needs the statistics of ALL rows of a frame before any row can be normalised, so a layer is
+// one launch that writes the raw post-ReLU activations and accumulates weighted per-channel sums in fp64;
+// the NEXT consumer applies (y - mean) * rstd while loading.  max over T commutes with the (monotone)
+// normalisation, so per-voxel maxima are taken on raw values with an integer atomicMax (y >= 0).
+//
+// This file holds the exact-fp32 SIMT implementation (FFMA, 128 x BN tiles). It is the parity baseline
+// for the tensor-core kernels and serves the small layers, which are bandwidth- not FLOP-bound.
+#include "layers.cuh"
+
+namespace mvx {
+
+namespace {
+
+constexpr int kBM = 128, kBK = 16, kTM = 8;
+constexpr int kAS = kBM + 4;  // padded A^T tile row (floats), keeps 16-byte alignment
+
+__device__ __forceinline__ void norm_coef(const double *stats, double R, double eps, float &mean, float &rstd) {
+    const double m = stats[0] / R;
+    double var = stats[1] / R - m * m;  // biased variance (BatchNorm2d batch statistics)
+    var = var < 0.0 ? 0.0 : var;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + eps));
+}
+
+__device__ __forceinline__ double stat_rows(const NormSrc &n, int f) {
+    return n.counts ? (double)n.counts[f * 4 + 0] * (double)n.T : (double)n.rows_fixed;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256) fcn_layer_kernel(LayerArgs a) {
+    constexpr int TN = BN / 16;
+    __shared__ __align__(16) float smem[kBK * kAS + kBK * 128];
+    __shared__ float s_mean[768], s_rstd[768];
+    float *As = smem, *Bs = smem + kBK * kAS;
+
+    const int f = blockIdx.z, n0 = blockIdx.y * BN, tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    long long n_rows = a.rows_fixed;
+    double Rstat = (double)a.rows_fixed;
+    int K = 0;
+    if (a.counts) {
+        const int N = a.counts[f * 4 + 0];
+        K = a.counts[f * 4 + 1];
+        n_rows = a.rows_mode == 1 ? K + 1 : (a.rows_mode == 2 ? K + N : a.rows_fixed);
+        Rstat = (double)N * (double)a.T;
+    }
+    const long long row0 = (long long)blockIdx.x * kBM;
+    if (row0 >= n_rows) return;
+
+    if (a.in_stats) {
+        for (int c = tid; c < a.Cin; c += 256)
+            norm_coef(a.in_stats + ((size_t)f * a.Cin + c) * 2, Rstat, a.eps, s_mean[c], s_rstd[c]);
+        __syncthreads();
+    }
+
+    float acc[kTM][TN];
+#pragma unroll
+    for (int i = 0; i < kTM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx;
+    for (int k0 = 0; k0 < a.Cin; k0 += kBK) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {  // A tile: 128 rows x 16 k, stored transposed
+            const int idx = tid + j * 256, r = idx >> 2, c4 = idx & 3;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < n_rows) {
+                v = *reinterpret_cast<const float4 *>(Xf + (size_t)r * a.ldx + k0 + c4 * 4);
+                if (a.in_stats) {
+                    const int k = k0 + c4 * 4;
+                    v.x = (v.x - s_mean[k + 0]) * s_rstd[k + 0];
+                    v.y = (v.y - s_mean[k + 1]) * s_rstd[k + 1];
+                    v.z = (v.z - s_mean[k + 2]) * s_rstd[k + 2];
+                    v.w = (v.w - s_mean[k + 3]) * s_rstd[k + 3];
+                }
+            }
+            As[(c4 * 4 + 0) * kAS + r] = v.x;
+            As[(c4 * 4 + 1) * kAS + r] = v.y;
+            As[(c4 * 4 + 2) * kAS + r] = v.z;
+            As[(c4 * 4 + 3) * kAS + r] = v.w;
+        }
+        for (int idx = tid; idx < BN * 4; idx += 256) {  // B tile: 16 k x BN
+            const int k = idx / (BN / 4), n4 = idx % (BN / 4);
+            *reinterpret_cast<float4 *>(Bs + k * BN + n4 * 4) =
+                __ldg(reinterpret_cast<const float4 *>(a.Wt + (size_t)(k0 + k) * a.Cout + n0 + n4 * 4));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kBK; ++k) {
+            float av[kTM], bv[TN];
+            *reinterpret_cast<float4 *>(av) = *reinterpret_cast<const float4 *>(As + k * kAS + ty * 8);
+            *reinterpret_cast<float4 *>(av + 4) = *reinterpret_cast<const float4 *>(As + k * kAS + ty * 8 + 4);
+            if constexpr (TN == 8) {
+                *reinterpret_cast<float4 *>(bv) = *reinterpret_cast<const float4 *>(Bs + k * BN + tx * 4);
+                *reinterpret_cast<float4 *>(bv + 4) = *reinterpret_cast<const float4 *>(Bs + k * BN + 64 + tx * 4);
+            } else if constexpr (TN == 4) {
+                *reinterpret_cast<float4 *>(bv) = *reinterpret_cast<const float4 *>(Bs + k * BN + tx * 4);
+            } else {
+                bv[0] = Bs[k * BN + tx];
+            }
+#pragma unroll
+            for (int i = 0; i < kTM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: bias, ReLU, raw store, weighted fp64 statistics, per-voxel max ------------------------
+    float w[kTM];
+    int vox[kTM];
+#pragma unroll
+    for (int i = 0; i < kTM; ++i) {
+        const long long r = row0 + ty * 8 + i;
+        const bool valid = r < n_rows;
+        const size_t ro = (size_t)f * a.rowcap + r;
+        w[i] = valid ? (a.row_w ? a.row_w[ro] : 1.f) : 0.f;
+        vox[i] = -1;
+        if (valid && a.vmax && w[i] != 0.f) {
+            if (a.row_v) vox[i] = (a.rows_mode == 1 && r >= K) ? -1 : a.row_v[(size_t)f * a.rowv_cap + r];
+            else vox[i] = (int)(r / a.T);
+        }
+    }
+    double *red = reinterpret_cast<double *>(smem);  // [2][8 warps][BN], aliases the (now idle) tiles
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const int col = TN == 8 ? (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4)) : (TN == 4 ? tx * 4 + j : tx);
+        const float b = __ldg(a.bias + n0 + col);
+        double s = 0.0, ss = 0.0;
+        int cv = -1;
+        float cm = 0.f;
+#pragma unroll
+        for (int i = 0; i < kTM; ++i) {
+            const float y = fmaxf(acc[i][j] + b, 0.f);
+            acc[i][j] = y;
+            if (w[i] != 0.f) {
+                const double yd = (double)y, wd = (double)w[i];
+                s += wd * yd;
+                ss += wd * yd * yd;
+            }
+            if (a.vmax) {
+                const int v = vox[i];
+                if (v != cv) {
+                    if (cv >= 0) atomicMax(a.vmax + ((size_t)f * a.vcap + cv) * a.Cout + n0 + col, __float_as_int(cm));
+                    cv = v;
+                    cm = y;
+                } else {
+                    cm = fmaxf(cm, y);
+                }
+            }
+        }
+        if (a.vmax && cv >= 0) atomicMax(a.vmax + ((size_t)f * a.vcap + cv) * a.Cout + n0 + col, __float_as_int(cm));
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+        if (lane < 16) {
+            red[(0 * 8 + warp) * BN + col] = s;
+            red[(1 * 8 + warp) * BN + col] = ss;
+        }
+    }
+    if (a.Y) {
+#pragma unroll
+        for (int i = 0; i < kTM; ++i) {
+            const long long r = row0 + ty * 8 + i;
+            if (r >= n_rows) continue;
+            float *yr = a.Y + ((size_t)f * a.rowcap + r) * a.ldy + n0;
+            if constexpr (TN == 8) {
+                *reinterpret_cast<float4 *>(yr + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                *reinterpret_cast<float4 *>(yr + 64 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+            } else if constexpr (TN == 4) {
+                *reinterpret_cast<float4 *>(yr + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            } else {
+                yr[tx] = acc[i][0];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < BN) {
+        double s = 0.0, ss = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) {
+            s += red[(0 * 8 + wv) * BN + tid];
+            ss += red[(1 * 8 + wv) * BN + tid];
+        }
+        double *o = a.out_stats + ((size_t)f * a.Cout + n0 + tid) * 2;
+        atomicAdd(o, s);
+        atomicAdd(o + 1, ss);
+    }
+}
+
+// ---- dense-API helpers ---------------------------------------------------------------------------------
+// y[r][0:C] = norm(y[r][0:C]) in place; optionally y[r][C:2C] = norm(vmax[r / T]) (VFE concat)
+__global__ void __launch_bounds__(256) normalize_rows_kernel(float *__restrict__ y, long long R, int C, int ldy, NormSrc n,
+                                                             const int *__restrict__ vmax, int T) {
+    __shared__ float s_mean[768], s_rstd[768];
+    const double Rs = stat_rows(n, 0);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) norm_coef(n.stats + (size_t)c * 2, Rs, n.eps, s_mean[c], s_rstd[c]);
+    __syncthreads();
+    const int c4n = C / 4;
+    const long long total = R * c4n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / c4n;
+        const int c = (int)(e - r * c4n) * 4;
+        float4 *p = reinterpret_cast<float4 *>(y + (size_t)r * ldy + c);
+        float4 v = *p;
+        v.x = (v.x - s_mean[c]) * s_rstd[c];
+        v.y = (v.y - s_mean[c + 1]) * s_rstd[c + 1];
+        v.z = (v.z - s_mean[c + 2]) * s_rstd[c + 2];
+        v.w = (v.w - s_mean[c + 3]) * s_rstd[c + 3];
+        *p = v;
+        if (vmax) {
+            const int4 m = *reinterpret_cast<const int4 *>(vmax + (size_t)(r / T) * C + c);
+            float4 q;
+            q.x = (__int_as_float(m.x) - s_mean[c]) * s_rstd[c];
+            q.y = (__int_as_float(m.y) - s_mean[c + 1]) * s_rstd[c + 1];
+            q.z = (__int_as_float(m.z) - s_mean[c + 2]) * s_rstd[c + 2];
+            q.w = (__int_as_float(m.w) - s_mean[c + 3]) * s_rstd[c + 3];
+            *reinterpret_cast<float4 *>(y + (size_t)r * ldy + C + c) = q;
+        }
+    }
+}
+
+// out[v][0:C] = norm(vmax[v][0:C])   (frames at stride vcap for both)
+__global__ void __launch_bounds__(256) normalize_vmax_kernel(const int *__restrict__ vmax, float *__restrict__ out, int C,
+                                                             int vcap, long long nvox_fixed, NormSrc n) {
+    __shared__ float s_mean[768], s_rstd[768];
+    const int f = blockIdx.y;
+    const double Rs = stat_rows(n, f);
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        norm_coef(n.stats + ((size_t)f * C + c) * 2, Rs, n.eps, s_mean[c], s_rstd[c]);
+    __syncthreads();
+    const long long nv = n.counts ? n.counts[f * 4 + 0] : nvox_fixed;
+    const int c4n = C / 4;
+    const long long total = nv * c4n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long v = e / c4n;
+        const int c = (int)(e - v * c4n) * 4;
+        const int4 m = *reinterpret_cast<const int4 *>(vmax + ((size_t)f * vcap + v) * C + c);
+        float4 q;
+        q.x = (__int_as_float(m.x) - s_mean[c]) * s_rstd[c];
+        q.y = (__int_as_float(m.y) - s_mean[c + 1]) * s_rstd[c + 1];
+        q.z = (__int_as_float(m.z) - s_mean[c + 2]) * s_rstd[c + 2];
+        q.w = (__int_as_float(m.w) - s_mean[c + 3]) * s_rstd[c + 3];
+        *reinterpret_cast<float4 *>(out + ((size_t)f * vcap + v) * C + c) = q;
+    }
+}
+
+// ---- fused-path glue ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_vfe1_kernel(VfePrepArgs a) {
+    __shared__ float s_mean[16], s_rstd[16];
+    const int f = blockIdx.y;
+    if (threadIdx.x < 16)
+        norm_coef(a.n5.stats + ((size_t)f * 16 + threadIdx.x) * 2, stat_rows(a.n5, f), a.n5.eps, s_mean[threadIdx.x],
+                  s_rstd[threadIdx.x]);
+    __syncthreads();
+    const int K = a.counts[f * 4 + 1];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > K) return;
+    const size_t ro = (size_t)f * a.capA + r;
+    const float4 v0 = *reinterpret_cast<const float4 *>(a.vox8 + ro * 8);
+    const float4 v1 = *reinterpret_cast<const float4 *>(a.vox8 + ro * 8 + 4);
+    float y[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4 *>(y + q * 4) = *reinterpret_cast<const float4 *>(a.Y5 + ro * 16 + q * 4);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) y[c] = (y[c] - s_mean[c]) * s_rstd[c];
+    // [x y z dx dy dz r | im16 | 0 x 9]  (MVXNet.py:26; Cin 23 zero-padded to 32)
+    float4 *o = reinterpret_cast<float4 *>(a.X6 + ro * 32);
+    o[0] = v0;
+    o[1] = make_float4(v1.x, v1.y, v1.z, y[0]);
+    o[2] = make_float4(y[1], y[2], y[3], y[4]);
+    o[3] = make_float4(y[5], y[6], y[7], y[8]);
+    o[4] = make_float4(y[9], y[10], y[11], y[12]);
+    o[5] = make_float4(y[13], y[14], y[15], 0.f);
+    o[6] = make_float4(0.f, 0.f, 0.f, 0.f);
+    o[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256) prep_vfe2_kernel(VfePrepArgs a) {
+    __shared__ float s_mean[16], s_rstd[16];
+    const int f = blockIdx.y;
+    if (threadIdx.x < 16)
+        norm_coef(a.n6.stats + ((size_t)f * 16 + threadIdx.x) * 2, stat_rows(a.n6, f), a.n6.eps, s_mean[threadIdx.x],
+                  s_rstd[threadIdx.x]);
+    __syncthreads();
+    const int N = a.counts[f * 4 + 0], K = a.counts[f * 4 + 1];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= K + N) return;
+    const bool pad = r >= K;
+    const int v = pad ? r - K : a.row_vox[(size_t)f * a.cap + r];
+    const int cnt = a.vox_cnt[(size_t)f * a.cap + v];
+    const float *ypad = a.Y6 + ((size_t)f * a.capA + K) * 16;            // the frame's pad row after VFE1's FCN
+    const float *ysrc = pad ? ypad : a.Y6 + ((size_t)f * a.capA + r) * 16;
+    const int *vm = a.vmax6 + ((size_t)f * a.cap + v) * 16;
+    float o[32];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        float m = __int_as_float(vm[c]);
+        if (cnt < a.T) m = fmaxf(m, ypad[c]);  // pad slots take part in the max over T (SURVEY.md trap 6)
+        o[c] = (ysrc[c] - s_mean[c]) * s_rstd[c];
+        o[16 + c] = (m - s_mean[c]) * s_rstd[c];
+    }
+    float4 *dst = reinterpret_cast<float4 *>(a.X7 + ((size_t)f * a.capB + r) * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+    const int wpad = a.T - cnt;
+    a.rowB_w[(size_t)f * a.capB + r] = pad ? (float)wpad : 1.f;
+    a.rowB_v[(size_t)f * a.capB + r] = (pad && wpad == 0) ? -1 : v;
+}
+
+__global__ void __launch_bounds__(256) prep_fcn_kernel(VfePrepArgs a) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int f = blockIdx.y;
+    if (threadIdx.x < 64)
+        norm_coef(a.n7.stats + ((size_t)f * 64 + threadIdx.x) * 2, stat_rows(a.n7, f), a.n7.eps, s_mean[threadIdx.x],
+                  s_rstd[threadIdx.x]);
+    __syncthreads();
+    const int N = a.counts[f * 4 + 0], K = a.counts[f * 4 + 1];
+    const int r = blockIdx.x * 32 + (threadIdx.x >> 3), part = threadIdx.x & 7;  // 8 threads per row, 16 floats each
+    if (r >= K + N) return;
+    const int v = r >= K ? r - K : a.row_vox[(size_t)f * a.cap + r];
+    const size_t ro = (size_t)f * a.capB + r;
+    float *dst = a.X8 + ro * 128 + part * 16;
+    if (part < 4) {
+        const float *src = a.Y7 + ro * 64 + part * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 t = *reinterpret_cast<const float4 *>(src + q * 4);
+            const int c = part * 16 + q * 4;
+            t.x = (t.x - s_mean[c]) * s_rstd[c];
+            t.y = (t.y - s_mean[c + 1]) * s_rstd[c + 1];
+            t.z = (t.z - s_mean[c + 2]) * s_rstd[c + 2];
+            t.w = (t.w - s_mean[c + 3]) * s_rstd[c + 3];
+            *reinterpret_cast<float4 *>(dst + q * 4) = t;
+        }
+    } else {
+        const int *src = a.vmax7 + ((size_t)f * a.cap + v) * 64 + (part - 4) * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int4 m = *reinterpret_cast<const int4 *>(src + q * 4);
+            const int c = (part - 4) * 16 + q * 4;
+            float4 t;
+            t.x = (__int_as_float(m.x) - s_mean[c]) * s_rstd[c];
+            t.y = (__int_as_float(m.y) - s_mean[c + 1]) * s_rstd[c + 1];
+            t.z = (__int_as_float(m.z) - s_mean[c + 2]) * s_rstd[c + 2];
+            t.w = (__int_as_float(m.w) - s_mean[c + 3]) * s_rstd[c + 3];
+            *reinterpret_cast<float4 *>(dst + q * 4) = t;
+        }
+    }
+}
+
+}  // namespace
+
+int launch_layer(const LayerArgs &a, int F, cudaStream_t st) {
+    MVX_REQUIRE(a.Cin % 16 == 0 && a.Cin <= 768 && a.ldx % 4 == 0, MVX_EINVAL, "layer: Cin must be a multiple of 16, <= 768");
+    MVX_REQUIRE(a.Cout % 16 == 0 && (a.Y == nullptr || a.ldy % 4 == 0), MVX_EINVAL, "layer: Cout must be a multiple of 16");
+    const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
+    if (max_rows <= 0) return MVX_OK;
+    const unsigned tiles = (unsigned)ceil_div(max_rows, kBM);
+    if (a.Cout % 128 == 0) {
+        fcn_layer_kernel<128><<<dim3(tiles, a.Cout / 128, F), 256, 0, st>>>(a);
+    } else if (a.Cout % 64 == 0) {
+        fcn_layer_kernel<64><<<dim3(tiles, a.Cout / 64, F), 256, 0, st>>>(a);
+    } else {
+        fcn_layer_kernel<16><<<dim3(tiles, a.Cout / 16, F), 256, 0, st>>>(a);
+    }
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+int launch_prep_vfe1(const VfePrepArgs &a, cudaStream_t st) {
+    prep_vfe1_kernel<<<dim3((a.cap + 1 + 255) / 256, a.B), 256, 0, st>>>(a);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+int launch_prep_vfe2(const VfePrepArgs &a, cudaStream_t st) {
+    prep_vfe2_kernel<<<dim3((a.capB + 255) / 256, a.B), 256, 0, st>>>(a);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+int launch_prep_fcn(const VfePrepArgs &a, cudaStream_t st) {
+    prep_fcn_kernel<<<dim3((a.capB + 31) / 32, a.B), 256, 0, st>>>(a);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+int launch_finalize_vfeat(const VfePrepArgs &a, cudaStream_t st) {
+    normalize_vmax_kernel<<<dim3(kSMs * 2, a.B), 256, 0, st>>>(a.vmax8, a.vfeat, 128, a.cap, 0, a.n8);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+// ---- dense module API ------------------------------------------------------------------------------------
+static int dense_layer(const float *x, int64_t R, int32_t T, int32_t Cin, const float *wt, const float *bias, int32_t Cout,
+                       double eps, float *y, int ldy, double *stats, int *vmax, cudaStream_t st) {
+    MVX_REQUIRE(x && wt && bias && stats && R > 0, MVX_EINVAL, "null pointer / empty input");
+    MVX_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)Cout * 2 * sizeof(double), st));
+    if (vmax) MVX_CUDA_CHECK(cudaMemsetAsync(vmax, 0, (size_t)(R / T) * Cout * sizeof(int), st));
+    LayerArgs a{};
+    a.X = x, a.ldx = Cin, a.Cin = Cin, a.Wt = wt, a.bias = bias, a.Cout = Cout, a.Y = y, a.ldy = ldy;
+    a.out_stats = stats, a.vmax = vmax, a.rows_mode = 0, a.rows_fixed = R, a.rowcap = 0, a.vcap = 0, a.T = T > 0 ? T : 1;
+    a.eps = eps;
+    return launch_layer(a, 1, st);
+}
+
+}  // namespace mvx
+
+extern "C" int mvx_fcn_forward(const float *x, int64_t R, int32_t Cin, const float *wt, const float *bias, int32_t Cout,
+                               double eps, float *y, void *stats_ws, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MVX_REQUIRE(y, MVX_EINVAL, "null output");
+    int rc = mvx::dense_layer(x, R, 1, Cin, wt, bias, Cout, eps, y, Cout, static_cast<double *>(stats_ws), nullptr, st);
+    if (rc) return rc;
+    mvx::NormSrc n{static_cast<const double *>(stats_ws), nullptr, R, 1, eps};
+    mvx::normalize_rows_kernel<<<mvx::kSMs * 8, 256, 0, st>>>(y, R, Cout, Cout, n, nullptr, 1);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+extern "C" int mvx_vfe_forward(const float *x, int64_t R, int32_t T, int32_t Cin, const float *wt, const float *bias,
+                               int32_t Cout, double eps, float *y, void *stats_ws, void *vmax_ws, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MVX_REQUIRE(y && vmax_ws && T > 0 && R % T == 0, MVX_EINVAL, "bad vfe argument");
+    int rc = mvx::dense_layer(x, R, T, Cin, wt, bias, Cout, eps, y, 2 * Cout, static_cast<double *>(stats_ws),
+                              static_cast<int *>(vmax_ws), st);
+    if (rc) return rc;
+    mvx::NormSrc n{static_cast<const double *>(stats_ws), nullptr, R, 1, eps};
+    mvx::normalize_rows_kernel<<<mvx::kSMs * 8, 256, 0, st>>>(y, R, Cout, 2 * Cout, n, static_cast<const int *>(vmax_ws), T);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+extern "C" int mvx_fcn_max_forward(const float *x, int64_t R, int32_t T, int32_t Cin, const float *wt, const float *bias,
+                                   int32_t Cout, double eps, float *y_max, void *stats_ws, void *vmax_ws, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MVX_REQUIRE(y_max && vmax_ws && T > 0 && R % T == 0, MVX_EINVAL, "bad fcn_max argument");
+    int rc = mvx::dense_layer(x, R, T, Cin, wt, bias, Cout, eps, nullptr, 0, static_cast<double *>(stats_ws),
+                              static_cast<int *>(vmax_ws), st);
+    if (rc) return rc;
+    mvx::NormSrc n{static_cast<const double *>(stats_ws), nullptr, R, 1, eps};
+    mvx::normalize_vmax_kernel<<<dim3(mvx::kSMs * 2, 1), 256, 0, st>>>(static_cast<const int *>(vmax_ws), y_max, Cout, 0,
+                                                                      R / T, n);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}

@@ -1,0 +1,67 @@
+// Internal interface of stage 3 (the Linear -> ReLU -> batch-stat BN layer primitive and the VFE glue).
+#pragma once
+#include "common.cuh"
+
+namespace mvx {
+
+// One launch = y = relu(norm_in(X) W^T + b) for every frame of the batch, plus the weighted per-channel
+// sums (sum w*y, sum w*y^2, fp64) that the consumer turns into (mean, rstd), plus an optional per-voxel max.
+struct LayerArgs {
+    const float *X;        // [F][rowcap][ldx] raw input rows
+    int ldx, Cin;          // Cin multiple of 16 (zero-padded columns/weights)
+    const float *Wt;       // (Cin, Cout) = W^T
+    const float *bias;     // (Cout)
+    int Cout;
+    float *Y;              // [F][rowcap][ldy] raw (pre-BN) output, or NULL
+    int ldy;
+    const double *in_stats;  // [F][Cin][2] sums of the producer layer -> normalise X on load; NULL = X is used as is
+    double *out_stats;       // [F][Cout][2]
+    int *vmax;               // [F][vcap][Cout] float bits (y >= 0), or NULL
+    const float *row_w;      // [F][rowcap] BN multiplicity of each row, or NULL (all 1)
+    const int *row_v;        // [F][rowv_cap] voxel of each row (-1: none), or NULL (v = r / T); in rows_mode 1 the
+                             // pad row (r == K_f) belongs to no voxel
+    int rowv_cap;            // frame stride of row_v
+    const int *counts;       // [F][4] device (N_f, K_f, ..), or NULL
+    int rows_mode;           // 0: rows_fixed rows; 1: K_f + 1 rows; 2: K_f + N_f rows
+    long long rows_fixed;
+    int rowcap, vcap, T;
+    double eps;
+};
+int launch_layer(const LayerArgs &a, int F, cudaStream_t st);
+
+// number of rows BN statistics are taken over for frame f: N_f * T (fused path) or rows_fixed (dense API)
+struct NormSrc {
+    const double *stats;   // [F][C][2]
+    const int *counts;     // [F][4] or NULL
+    long long rows_fixed;
+    int T;
+    double eps;
+};
+
+struct VfePrepArgs {
+    int B, cap, capA, capB, T;
+    const int *counts, *vox_cnt, *row_vox;
+    // VFE1 input: X6[r] = [vox7 | norm5(Y5[r]) | 0-pad] (32 cols), rows 0..K_f
+    const float *vox8, *Y5;
+    float *X6;
+    // VFE2 input: X7[r] = [norm6(Y6[r]) | norm6(vmax6[v])] (32), rows 0..K_f-1 real + one pad row per voxel
+    const float *Y6;
+    const int *vmax6;
+    float *X7;
+    float *rowB_w;
+    int *rowB_v;
+    // FCN input: X8[r] = [norm7(Y7[r]) | norm7(vmax7[v])] (128)
+    const float *Y7;
+    const int *vmax7;
+    float *X8;
+    // final: vfeat[v] = norm8(vmax8[v]) (128)
+    const int *vmax8;
+    float *vfeat;
+    NormSrc n5, n6, n7, n8;
+};
+int launch_prep_vfe1(const VfePrepArgs &a, cudaStream_t st);
+int launch_prep_vfe2(const VfePrepArgs &a, cudaStream_t st);
+int launch_prep_fcn(const VfePrepArgs &a, cudaStream_t st);
+int launch_finalize_vfeat(const VfePrepArgs &a, cudaStream_t st);
+
+}  // namespace mvx

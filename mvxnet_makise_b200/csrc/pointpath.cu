@@ -1,0 +1,256 @@
+// The fused batched point path: voxelize -> project + gather -> fusion/VFE layer stack -> dense grid, for B
+// frames per call, stream-ordered, no host synchronisation (MVXNet.py:21-27 up to the CML input, with
+// train.py:26-49's CPU half moved onto the GPU).
+//
+// Compact formulation (SURVEY.md §7 hard part 4): the reference pushes all R = N*T rows (86 % of them
+// identical pad rows) through every layer. Here only the K kept points are rows; pad slots are one weighted
+// row per frame (fusion stack, VFE1) or one per voxel (VFE2, FCN) whose multiplicity enters the BatchNorm
+// sums and whose value joins the per-voxel max, so statistics and outputs equal the dense computation.
+#include "gather.cuh"
+#include "layers.cuh"
+#include "scatter.cuh"
+#include "voxelize.cuh"
+
+namespace mvx {
+
+enum Region {
+    R_VOXWS = 0, R_VOX_COORD, R_VOX_CNT, R_VOX_ROW0, R_ROW_POINT, R_ROW_VOX, R_CELL2VID, R_NHWC0, R_NHWC1, R_NHWC2,
+    R_VOX8, R_PROJ, R_ROWA_W, R_A1, R_Y1, R_Y2, R_Y3, R_Y4, R_Y5, R_X6, R_Y6, R_X7, R_Y7, R_ROWB_W, R_ROWB_V, R_X8,
+    R_VFEAT, R_STATS, R_VMAX6, R_VMAX7, R_VMAX8, R_COUNT
+};
+static_assert(R_COUNT <= MVX_WS_REGIONS, "too many regions");
+
+const char *kRegionNames[R_COUNT] = {
+    "vox_ws", "vox_coord", "vox_cnt", "vox_row0", "row_point", "row_vox", "cell2vid", "nhwc0", "nhwc1", "nhwc2",
+    "vox8", "proj", "rowA_w", "A1", "Y1", "Y2", "Y3", "Y4", "Y5", "X6", "Y6", "X7", "Y7", "rowB_w", "rowB_v", "X8",
+    "vfeat", "stats", "vmax6", "vmax7", "vmax8"};
+
+constexpr int kCin[MVX_NUM_LAYERS] = {768, 768, 128, 128, 16, 32, 32, 128};   // padded
+constexpr int kCout[MVX_NUM_LAYERS] = {768, 128, 128, 16, 16, 16, 64, 128};
+constexpr int kStatStride = 768 * 2;  // doubles per (layer, frame)
+
+struct Layout {
+    size_t off[R_COUNT];
+    size_t total;
+    int capA, capB;
+    long long G;
+};
+
+int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
+    MVX_REQUIRE(a, MVX_EINVAL, "null args");
+    MVX_REQUIRE(a->B >= 1 && a->B <= kMaxFrames, MVX_EINVAL, "B must be in [1,32]");
+    MVX_REQUIRE(a->cap >= 128 && a->cap % 128 == 0, MVX_EINVAL, "cap must be a positive multiple of 128");
+    MVX_REQUIRE(a->map_c == 256, MVX_EINVAL, "map_c must be 256 (3 x 256 = the 768 inputs of fcn1)");
+    const size_t B = a->B, cap = a->cap;
+    L.capA = a->cap + 128;
+    L.capB = 2 * a->cap;
+    L.G = (long long)a->grid.shape[0] * a->grid.shape[1] * a->grid.shape[2];
+    MVX_REQUIRE(L.G > 0 && L.G % 4 == 0, MVX_EINVAL, "grid cell count must be a positive multiple of 4");
+    size_t o = 0;
+    auto take = [&](Region r, size_t bytes) {
+        L.off[r] = o;
+        o += (bytes + 255) / 256 * 256;
+    };
+    take(R_VOXWS, vox_workspace_bytes(a->B, a->cap));
+    take(R_VOX_COORD, B * cap * 16);
+    take(R_VOX_CNT, B * cap * 4);
+    take(R_VOX_ROW0, B * (cap + 1) * 4);
+    take(R_ROW_POINT, B * cap * 4);
+    take(R_ROW_VOX, B * cap * 4);
+    take(R_CELL2VID, B * (size_t)L.G * 4);
+    for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+        MVX_REQUIRE(a->map_h[l] > 0 && a->map_w[l] > 0, MVX_EINVAL, "bad FPN map extent");
+        take((Region)(R_NHWC0 + l), B * (size_t)a->map_h[l] * a->map_w[l] * a->map_c * 4);
+    }
+    const size_t capA = L.capA, capB = L.capB;
+    take(R_VOX8, B * capA * 8 * 4);
+    take(R_PROJ, B * capA * 2 * 4);
+    take(R_ROWA_W, B * capA * 4);
+    take(R_A1, B * capA * 768 * 4);
+    take(R_Y1, B * capA * 768 * 4);
+    take(R_Y2, B * capA * 128 * 4);
+    take(R_Y3, B * capA * 128 * 4);
+    take(R_Y4, B * capA * 16 * 4);
+    take(R_Y5, B * capA * 16 * 4);
+    take(R_X6, B * capA * 32 * 4);
+    take(R_Y6, B * capA * 16 * 4);
+    take(R_X7, B * capB * 32 * 4);
+    take(R_Y7, B * capB * 64 * 4);
+    take(R_ROWB_W, B * capB * 4);
+    take(R_ROWB_V, B * capB * 4);
+    take(R_X8, B * capB * 128 * 4);
+    take(R_VFEAT, B * cap * 128 * 4);
+    take(R_STATS, (size_t)MVX_NUM_LAYERS * B * kStatStride * 8);
+    take(R_VMAX6, B * cap * 16 * 4);
+    take(R_VMAX7, B * cap * 64 * 4);
+    take(R_VMAX8, B * cap * 128 * 4);
+    L.total = o;
+    return MVX_OK;
+}
+
+// zero vmax rows [0, N_f) of each frame (bounded by the device-side voxel count, not by cap)
+__global__ void __launch_bounds__(256) zero_vmax_kernel(const int *__restrict__ counts, int cap, int *__restrict__ v6,
+                                                        int *__restrict__ v7, int *__restrict__ v8) {
+    const int f = blockIdx.y;
+    const long long N = counts[f * 4 + 0];
+    const int4 z = make_int4(0, 0, 0, 0);
+    int4 *p6 = reinterpret_cast<int4 *>(v6 + (size_t)f * cap * 16);
+    int4 *p7 = reinterpret_cast<int4 *>(v7 + (size_t)f * cap * 64);
+    int4 *p8 = reinterpret_cast<int4 *>(v8 + (size_t)f * cap * 128);
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long e = t0; e < N * 4; e += stride) p6[e] = z;
+    for (long long e = t0; e < N * 16; e += stride) p7[e] = z;
+    for (long long e = t0; e < N * 32; e += stride) p8[e] = z;
+}
+
+int pointpath_forward(const mvx_pointpath_args_t *a) {
+    Layout L;
+    int rc = make_layout(a, L);
+    if (rc) return rc;
+    MVX_REQUIRE(a->workspace && a->workspace_bytes >= L.total, MVX_ESPACE, "pointpath workspace too small");
+    MVX_REQUIRE(a->points && a->pt_off_host && a->calib32 && a->counts, MVX_EINVAL, "null input pointer");
+    MVX_REQUIRE(a->point_stride >= 4, MVX_EINVAL, "point_stride must be >= 4");
+    for (int l = 0; l < MVX_NUM_LEVELS; ++l) MVX_REQUIRE(a->maps[l], MVX_EINVAL, "null FPN map");
+    for (int l = 0; l < MVX_NUM_LAYERS; ++l) MVX_REQUIRE(a->wt[l] && a->bias[l], MVX_EINVAL, "null layer weights");
+    cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+    char *ws = static_cast<char *>(a->workspace);
+    const int B = a->B, cap = a->cap, T = a->grid.T;
+    auto F32 = [&](Region r) { return reinterpret_cast<float *>(ws + L.off[r]); };
+    auto I32 = [&](Region r) { return reinterpret_cast<int *>(ws + L.off[r]); };
+
+    // ---- stage 1 ----------------------------------------------------------------------------------------
+    mvx_voxel_out_t vo{};
+    vo.counts = a->counts;
+    vo.vox_coord = I32(R_VOX_COORD), vo.vox_cnt = I32(R_VOX_CNT), vo.vox_row0 = I32(R_VOX_ROW0);
+    vo.row_point = I32(R_ROW_POINT), vo.row_vox = I32(R_ROW_VOX), vo.cell2vid = I32(R_CELL2VID);
+    rc = vox_run(&a->grid, B, cap, a->points, a->point_stride, a->pt_off_host, nullptr, T, &vo, ws + L.off[R_VOXWS],
+                 vox_workspace_bytes(B, cap), st);
+    if (rc) return rc;
+
+    // ---- stage 2 ----------------------------------------------------------------------------------------
+    MapSet m{};
+    m.C = a->map_c;
+    for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+        const int HW = a->map_h[l] * a->map_w[l];
+        m.h[l] = a->map_h[l], m.w[l] = a->map_w[l];
+        m.rs_h[l] = a->imsize_h / (float)a->map_h[l];
+        m.rs_w[l] = a->imsize_w / (float)a->map_w[l];
+        m.nhwc[l] = F32((Region)(R_NHWC0 + l));
+        m.frame_stride[l] = (size_t)HW * a->map_c;
+        rc = launch_nchw_to_nhwc(a->maps[l], F32((Region)(R_NHWC0 + l)), B, a->map_c, HW, st);
+        if (rc) return rc;
+    }
+    RowsParams rp{};
+    rp.B = B, rp.cap = cap, rp.capA = L.capA, rp.T = T;
+    rp.points = a->points, rp.point_stride = a->point_stride;
+    for (int f = 0; f <= B; ++f) rp.off[f] = a->pt_off_host[f];
+    rp.calib32 = a->calib32, rp.counts = a->counts;
+    rp.vox_cnt = vo.vox_cnt, rp.vox_row0 = vo.vox_row0, rp.row_point = vo.row_point, rp.row_vox = vo.row_vox;
+    rp.vox8 = F32(R_VOX8), rp.proj = F32(R_PROJ), rp.rowA_w = F32(R_ROWA_W);
+    rc = launch_rows_build(rp, st);
+    if (rc) return rc;
+    rc = launch_gather_rows(m, B, L.capA, a->counts, F32(R_VOX8), F32(R_PROJ), a->gather_eps, F32(R_A1), st);
+    if (rc) return rc;
+
+    // ---- stage 3 ----------------------------------------------------------------------------------------
+    double *stats = reinterpret_cast<double *>(ws + L.off[R_STATS]);
+    MVX_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)MVX_NUM_LAYERS * B * kStatStride * 8, st));
+    zero_vmax_kernel<<<dim3(kSMs, B), 256, 0, st>>>(a->counts, cap, I32(R_VMAX6), I32(R_VMAX7), I32(R_VMAX8));
+    MVX_LAUNCH_CHECK();
+    auto stat_of = [&](int layer) { return stats + (size_t)layer * B * kStatStride; };
+    // NOTE: stats are stored [F][Cout][2] with the layer's own Cout as the frame stride
+    const float *xin[5] = {F32(R_A1), F32(R_Y1), F32(R_Y2), F32(R_Y3), F32(R_Y4)};
+    float *yout[5] = {F32(R_Y1), F32(R_Y2), F32(R_Y3), F32(R_Y4), F32(R_Y5)};
+    for (int l = 0; l < 5; ++l) {  // fusion stack: fcn1 conv1 fcn2 conv2 fcn3 (Pipe.py:94-104)
+        LayerArgs la{};
+        la.X = xin[l], la.ldx = kCin[l], la.Cin = kCin[l], la.Wt = a->wt[l], la.bias = a->bias[l], la.Cout = kCout[l];
+        la.Y = yout[l], la.ldy = kCout[l];
+        la.in_stats = l == 0 ? nullptr : stat_of(l - 1);
+        la.out_stats = stat_of(l);
+        la.row_w = F32(R_ROWA_W), la.counts = a->counts, la.rows_mode = 1, la.rowcap = L.capA, la.vcap = cap, la.T = T;
+        la.eps = a->bn_eps;
+        rc = launch_layer(la, B, st);
+        if (rc) return rc;
+    }
+    VfePrepArgs vp{};
+    vp.B = B, vp.cap = cap, vp.capA = L.capA, vp.capB = L.capB, vp.T = T;
+    vp.counts = a->counts, vp.vox_cnt = vo.vox_cnt, vp.row_vox = vo.row_vox;
+    vp.vox8 = F32(R_VOX8), vp.Y5 = F32(R_Y5), vp.X6 = F32(R_X6);
+    vp.Y6 = F32(R_Y6), vp.vmax6 = I32(R_VMAX6), vp.X7 = F32(R_X7), vp.rowB_w = F32(R_ROWB_W), vp.rowB_v = I32(R_ROWB_V);
+    vp.Y7 = F32(R_Y7), vp.vmax7 = I32(R_VMAX7), vp.X8 = F32(R_X8);
+    vp.vmax8 = I32(R_VMAX8), vp.vfeat = F32(R_VFEAT);
+    vp.n5 = NormSrc{stat_of(4), a->counts, 0, T, a->bn_eps};
+    vp.n6 = NormSrc{stat_of(5), a->counts, 0, T, a->bn_eps};
+    vp.n7 = NormSrc{stat_of(6), a->counts, 0, T, a->bn_eps};
+    vp.n8 = NormSrc{stat_of(7), a->counts, 0, T, a->bn_eps};
+
+    rc = launch_prep_vfe1(vp, st);
+    if (rc) return rc;
+    {  // VFE1's FCN (23 -> 16) + per-voxel max (voxelnet/Pipe.py:12-18)
+        LayerArgs la{};
+        la.X = F32(R_X6), la.ldx = 32, la.Cin = 32, la.Wt = a->wt[5], la.bias = a->bias[5], la.Cout = 16;
+        la.Y = F32(R_Y6), la.ldy = 16, la.out_stats = stat_of(5), la.vmax = I32(R_VMAX6);
+        la.row_w = F32(R_ROWA_W), la.row_v = vo.row_vox, la.rowv_cap = cap, la.counts = a->counts, la.rows_mode = 1;
+        la.rowcap = L.capA, la.vcap = cap, la.T = T, la.eps = a->bn_eps;
+        rc = launch_layer(la, B, st);
+        if (rc) return rc;
+    }
+    rc = launch_prep_vfe2(vp, st);
+    if (rc) return rc;
+    {  // VFE2's FCN (32 -> 64) + per-voxel max; rows = K_f kept points + one weighted pad row per voxel
+        LayerArgs la{};
+        la.X = F32(R_X7), la.ldx = 32, la.Cin = 32, la.Wt = a->wt[6], la.bias = a->bias[6], la.Cout = 64;
+        la.Y = F32(R_Y7), la.ldy = 64, la.out_stats = stat_of(6), la.vmax = I32(R_VMAX7);
+        la.row_w = F32(R_ROWB_W), la.row_v = I32(R_ROWB_V), la.rowv_cap = L.capB, la.counts = a->counts, la.rows_mode = 2;
+        la.rowcap = L.capB, la.vcap = cap, la.T = T, la.eps = a->bn_eps;
+        rc = launch_layer(la, B, st);
+        if (rc) return rc;
+    }
+    rc = launch_prep_fcn(vp, st);
+    if (rc) return rc;
+    {  // FCN(128,128) + max over T (VoxelNet.py:27-32): only the per-voxel max and the statistics are kept
+        LayerArgs la{};
+        la.X = F32(R_X8), la.ldx = 128, la.Cin = 128, la.Wt = a->wt[7], la.bias = a->bias[7], la.Cout = 128;
+        la.Y = nullptr, la.ldy = 0, la.out_stats = stat_of(7), la.vmax = I32(R_VMAX8);
+        la.row_w = F32(R_ROWB_W), la.row_v = I32(R_ROWB_V), la.rowv_cap = L.capB, la.counts = a->counts, la.rows_mode = 2;
+        la.rowcap = L.capB, la.vcap = cap, la.T = T, la.eps = a->bn_eps;
+        rc = launch_layer(la, B, st);
+        if (rc) return rc;
+    }
+    rc = launch_finalize_vfeat(vp, st);   // vfeat[v] = BN8(max_T) : the (N,128) voxel features in reference voxel order
+    if (rc) return rc;
+
+    // ---- stage 4 ----------------------------------------------------------------------------------------
+    if (a->grid_out) {
+        MVX_REQUIRE((reinterpret_cast<uintptr_t>(a->grid_out) & 15) == 0, MVX_EINVAL, "grid_out must be 16-byte aligned");
+        rc = launch_grid_fill(vo.cell2vid, F32(R_VFEAT), a->grid_out, B, L.G, 128, cap, st);
+        if (rc) return rc;
+    }
+    return MVX_OK;
+}
+
+}  // namespace mvx
+
+extern "C" int mvx_pointpath_workspace_bytes(const mvx_pointpath_args_t *args, size_t *bytes) {
+    mvx::Layout L;
+    int rc = mvx::make_layout(args, L);
+    if (rc) return rc;
+    if (!bytes) return MVX_EINVAL;
+    *bytes = L.total;
+    return MVX_OK;
+}
+
+extern "C" int mvx_pointpath_layout(const mvx_pointpath_args_t *args, int64_t *offsets) {
+    mvx::Layout L;
+    int rc = mvx::make_layout(args, L);
+    if (rc) return rc;
+    if (!offsets) return MVX_EINVAL;
+    for (int r = 0; r < MVX_WS_REGIONS; ++r) offsets[r] = r < mvx::R_COUNT ? (int64_t)L.off[r] : -1;
+    return MVX_OK;
+}
+
+extern "C" const char *mvx_pointpath_layout_name(int32_t region) {
+    return (region >= 0 && region < mvx::R_COUNT) ? mvx::kRegionNames[region] : nullptr;
+}
+
+extern "C" int mvx_pointpath_forward(const mvx_pointpath_args_t *args) { return mvx::pointpath_forward(args); }

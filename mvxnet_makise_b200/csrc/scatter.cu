@@ -1,0 +1,89 @@
+// Stage 4 — dense middle-layer grid (modules/voxelnet/VoxelNet.py:16-22 `reindex`).
+// The reference zero-fills 721 MB and then scatters N*128 isolated 4-byte values (stride G between channels).
+// Here the grid is produced in ONE streaming pass: every CTA owns a run of cells, reads the dense
+// cell -> voxel map (int32, L2 resident) and writes each channel plane with coalesced 16-byte evict-first
+// stores: value = map < 0 ? 0 : feat[vid][c].  HBM traffic = the grid once + the map.
+#include "scatter.cuh"
+
+namespace mvx {
+
+namespace {
+
+constexpr int kCellsPerBlock = 1024;  // 256 threads x 4 consecutive cells
+
+__global__ void __launch_bounds__(256) grid_fill_kernel(const int *__restrict__ cell2vid, const float *__restrict__ feat,
+                                                        float *__restrict__ out, long long G, int C, int vcap, int cgroups) {
+    const int f = blockIdx.z;
+    const int cg = blockIdx.y;                      // channel group
+    const int cper = C / cgroups;
+    const long long cell = (long long)blockIdx.x * kCellsPerBlock + threadIdx.x * 4;
+    if (cell >= G) return;
+    const int *map = cell2vid + (size_t)f * G;
+    const float *ff = feat + (size_t)f * vcap * C;
+    float *o = out + ((size_t)f * C + (size_t)cg * cper) * G + cell;
+    if (cell + 3 < G) {
+        const int4 v = *reinterpret_cast<const int4 *>(map + cell);
+        if ((v.x & v.y & v.z & v.w) < 0) {          // all four empty (-1): the common case, pure zero fill
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+            for (int c = 0; c < cper; ++c) st_cs_f4(reinterpret_cast<float4 *>(o + (size_t)c * G), z4);
+        } else {
+            const float *p0 = v.x >= 0 ? ff + (size_t)v.x * C + cg * cper : nullptr;
+            const float *p1 = v.y >= 0 ? ff + (size_t)v.y * C + cg * cper : nullptr;
+            const float *p2 = v.z >= 0 ? ff + (size_t)v.z * C + cg * cper : nullptr;
+            const float *p3 = v.w >= 0 ? ff + (size_t)v.w * C + cg * cper : nullptr;
+            for (int c = 0; c < cper; ++c) {
+                float4 q;
+                q.x = p0 ? p0[c] : 0.f;
+                q.y = p1 ? p1[c] : 0.f;
+                q.z = p2 ? p2[c] : 0.f;
+                q.w = p3 ? p3[c] : 0.f;
+                st_cs_f4(reinterpret_cast<float4 *>(o + (size_t)c * G), q);
+            }
+        }
+    } else {  // ragged tail (G not a multiple of 4)
+        for (long long g = cell; g < G; ++g) {
+            const int v = map[g];
+            for (int c = 0; c < cper; ++c) out[((size_t)f * C + (size_t)cg * cper + c) * G + g] = v >= 0 ? ff[(size_t)v * C + cg * cper + c] : 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) map_from_idx_kernel(const long long *__restrict__ idx, long long N, int nx, int ny,
+                                                           int nz, int *__restrict__ map) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    // idx row = [batch, ix, iy, iz] (train.py:119); grid is (nz, nx, ny) (VoxelNet.py:19-21)
+    const long long ix = idx[n * 4 + 1], iy = idx[n * 4 + 2], iz = idx[n * 4 + 3];
+    if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) return;
+    map[(iz * nx + ix) * ny + iy] = (int)n;
+}
+
+}  // namespace
+
+int launch_grid_fill(const int *cell2vid, const float *feat, float *out, int B, long long G, int C, int vcap, cudaStream_t st) {
+    const int cgroups = (C % 4 == 0) ? 4 : 1;
+    dim3 grid((unsigned)ceil_div(G, kCellsPerBlock), cgroups, B);
+    grid_fill_kernel<<<grid, 256, 0, st>>>(cell2vid, feat, out, G, C, vcap, cgroups);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+}  // namespace mvx
+
+extern "C" int mvx_scatter_dense(const float *feat, const int64_t *idx, int64_t N, int32_t C, int32_t nx, int32_t ny,
+                                 int32_t nz, float *out, int32_t *map_ws, void *stream) {
+    MVX_REQUIRE(out && map_ws && nx > 0 && ny > 0 && nz > 0 && C > 0, MVX_EINVAL, "bad scatter argument");
+    MVX_REQUIRE(N == 0 || (feat && idx), MVX_EINVAL, "null feat/idx");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long G = (long long)nx * ny * nz;
+    MVX_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (G % 4 == 0), MVX_EINVAL,
+                "grid must be 16-byte aligned with a cell count divisible by 4");
+    MVX_CUDA_CHECK(cudaMemsetAsync(map_ws, 0xFF, (size_t)G * sizeof(int), st));
+    if (N > 0) {
+        mvx::map_from_idx_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(reinterpret_cast<const long long *>(idx), N, nx,
+                                                                               ny, nz, map_ws);
+        MVX_LAUNCH_CHECK();
+    }
+    return mvx::launch_grid_fill(map_ws, feat, out, 1, G, C, (int)N, st);
+}

@@ -1,0 +1,133 @@
+"""The fused batched point path (stages 1-4) behind one call — what ``MVXNet.forward`` does between the image
+backbone and ``VoxelNet.cml`` (MVXNet.py:21-27; Head.py:14-22; VoxelNet.py:24-34), with the CPU half of
+train.py:26-49 (projection + voxelization) moved onto the GPU.
+
+    path = PointPath(state_dict)                      # reference parameter names
+    grid, counts = path(points_list, calibs, fpn_maps)   # (B,128,nz,nx,ny) fp32 on the GPU, counts (B,4) int32
+
+Frames are independent (per-frame BatchNorm statistics, as in the batch-1 reference), so multi-GPU use is pure
+frame sharding: see ``mvxnet_makise_b200.dist``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, synth
+from ._lib import lib, check, ptr, stream_ptr
+from .modules import _wt, pack_calib
+
+LAYER_NAMES = [name for name, *_ in synth.HOT_LAYERS]
+
+
+class PointPath:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], grid: synth.GridSpec = synth.KITTI_GRID,
+                 imsize_hw: Sequence[int] = synth.KITTI_IMSIZE_HW, eps: float = 1e-6, device='cuda'):
+        _lib.require_cuda()
+        self.device = torch.device(device)
+        self.grid_spec = grid
+        self.grid = _lib.make_grid(grid.velorange, grid.voxelsize, grid.voxelshape, grid.T)
+        self.imsize_hw = (float(imsize_hw[0]), float(imsize_hw[1]))
+        self.eps = float(eps)
+        self.load_state_dict(state_dict)
+        self._ws = None
+        self._ws_key = None
+        self._args = None
+
+    def load_state_dict(self, sd):
+        self.wt, self.bias = [], []
+        for name in LAYER_NAMES:
+            w = torch.as_tensor(np.asarray(sd[name + '.weight']) if not isinstance(sd[name + '.weight'], torch.Tensor)
+                                else sd[name + '.weight'])
+            b = torch.as_tensor(np.asarray(sd[name + '.bias']) if not isinstance(sd[name + '.bias'], torch.Tensor)
+                                else sd[name + '.bias'])
+            self.wt.append(_wt(w.to(self.device)))
+            self.bias.append(b.detach().to(self.device, torch.float32).contiguous())
+
+    # ------------------------------------------------------------------------------------------------
+    def _prepare(self, B: int, cap: int, map_hw):
+        key = (B, cap, tuple(map_hw))
+        if self._ws_key == key:
+            return
+        a = _lib.PointPathArgs()
+        a.grid = self.grid
+        a.B, a.cap = B, cap
+        for l, (h, w) in enumerate(map_hw):
+            a.map_h[l], a.map_w[l] = h, w
+        a.map_c = 256
+        nbytes = ctypes.c_size_t()
+        check(lib.mvx_pointpath_workspace_bytes(ctypes.byref(a), ctypes.byref(nbytes)), 'pointpath_workspace_bytes')
+        offs = (ctypes.c_int64 * _lib.WS_REGIONS)()
+        check(lib.mvx_pointpath_layout(ctypes.byref(a), offs), 'pointpath_layout')
+        self.layout = {}
+        for r in range(_lib.WS_REGIONS):
+            n = lib.mvx_pointpath_layout_name(r)
+            if n:
+                self.layout[n.decode()] = int(offs[r])
+        self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        self._ws_key = key
+        self.cap, self.B = cap, B
+        nz, nx, ny = self.grid.shape[2], self.grid.shape[0], self.grid.shape[1]
+        self.grid_out = torch.empty((B, 128, nz, nx, ny), dtype=torch.float32, device=self.device)
+        self.counts = torch.empty((B, 4), dtype=torch.int32, device=self.device)
+
+    def region(self, name: str, dtype, shape):
+        """Typed view into a named workspace region (tests / diagnostics)."""
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        off = self.layout[name]
+        return self._ws[off:off + n].view(dtype).view(*shape)
+
+    # ------------------------------------------------------------------------------------------------
+    def forward_device(self, points: torch.Tensor, offsets: Sequence[int], calib32: torch.Tensor,
+                       maps: List[torch.Tensor], want_grid: bool = True, cap: int | None = None):
+        """points (sum P, stride>=4) fp32 CUDA, offsets host [B+1], calib32 (B,32) CUDA, maps 3 x (B,256,Hf,Wf) CUDA."""
+        B = len(offsets) - 1
+        maxp = max(offsets[i + 1] - offsets[i] for i in range(B))
+        cap = cap or max(128, (maxp + 127) // 128 * 128)
+        map_hw = [(int(m.shape[-2]), int(m.shape[-1])) for m in maps]
+        self._prepare(B, cap, map_hw)
+        a = _lib.PointPathArgs()
+        a.grid = self.grid
+        a.B, a.cap = B, cap
+        a.points, a.point_stride = points.data_ptr(), points.shape[1]
+        off = (ctypes.c_int32 * (B + 1))(*[int(o) for o in offsets])
+        a.pt_off_host = off
+        a.calib32 = calib32.data_ptr()
+        for l in range(3):
+            assert maps[l].is_contiguous() and maps[l].shape[0] == B and maps[l].shape[1] == 256
+            a.maps[l] = maps[l].data_ptr()
+            a.map_h[l], a.map_w[l] = map_hw[l]
+        a.map_c = 256
+        a.imsize_h, a.imsize_w = self.imsize_hw
+        a.gather_eps, a.bn_eps = self.eps, self.eps
+        for l in range(8):
+            a.wt[l] = self.wt[l].data_ptr()
+            a.bias[l] = self.bias[l].data_ptr()
+        a.grid_out = self.grid_out.data_ptr() if want_grid else None
+        a.counts = self.counts.data_ptr()
+        a.workspace, a.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        a.stream = torch.cuda.current_stream().cuda_stream
+        check(lib.mvx_pointpath_forward(ctypes.byref(a)), 'pointpath_forward')
+        return (self.grid_out if want_grid else None), self.counts
+
+    def __call__(self, points_list: List, calibs: List[dict], fpn_maps: List, want_grid: bool = True):
+        """points_list: B arrays/tensors (P_f, >=4) [x,y,z,r]; calibs: B dicts of 4x4 matrices (Load.py:24-41);
+        fpn_maps: 3 tensors (B,256,Hf,Wf) (FPN levels '0','1','2')."""
+        pts = [torch.as_tensor(np.asarray(p, dtype=np.float32)) if not isinstance(p, torch.Tensor) else p for p in points_list]
+        offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in pts])]).tolist()
+        points = torch.cat([p[:, :4].to(torch.float32) for p in pts], dim=0).contiguous().to(self.device, non_blocking=True)
+        calib32 = torch.stack([pack_calib(c) for c in calibs]).to(self.device, non_blocking=True)
+        maps = [torch.as_tensor(m).to(self.device, torch.float32).contiguous() for m in fpn_maps]
+        return self.forward_device(points, offsets, calib32, maps, want_grid)
+
+    # ---- compact outputs (reference voxel order), for callers that do not want the dense grid -----------
+    def voxel_features(self, f: int):
+        """(N_f,128) fp32 features and (N_f,4) int64 idx [batch, ix, iy, iz] of frame f (after a forward)."""
+        n = int(self.counts[f, 0].item())
+        vfeat = self.region('vfeat', torch.float32, (self.B, self.cap, 128))[f, :n]
+        coord = self.region('vox_coord', torch.int32, (self.B, self.cap, 4))[f, :n, :3].to(torch.int64)
+        idx = torch.cat([torch.full((n, 1), f, dtype=torch.int64, device=coord.device), coord], dim=1)
+        return vfeat, idx

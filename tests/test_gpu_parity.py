@@ -1,0 +1,282 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference-generated golden vectors.
+
+Bars (BASELINE.json north_star): voxel coordinates, point->voxel assignment, slots and counts BIT-EXACT;
+gather bit-exact for identical `proj`; layer-stack outputs within 1e-4 relative (fp32), measured per tensor as
+max|a-ref| / max|ref| (BatchNorm with eps=1e-6 amplifies noise on near-dead channels, SURVEY.md §7 hard part 3,
+so the denominator is the tensor's scale, stated here)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mvxnet_makise_b200 import synth
+from oracle import pointpath_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = synth.KITTI_GRID
+TOL = 1e-4
+SMALL_FPN = ((13, 42), (7, 21), (4, 11))
+
+
+def small_maps(seed, shapes=SMALL_FPN, B=1):
+    rng = np.random.default_rng(seed)
+    return [rng.standard_normal((B, 256, h, w), dtype=np.float32) for (h, w) in shapes]
+
+
+def rel_err(a, ref):
+    a = torch.as_tensor(a).double().cpu()
+    ref = torch.as_tensor(ref).double().cpu()
+    return ((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope='module')
+def mvx():
+    import mvxnet_makise_b200.voxelize as V
+    import mvxnet_makise_b200.modules as M
+    import mvxnet_makise_b200.pipeline as P
+    assert torch.cuda.is_available()
+    return type('NS', (), dict(V=V, M=M, P=P))
+
+
+# ------------------------------------------------------------------------------------------- stage 1
+@pytest.mark.parametrize('tag', ['vox_a', 'vox_b'])
+def test_group_matches_reference_golden(mvx, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + '.npz'))
+    vox7, (x, y, z), cnt = mvx.V.cpp._group(g['pcd4'], g['idx'], G.T)
+    assert vox7.dtype == np.float32 and np.array_equal(vox7, g['vox7'])
+    assert x.dtype == np.int64 and np.array_equal(np.stack([x, y, z], 1), g['uidx7'])
+    assert np.array_equal(cnt, g['cnt7'])
+    # numba `group` layout, index math on the GPU in fp64
+    pcd6 = np.concatenate([g['pcd4'], g['proj_uv'][:, [1, 0]]], axis=1).astype(np.float32)
+    vox9, uidx9 = mvx.V.group(pcd6, list(G.velorange), list(G.voxelsize), G.T, shuffle=False)
+    assert vox9.dtype == np.float64 and np.array_equal(uidx9, g['uidx9'])
+    assert np.array_equal(vox9[..., [0, 1, 2, 6, 7, 8]], g['vox9'][..., [0, 1, 2, 6, 7, 8]])
+    np.testing.assert_allclose(vox9[..., 3:6], g['vox9'][..., 3:6], rtol=0, atol=1e-12)
+    assert np.array_equal(vox9.astype(np.float32), g['vox9'].astype(np.float32))
+    # group_ (reference numpy glue around our _group)
+    v7, u7 = mvx.V.group_(g['pcd4'].copy(), list(G.velorange), list(G.voxelsize), G.T, shuffle=False)
+    v7o, u7o = O.group_(g['pcd4'], G.velorange, G.voxelsize, G.T)
+    assert np.array_equal(v7, v7o) and np.array_equal(u7, u7o)
+
+
+def test_group_edge_cases(mvx):
+    T = 35
+    # empty
+    v, (x, y, z), c = mvx.V.cpp._group(np.zeros((0, 4), np.float32), np.zeros((0, 3), np.int32), T)
+    assert v.shape == (0, T, 7) and c.shape == (0,)
+    # single point, P not a multiple of 32, > T points in one voxel, duplicates, negative keys
+    rng = np.random.default_rng(0)
+    for P in (1, 33, 127, 1000):
+        pcd = rng.standard_normal((P, 4)).astype(np.float32)
+        idx = rng.integers(-3, 3, (P, 3)).astype(np.int32)
+        if P == 1000:
+            idx[:600] = (1, 1, 1)            # 600 points in one voxel
+            pcd[10:20] = pcd[0]              # duplicate points
+        a = mvx.V.cpp._group(pcd, idx, T)
+        b = O.cpp_group(pcd, idx, T)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+        assert all(np.array_equal(p, q) for p, q in zip(a[1], b[1]))
+    # fp64 input is force-cast like pybind's array_t<float>
+    pcd64 = rng.standard_normal((50, 5))
+    idx64 = rng.integers(0, 4, (50, 3))
+    a = mvx.V.cpp._group(pcd64, idx64, 4)
+    b = O.cpp_group(pcd64, idx64, 4)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    with pytest.raises(ValueError):
+        mvx.V.cpp._group(np.zeros((4,), np.float32), np.zeros((4, 3), np.int32), T)
+
+
+def test_cell_index_boundary_floats(mvx):
+    """fp64 subtract + TRUE division + truncation on fp32 neighbours of every cell boundary (trap 1)."""
+    r, s = G.velorange, G.voxelsize
+    pts = []
+    for d, n in enumerate(G.voxelshape):
+        b = (np.arange(1, n) * s[d] + r[d]).astype(np.float32)
+        for w in (np.nextafter(b, np.float32(-1e9)), b, np.nextafter(b, np.float32(1e9))):
+            p = np.tile(np.array([[1.0, 1.0, -1.0, 0.5]], np.float32), (len(w), 1))
+            p[:, d] = w
+            pts.append(p)
+    pts = np.concatenate(pts)
+    lo, hi = np.array(r[:3]), np.array(r[3:])
+    pts = pts[np.all((pts[:, :3] >= lo) & (pts[:, :3] < hi), axis=1)]
+    pcd6 = np.concatenate([pts, np.zeros((len(pts), 2), np.float32)], 1)
+    _, uidx = mvx.V.group(pcd6, list(r), list(s), G.T, shuffle=False)
+    _, uidx_o = O.group(pcd6, r, s, G.T)
+    assert np.array_equal(uidx, uidx_o)
+
+
+def test_voxelize_full_size_bit_exact(mvx):
+    """BASELINE size (P = 120 000), against the C oracle (finishes in milliseconds)."""
+    pcd = synth.make_points(0, 120_000)
+    idx = O.cell_index(pcd, G.velorange, G.voxelsize)
+    a = mvx.V.cpp._group(pcd, idx, G.T)
+    b = O.cpp_group(pcd, idx, G.T)
+    assert a[0].shape == b[0].shape and np.array_equal(a[0], b[0])
+    assert np.array_equal(a[2], b[2]) and all(np.array_equal(p, q) for p, q in zip(a[1], b[1]))
+    assert (a[2] == G.T).sum() > 0      # the case exercises the T cap
+
+
+# ------------------------------------------------------------------------------------------- stage 2
+@pytest.mark.parametrize('tag', ['vox_a', 'vox_b'])
+def test_lidar2img_matches_reference_golden(mvx, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + '.npz'))
+    uv = mvx.M.lidar2Img(g['pcd4'], synth.kitti_calib(), True)
+    exact = (uv == g['proj_uv']).all(1).mean()
+    np.testing.assert_allclose(uv, g['proj_uv'], rtol=2e-6, atol=1e-4)
+    assert exact > 0.999, f'only {exact:.4f} of projections bit-exact'
+
+
+@pytest.mark.parametrize('tag', ['path_a', 'path_b'])
+def test_feature_mapping_bit_exact(mvx, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + '.npz'))
+    maps = small_maps(int(g['map_seed']))
+    pcd6 = O.points_with_proj(g['pcd4'], synth.kitti_calib())
+    vox9, _ = O.group(pcd6, G.velorange, G.voxelsize, G.T)
+    v_ref = torch.Tensor(vox9)
+    v_gpu = v_ref.clone().cuda()[None]
+    ref = O.feature_mapping(v_ref, [torch.from_numpy(m) for m in maps], torch.Tensor(list(synth.KITTI_IMSIZE_HW)))
+    out = mvx.M.featureMaping(v_gpu, [torch.from_numpy(m).cuda() for m in maps], [None],
+                              torch.Tensor(list(synth.KITTI_IMSIZE_HW)))[0]
+    assert torch.equal(v_gpu[0].cpu(), v_ref), 'in-place pad zeroing differs'
+    assert np.array_equal(v_gpu[0].cpu().numpy(), g['voxels9_after'])
+    out = out.cpu()
+    assert out.shape == ref.shape
+    assert torch.equal(out, ref), f'gather not bit-exact: max diff {(out - ref).abs().max().item()}'
+    assert np.array_equal(out.reshape(-1, 768)[g['im768_rows']].numpy(), g['im768_sample'])   # the reference itself
+
+
+# ------------------------------------------------------------------------------------------- stage 3
+def test_layer_modules_match_oracle(mvx):
+    torch.manual_seed(0)
+    N, T = 300, 35
+    sd = {k: torch.from_numpy(v) for k, v in synth.make_weights(9).items()}
+    x = torch.randn(1, N, T, 768)
+    x[:, :, 20:] = 0          # pad-like rows
+    fus = mvx.M.ImageFeatureFusion().cuda()
+    fus.load_state_dict({k[len('head.fusion.'):]: v for k, v in sd.items() if k.startswith('head.fusion.')})
+    with torch.no_grad():
+        ref = O.fusion(x, sd)
+        got = fus(x.cuda())
+    assert got.shape == ref.shape and rel_err(got, ref) < TOL
+    head = mvx.M.VoxelNetHead().cuda()
+    head.load_state_dict({k[len('backbone.'):]: v for k, v in sd.items() if k.startswith('backbone.')})
+    x23 = torch.randn(1, N, T, 23)
+    x23[:, :, 25:] = 0
+    with torch.no_grad():
+        ref_v = O.voxel_features(x23, sd)
+        got_v = head.voxel_features(x23.cuda())
+        r1 = O.vfe(x23, sd['backbone.svfe.vfe1.fcn.fc.weight'], sd['backbone.svfe.vfe1.fcn.fc.bias'])
+        g1 = head.svfe.vfe1(x23.cuda())
+    assert g1.shape == r1.shape and rel_err(g1, r1) < TOL
+    assert got_v.shape == ref_v.shape and rel_err(got_v, ref_v) < TOL
+
+
+def test_reindex_exact(mvx):
+    rng = np.random.default_rng(1)
+    N = 500
+    cells = rng.choice(352 * 400 * 10, N, replace=False)
+    iz, rem = np.divmod(cells, 352 * 400)
+    ix, iy = np.divmod(rem, 400)
+    idx = torch.from_numpy(np.stack([np.zeros(N, np.int64), ix, iy, iz], 1))
+    x = torch.randn(N, 128)
+    ref = O.reindex(x, idx, G.voxelshape)
+    got = mvx.M.reindex(x.cuda(), idx.cuda(), G.voxelshape)
+    assert got.shape == ref.shape and torch.equal(got.cpu(), ref)
+    empty = mvx.M.reindex(torch.zeros(0, 128).cuda(), torch.zeros(0, 4, dtype=torch.int64).cuda(), G.voxelshape)
+    assert float(empty.abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------- fused path
+def _check_frame(path, f, ref, counts, gold=None):
+    n = ref['idx'].shape[0]
+    assert counts[f, 0] == n and counts[f, 2] == 0
+    vfeat, idx = path.voxel_features(f)
+    assert np.array_equal(idx.cpu().numpy()[:, 1:], ref['idx'].numpy()[:, 1:])
+    e = rel_err(vfeat, ref['vfeat'])
+    assert e < TOL, f'voxel features rel err {e}'
+    if gold is not None:
+        assert rel_err(vfeat, gold['vfeat']) < TOL      # against the reference's own output
+    return e
+
+
+@pytest.mark.parametrize('tag', ['path_a', 'path_b'])
+def test_fused_path_matches_reference_golden(mvx, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + '.npz'))
+    maps = small_maps(int(g['map_seed']))
+    sd = synth.make_weights(int(g['weight_seed']))
+    calib = synth.kitti_calib()
+    path = mvx.P.PointPath(sd, G)
+    grid, counts = path([g['pcd4']], [calib], [torch.from_numpy(m) for m in maps])
+    torch.cuda.synchronize()
+    counts = counts.cpu().numpy()
+    with torch.no_grad():
+        ref = O.forward_frame(g['pcd4'], calib, maps, sd, G, synth.KITTI_IMSIZE_HW)
+    _check_frame(path, 0, ref, counts, g)
+    # compact rows vs the dense reference tensors: voxel columns bit-exact, fused image features toleranced
+    N, K = int(counts[0, 0]), int(counts[0, 1])
+    cap = path.cap
+    row0 = path.region('vox_row0', torch.int32, (1, cap + 1))[0, :N + 1].cpu().numpy()
+    cnt = path.region('vox_cnt', torch.int32, (1, cap))[0, :N].cpu().numpy()
+    assert row0[N] == K and np.array_equal(cnt, (ref['voxels9'][..., :3] != 0).any(-1).sum(1).numpy())
+    x6 = path.region('X6', torch.float32, (1, cap + 128, 32))[0, :K].cpu()
+    dense_rows = np.concatenate([v * G.T + np.arange(c) for v, c in enumerate(cnt)])
+    v9 = ref['voxels9'].reshape(-1, 9)[dense_rows]
+    assert torch.equal(x6[:, :7], v9[:, :7]), 'voxel feature columns (x,y,z,dx,dy,dz,r) not bit-exact'
+    im16 = ref['im16'].reshape(-1, 16)[dense_rows]
+    assert rel_err(x6[:, 7:23], im16) < TOL
+    assert rel_err(x6[:, 7:23], torch.from_numpy(g['im16']).reshape(-1, 16)[dense_rows]) < TOL
+    # stage 4: exact placement (a copy) and exact zero elsewhere
+    gcpu = grid[0].cpu()
+    assert tuple(gcpu.shape) == tuple(g['grid_shape'][1:])
+    assert int((gcpu != 0).sum()) == int((ref['grid'] != 0).sum())
+    vfeat, idx = path.voxel_features(0)
+    i = idx.cpu()
+    assert torch.equal(gcpu[:, i[:, 3], i[:, 1], i[:, 2]].T, vfeat.cpu())
+    assert rel_err(gcpu, ref['grid'][0]) < TOL
+
+
+def test_fused_batch_equals_single_frames(mvx):
+    """Batch = independent frames with per-frame BatchNorm statistics (SURVEY.md §7 hard part 6)."""
+    sd = synth.make_weights(2)
+    calib = synth.kitti_calib()
+    frames = [synth.make_points(30 + f, P) for f, P in enumerate((900, 2000, 1311))]
+    maps = small_maps(77, B=3)
+    path = mvx.P.PointPath(sd, G)
+    _, counts = path(frames, [calib] * 3, [torch.from_numpy(m) for m in maps], want_grid=False)
+    counts = counts.cpu().numpy()
+    batch = [tuple(t.clone() for t in path.voxel_features(f)) for f in range(3)]
+    for f in range(3):
+        with torch.no_grad():
+            ref = O.forward_frame(frames[f], calib, [m[f:f + 1] for m in maps], sd, G, synth.KITTI_IMSIZE_HW, want_grid=False)
+        _check_frame(path, f, ref, counts)
+    for f in range(3):
+        single = mvx.P.PointPath(sd, G)
+        single([frames[f]], [calib], [torch.from_numpy(m[f:f + 1]) for m in maps], want_grid=False)
+        vf, idx = single.voxel_features(0)
+        assert torch.equal(idx[:, 1:], batch[f][1][:, 1:])
+        assert rel_err(vf, batch[f][0]) < 1e-6      # fp64 atomic accumulation order is the only difference
+
+
+def test_fused_path_full_size_properties(mvx):
+    """BASELINE-size frame (P = 120 000, real FPN shapes): size-independent properties."""
+    sd = synth.make_weights(0)
+    calib = synth.kitti_calib()
+    pts = synth.make_points(0, 120_000)
+    maps = [torch.from_numpy(m) for m in synth.make_fpn_maps(0)]
+    path = mvx.P.PointPath(sd, G)
+    grid, counts = path([pts], [calib], maps)
+    torch.cuda.synchronize()
+    c = counts.cpu().numpy()[0]
+    idx = O.cell_index(pts, G.velorange, G.voxelsize)
+    _, _, coords, cnt = O.group_assign(idx, G.T)
+    assert c[0] == coords.shape[0] and c[1] == cnt.sum() and c[2] == 0
+    vfeat, vidx = path.voxel_features(0)
+    assert np.array_equal(vidx[:, 1:].cpu().numpy(), coords)
+    assert torch.isfinite(vfeat).all()
+    g0 = grid[0]
+    assert int((g0 != 0).sum()) == int((vfeat != 0).sum())
+    assert torch.equal(g0[:, vidx[:, 3], vidx[:, 1], vidx[:, 2]].T, vfeat)
+    # BatchNorm property: over the N*T dense rows every channel of the last layer has mean 0 / var 1; the max over T
+    # of such a channel is >= its mean, so every per-voxel max is >= the smallest normalised value (finite, bounded)
+    assert float(vfeat.abs().max()) < 1e4
