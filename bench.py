@@ -1,0 +1,302 @@
+"""bench.py — frames/s of the point-side hot path (voxelize + fuse + VFE + scatter) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                       # ours (CUDA, through the C ABI)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                           # N ranks, frame-sharded, no collective
+    python bench.py --impl reference --steps K --warmup W                # the reference algorithm on the host cores
+
+A step = one pass of the hot path over one batch of 8 synthetic KITTI-shaped frames per GPU (BASELINE.json
+configs[1]): P = 120 000 points, FPN maps (256,104,336)/(256,52,168)/(256,26,84), grid 352x400x10, T = 35.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_GPU = 8
+POINTS = 120_000
+METRIC = 'frames/sec voxelize+fuse+VFE+scatter'
+WORKLOAD = ('configs[1]: batch-8 synthetic KITTI-shaped frames per GPU (P=120000 pts/frame, FPN maps '
+            '256x{104x336,52x168,26x84} fp32, grid 352x400x10, T=35): voxelize + project + 4-corner gather + '
+            '8-layer fusion/VFE stack (fp32) + dense (128,10,352,400) grid')
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tensor=d.get('bf16_tflops_sustained', d['bf16_tflops']), src='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, tensor=1400.0, src='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if v.strip().lower() == 'active':
+                    reasons.add(name)
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]          # samples under load = upper half
+            out = dict(sm_mhz=statistics.median(top), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_frame(frame_id: int, threads: int):
+    """One full-size frame through the oracle port of the reference path on the host cores; returns seconds + stages."""
+    import torch
+    from mvxnet_makise_b200 import synth
+    from oracle import pointpath_oracle as O
+    torch.set_num_threads(threads)
+    pts = synth.make_points(frame_id, POINTS)
+    maps = synth.make_fpn_maps(frame_id)
+    sd = synth.make_weights(0)
+    stages = {}
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.forward_frame(pts, synth.kitti_calib(), maps, sd, synth.KITTI_GRID, synth.KITTI_IMSIZE_HW, stages=stages)
+    return time.perf_counter() - t0, stages
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    from oracle import pointpath_oracle as O
+    O.build_c_oracle() if not os.path.exists(os.path.join(ROOT, 'oracle', '_build', 'libvoxel_oracle.so')) else None
+    threads = os.cpu_count() or 1
+    budget = 240.0
+    t_first, _ = cpu_reference_frame(0, threads)            # warm-up step 1 (also sizes the run)
+    steps = max(1, min(args.steps, int(budget / max(t_first, 1e-3)) - 1))
+    warm = max(0, min(args.warmup - 1, int((budget - steps * t_first) / max(t_first, 1e-3)) - 1))
+    for w in range(warm):
+        cpu_reference_frame(1 + w, threads)
+    times, stages_acc = [], {}
+    for s in range(steps):
+        t, st = cpu_reference_frame(100 + s, threads)
+        times.append(t)
+        for k, v in st.items():
+            stages_acc[k] = stages_acc.get(k, 0.0) + v / steps
+    total = sum(times)
+    fps = steps / total
+    sample = (f'each step = ONE full-size frame (1 of the 8 frames of the batch, P={POINTS}) through the numpy/torch-CPU port of '
+              f'the reference path (oracle/pointpath_oracle.py), {threads} torch threads; {steps} of {args.steps} requested steps '
+              f'(time-bounded to ~{int(budget)} s)')
+    line = dict(impl='reference', metric=METRIC, value=fps, unit='frames/s', n_gpus=args.gpus, steps=steps, warmup=warm + 1,
+                ms_per_step=1e3 * total / steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', config=dict(workload=WORKLOAD),
+                cpu_baseline=dict(value=fps, unit='frames/s', cores=threads, kind='port', sample=sample,
+                                  stages_s={k: round(v, 4) for k, v in stages_acc.items()}),
+                e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def algorithmic_work(seg: str, N, K, B, G):
+    """(bound, work per launch) for a timed segment: bytes for HBM-bound kernels, flops for the GEMM layers
+    (SURVEY.md §8d minimal figures: kept rows + weighted pad rows only)."""
+    sumK, sumN = float(sum(K)), float(sum(N))
+    rowsA, rowsB = sumK + B, sumK + sumN
+    maps_b = 4.0 * 256 * (104 * 336 + 52 * 168 + 26 * 84)
+    gemm = dict(fcn1=(768, 768, rowsA), conv1=(768, 128, rowsA), fcn2=(128, 128, rowsA), conv2=(128, 16, rowsA),
+                fcn3=(16, 16, rowsA), vfe1=(23, 16, rowsA), vfe2=(32, 64, rowsB), fcn=(128, 128, rowsB))
+    if seg in gemm:
+        cin, cout, rows = gemm[seg]
+        return 'tensor', 2.0 * cin * cout * rows
+    if seg == 'grid_fill':
+        return 'hbm', B * (128.0 * G * 4 + G * 4) + sumN * 512
+    if seg == 'gather':
+        return 'hbm', B * maps_b + rowsA * (3072 + 40)
+    if seg == 'maps_nhwc':
+        return 'hbm', 2 * B * maps_b
+    if seg == 'voxelize':
+        return 'hbm', B * POINTS * 16.0 + sumK * 8 + sumN * 32 + B * G * 4
+    return 'hbm', 0.0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mvxnet_makise_b200 import synth, _lib
+    from mvxnet_makise_b200.pipeline import PointPath
+    from mvxnet_makise_b200.modules import pack_calib
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B, G = FRAMES_PER_GPU, synth.KITTI_GRID.cells
+
+    # ---- synthetic inputs for THIS rank's frames (frame ids are global: weak scaling, frames sharded by rank)
+    frames = [synth.make_points(rank * B + f, POINTS) for f in range(B)]
+    offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in frames])]).tolist()
+    points_h = torch.from_numpy(np.concatenate(frames, 0)).pin_memory()
+    calib_h = torch.stack([pack_calib(synth.kitti_calib()) for _ in range(B)]).pin_memory()
+    g = torch.Generator().manual_seed(1234 + rank)
+    maps_h = [torch.randn((B, 256, h, w), generator=g).pin_memory() for (h, w) in synth.fpn_shapes()]
+    points_d, calib_d = points_h.to(dev), calib_h.to(dev)
+    maps_d = [m.to(dev) for m in maps_h]
+    path = PointPath(synth.make_weights(0), synth.KITTI_GRID, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg (`value`) ----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        path.forward_device(points_d, offsets, calib_d, maps_d)
+    barrier()
+    _lib.check(_lib.lib.mvx_timing_enable(args.steps), 'timing_enable')
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        path.forward_device(points_d, offsets, calib_d, maps_d)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    seg_ms = np.zeros(_lib.NUM_SEGMENTS)
+    buf = (_lib.c_float * _lib.NUM_SEGMENTS)()
+    for c in range(args.steps):
+        _lib.check(_lib.lib.mvx_timing_read(c, buf), 'timing_read')
+        seg_ms += np.array(buf[:]) / args.steps
+    _lib.lib.mvx_timing_enable(0)
+    counts = path.counts.cpu().numpy()
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+
+    # ---- host-buffer leg (`e2e`): pinned H2D of every input + path + D2H of the result, every step -------
+    for _ in range(2):
+        path.forward_host(points_h, offsets, calib_h, maps_h)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        path.forward_host(points_h, offsets, calib_h, maps_h)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    names = [(_lib.lib.mvx_timing_segment_name(i) or b'').decode() for i in range(_lib.NUM_SEGMENTS)]
+    stages = {n: round(float(ms), 4) for n, ms in zip(names, seg_ms) if n}
+    dom = max(stages, key=stages.get)
+    bound, work = algorithmic_work(dom, counts[:, 0], counts[:, 1], B, G)
+    dur_s = stages[dom] * 1e-3
+    if bound == 'tensor':
+        achieved, peak, unit = work / dur_s / 1e12, pk['tensor'], 'TFLOP/s'
+    else:
+        achieved, peak, unit = work / dur_s / 1e9, pk['hbm'], 'GB/s'
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    roofline = dict(kernel=dom, bound=bound, achieved=round(achieved, 3), peak=peak, unit=unit, frac=round(achieved / peak, 4),
+                    traffic=traffic, peak_source=pk['src'], ms_per_launch=stages[dom], share_of_step=round(stages[dom] / (ms_total / args.steps), 4))
+    # every memory-bound stage against the HBM roofline (the north star's per-stage report)
+    per_stage = {}
+    for n in ('voxelize', 'maps_nhwc', 'gather', 'grid_fill'):
+        b, w = algorithmic_work(n, counts[:, 0], counts[:, 1], B, G)
+        if stages.get(n, 0) > 0:
+            per_stage[n] = dict(gbs=round(w / (stages[n] * 1e-3) / 1e9, 1), frac_hbm=round(w / (stages[n] * 1e-3) / 1e9 / pk['hbm'], 4))
+    for n in ('fcn1', 'conv1'):
+        b, w = algorithmic_work(n, counts[:, 0], counts[:, 1], B, G)
+        per_stage[n] = dict(tflops=round(w / (stages[n] * 1e-3) / 1e12, 2), frac_tensor=round(w / (stages[n] * 1e-3) / 1e12 / pk['tensor'], 4))
+
+    line = dict(metric=METRIC, value=world * B * args.steps / (ms_total * 1e-3), unit='frames/s', n_gpus=world, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload=WORKLOAD, frames_per_gpu=B, points_per_frame=POINTS,
+                            voxels_per_frame=int(counts[:, 0].mean()), kept_points_per_frame=int(counts[:, 1].mean()),
+                            l2='no flush: per step the inputs (376 MB FPN maps) and outputs (5.8 GB grid) exceed the 126 MB L2',
+                            parallelism=f'frame-sharded x{world}, no forward collective'),
+                clocks=clocks,
+                e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=int(path.h2d_bytes),
+                         d2h_bytes_per_step=int(path.d2h_bytes), ms_per_step=ms_e2e / args.steps,
+                         note='PointPath.forward_host: pinned-host points+calib+FPN maps -> H2D -> fused path -> D2H counts + feature head'),
+                gpu_launches=int(launches), roofline=roofline, stages_ms=stages, stage_rooflines=per_stage)
+    if world == 1 and not args.no_cpu_baseline:
+        t, st = cpu_reference_frame(0, os.cpu_count() or 1)
+        line['cpu_baseline'] = dict(value=1.0 / t, unit='frames/s', cores=os.cpu_count() or 1, kind='port',
+                                    sample=f'1 full-size frame (P={POINTS}) of the batch through oracle/pointpath_oracle.py (numpy + torch CPU fp32)',
+                                    stages_s={k: round(v, 3) for k, v in st.items()})
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -158,6 +158,15 @@ int mvx_pointpath_layout(const mvx_pointpath_args_t *args, int64_t *offsets /* [
 const char *mvx_pointpath_layout_name(int32_t region);
 int mvx_pointpath_forward(const mvx_pointpath_args_t *args);
 
+/* Optional per-kernel timing of mvx_pointpath_forward with CUDA events recorded on the launching stream
+ * (bench.py's roofline leg). mvx_timing_enable(n) arms n event sets (one per forward call, n = 0 disables);
+ * mvx_timing_read(call, ms) waits for that call's last event and returns MVX_NUM_SEGMENTS durations in ms, in the
+ * order of mvx_timing_segment_name(). */
+#define MVX_NUM_SEGMENTS 20
+int mvx_timing_enable(int32_t max_calls);
+int mvx_timing_read(int32_t call, float *ms /* [MVX_NUM_SEGMENTS] */);
+const char *mvx_timing_segment_name(int32_t segment);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_PKG, 'libmvx_b200.so')
 NUM_LAYERS = 8
 NUM_LEVELS = 3
 WS_REGIONS = 40
+NUM_SEGMENTS = 20
 
 # every symbol include/mvx_b200.h declares (tests check that the .so exports all of them)
 EXPORTS = [
@@ -27,6 +28,7 @@ EXPORTS = [
     'mvx_lidar2img', 'mvx_maps_nhwc_bytes', 'mvx_feature_mapping',
     'mvx_fcn_forward', 'mvx_vfe_forward', 'mvx_fcn_max_forward', 'mvx_scatter_dense',
     'mvx_pointpath_workspace_bytes', 'mvx_pointpath_layout', 'mvx_pointpath_layout_name', 'mvx_pointpath_forward',
+    'mvx_timing_enable', 'mvx_timing_read', 'mvx_timing_segment_name',
 ]
 
 
@@ -85,6 +87,10 @@ def _load():
     lib.mvx_pointpath_layout_name.argtypes = [i32]
     lib.mvx_pointpath_layout_name.restype = c_char_p
     lib.mvx_pointpath_forward.argtypes = [POINTER(PointPathArgs)]
+    lib.mvx_timing_enable.argtypes = [i32]
+    lib.mvx_timing_read.argtypes = [i32, POINTER(c_float)]
+    lib.mvx_timing_segment_name.argtypes = [i32]
+    lib.mvx_timing_segment_name.restype = c_char_p
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is ctypes.c_int:   # default restype: the int status code
@@ -116,6 +122,9 @@ def stream_ptr():
 
 def ptr(t) -> c_void_p:
     return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+c_float = c_float  # re-export for callers building timing buffers
 
 
 def launch_count() -> int:

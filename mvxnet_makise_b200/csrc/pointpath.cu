@@ -11,6 +11,8 @@
 #include "scatter.cuh"
 #include "voxelize.cuh"
 
+#include <vector>
+
 namespace mvx {
 
 enum Region {
@@ -88,6 +90,32 @@ int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
     return MVX_OK;
 }
 
+// ---- optional CUDA-event timing of the stages (bench.py roofline leg) -------------------------------------
+enum Segment {
+    S_VOXELIZE = 0, S_NHWC, S_ROWS, S_GATHER, S_CLEAR, S_FCN1, S_CONV1, S_FCN2, S_CONV2, S_FCN3, S_PREP1, S_VFE1,
+    S_PREP2, S_VFE2, S_PREP3, S_FCN, S_VFEAT, S_GRID, S_COUNT
+};
+static_assert(S_COUNT <= MVX_NUM_SEGMENTS, "too many segments");
+const char *kSegmentNames[S_COUNT] = {"voxelize", "maps_nhwc", "rows_build", "gather", "clear", "fcn1", "conv1", "fcn2",
+                                      "conv2", "fcn3", "prep_vfe1", "vfe1", "prep_vfe2", "vfe2", "prep_fcn", "fcn",
+                                      "finalize_vfeat", "grid_fill"};
+struct Timing {
+    std::vector<cudaEvent_t> ev;  // [calls][S_COUNT + 1]
+    int max_calls = 0, next = 0;
+};
+static Timing g_timing;
+
+struct Stamp {
+    cudaEvent_t *ev = nullptr;
+    cudaStream_t st;
+    explicit Stamp(cudaStream_t s) : st(s) {
+        if (g_timing.max_calls > 0 && g_timing.next < g_timing.max_calls) ev = &g_timing.ev[(size_t)g_timing.next++ * (S_COUNT + 1)];
+    }
+    void mark(int i) const {
+        if (ev) cudaEventRecord(ev[i], st);
+    }
+};
+
 // zero vmax rows [0, N_f) of each frame (bounded by the device-side voxel count, not by cap)
 __global__ void __launch_bounds__(256) zero_vmax_kernel(const int *__restrict__ counts, int cap, int *__restrict__ v6,
                                                         int *__restrict__ v7, int *__restrict__ v8) {
@@ -118,6 +146,8 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
     auto F32 = [&](Region r) { return reinterpret_cast<float *>(ws + L.off[r]); };
     auto I32 = [&](Region r) { return reinterpret_cast<int *>(ws + L.off[r]); };
 
+    const Stamp stamp(st);
+    stamp.mark(S_VOXELIZE);
     // ---- stage 1 ----------------------------------------------------------------------------------------
     mvx_voxel_out_t vo{};
     vo.counts = a->counts;
@@ -127,6 +157,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
                  vox_workspace_bytes(B, cap), st);
     if (rc) return rc;
 
+    stamp.mark(S_NHWC);
     // ---- stage 2 ----------------------------------------------------------------------------------------
     MapSet m{};
     m.C = a->map_c;
@@ -140,6 +171,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
         rc = launch_nchw_to_nhwc(a->maps[l], F32((Region)(R_NHWC0 + l)), B, a->map_c, HW, st);
         if (rc) return rc;
     }
+    stamp.mark(S_ROWS);
     RowsParams rp{};
     rp.B = B, rp.cap = cap, rp.capA = L.capA, rp.T = T;
     rp.points = a->points, rp.point_stride = a->point_stride;
@@ -149,9 +181,11 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
     rp.vox8 = F32(R_VOX8), rp.proj = F32(R_PROJ), rp.rowA_w = F32(R_ROWA_W);
     rc = launch_rows_build(rp, st);
     if (rc) return rc;
+    stamp.mark(S_GATHER);
     rc = launch_gather_rows(m, B, L.capA, a->counts, F32(R_VOX8), F32(R_PROJ), a->gather_eps, F32(R_A1), st);
     if (rc) return rc;
 
+    stamp.mark(S_CLEAR);
     // ---- stage 3 ----------------------------------------------------------------------------------------
     double *stats = reinterpret_cast<double *>(ws + L.off[R_STATS]);
     MVX_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)MVX_NUM_LAYERS * B * kStatStride * 8, st));
@@ -162,6 +196,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
     const float *xin[5] = {F32(R_A1), F32(R_Y1), F32(R_Y2), F32(R_Y3), F32(R_Y4)};
     float *yout[5] = {F32(R_Y1), F32(R_Y2), F32(R_Y3), F32(R_Y4), F32(R_Y5)};
     for (int l = 0; l < 5; ++l) {  // fusion stack: fcn1 conv1 fcn2 conv2 fcn3 (Pipe.py:94-104)
+        stamp.mark(S_FCN1 + l);
         LayerArgs la{};
         la.X = xin[l], la.ldx = kCin[l], la.Cin = kCin[l], la.Wt = a->wt[l], la.bias = a->bias[l], la.Cout = kCout[l];
         la.Y = yout[l], la.ldy = kCout[l];
@@ -184,9 +219,11 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
     vp.n7 = NormSrc{stat_of(6), a->counts, 0, T, a->bn_eps};
     vp.n8 = NormSrc{stat_of(7), a->counts, 0, T, a->bn_eps};
 
+    stamp.mark(S_PREP1);
     rc = launch_prep_vfe1(vp, st);
     if (rc) return rc;
     {  // VFE1's FCN (23 -> 16) + per-voxel max (voxelnet/Pipe.py:12-18)
+        stamp.mark(S_VFE1);
         LayerArgs la{};
         la.X = F32(R_X6), la.ldx = 32, la.Cin = 32, la.Wt = a->wt[5], la.bias = a->bias[5], la.Cout = 16;
         la.Y = F32(R_Y6), la.ldy = 16, la.out_stats = stat_of(5), la.vmax = I32(R_VMAX6);
@@ -195,9 +232,11 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
         rc = launch_layer(la, B, st);
         if (rc) return rc;
     }
+    stamp.mark(S_PREP2);
     rc = launch_prep_vfe2(vp, st);
     if (rc) return rc;
     {  // VFE2's FCN (32 -> 64) + per-voxel max; rows = K_f kept points + one weighted pad row per voxel
+        stamp.mark(S_VFE2);
         LayerArgs la{};
         la.X = F32(R_X7), la.ldx = 32, la.Cin = 32, la.Wt = a->wt[6], la.bias = a->bias[6], la.Cout = 64;
         la.Y = F32(R_Y7), la.ldy = 64, la.out_stats = stat_of(6), la.vmax = I32(R_VMAX7);
@@ -206,9 +245,11 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
         rc = launch_layer(la, B, st);
         if (rc) return rc;
     }
+    stamp.mark(S_PREP3);
     rc = launch_prep_fcn(vp, st);
     if (rc) return rc;
     {  // FCN(128,128) + max over T (VoxelNet.py:27-32): only the per-voxel max and the statistics are kept
+        stamp.mark(S_FCN);
         LayerArgs la{};
         la.X = F32(R_X8), la.ldx = 128, la.Cin = 128, la.Wt = a->wt[7], la.bias = a->bias[7], la.Cout = 128;
         la.Y = nullptr, la.ldy = 0, la.out_stats = stat_of(7), la.vmax = I32(R_VMAX8);
@@ -217,19 +258,48 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
         rc = launch_layer(la, B, st);
         if (rc) return rc;
     }
+    stamp.mark(S_VFEAT);
     rc = launch_finalize_vfeat(vp, st);   // vfeat[v] = BN8(max_T) : the (N,128) voxel features in reference voxel order
     if (rc) return rc;
 
+    stamp.mark(S_GRID);
     // ---- stage 4 ----------------------------------------------------------------------------------------
     if (a->grid_out) {
         MVX_REQUIRE((reinterpret_cast<uintptr_t>(a->grid_out) & 15) == 0, MVX_EINVAL, "grid_out must be 16-byte aligned");
         rc = launch_grid_fill(vo.cell2vid, F32(R_VFEAT), a->grid_out, B, L.G, 128, cap, st);
         if (rc) return rc;
     }
+    stamp.mark(S_COUNT);
     return MVX_OK;
 }
 
 }  // namespace mvx
+
+extern "C" int mvx_timing_enable(int32_t max_calls) {
+    auto &t = mvx::g_timing;
+    for (cudaEvent_t e : t.ev) cudaEventDestroy(e);
+    t.ev.clear();
+    t.max_calls = 0, t.next = 0;
+    if (max_calls <= 0) return MVX_OK;
+    t.ev.resize((size_t)max_calls * (mvx::S_COUNT + 1));
+    for (auto &e : t.ev) MVX_CUDA_CHECK(cudaEventCreate(&e));
+    t.max_calls = max_calls;
+    return MVX_OK;
+}
+
+extern "C" int mvx_timing_read(int32_t call, float *ms) {
+    auto &t = mvx::g_timing;
+    MVX_REQUIRE(ms && call >= 0 && call < t.next, MVX_EINVAL, "no timing recorded for this call");
+    cudaEvent_t *ev = &t.ev[(size_t)call * (mvx::S_COUNT + 1)];
+    MVX_CUDA_CHECK(cudaEventSynchronize(ev[mvx::S_COUNT]));
+    for (int i = 0; i < MVX_NUM_SEGMENTS; ++i) ms[i] = 0.f;
+    for (int i = 0; i < mvx::S_COUNT; ++i) MVX_CUDA_CHECK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    return MVX_OK;
+}
+
+extern "C" const char *mvx_timing_segment_name(int32_t segment) {
+    return (segment >= 0 && segment < mvx::S_COUNT) ? mvx::kSegmentNames[segment] : nullptr;
+}
 
 extern "C" int mvx_pointpath_workspace_bytes(const mvx_pointpath_args_t *args, size_t *bytes) {
     mvx::Layout L;

@@ -123,6 +123,41 @@ class PointPath:
         maps = [torch.as_tensor(m).to(self.device, torch.float32).contiguous() for m in fpn_maps]
         return self.forward_device(points, offsets, calib32, maps, want_grid)
 
+    # ---- host-buffer entry: H2D of this batch's inputs, the fused path, D2H of the counts ---------------
+    def forward_host(self, points_host: torch.Tensor, offsets: Sequence[int], calib32_host: torch.Tensor,
+                     maps_host: List[torch.Tensor], want_grid: bool = True, head_rows: int = 1024):
+        """Inputs in (ideally pinned) HOST memory: points (sum P, 4) fp32, calib32 (B,32), maps 3 x (B,256,Hf,Wf).
+        Copies them to persistent device buffers on the current stream, runs the fused path and reads back the
+        per-frame counts and the first `head_rows` voxel feature rows of frame 0 (the host-visible result).
+        Returns (grid on device, counts on host, head block on host); synchronises the stream."""
+        dev = self.device
+        key = (tuple(points_host.shape), tuple(calib32_host.shape), tuple(tuple(m.shape) for m in maps_host))
+        if getattr(self, '_in_key', None) != key:
+            self._in_points = torch.empty(points_host.shape, dtype=torch.float32, device=dev)
+            self._in_calib = torch.empty(calib32_host.shape, dtype=torch.float32, device=dev)
+            self._in_maps = [torch.empty(m.shape, dtype=torch.float32, device=dev) for m in maps_host]
+            self._out_counts = torch.empty((len(offsets) - 1, 4), dtype=torch.int32).pin_memory()
+            self._out_head = torch.empty((head_rows, 128), dtype=torch.float32).pin_memory()
+            self._in_key = key
+        self._in_points.copy_(points_host, non_blocking=True)
+        self._in_calib.copy_(calib32_host, non_blocking=True)
+        for d, h in zip(self._in_maps, maps_host):
+            d.copy_(h, non_blocking=True)
+        grid, counts = self.forward_device(self._in_points, offsets, self._in_calib, self._in_maps, want_grid)
+        self._out_counts.copy_(counts, non_blocking=True)
+        head = self.region('vfeat', torch.float32, (self.B, self.cap, 128))[0, :head_rows]
+        self._out_head.copy_(head, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return grid, self._out_counts, self._out_head
+
+    @property
+    def h2d_bytes(self):
+        return (self._in_points.numel() + self._in_calib.numel() + sum(m.numel() for m in self._in_maps)) * 4
+
+    @property
+    def d2h_bytes(self):
+        return self._out_counts.numel() * 4 + self._out_head.numel() * 4
+
     # ---- compact outputs (reference voxel order), for callers that do not want the dense grid -----------
     def voxel_features(self, f: int):
         """(N_f,128) fp32 features and (N_f,4) int64 idx [batch, ix, iy, iz] of frame f (after a forward)."""

@@ -225,13 +225,19 @@ def reindex(x: torch.Tensor, idx: torch.Tensor, voxelshape) -> torch.Tensor:
 
 # --------------------------------------------------------------------------- whole path, one frame
 def forward_frame(pcd4: np.ndarray, calib_np, fpn_maps: List[np.ndarray], sd_np, grid, imsize_hw,
-                  eps: float = 1e-6, want_grid: bool = True, stages: dict | None = None):
+                  eps: float = 1e-6, want_grid: bool = True, stages: dict | None = None,
+                  dtype: torch.dtype = torch.float32):
     """The reference's chain for ONE frame, shuffle disabled (trap 3):
     lidar2Img -> group -> [host glue train.py:118-128] -> featureMaping -> fusion -> concat
-    (MVXNet.py:25-26) -> SVFE/FCN/max -> reindex. Returns dict of intermediate results."""
+    (MVXNet.py:25-26) -> SVFE/FCN/max -> reindex. Returns dict of intermediate results.
+
+    dtype=torch.float64 evaluates the SAME layer stack (stage 3) in double precision on the fp32 gather
+    output: the rounding-free value of the reference algorithm, used by the tests to separate the fp32
+    reference's own rounding noise (BatchNorm with 86 % identical pad rows normalises real rows to tens of
+    sigma, so fp32 statistics noise is amplified) from errors of the implementation under test."""
     import time
     t = {}
-    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()}
+    sd = {k: torch.from_numpy(np.asarray(v)).to(dtype) for k, v in sd_np.items()}
     t0 = time.perf_counter()
     pcd6 = points_with_proj(pcd4, calib_np)
     t['project'] = time.perf_counter() - t0
@@ -246,10 +252,10 @@ def forward_frame(pcd4: np.ndarray, calib_np, fpn_maps: List[np.ndarray], sd_np,
     im768 = feature_mapping(voxels, feats, imsize, eps)
     t['gather'] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    im16 = fusion(im768[None], sd, eps)
+    im16 = fusion(im768[None].to(dtype), sd, eps)
     t['fusion'] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    x23 = torch.concat([voxels[None][..., :7], im16], dim=-1)            # MVXNet.py:26
+    x23 = torch.concat([voxels[None][..., :7].to(dtype), im16], dim=-1)  # MVXNet.py:26
     vfeat = voxel_features(x23, sd, eps)
     t['vfe'] = time.perf_counter() - t0
     out = {'voxels9': voxels, 'idx': idx, 'im768': im768, 'im16': im16[0], 'vfeat': vfeat, 'times': t}

@@ -1,9 +1,16 @@
 """Parity of the CUDA path (through the C ABI) against the oracle and the reference-generated golden vectors.
 
 Bars (BASELINE.json north_star): voxel coordinates, point->voxel assignment, slots and counts BIT-EXACT;
-gather bit-exact for identical `proj`; layer-stack outputs within 1e-4 relative (fp32), measured per tensor as
-max|a-ref| / max|ref| (BatchNorm with eps=1e-6 amplifies noise on near-dead channels, SURVEY.md §7 hard part 3,
-so the denominator is the tensor's scale, stated here)."""
+gather bit-exact for identical `proj`; layer-stack outputs within TOL = 1e-4 relative (fp32), measured per
+tensor as max|a-ref| / max|ref|.
+
+What "ref" is for the 8-layer chain: the fp32 reference is itself noisy at this level. 86 % of the N*T rows are
+identical pad rows, so BatchNorm normalises real rows to tens of sigma and the fp32 rounding of the reference's
+own GEMMs/statistics shows up as 1.2e-4 .. 3.5e-4 relative at the end of the chain (measured: the reference vs
+the same algorithm evaluated in fp64, tools/diag_layers.py). The end-to-end checks therefore
+assert (i) CUDA vs the fp64 evaluation of the oracle < TOL (measured ~5e-6), and (ii) CUDA vs the fp32 oracle
+/ the reference's golden output <= that oracle's own distance to fp64 + 1e-5 (all disagreement is the
+reference's rounding), capped at 5e-4. Single layers and the 5-layer fusion stack meet TOL against fp32 directly."""
 import os
 
 import numpy as np
@@ -188,16 +195,23 @@ def test_reindex_exact(mvx):
 
 
 # ------------------------------------------------------------------------------------------- fused path
-def _check_frame(path, f, ref, counts, gold=None):
+def _check_close(got, ref32, ref64, what):
+    e64 = rel_err(got, ref64)
+    assert e64 < TOL, f'{what}: rel err vs fp64 evaluation {e64}'
+    noise = rel_err(ref32, ref64)
+    e32 = rel_err(got, ref32)
+    assert e32 <= noise + 1e-5 and e32 < 5e-4, f'{what}: rel err vs fp32 {e32}, fp32 reference noise {noise}'
+    return e64, e32
+
+
+def _check_frame(path, f, ref, ref64, counts, gold=None):
     n = ref['idx'].shape[0]
     assert counts[f, 0] == n and counts[f, 2] == 0
     vfeat, idx = path.voxel_features(f)
     assert np.array_equal(idx.cpu().numpy()[:, 1:], ref['idx'].numpy()[:, 1:])
-    e = rel_err(vfeat, ref['vfeat'])
-    assert e < TOL, f'voxel features rel err {e}'
-    if gold is not None:
-        assert rel_err(vfeat, gold['vfeat']) < TOL      # against the reference's own output
-    return e
+    _check_close(vfeat, ref['vfeat'], ref64['vfeat'], 'voxel features')
+    if gold is not None:      # the unmodified reference's own output
+        _check_close(vfeat, gold['vfeat'], ref64['vfeat'], 'voxel features (reference golden)')
 
 
 @pytest.mark.parametrize('tag', ['path_a', 'path_b'])
@@ -212,7 +226,8 @@ def test_fused_path_matches_reference_golden(mvx, golden_dir, tag):
     counts = counts.cpu().numpy()
     with torch.no_grad():
         ref = O.forward_frame(g['pcd4'], calib, maps, sd, G, synth.KITTI_IMSIZE_HW)
-    _check_frame(path, 0, ref, counts, g)
+        ref64 = O.forward_frame(g['pcd4'], calib, maps, sd, G, synth.KITTI_IMSIZE_HW, dtype=torch.float64)
+    _check_frame(path, 0, ref, ref64, counts, g)
     # compact rows vs the dense reference tensors: voxel columns bit-exact, fused image features toleranced
     N, K = int(counts[0, 0]), int(counts[0, 1])
     cap = path.cap
@@ -224,8 +239,9 @@ def test_fused_path_matches_reference_golden(mvx, golden_dir, tag):
     v9 = ref['voxels9'].reshape(-1, 9)[dense_rows]
     assert torch.equal(x6[:, :7], v9[:, :7]), 'voxel feature columns (x,y,z,dx,dy,dz,r) not bit-exact'
     im16 = ref['im16'].reshape(-1, 16)[dense_rows]
-    assert rel_err(x6[:, 7:23], im16) < TOL
-    assert rel_err(x6[:, 7:23], torch.from_numpy(g['im16']).reshape(-1, 16)[dense_rows]) < TOL
+    im16_64 = ref64['im16'].reshape(-1, 16)[dense_rows]
+    _check_close(x6[:, 7:23], im16, im16_64, 'fused image features')
+    _check_close(x6[:, 7:23], torch.from_numpy(g['im16']).reshape(-1, 16)[dense_rows], im16_64, 'fused image features (golden)')
     # stage 4: exact placement (a copy) and exact zero elsewhere
     gcpu = grid[0].cpu()
     assert tuple(gcpu.shape) == tuple(g['grid_shape'][1:])
@@ -233,7 +249,7 @@ def test_fused_path_matches_reference_golden(mvx, golden_dir, tag):
     vfeat, idx = path.voxel_features(0)
     i = idx.cpu()
     assert torch.equal(gcpu[:, i[:, 3], i[:, 1], i[:, 2]].T, vfeat.cpu())
-    assert rel_err(gcpu, ref['grid'][0]) < TOL
+    assert rel_err(gcpu, ref64['grid'][0]) < TOL
 
 
 def test_fused_batch_equals_single_frames(mvx):
@@ -248,8 +264,11 @@ def test_fused_batch_equals_single_frames(mvx):
     batch = [tuple(t.clone() for t in path.voxel_features(f)) for f in range(3)]
     for f in range(3):
         with torch.no_grad():
-            ref = O.forward_frame(frames[f], calib, [m[f:f + 1] for m in maps], sd, G, synth.KITTI_IMSIZE_HW, want_grid=False)
-        _check_frame(path, f, ref, counts)
+            kw = dict(want_grid=False)
+            ref = O.forward_frame(frames[f], calib, [m[f:f + 1] for m in maps], sd, G, synth.KITTI_IMSIZE_HW, **kw)
+            ref64 = O.forward_frame(frames[f], calib, [m[f:f + 1] for m in maps], sd, G, synth.KITTI_IMSIZE_HW,
+                                    dtype=torch.float64, **kw)
+        _check_frame(path, f, ref, ref64, counts)
     for f in range(3):
         single = mvx.P.PointPath(sd, G)
         single([frames[f]], [calib], [torch.from_numpy(m[f:f + 1]) for m in maps], want_grid=False)
