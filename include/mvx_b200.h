@@ -102,11 +102,15 @@ int mvx_feature_mapping(float *voxels, int64_t R, const float *const *maps, cons
 /* ------------------------------------------------------------------------------------------------
  * Stage 3 — one layer primitive.  Replaces modules/layers/Blocks.py:5-18 (FCN) and :31-40 (CRB2d, k=1):
  * y = BatchNorm(relu(x W^T + b)), batch statistics over all R rows, biased variance, no affine.
- * x (R,Cin) fp32 row-major (Cin multiple of 4, <= 768), wt (Cin,Cout) = W^T, bias (Cout), y (R,Cout).
- * stats_ws: >= 2*Cout doubles of scratch.  mvx_vfe_forward additionally appends the per-voxel max over each
+ * x (R,Cin) fp32 row-major (Cin multiple of 16, <= 768), wt (Cin,Cout) = W^T, bias (Cout), y (R,Cout).
+ * stats_ws: mvx_layer_workspace_bytes(Cin, Cout) of scratch.  Layers with Cout % 128 == 0 run on the tensor cores
+ * (tcgen05, 3xTF32 split: fp32-accurate) unless mvx_set_gemm_mode(0) selects the exact-fp32 SIMT kernel everywhere.
+ * mvx_vfe_forward additionally appends the per-voxel max over each
  * group of T rows: y (R, 2*Cout) = [pointwise | max] (modules/voxelnet/Pipe.py:12-18).
  * mvx_fcn_max_forward returns only the per-voxel max (R/T, Cout) (VoxelNet.py:28-32).
  * ------------------------------------------------------------------------------------------------ */
+int mvx_set_gemm_mode(int32_t mode); /* 0 = SIMT fp32 everywhere, 1 = tensor cores where eligible (default) */
+int mvx_layer_workspace_bytes(int32_t Cin, int32_t Cout, size_t *bytes);
 int mvx_fcn_forward(const float *x, int64_t R, int32_t Cin, const float *wt, const float *bias, int32_t Cout,
                     double eps, float *y, void *stats_ws, void *stream);
 int mvx_vfe_forward(const float *x, int64_t R, int32_t T, int32_t Cin, const float *wt, const float *bias,

@@ -26,7 +26,7 @@ EXPORTS = [
     'mvx_last_error', 'mvx_version', 'mvx_launch_count',
     'mvx_voxelize_workspace_bytes', 'mvx_voxelize', 'mvx_group_emit7', 'mvx_group_emit9',
     'mvx_lidar2img', 'mvx_maps_nhwc_bytes', 'mvx_feature_mapping',
-    'mvx_fcn_forward', 'mvx_vfe_forward', 'mvx_fcn_max_forward', 'mvx_scatter_dense',
+    'mvx_set_gemm_mode', 'mvx_layer_workspace_bytes', 'mvx_fcn_forward', 'mvx_vfe_forward', 'mvx_fcn_max_forward', 'mvx_scatter_dense',
     'mvx_pointpath_workspace_bytes', 'mvx_pointpath_layout', 'mvx_pointpath_layout_name', 'mvx_pointpath_forward',
     'mvx_timing_enable', 'mvx_timing_read', 'mvx_timing_segment_name',
 ]
@@ -78,6 +78,8 @@ def _load():
     lib.mvx_maps_nhwc_bytes.argtypes = [POINTER(i32), POINTER(i32), i32, POINTER(c_size_t)]
     lib.mvx_feature_mapping.argtypes = [vp, i64, POINTER(vp), POINTER(i32), POINTER(i32), i32, c_float, c_float, c_float,
                                         vp, vp, c_size_t, vp]
+    lib.mvx_set_gemm_mode.argtypes = [i32]
+    lib.mvx_layer_workspace_bytes.argtypes = [i32, i32, POINTER(c_size_t)]
     lib.mvx_fcn_forward.argtypes = [vp, i64, i32, vp, vp, i32, c_double, vp, vp, vp]
     lib.mvx_vfe_forward.argtypes = [vp, i64, i32, i32, vp, vp, i32, c_double, vp, vp, vp, vp]
     lib.mvx_fcn_max_forward.argtypes = [vp, i64, i32, i32, vp, vp, i32, c_double, vp, vp, vp, vp]
@@ -125,6 +127,11 @@ def ptr(t) -> c_void_p:
 
 
 c_float = c_float  # re-export for callers building timing buffers
+
+
+def set_gemm_mode(mode: int):
+    """0 = exact-fp32 SIMT layers everywhere, 1 = tcgen05 3xTF32 tensor-core layers where eligible (default)."""
+    check(lib.mvx_set_gemm_mode(int(mode)), 'set_gemm_mode')
 
 
 def launch_count() -> int:

@@ -373,6 +373,14 @@ int launch_layer(const LayerArgs &a, int F, cudaStream_t st) {
     return MVX_OK;
 }
 
+static int g_gemm_mode = 1;
+int gemm_mode() { return g_gemm_mode; }
+
+int launch_layer_auto(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
+    if (g_gemm_mode == 1 && wpack && tc_layer_eligible(a)) return launch_layer_tc(a, F, wpack, st);
+    return launch_layer(a, F, st);
+}
+
 int launch_prep_vfe1(const VfePrepArgs &a, cudaStream_t st) {
     prep_vfe1_kernel<<<dim3((a.cap + 1 + 255) / 256, a.B), 256, 0, st>>>(a);
     MVX_LAUNCH_CHECK();
@@ -395,25 +403,41 @@ int launch_finalize_vfeat(const VfePrepArgs &a, cudaStream_t st) {
 }
 
 // ---- dense module API ------------------------------------------------------------------------------------
+static size_t dense_stats_bytes(int Cout) { return ((size_t)Cout * 2 * sizeof(double) + 255) / 256 * 256; }
+
 static int dense_layer(const float *x, int64_t R, int32_t T, int32_t Cin, const float *wt, const float *bias, int32_t Cout,
-                       double eps, float *y, int ldy, double *stats, int *vmax, cudaStream_t st) {
-    MVX_REQUIRE(x && wt && bias && stats && R > 0, MVX_EINVAL, "null pointer / empty input");
+                       double eps, float *y, int ldy, void *ws, int *vmax, cudaStream_t st) {
+    MVX_REQUIRE(x && wt && bias && ws && R > 0, MVX_EINVAL, "null pointer / empty input");
+    double *stats = static_cast<double *>(ws);
+    float *wpack = reinterpret_cast<float *>(static_cast<char *>(ws) + dense_stats_bytes(Cout));
     MVX_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)Cout * 2 * sizeof(double), st));
     if (vmax) MVX_CUDA_CHECK(cudaMemsetAsync(vmax, 0, (size_t)(R / T) * Cout * sizeof(int), st));
     LayerArgs a{};
     a.X = x, a.ldx = Cin, a.Cin = Cin, a.Wt = wt, a.bias = bias, a.Cout = Cout, a.Y = y, a.ldy = ldy;
     a.out_stats = stats, a.vmax = vmax, a.rows_mode = 0, a.rows_fixed = R, a.rowcap = 0, a.vcap = 0, a.T = T > 0 ? T : 1;
     a.eps = eps;
-    return launch_layer(a, 1, st);
+    return launch_layer_auto(a, 1, wpack, st);
 }
 
 }  // namespace mvx
+
+extern "C" int mvx_set_gemm_mode(int32_t mode) {
+    if (mode != 0 && mode != 1) return MVX_EINVAL;
+    mvx::g_gemm_mode = mode;
+    return MVX_OK;
+}
+
+extern "C" int mvx_layer_workspace_bytes(int32_t Cin, int32_t Cout, size_t *bytes) {
+    if (!bytes || Cin <= 0 || Cout <= 0) return MVX_EINVAL;
+    *bytes = mvx::dense_stats_bytes(Cout) + mvx::tc_wpack_bytes(Cin, Cout);
+    return MVX_OK;
+}
 
 extern "C" int mvx_fcn_forward(const float *x, int64_t R, int32_t Cin, const float *wt, const float *bias, int32_t Cout,
                                double eps, float *y, void *stats_ws, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MVX_REQUIRE(y, MVX_EINVAL, "null output");
-    int rc = mvx::dense_layer(x, R, 1, Cin, wt, bias, Cout, eps, y, Cout, static_cast<double *>(stats_ws), nullptr, st);
+    int rc = mvx::dense_layer(x, R, 1, Cin, wt, bias, Cout, eps, y, Cout, stats_ws, nullptr, st);
     if (rc) return rc;
     mvx::NormSrc n{static_cast<const double *>(stats_ws), nullptr, R, 1, eps};
     mvx::normalize_rows_kernel<<<mvx::kSMs * 8, 256, 0, st>>>(y, R, Cout, Cout, n, nullptr, 1);
@@ -425,8 +449,7 @@ extern "C" int mvx_vfe_forward(const float *x, int64_t R, int32_t T, int32_t Cin
                                int32_t Cout, double eps, float *y, void *stats_ws, void *vmax_ws, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MVX_REQUIRE(y && vmax_ws && T > 0 && R % T == 0, MVX_EINVAL, "bad vfe argument");
-    int rc = mvx::dense_layer(x, R, T, Cin, wt, bias, Cout, eps, y, 2 * Cout, static_cast<double *>(stats_ws),
-                              static_cast<int *>(vmax_ws), st);
+    int rc = mvx::dense_layer(x, R, T, Cin, wt, bias, Cout, eps, y, 2 * Cout, stats_ws, static_cast<int *>(vmax_ws), st);
     if (rc) return rc;
     mvx::NormSrc n{static_cast<const double *>(stats_ws), nullptr, R, 1, eps};
     mvx::normalize_rows_kernel<<<mvx::kSMs * 8, 256, 0, st>>>(y, R, Cout, 2 * Cout, n, static_cast<const int *>(vmax_ws), T);
@@ -438,8 +461,7 @@ extern "C" int mvx_fcn_max_forward(const float *x, int64_t R, int32_t T, int32_t
                                    int32_t Cout, double eps, float *y_max, void *stats_ws, void *vmax_ws, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MVX_REQUIRE(y_max && vmax_ws && T > 0 && R % T == 0, MVX_EINVAL, "bad fcn_max argument");
-    int rc = mvx::dense_layer(x, R, T, Cin, wt, bias, Cout, eps, nullptr, 0, static_cast<double *>(stats_ws),
-                              static_cast<int *>(vmax_ws), st);
+    int rc = mvx::dense_layer(x, R, T, Cin, wt, bias, Cout, eps, nullptr, 0, stats_ws, static_cast<int *>(vmax_ws), st);
     if (rc) return rc;
     mvx::NormSrc n{static_cast<const double *>(stats_ws), nullptr, R, 1, eps};
     mvx::normalize_vmax_kernel<<<dim3(mvx::kSMs * 2, 1), 256, 0, st>>>(static_cast<const int *>(vmax_ws), y_max, Cout, 0,

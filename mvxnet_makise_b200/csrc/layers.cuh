@@ -27,7 +27,15 @@ struct LayerArgs {
     int rowcap, vcap, T;
     double eps;
 };
-int launch_layer(const LayerArgs &a, int F, cudaStream_t st);
+int launch_layer(const LayerArgs &a, int F, cudaStream_t st);            // exact-fp32 SIMT kernel
+
+// tensor-core (tcgen05, 3xTF32) implementation of the same layer; wpack = tc_wpack_bytes() of scratch
+bool tc_layer_eligible(const LayerArgs &a);
+size_t tc_wpack_bytes(int Cin, int Cout);
+int launch_layer_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
+// dispatch by mvx_set_gemm_mode(): 0 = SIMT everywhere, 1 = tensor cores where eligible (default)
+int gemm_mode();
+int launch_layer_auto(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
 
 // number of rows BN statistics are taken over for frame f: N_f * T (fused path) or rows_fixed (dense API)
 struct NormSrc {

@@ -18,14 +18,14 @@ namespace mvx {
 enum Region {
     R_VOXWS = 0, R_VOX_COORD, R_VOX_CNT, R_VOX_ROW0, R_ROW_POINT, R_ROW_VOX, R_CELL2VID, R_NHWC0, R_NHWC1, R_NHWC2,
     R_VOX8, R_PROJ, R_ROWA_W, R_A1, R_Y1, R_Y2, R_Y3, R_Y4, R_Y5, R_X6, R_Y6, R_X7, R_Y7, R_ROWB_W, R_ROWB_V, R_X8,
-    R_VFEAT, R_STATS, R_VMAX6, R_VMAX7, R_VMAX8, R_COUNT
+    R_VFEAT, R_STATS, R_VMAX6, R_VMAX7, R_VMAX8, R_WPACK, R_COUNT
 };
 static_assert(R_COUNT <= MVX_WS_REGIONS, "too many regions");
 
 const char *kRegionNames[R_COUNT] = {
     "vox_ws", "vox_coord", "vox_cnt", "vox_row0", "row_point", "row_vox", "cell2vid", "nhwc0", "nhwc1", "nhwc2",
     "vox8", "proj", "rowA_w", "A1", "Y1", "Y2", "Y3", "Y4", "Y5", "X6", "Y6", "X7", "Y7", "rowB_w", "rowB_v", "X8",
-    "vfeat", "stats", "vmax6", "vmax7", "vmax8"};
+    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack"};
 
 constexpr int kCin[MVX_NUM_LAYERS] = {768, 768, 128, 128, 16, 32, 32, 128};   // padded
 constexpr int kCout[MVX_NUM_LAYERS] = {768, 128, 128, 16, 16, 16, 64, 128};
@@ -86,6 +86,7 @@ int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
     take(R_VMAX6, B * cap * 16 * 4);
     take(R_VMAX7, B * cap * 64 * 4);
     take(R_VMAX8, B * cap * 128 * 4);
+    take(R_WPACK, tc_wpack_bytes(768, 768));
     L.total = o;
     return MVX_OK;
 }
@@ -204,7 +205,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
         la.out_stats = stat_of(l);
         la.row_w = F32(R_ROWA_W), la.counts = a->counts, la.rows_mode = 1, la.rowcap = L.capA, la.vcap = cap, la.T = T;
         la.eps = a->bn_eps;
-        rc = launch_layer(la, B, st);
+        rc = launch_layer_auto(la, B, F32(R_WPACK), st);
         if (rc) return rc;
     }
     VfePrepArgs vp{};

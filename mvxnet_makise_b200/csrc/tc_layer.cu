@@ -1,0 +1,391 @@
+// Stage 3 on the 5th-generation tensor cores: y = relu(norm_in(X) W^T + b) + weighted BatchNorm sums, for the
+// GEMM-shaped layers (fcn1 768->768, conv1 768->128, fcn2 128->128), hand-written tcgen05 / TMEM / bulk-copy PTX.
+//
+// fp32-accurate on TF32 hardware ("3xTF32"): every fp32 operand is split hi = top 19 bits, lo = x - hi (exact), and
+// D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32 accumulation in TMEM; the dropped A_lo*B_lo term and the
+// truncation of the lo parts are ~2^-22 relative (measured parity: see tests/test_gpu_parity.py).
+//
+// One CTA = 256 rows x BN columns (two M=128 accumulators in TMEM, 2*BN columns), K in chunks of 16 fp32
+// (64-byte rows, SWIZZLE_64B K-major canonical layout), 3-stage mbarrier pipeline:
+//   warps 0-7 : A producers. Coalesced 16-byte loads of the raw activations, BatchNorm of the producer layer
+//               applied in registers ((x - mean) * rstd), hi/lo split, swizzled st.shared, fence.proxy.async,
+//               mbarrier arrive. After the main loop the same warps run the epilogue.
+//   warp 8    : B producer. One cp.async.bulk (TMA engine, SASS UBLKCP) per stage: the weights were pre-split
+//               and pre-swizzled into the exact shared-memory image by pack_weights_kernel (32 KB per stage).
+//   warp 9    : TMEM allocation, then the single-thread tcgen05.mma issuer; tcgen05.commit frees the stage.
+// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> +bias, ReLU -> padded smem tile -> (a) coalesced
+// row-major stores of the raw activations, (b) per-column weighted sums in fp64 -> one atomicAdd per column.
+// A 256-row tile amortises the weight stream: per 16-k chunk a CTA pulls 16 KB of A and 32 KB of B for
+// 1536 tensor cycles (31 B/cycle/SM), which the 148-SM L2 can sustain; a 128-row tile could not (53 B/cycle/SM).
+#include "layers.cuh"
+
+namespace mvx {
+
+namespace {
+
+constexpr int kTM = 256;        // rows per CTA
+constexpr int kBK = 16;         // fp32 k per stage (64-byte swizzle atom)
+constexpr int kStages = 3;
+constexpr int kProducerThreads = 256;
+constexpr int kThreads = kProducerThreads + 64;
+constexpr int kEpiCols = 128;   // columns per epilogue pass
+constexpr int kEpiLd = kEpiCols + 4;
+
+template <int BN>
+struct Smem {
+    static constexpr int kAHalf = kTM * kBK * 4;      // 16 KB: A_hi (then A_lo)
+    static constexpr int kBHalf = BN * kBK * 4;       // B_hi (then B_lo)
+    static constexpr int kStage = 2 * kAHalf + 2 * kBHalf;
+    static constexpr int kTiles = kStages * kStage;
+    static constexpr int kEpi = 2 * 128 * kEpiLd * 4;  // two 128-row halves of one 128-column pass
+    static constexpr int kMain = kTiles > kEpi ? kTiles : kEpi;
+    // after the tiles: mean[768], rstd[768], bias[BN], row_w[256], barriers, tmem pointer
+    static constexpr int kMean = kMain;
+    static constexpr int kRstd = kMean + 768 * 4;
+    static constexpr int kBias = kRstd + 768 * 4;
+    static constexpr int kRowW = kBias + BN * 4;
+    static constexpr int kBars = kRowW + kTM * 4;      // full[3], empty[3], accum
+    static constexpr int kTmemPtr = kBars + 8 * 8;
+    static constexpr int kTotal = kTmemPtr + 16 + 1024;  // + slack for the 1024-byte alignment of the base
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_64B canonical layout (in 16-byte units: ((8,n),2):((4,SBO),1) under Swizzle<2,4,3>):
+// row r of a tile at r*64 bytes, its 16-byte chunk c stored at chunk position c ^ ((r >> 1) & 3).
+__device__ __host__ __forceinline__ uint32_t sw64_offset(uint32_t r, uint32_t c) { return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    // start address | LBO = 1 (unused for swizzled K-major) | SBO = 512 B (8 rows x 64 B) | version 1 | SWIZZLE_64B
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
+    hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    lo = v - hi;
+}
+
+// ---- weight packing: W^T (Cin, Cout) fp32 -> per (column tile, k chunk) the shared-memory image [hi | lo] ----
+template <int BN>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ Wt, int Cin, int Cout, float *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Cin * Cout) return;
+    const int k = e / Cout, n = e - k * Cout;
+    const int ct = n / BN, nl = n - ct * BN, kc = k / kBK, kl = k - kc * kBK;
+    float hi, lo;
+    split_tf32(Wt[e], hi, lo);
+    const size_t blob = ((size_t)ct * (Cin / kBK) + kc) * (2 * BN * kBK);  // floats
+    const uint32_t off = sw64_offset(nl, kl >> 2) / 4 + (kl & 3);
+    out[blob + off] = hi;
+    out[blob + BN * kBK + off] = lo;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, const float *__restrict__ wpack) {
+    using S = Smem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    float *s_mean = reinterpret_cast<float *>(smem + S::kMean);
+    float *s_rstd = reinterpret_cast<float *>(smem + S::kRstd);
+    float *s_bias = reinterpret_cast<float *>(smem + S::kBias);
+    float *s_roww = reinterpret_cast<float *>(smem + S::kRowW);
+    const uint32_t bars = sbase + S::kBars;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * kStages);
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(smem + S::kTmemPtr);
+
+    const int f = blockIdx.z, n0 = blockIdx.y * BN, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    long long n_rows = a.rows_fixed;
+    double Rstat = (double)a.rows_fixed;
+    if (a.counts) {
+        const int N = a.counts[f * 4 + 0], K = a.counts[f * 4 + 1];
+        n_rows = a.rows_mode == 1 ? K + 1 : (a.rows_mode == 2 ? K + N : a.rows_fixed);
+        Rstat = (double)N * (double)a.T;
+    }
+    const long long row0 = (long long)blockIdx.x * kTM;
+    if (row0 >= n_rows) return;  // uniform for the CTA, before any barrier / TMEM allocation
+    const int nk = a.Cin / kBK;
+
+    // ---- one-time setup ------------------------------------------------------------------------------------
+    if (a.in_stats) {
+        for (int c = tid; c < a.Cin; c += kThreads) {
+            const double *st = a.in_stats + ((size_t)f * a.Cin + c) * 2;
+            const double m = st[0] / Rstat;
+            double var = st[1] / Rstat - m * m;
+            var = var < 0.0 ? 0.0 : var;
+            s_mean[c] = (float)m;
+            s_rstd[c] = (float)(1.0 / sqrt(var + a.eps));
+        }
+    }
+    for (int c = tid; c < BN; c += kThreads) s_bias[c] = a.bias[n0 + c];
+    for (int r = tid; r < kTM; r += kThreads) {
+        const long long rr = row0 + r;
+        s_roww[r] = rr < n_rows ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + rr] : 1.f) : 0.f;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), kProducerThreads + 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {  // TMEM: 2*BN fp32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::kTmemPtr), "r"(2 * BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 8) {
+        // ================= A producers ===========================================================================
+        const int c = tid & 3, rsub = tid >> 2;  // 16-byte chunk of the 64-byte k-chunk row; rows rsub + 64*i
+        const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx + c * 4;
+        bool valid[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) valid[i] = row0 + rsub + 64 * i < n_rows;
+        float4 nxt[4];
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            nxt[i] = valid[i] ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx)) : z4;
+        for (int kc = 0; kc < nk; ++kc) {
+            const int s = kc % kStages;
+            const uint32_t ph = (kc / kStages) & 1;
+            float4 cur[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+            if (kc + 1 < nk) {  // prefetch the next chunk into registers before blocking on the stage
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    nxt[i] = valid[i] ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + (kc + 1) * kBK)) : z4;
+            }
+            if (a.in_stats) {
+                const int k = kc * kBK + c * 4;
+                const float m0 = s_mean[k], m1 = s_mean[k + 1], m2 = s_mean[k + 2], m3 = s_mean[k + 3];
+                const float r0 = s_rstd[k], r1 = s_rstd[k + 1], r2 = s_rstd[k + 2], r3 = s_rstd[k + 3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (valid[i]) {
+                        cur[i].x = (cur[i].x - m0) * r0;
+                        cur[i].y = (cur[i].y - m1) * r1;
+                        cur[i].z = (cur[i].z - m2) * r2;
+                        cur[i].w = (cur[i].w - m3) * r3;
+                    }
+                }
+            }
+            mbar_wait(empty_bar(s), ph ^ 1);
+            uint8_t *stage = smem + (size_t)s * S::kStage;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 hi, lo;
+                split_tf32(cur[i].x, hi.x, lo.x);
+                split_tf32(cur[i].y, hi.y, lo.y);
+                split_tf32(cur[i].z, hi.z, lo.z);
+                split_tf32(cur[i].w, hi.w, lo.w);
+                const uint32_t off = sw64_offset(rsub + 64 * i, c);
+                *reinterpret_cast<float4 *>(stage + off) = hi;
+                *reinterpret_cast<float4 *>(stage + S::kAHalf + off) = lo;
+            }
+            fence_async_smem();  // make the generic-proxy writes visible to the tensor core (async proxy)
+            mbar_arrive(full_bar(s));
+        }
+    } else if (warp == 8) {
+        // ================= B producer: one bulk copy per stage ===================================================
+        if (lane == 0) {
+            const float *src = wpack + (size_t)blockIdx.y * nk * (2 * BN * kBK);
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % kStages;
+                const uint32_t ph = (kc / kStages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_arrive_expect_tx(full_bar(s), 2 * S::kBHalf);
+                bulk_g2s(sbase + s * S::kStage + 2 * S::kAHalf, src + (size_t)kc * (2 * BN * kBK), 2 * S::kBHalf, full_bar(s));
+            }
+        }
+    } else {
+        // ================= MMA issuer (one thread) ================================================================
+        if (lane == 0) {
+            // D fp32, A/B TF32, K-major both, N = BN, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % kStages;
+                const uint32_t ph = (kc / kStages) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sA = sbase + s * S::kStage, sB = sA + 2 * S::kAHalf;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {          // the two 128-row halves -> two accumulators
+                    const uint32_t d = tmem_base + h * BN;
+                    const uint32_t aoff = h * (128 * 64);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {   // two K=8 steps per 16-k chunk: +32 bytes inside the swizzle atom
+                        const uint64_t a_hi = make_desc(sA + aoff + ks * 32), a_lo = make_desc(sA + S::kAHalf + aoff + ks * 32);
+                        const uint64_t b_hi = make_desc(sB + ks * 32), b_lo = make_desc(sB + S::kBHalf + ks * 32);
+                        mma_tf32(d, a_lo, b_hi, idesc, (kc | ks) != 0);
+                        mma_tf32(d, a_hi, b_lo, idesc, 1);
+                        mma_tf32(d, a_hi, b_hi, idesc, 1);
+                    }
+                }
+                mma_commit(empty_bar(s));  // frees the stage when the MMAs above have read it
+            }
+            mma_commit(accum_bar);         // accumulators complete
+        }
+    }
+
+    // ================= epilogue (warps 0-7; warps 8-9 only join the barriers) =====================================
+    __syncwarp();
+    if (warp < 8) {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+    }
+    __syncthreads();  // every stage buffer is idle now: reuse the tile memory for the output staging
+    float *ytile = reinterpret_cast<float *>(smem);  // [2 halves][128 rows][kEpiLd]
+    const int half = warp >> 2, q = warp & 3;        // accumulator, TMEM lane quarter
+    for (int pass = 0; pass < BN / kEpiCols; ++pass) {
+        if (warp < 8) {
+            float *yrow = ytile + ((size_t)half * 128 + q * 32 + lane) * kEpiLd;
+#pragma unroll 1
+            for (int cb = 0; cb < kEpiCols / 32; ++cb) {
+                float v[32];
+                const int col = pass * kEpiCols + cb * 32;
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + half * BN + col, v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = fmaxf(v[j] + s_bias[col + j], 0.f);
+                    o.y = fmaxf(v[j + 1] + s_bias[col + j + 1], 0.f);
+                    o.z = fmaxf(v[j + 2] + s_bias[col + j + 2], 0.f);
+                    o.w = fmaxf(v[j + 3] + s_bias[col + j + 3], 0.f);
+                    *reinterpret_cast<float4 *>(yrow + cb * 32 + j) = o;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 256) {
+            // (a) weighted column sums in fp64: threads 0-127 sum w*y, threads 128-255 sum w*y^2
+            const int col = tid & 127, which = tid >> 7;
+            double acc = 0.0;
+            for (int r = 0; r < kTM; ++r) {
+                const float w = s_roww[r];
+                if (w != 0.f) {
+                    const double y = (double)ytile[(size_t)r * kEpiLd + col];
+                    acc += which ? (double)w * y * y : (double)w * y;
+                }
+            }
+            atomicAdd(a.out_stats + ((size_t)f * a.Cout + n0 + pass * kEpiCols + col) * 2 + which, acc);
+            // (b) coalesced raw stores: one warp per row, 32 lanes x 16 bytes = 128 columns
+            if (a.Y) {
+                for (int r = warp; r < kTM; r += 8) {
+                    if (row0 + r >= n_rows) break;
+                    const float4 o = *reinterpret_cast<const float4 *>(ytile + (size_t)r * kEpiLd + lane * 4);
+                    *reinterpret_cast<float4 *>(a.Y + ((size_t)f * a.rowcap + row0 + r) * a.ldy + n0 + pass * kEpiCols + lane * 4) = o;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
+template <int BN>
+int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
+    using S = Smem<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        attr_set = true;
+    }
+    const int total = a.Cin * a.Cout;
+    pack_weights_kernel<BN><<<(total + 255) / 256, 256, 0, st>>>(a.Wt, a.Cin, a.Cout, wpack);
+    MVX_LAUNCH_CHECK();
+    const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
+    dim3 grid((unsigned)ceil_div(max_rows, kTM), a.Cout / BN, F);
+    tc_layer_kernel<BN><<<grid, kThreads, S::kTotal, st>>>(a, wpack);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+}  // namespace
+
+bool tc_layer_eligible(const LayerArgs &a) {
+    return a.vmax == nullptr && a.Cin % kBK == 0 && a.Cin <= 768 && a.Cout % 128 == 0 && a.ldx % 4 == 0 &&
+           (a.Y == nullptr || a.ldy % 4 == 0);
+}
+
+size_t tc_wpack_bytes(int Cin, int Cout) { return (size_t)2 * Cin * Cout * sizeof(float); }
+
+int launch_layer_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
+    MVX_REQUIRE(tc_layer_eligible(a) && wpack, MVX_EINVAL, "layer not eligible for the tensor-core kernel");
+    const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
+    if (max_rows <= 0) return MVX_OK;
+    if (a.Cout % 256 == 0) return launch_tc<256>(a, F, wpack, st);
+    return launch_tc<128>(a, F, wpack, st);
+}
+
+}  // namespace mvx

@@ -112,7 +112,9 @@ def _layer_forward(kind: str, x: torch.Tensor, weight, bias, eps: float, T: int 
     wt = _wt(weight)
     b = bias.detach().to(torch.float32).contiguous()
     R, cin = x2.shape
-    stats = torch.empty(2 * cout, dtype=torch.float64, device=x.device)
+    nbytes = ctypes.c_size_t()
+    check(lib.mvx_layer_workspace_bytes(cin, cout, ctypes.byref(nbytes)), 'layer_workspace_bytes')
+    stats = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
     if kind == 'fcn':
         y = torch.empty((R, cout), dtype=torch.float32, device=x.device)
         check(lib.mvx_fcn_forward(ptr(x2), R, cin, ptr(wt), ptr(b), cout, float(eps), ptr(y), ptr(stats), stream_ptr()),

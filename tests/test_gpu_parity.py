@@ -179,6 +179,28 @@ def test_layer_modules_match_oracle(mvx):
     assert got_v.shape == ref_v.shape and rel_err(got_v, ref_v) < TOL
 
 
+@pytest.mark.parametrize('R,cin,cout', [(1000, 768, 768), (5003, 768, 128), (777, 128, 128), (256, 768, 768)])
+def test_tensor_core_layer_is_fp32_accurate(mvx, R, cin, cout):
+    """tcgen05 3xTF32 layer vs the exact-fp32 SIMT layer and vs an fp64 evaluation (ragged row counts)."""
+    from mvxnet_makise_b200 import _lib
+    torch.manual_seed(R)
+    x = torch.randn(1, R, 1, cin, device='cuda')
+    x[:, R // 2:] *= 0.01
+    fcn = mvx.M.FCN(cin, cout).cuda()
+    try:
+        with torch.no_grad():
+            _lib.set_gemm_mode(0)
+            y_simt = fcn(x)
+            _lib.set_gemm_mode(1)
+            y_tc = fcn(x)
+    finally:
+        _lib.set_gemm_mode(1)
+    y = torch.relu(x.double().reshape(-1, cin) @ fcn.fc.weight.double().t() + fcn.fc.bias.double())
+    ref = (y - y.mean(0)) / torch.sqrt(y.var(0, unbiased=False) + 1e-6)
+    assert rel_err(y_tc, y_simt) < 2e-5
+    assert rel_err(y_tc.reshape(-1, cout), ref) < 2e-5 and rel_err(y_simt.reshape(-1, cout), ref) < 2e-5
+
+
 def test_reindex_exact(mvx):
     rng = np.random.default_rng(1)
     N = 500
