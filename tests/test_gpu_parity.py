@@ -8,9 +8,10 @@ What "ref" is for the 8-layer chain: the fp32 reference is itself noisy at this 
 identical pad rows, so BatchNorm normalises real rows to tens of sigma and the fp32 rounding of the reference's
 own GEMMs/statistics shows up as 1.2e-4 .. 3.5e-4 relative at the end of the chain (measured: the reference vs
 the same algorithm evaluated in fp64, tools/diag_layers.py). The end-to-end checks therefore
-assert (i) CUDA vs the fp64 evaluation of the oracle < TOL (measured ~5e-6), and (ii) CUDA vs the fp32 oracle
-/ the reference's golden output <= that oracle's own distance to fp64 + 1e-5 (all disagreement is the
-reference's rounding), capped at 5e-4. Single layers and the 5-layer fusion stack meet TOL against fp32 directly."""
+assert (i) CUDA vs the fp64 evaluation of the oracle < TOL (measured 5e-6 with the exact-fp32 SIMT layers,
+~3e-5 with the 3xTF32 tensor-core layers), and (ii) CUDA vs the fp32 oracle / the reference's golden output
+<= that reference's own distance to fp64 + TOL (what is left after the reference's rounding is within TOL),
+capped at 5e-4. Single layers and the 5-layer fusion stack meet TOL against fp32 directly."""
 import os
 
 import numpy as np
@@ -222,7 +223,7 @@ def _check_close(got, ref32, ref64, what):
     assert e64 < TOL, f'{what}: rel err vs fp64 evaluation {e64}'
     noise = rel_err(ref32, ref64)
     e32 = rel_err(got, ref32)
-    assert e32 <= noise + 1e-5 and e32 < 5e-4, f'{what}: rel err vs fp32 {e32}, fp32 reference noise {noise}'
+    assert e32 <= noise + TOL and e32 < 5e-4, f'{what}: rel err vs fp32 {e32}, fp32 reference noise {noise}'
     return e64, e32
 
 
