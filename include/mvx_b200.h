@@ -123,6 +123,7 @@ int mvx_fcn_max_forward(const float *x, int64_t R, int32_t T, int32_t Cin, const
  * (`reindex`): out (1,C,nz,nx,ny) fp32 fully written (zeros + features) in ONE streaming pass.
  * idx (N,4) int64 [batch, ix, iy, iz] (train.py:119,126).  map_ws: nz*nx*ny int32 scratch.
  * ------------------------------------------------------------------------------------------------ */
+int mvx_set_grid_mode(int32_t mode); /* 1 = cp.async.bulk shared->global stores (default), 0 = per-thread st.global.cs */
 int mvx_scatter_dense(const float *feat, const int64_t *idx, int64_t N, int32_t C, int32_t nx, int32_t ny,
                       int32_t nz, float *out, int32_t *map_ws, void *stream);
 

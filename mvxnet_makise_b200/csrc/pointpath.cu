@@ -230,7 +230,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
         la.Y = F32(R_Y6), la.ldy = 16, la.out_stats = stat_of(5), la.vmax = I32(R_VMAX6);
         la.row_w = F32(R_ROWA_W), la.row_v = vo.row_vox, la.rowv_cap = cap, la.counts = a->counts, la.rows_mode = 1;
         la.rowcap = L.capA, la.vcap = cap, la.T = T, la.eps = a->bn_eps;
-        rc = launch_layer(la, B, st);
+        rc = launch_layer_auto(la, B, F32(R_WPACK), st);
         if (rc) return rc;
     }
     stamp.mark(S_PREP2);
@@ -243,7 +243,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
         la.Y = F32(R_Y7), la.ldy = 64, la.out_stats = stat_of(6), la.vmax = I32(R_VMAX7);
         la.row_w = F32(R_ROWB_W), la.row_v = I32(R_ROWB_V), la.rowv_cap = L.capB, la.counts = a->counts, la.rows_mode = 2;
         la.rowcap = L.capB, la.vcap = cap, la.T = T, la.eps = a->bn_eps;
-        rc = launch_layer(la, B, st);
+        rc = launch_layer_auto(la, B, F32(R_WPACK), st);
         if (rc) return rc;
     }
     stamp.mark(S_PREP3);
@@ -256,7 +256,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
         la.Y = nullptr, la.ldy = 0, la.out_stats = stat_of(7), la.vmax = I32(R_VMAX8);
         la.row_w = F32(R_ROWB_W), la.row_v = I32(R_ROWB_V), la.rowv_cap = L.capB, la.counts = a->counts, la.rows_mode = 2;
         la.rowcap = L.capB, la.vcap = cap, la.T = T, la.eps = a->bn_eps;
-        rc = launch_layer(la, B, st);
+        rc = launch_layer_auto(la, B, F32(R_WPACK), st);
         if (rc) return rc;
     }
     stamp.mark(S_VFEAT);

@@ -44,7 +44,8 @@ struct Smem {
     static constexpr int kRstd = kMean + 768 * 4;
     static constexpr int kBias = kRstd + 768 * 4;
     static constexpr int kRowW = kBias + BN * 4;
-    static constexpr int kBars = kRowW + kTM * 4;      // full[3], empty[3], accum
+    static constexpr int kRowV = kRowW + kTM * 4;      // voxel id of each row (per-voxel max), -1 = none
+    static constexpr int kBars = kRowV + kTM * 4;      // full[3], empty[3], accum
     static constexpr int kTmemPtr = kBars + 8 * 8;
     static constexpr int kTotal = kTmemPtr + 16 + 1024;  // + slack for the 1024-byte alignment of the base
 };
@@ -140,28 +141,32 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, const float *__restrict__ wpack) {
     using S = Smem<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // keep the pointer in the shared address space (pointer arithmetic only, no integer round trip): STS/LDS, not ST.E/LD.E
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     float *s_mean = reinterpret_cast<float *>(smem + S::kMean);
     float *s_rstd = reinterpret_cast<float *>(smem + S::kRstd);
     float *s_bias = reinterpret_cast<float *>(smem + S::kBias);
     float *s_roww = reinterpret_cast<float *>(smem + S::kRowW);
+    int *s_rowv = reinterpret_cast<int *>(smem + S::kRowV);
     const uint32_t bars = sbase + S::kBars;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
     const uint32_t accum_bar = bars + 8u * (2 * kStages);
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(smem + S::kTmemPtr);
 
-    const int f = blockIdx.z, n0 = blockIdx.y * BN, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int f = blockIdx.z, ctile = blockIdx.x, n0 = ctile * BN, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     long long n_rows = a.rows_fixed;
     double Rstat = (double)a.rows_fixed;
+    int Kf = 0;
     if (a.counts) {
-        const int N = a.counts[f * 4 + 0], K = a.counts[f * 4 + 1];
-        n_rows = a.rows_mode == 1 ? K + 1 : (a.rows_mode == 2 ? K + N : a.rows_fixed);
+        const int N = a.counts[f * 4 + 0];
+        Kf = a.counts[f * 4 + 1];
+        n_rows = a.rows_mode == 1 ? Kf + 1 : (a.rows_mode == 2 ? Kf + N : a.rows_fixed);
         Rstat = (double)N * (double)a.T;
     }
-    const long long row0 = (long long)blockIdx.x * kTM;
+    const long long row0 = (long long)blockIdx.y * kTM;  // column tiles of one row tile are launch-adjacent: A hits L2
     if (row0 >= n_rows) return;  // uniform for the CTA, before any barrier / TMEM allocation
     const int nk = a.Cin / kBK;
 
@@ -179,7 +184,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
     for (int c = tid; c < BN; c += kThreads) s_bias[c] = a.bias[n0 + c];
     for (int r = tid; r < kTM; r += kThreads) {
         const long long rr = row0 + r;
-        s_roww[r] = rr < n_rows ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + rr] : 1.f) : 0.f;
+        const float w = rr < n_rows ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + rr] : 1.f) : 0.f;
+        s_roww[r] = w;
+        int v = -1;
+        if (a.vmax && w != 0.f) {
+            if (a.row_v) v = (a.rows_mode == 1 && rr >= Kf) ? -1 : a.row_v[(size_t)f * a.rowv_cap + rr];
+            else v = (int)(rr / a.T);
+        }
+        s_rowv[r] = v;
     }
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -206,22 +218,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         bool valid[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) valid[i] = row0 + rsub + 64 * i < n_rows;
-        float4 nxt[4];
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load_chunk = [&](float4 (&buf)[4], int kc) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            nxt[i] = valid[i] ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx)) : z4;
-        for (int kc = 0; kc < nk; ++kc) {
-            const int s = kc % kStages;
-            const uint32_t ph = (kc / kStages) & 1;
+            for (int i = 0; i < 4; ++i)
+                buf[i] = valid[i] ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + kc * kBK)) : z4;
+        };
+        // two chunks of raw activations are always in flight in registers (DRAM/L2 latency >> one chunk of MMA time)
+        auto produce = [&](float4 (&buf)[4], int kc) {
             float4 cur[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-            if (kc + 1 < nk) {  // prefetch the next chunk into registers before blocking on the stage
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    nxt[i] = valid[i] ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + (kc + 1) * kBK)) : z4;
-            }
+            for (int i = 0; i < 4; ++i) cur[i] = buf[i];
             if (a.in_stats) {
                 const int k = kc * kBK + c * 4;
                 const float m0 = s_mean[k], m1 = s_mean[k + 1], m2 = s_mean[k + 2], m3 = s_mean[k + 3];
@@ -236,7 +243,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
                     }
                 }
             }
-            mbar_wait(empty_bar(s), ph ^ 1);
+            if (kc + 2 < nk) load_chunk(buf, kc + 2);
+            const int s = kc % kStages;
+            const uint32_t ph = (kc / kStages) & 1;
+            if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);  // one poller per warp
+            __syncwarp();
             uint8_t *stage = smem + (size_t)s * S::kStage;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -251,11 +262,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
             }
             fence_async_smem();  // make the generic-proxy writes visible to the tensor core (async proxy)
             mbar_arrive(full_bar(s));
+        };
+        float4 buf0[4], buf1[4];
+        load_chunk(buf0, 0);
+        if (nk > 1) load_chunk(buf1, 1);
+        for (int kc = 0; kc < nk; kc += 2) {
+            produce(buf0, kc);
+            if (kc + 1 < nk) produce(buf1, kc + 1);
         }
     } else if (warp == 8) {
         // ================= B producer: one bulk copy per stage ===================================================
         if (lane == 0) {
-            const float *src = wpack + (size_t)blockIdx.y * nk * (2 * BN * kBK);
+            const float *src = wpack + (size_t)ctile * nk * (2 * BN * kBK);
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % kStages;
                 const uint32_t ph = (kc / kStages) & 1;
@@ -324,17 +342,42 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         }
         __syncthreads();
         if (tid < 256) {
-            // (a) weighted column sums in fp64: threads 0-127 sum w*y, threads 128-255 sum w*y^2
-            const int col = tid & 127, which = tid >> 7;
-            double acc = 0.0;
-            for (int r = 0; r < kTM; ++r) {
+            // (a) weighted column sums in fp64: thread = (column, 128-row group); one load feeds both sums
+            const int col = tid & 127, rg = tid >> 7;
+            double sy = 0.0, syy = 0.0;
+#pragma unroll 4
+            for (int r = rg * 128; r < rg * 128 + 128; ++r) {
                 const float w = s_roww[r];
-                if (w != 0.f) {
-                    const double y = (double)ytile[(size_t)r * kEpiLd + col];
-                    acc += which ? (double)w * y * y : (double)w * y;
+                const double y = (double)ytile[(size_t)r * kEpiLd + col];
+                if (w == 1.f) {
+                    sy += y;
+                    syy = fma(y, y, syy);
+                } else if (w != 0.f) {
+                    const double wy = (double)w * y;
+                    sy += wy;
+                    syy = fma(wy, y, syy);
                 }
             }
-            atomicAdd(a.out_stats + ((size_t)f * a.Cout + n0 + pass * kEpiCols + col) * 2 + which, acc);
+            double *o = a.out_stats + ((size_t)f * a.Cout + n0 + pass * kEpiCols + col) * 2;
+            atomicAdd(o, sy);
+            atomicAdd(o + 1, syy);
+            if (a.vmax) {  // per-voxel max of the raw (>= 0) activations: rows of a voxel are consecutive
+                int *vm = a.vmax + (size_t)f * a.vcap * a.Cout + n0 + pass * kEpiCols + col;
+                int cv = -1;
+                float cm = 0.f;
+                for (int r = rg * 128; r < rg * 128 + 128; ++r) {
+                    const int v = s_rowv[r];
+                    const float y = ytile[(size_t)r * kEpiLd + col];
+                    if (v != cv) {
+                        if (cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
+                        cv = v;
+                        cm = y;
+                    } else {
+                        cm = fmaxf(cm, y);
+                    }
+                }
+                if (cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
+            }
             // (b) coalesced raw stores: one warp per row, 32 lanes x 16 bytes = 128 columns
             if (a.Y) {
                 for (int r = warp; r < kTM; r += 8) {
@@ -365,7 +408,7 @@ int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     pack_weights_kernel<BN><<<(total + 255) / 256, 256, 0, st>>>(a.Wt, a.Cin, a.Cout, wpack);
     MVX_LAUNCH_CHECK();
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
-    dim3 grid((unsigned)ceil_div(max_rows, kTM), a.Cout / BN, F);
+    dim3 grid(a.Cout / BN, (unsigned)ceil_div(max_rows, kTM), F);
     tc_layer_kernel<BN><<<grid, kThreads, S::kTotal, st>>>(a, wpack);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
@@ -374,7 +417,7 @@ int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
 }  // namespace
 
 bool tc_layer_eligible(const LayerArgs &a) {
-    return a.vmax == nullptr && a.Cin % kBK == 0 && a.Cin <= 768 && a.Cout % 128 == 0 && a.ldx % 4 == 0 &&
+    return a.Cin % kBK == 0 && a.Cin <= 768 && a.Cout % 128 == 0 && a.ldx % 4 == 0 &&
            (a.Y == nullptr || a.ldy % 4 == 0);
 }
 
