@@ -42,22 +42,32 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """nvidia-smi sampled every 20 ms from before the warm-up; only rows inside the timed window are used."""
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index: int):
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         self.p = None
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       '-lms', '20'], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def stop(self):
-        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        import datetime
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -66,18 +76,25 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, allsm = [], [], set(), []
         for r in rows:
             try:
-                sm.append(float(r[1])), mx.append(float(r[2]))
+                ts = datetime.datetime.strptime(r[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                clk, cmax = float(r[1]), float(r[2])
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+            allsm.append(clk)
+            mx.append(cmax)
+            if self.t0 is not None and not (self.t0 - 0.02 <= ts <= self.t1 + 0.02):
+                continue
+            sm.append(clk)
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
                 if v.strip().lower() == 'active':
                     reasons.add(name)
+        if not sm and allsm:          # window shorter than the sampling period: fall back to the whole run
+            sm = allsm
         if sm:
-            top = sorted(sm)[len(sm) // 2:]          # samples under load = upper half
-            out = dict(sm_mhz=statistics.median(top), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out = dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
         return out
 
 
@@ -188,19 +205,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident leg (`value`) ----------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         path.forward_device(points_d, offsets, calib_d, maps_d)
     barrier()
     _lib.check(_lib.lib.mvx_timing_enable(args.steps), 'timing_enable')
     launches0 = _lib.launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.begin()
     e0.record()
     for _ in range(args.steps):
         path.forward_device(points_d, offsets, calib_d, maps_d)
     e1.record()
     barrier()
+    if sampler:
+        sampler.end()
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
@@ -287,7 +308,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -121,9 +121,9 @@ int mvx_fcn_max_forward(const float *x, int64_t R, int32_t T, int32_t Cin, const
 /* ------------------------------------------------------------------------------------------------
  * Stage 4 — scatter into the dense middle-layer grid.  Replaces modules/voxelnet/VoxelNet.py:16-22
  * (`reindex`): out (1,C,nz,nx,ny) fp32 fully written (zeros + features) in ONE streaming pass.
- * idx (N,4) int64 [batch, ix, iy, iz] (train.py:119,126).  map_ws: nz*nx*ny int32 scratch.
+ * idx (N,4) int64 [batch, ix, iy, iz] (train.py:119,126).  map_ws: (G + G/32 + 1) int32 of scratch, G = nz*nx*ny.
  * ------------------------------------------------------------------------------------------------ */
-int mvx_set_grid_mode(int32_t mode); /* 1 = cp.async.bulk shared->global stores (default), 0 = per-thread st.global.cs */
+int mvx_set_grid_mode(int32_t mode); /* 2 = plane-sequential stores + occupancy bits (default), 0 = cell-major st.global.cs, 1 = cp.async.bulk stores */
 int mvx_scatter_dense(const float *feat, const int64_t *idx, int64_t N, int32_t C, int32_t nx, int32_t ny,
                       int32_t nz, float *out, int32_t *map_ws, void *stream);
 

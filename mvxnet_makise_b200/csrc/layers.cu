@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(float *__restrict__
 
 // out[v][0:C] = norm(vmax[v][0:C])   (frames at stride vcap for both)
 __global__ void __launch_bounds__(256) normalize_vmax_kernel(const int *__restrict__ vmax, float *__restrict__ out, int C,
-                                                             int vcap, long long nvox_fixed, NormSrc n) {
+                                                             int vcap, long long nvox_fixed, NormSrc n,
+                                                             float *__restrict__ out_t = nullptr) {
     __shared__ float s_mean[768], s_rstd[768];
     const int f = blockIdx.y;
     const double Rs = stat_rows(n, f);
@@ -247,6 +248,10 @@ __global__ void __launch_bounds__(256) normalize_vmax_kernel(const int *__restri
         q.z = (__int_as_float(m.z) - s_mean[c + 2]) * s_rstd[c + 2];
         q.w = (__int_as_float(m.w) - s_mean[c + 3]) * s_rstd[c + 3];
         *reinterpret_cast<float4 *>(out + ((size_t)f * vcap + v) * C + c) = q;
+        if (out_t) {  // channel-major copy (C, vcap) for the plane-sequential grid fill
+            float *t = out_t + ((size_t)f * C + c) * vcap + v;
+            t[0] = q.x, t[vcap] = q.y, t[2 * (size_t)vcap] = q.z, t[3 * (size_t)vcap] = q.w;
+        }
     }
 }
 
@@ -397,7 +402,7 @@ int launch_prep_fcn(const VfePrepArgs &a, cudaStream_t st) {
     return MVX_OK;
 }
 int launch_finalize_vfeat(const VfePrepArgs &a, cudaStream_t st) {
-    normalize_vmax_kernel<<<dim3(kSMs * 2, a.B), 256, 0, st>>>(a.vmax8, a.vfeat, 128, a.cap, 0, a.n8);
+    normalize_vmax_kernel<<<dim3(kSMs * 2, a.B), 256, 0, st>>>(a.vmax8, a.vfeat, 128, a.cap, 0, a.n8, a.vfeat_t);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }

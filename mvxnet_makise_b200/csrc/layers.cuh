@@ -65,6 +65,7 @@ struct VfePrepArgs {
     // final: vfeat[v] = norm8(vmax8[v]) (128)
     const int *vmax8;
     float *vfeat;
+    float *vfeat_t;        // optional channel-major copy (128, cap) per frame
     NormSrc n5, n6, n7, n8;
 };
 int launch_prep_vfe1(const VfePrepArgs &a, cudaStream_t st);

@@ -18,14 +18,14 @@ namespace mvx {
 enum Region {
     R_VOXWS = 0, R_VOX_COORD, R_VOX_CNT, R_VOX_ROW0, R_ROW_POINT, R_ROW_VOX, R_CELL2VID, R_NHWC0, R_NHWC1, R_NHWC2,
     R_VOX8, R_PROJ, R_ROWA_W, R_A1, R_Y1, R_Y2, R_Y3, R_Y4, R_Y5, R_X6, R_Y6, R_X7, R_Y7, R_ROWB_W, R_ROWB_V, R_X8,
-    R_VFEAT, R_STATS, R_VMAX6, R_VMAX7, R_VMAX8, R_WPACK, R_COUNT
+    R_VFEAT, R_STATS, R_VMAX6, R_VMAX7, R_VMAX8, R_WPACK, R_OCC, R_VFEAT_T, R_COUNT
 };
 static_assert(R_COUNT <= MVX_WS_REGIONS, "too many regions");
 
 const char *kRegionNames[R_COUNT] = {
     "vox_ws", "vox_coord", "vox_cnt", "vox_row0", "row_point", "row_vox", "cell2vid", "nhwc0", "nhwc1", "nhwc2",
     "vox8", "proj", "rowA_w", "A1", "Y1", "Y2", "Y3", "Y4", "Y5", "X6", "Y6", "X7", "Y7", "rowB_w", "rowB_v", "X8",
-    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack"};
+    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t"};
 
 constexpr int kCin[MVX_NUM_LAYERS] = {768, 768, 128, 128, 16, 32, 32, 128};   // padded
 constexpr int kCout[MVX_NUM_LAYERS] = {768, 128, 128, 16, 16, 16, 64, 128};
@@ -87,6 +87,8 @@ int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
     take(R_VMAX7, B * cap * 64 * 4);
     take(R_VMAX8, B * cap * 128 * 4);
     take(R_WPACK, tc_wpack_bytes(768, 768));
+    take(R_OCC, B * (size_t)(L.G / 32 + 1) * 4);
+    take(R_VFEAT_T, B * cap * 128 * 4);
     L.total = o;
     return MVX_OK;
 }
@@ -215,6 +217,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
     vp.Y6 = F32(R_Y6), vp.vmax6 = I32(R_VMAX6), vp.X7 = F32(R_X7), vp.rowB_w = F32(R_ROWB_W), vp.rowB_v = I32(R_ROWB_V);
     vp.Y7 = F32(R_Y7), vp.vmax7 = I32(R_VMAX7), vp.X8 = F32(R_X8);
     vp.vmax8 = I32(R_VMAX8), vp.vfeat = F32(R_VFEAT);
+    vp.vfeat_t = (grid_mode() == 2 && L.G % 32 == 0 && a->grid_out) ? F32(R_VFEAT_T) : nullptr;
     vp.n5 = NormSrc{stat_of(4), a->counts, 0, T, a->bn_eps};
     vp.n6 = NormSrc{stat_of(5), a->counts, 0, T, a->bn_eps};
     vp.n7 = NormSrc{stat_of(6), a->counts, 0, T, a->bn_eps};
@@ -267,7 +270,14 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
     // ---- stage 4 ----------------------------------------------------------------------------------------
     if (a->grid_out) {
         MVX_REQUIRE((reinterpret_cast<uintptr_t>(a->grid_out) & 15) == 0, MVX_EINVAL, "grid_out must be 16-byte aligned");
-        rc = launch_grid_fill(vo.cell2vid, F32(R_VFEAT), a->grid_out, B, L.G, 128, cap, st);
+        if (vp.vfeat_t) {
+            unsigned *occ = reinterpret_cast<unsigned *>(ws + L.off[R_OCC]);
+            rc = launch_occ_from_map(vo.cell2vid, occ, B, L.G, st);
+            if (rc) return rc;
+            rc = launch_grid_fill_planes(occ, vo.cell2vid, F32(R_VFEAT_T), (long long)cap * 128, 1, cap, a->grid_out, B, L.G, 128, st);
+        } else {
+            rc = launch_grid_fill(vo.cell2vid, F32(R_VFEAT), a->grid_out, B, L.G, 128, cap, st);
+        }
         if (rc) return rc;
     }
     stamp.mark(S_COUNT);

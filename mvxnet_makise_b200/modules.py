@@ -211,7 +211,8 @@ def reindex(x: torch.Tensor, idx: torch.Tensor, voxelshape: Sequence[int] = VOXE
     idx = idx.to(torch.int64).contiguous()
     N, C = x.shape
     out = torch.empty((1, C, nz, nx, ny), dtype=torch.float32, device=x.device)
-    mapws = torch.empty(nx * ny * nz, dtype=torch.int32, device=x.device)
+    G = nx * ny * nz
+    mapws = torch.empty(G + G // 32 + 1, dtype=torch.int32, device=x.device)
     check(lib.mvx_scatter_dense(ptr(x), ptr(idx), N, C, nx, ny, nz, ptr(out), ptr(mapws), stream_ptr()), 'scatter_dense')
     return out
 
