@@ -227,8 +227,7 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(float *__restrict__
 
 // out[v][0:C] = norm(vmax[v][0:C])   (frames at stride vcap for both)
 __global__ void __launch_bounds__(256) normalize_vmax_kernel(const int *__restrict__ vmax, float *__restrict__ out, int C,
-                                                             int vcap, long long nvox_fixed, NormSrc n,
-                                                             float *__restrict__ out_t = nullptr) {
+                                                             int vcap, long long nvox_fixed, NormSrc n) {
     __shared__ float s_mean[768], s_rstd[768];
     const int f = blockIdx.y;
     const double Rs = stat_rows(n, f);
@@ -248,11 +247,41 @@ __global__ void __launch_bounds__(256) normalize_vmax_kernel(const int *__restri
         q.z = (__int_as_float(m.z) - s_mean[c + 2]) * s_rstd[c + 2];
         q.w = (__int_as_float(m.w) - s_mean[c + 3]) * s_rstd[c + 3];
         *reinterpret_cast<float4 *>(out + ((size_t)f * vcap + v) * C + c) = q;
-        if (out_t) {  // channel-major copy (C, vcap) for the plane-sequential grid fill
-            float *t = out_t + ((size_t)f * C + c) * vcap + v;
-            t[0] = q.x, t[vcap] = q.y, t[2 * (size_t)vcap] = q.z, t[3 * (size_t)vcap] = q.w;
+    }
+}
+
+// fused-path finalize: vfeat[v][0:128] = norm8(vmax8[v]) (voxel-major, the (N,128) result) and, through a padded
+// shared-memory tile, the channel-major copy vfeat_t[c][v] that the plane-sequential grid fill reads.
+__global__ void __launch_bounds__(256) finalize_vfeat_kernel(const int *__restrict__ vmax, float *__restrict__ out,
+                                                             float *__restrict__ out_t, int vcap, NormSrc n) {
+    constexpr int C = 128;
+    __shared__ float s_mean[C], s_rstd[C];
+    __shared__ float tile[C][33];
+    const int f = blockIdx.y;
+    const int N = n.counts[f * 4 + 0];
+    const int v0 = blockIdx.x * 32;
+    if (v0 >= N) return;
+    if (threadIdx.x < C) norm_coef(n.stats + ((size_t)f * C + threadIdx.x) * 2, stat_rows(n, f), n.eps, s_mean[threadIdx.x], s_rstd[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {  // 32 voxels x 32 float4 per voxel
+        const int e = it * 256 + threadIdx.x, vl = e >> 5, c = (e & 31) * 4;
+        if (v0 + vl < N) {
+            const int4 m = *reinterpret_cast<const int4 *>(vmax + ((size_t)f * vcap + v0 + vl) * C + c);
+            float4 q;
+            q.x = (__int_as_float(m.x) - s_mean[c]) * s_rstd[c];
+            q.y = (__int_as_float(m.y) - s_mean[c + 1]) * s_rstd[c + 1];
+            q.z = (__int_as_float(m.z) - s_mean[c + 2]) * s_rstd[c + 2];
+            q.w = (__int_as_float(m.w) - s_mean[c + 3]) * s_rstd[c + 3];
+            *reinterpret_cast<float4 *>(out + ((size_t)f * vcap + v0 + vl) * C + c) = q;
+            tile[c][vl] = q.x, tile[c + 1][vl] = q.y, tile[c + 2][vl] = q.z, tile[c + 3][vl] = q.w;
         }
     }
+    if (!out_t) return;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int c = w; c < C; c += 8)
+        if (v0 + lane < N) out_t[((size_t)f * C + c) * vcap + v0 + lane] = tile[c][lane];
 }
 
 // ---- fused-path glue ------------------------------------------------------------------------------------
@@ -402,7 +431,7 @@ int launch_prep_fcn(const VfePrepArgs &a, cudaStream_t st) {
     return MVX_OK;
 }
 int launch_finalize_vfeat(const VfePrepArgs &a, cudaStream_t st) {
-    normalize_vmax_kernel<<<dim3(kSMs * 2, a.B), 256, 0, st>>>(a.vmax8, a.vfeat, 128, a.cap, 0, a.n8, a.vfeat_t);
+    finalize_vfeat_kernel<<<dim3((a.cap + 31) / 32, a.B), 256, 0, st>>>(a.vmax8, a.vfeat, a.vfeat_t, a.cap, a.n8);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }

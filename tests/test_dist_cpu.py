@@ -1,0 +1,76 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: frame sharding and the single-bucket gradient all-reduce."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mvxnet_makise_b200 import dist as mdist
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_frames, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    r, w, _ = mdist.init('gloo')
+    assert (r, w) == (rank, world)
+    mine = mdist.shard_frames(n_frames, rank, world)
+    # stand-in for the per-frame forward: a deterministic function of the global frame id
+    local = [(b, b * b + 1) for b in mine]
+    allres = mdist.gather_frame_results(local, n_frames, rank, world)
+    # gradients: each rank contributes the sum over its frames of a frame-dependent gradient
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)
+    lin.weight.grad = torch.zeros_like(lin.weight)
+    lin.bias.grad = torch.zeros_like(lin.bias)
+    for b in mine:
+        lin.weight.grad += float(b + 1)
+        lin.bias.grad += float(2 * b)
+    bucket = mdist.GradBucket(lin.parameters())
+    flat = bucket.allreduce(global_frames=n_frames, average=True).clone()
+    q.put((rank, mine, allres, flat, lin.weight.grad.clone(), lin.bias.grad.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_frames', [8, 5])
+def test_frame_sharding_and_grad_allreduce_gloo(n_frames):
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    owned = sorted(b for _, mine, *_ in res for b in mine)
+    assert owned == list(range(n_frames))                                  # every frame exactly once
+    for rank, mine, allres, flat, wg, bg in res:
+        assert all(mdist.owner_of(b, world) == rank for b in mine)
+        assert allres == [(b, b * b + 1) for b in range(n_frames)]         # global order restored on every rank
+        exp_w = sum(b + 1 for b in range(n_frames)) / n_frames
+        exp_b = sum(2 * b for b in range(n_frames)) / n_frames
+        assert torch.allclose(wg, torch.full_like(wg, exp_w)) and torch.allclose(bg, torch.full_like(bg, exp_b))
+        assert flat.numel() == 5 * 3 + 3
+    assert torch.equal(res[0][3], res[1][3])                               # identical on both ranks
+
+
+def test_single_process_paths():
+    assert mdist.shard_frames(8, 0, 1) == list(range(8))
+    assert mdist.shard_frames(8, 3, 8) == [3] and mdist.shard_frames(16, 1, 8) == [1, 9]
+    assert mdist.gather_frame_results([1, 2, 3], 3, 0, 1) == [1, 2, 3]
+    lin = torch.nn.Linear(2, 2)
+    lin.weight.grad = torch.ones_like(lin.weight)
+    b = mdist.GradBucket(lin.parameters())
+    b.allreduce(global_frames=2)
+    assert torch.allclose(lin.weight.grad, torch.full_like(lin.weight, 0.5)) and lin.bias.grad is not None
