@@ -322,3 +322,26 @@ def test_fused_path_full_size_properties(mvx):
     # BatchNorm property: over the N*T dense rows every channel of the last layer has mean 0 / var 1; the max over T
     # of such a channel is >= its mean, so every per-voxel max is >= the smallest normalised value (finite, bounded)
     assert float(vfeat.abs().max()) < 1e4
+
+
+def test_dense_config5_frame(mvx):
+    """BASELINE.json configs[4]: dense 128-beam-like frame (P = 250 000) on the larger 512x512x10 grid."""
+    DG = synth.DENSE_GRID
+    sd = synth.make_weights(0)
+    calib = synth.kitti_calib()
+    pts = synth.make_points(7, 250_000, grid=DG, beams=128)
+    assert pts.shape[0] == 250_000
+    maps = [torch.from_numpy(m) for m in synth.make_fpn_maps(7)]
+    path = mvx.P.PointPath(sd, DG)
+    grid, counts = path([pts], [calib], maps)
+    torch.cuda.synchronize()
+    c = counts.cpu().numpy()[0]
+    idx = O.cell_index(pts, DG.velorange, DG.voxelsize)
+    _, _, coords, cnt = O.group_assign(idx, DG.T)
+    assert c[0] == coords.shape[0] and c[1] == cnt.sum() and c[2] == 0
+    vfeat, vidx = path.voxel_features(0)
+    assert np.array_equal(vidx[:, 1:].cpu().numpy(), coords) and torch.isfinite(vfeat).all()
+    g0 = grid[0]
+    assert tuple(g0.shape) == (128, 10, 512, 512)
+    assert int((g0 != 0).sum()) == int((vfeat != 0).sum())
+    assert torch.equal(g0[:, vidx[:, 3], vidx[:, 1], vidx[:, 2]].T, vfeat)
