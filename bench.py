@@ -185,6 +185,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', os.devnull)   # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     B, G = FRAMES_PER_GPU, synth.KITTI_GRID.cells
 
