@@ -456,8 +456,9 @@ static int dense_layer(const float *x, int64_t R, int32_t T, int32_t Cin, const 
 }  // namespace mvx
 
 extern "C" int mvx_set_gemm_mode(int32_t mode) {
-    if (mode != 0 && mode != 1) return MVX_EINVAL;
-    mvx::g_gemm_mode = mode;
+    if (mode < 0 || mode > 2) return MVX_EINVAL;   // 2 = tensor cores, one tile per CTA (non-persistent variant)
+    mvx::g_gemm_mode = mode == 0 ? 0 : 1;
+    mvx::set_tc_persistent(mode == 1);
     return MVX_OK;
 }
 

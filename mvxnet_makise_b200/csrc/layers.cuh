@@ -33,6 +33,8 @@ int launch_layer(const LayerArgs &a, int F, cudaStream_t st);            // exac
 bool tc_layer_eligible(const LayerArgs &a);
 size_t tc_wpack_bytes(int Cin, int Cout);
 int launch_layer_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
+bool tc_persistent_enabled();
+void set_tc_persistent(int on);  // 1 = persistent kernel with overlapped epilogue (default), 0 = one tile per CTA
 // dispatch by mvx_set_gemm_mode(): 0 = SIMT everywhere, 1 = tensor cores where eligible (default)
 int gemm_mode();
 int launch_layer_auto(const LayerArgs &a, int F, float *wpack, cudaStream_t st);

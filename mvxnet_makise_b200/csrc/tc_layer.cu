@@ -414,7 +414,346 @@ int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     return MVX_OK;
 }
 
+
+// =====================================================================================================================
+// Persistent variant (layers without a per-voxel max: fcn1, conv1, fcn2). One CTA per SM walks the (frame, row tile,
+// column tile) list; the epilogue has its own four warps and works from registers (no shared staging tile), so while
+// tile i drains from TMEM the producers already fill the stages of tile i+1 and the tensor pipe only idles for the
+// TMEM drain itself:
+//   warps 0-7  A producers      warp 8  B bulk-copy producer      warp 9  MMA issuer (+ TMEM alloc)
+//   warps 10-13 epilogue: tcgen05.ld -> bias/ReLU -> direct 16-byte row stores; column sums by a 31-shuffle butterfly
+//               transpose-reduction per 32x32 block (fp32 inside a warp's 32 rows, fp64 across warps/tiles/CTAs).
+// =====================================================================================================================
+constexpr int kPThreads = 14 * 32;
+
+template <int BN>
+struct PSmem {
+    static constexpr int kAHalf = kTM * kBK * 4;
+    static constexpr int kBHalf = BN * kBK * 4;
+    static constexpr int kStage = 2 * kAHalf + 2 * kBHalf;
+    static constexpr int kTiles = kStages * kStage;
+    static constexpr int kMean = kTiles;
+    static constexpr int kRstd = kMean + 768 * 4;
+    static constexpr int kPart = kRstd + 768 * 4;              // [4 warps][BN][2] fp64 column partials
+    static constexpr int kBars = kPart + 4 * BN * 2 * 8;       // full[3], empty[3], accum_full, tmem_empty
+    static constexpr int kTmemPtr = kBars + 8 * 8;
+    static constexpr int kTotal = kTmemPtr + 16 + 1024;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// lane j ends up with the sum over the 32 lanes of x[j] (x is destroyed): 16+8+4+2+1 = 31 shuffles
+__device__ __forceinline__ float butterfly_colsum(float (&x)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? x[i] : x[i + s];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+            x[i] = (up ? x[i + s] : x[i]) + recv;
+        }
+    }
+    return x[0];
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArgs a, const float *__restrict__ wpack, int F,
+                                                                         int row_tiles, int col_tiles) {
+    using S = PSmem<BN>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    float *s_mean = reinterpret_cast<float *>(smem + S::kMean);
+    float *s_rstd = reinterpret_cast<float *>(smem + S::kRstd);
+    double *s_part = reinterpret_cast<double *>(smem + S::kPart);
+    const uint32_t bars = sbase + S::kBars;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * kStages), tmem_empty_bar = bars + 8u * (2 * kStages + 1);
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(smem + S::kTmemPtr);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nk = a.Cin / kBK;
+    const int total = F * row_tiles * col_tiles;
+
+    // tile decode shared by every role: identical decisions => identical pipeline phase bookkeeping
+    auto decode = [&](int t, int &f, int &ct, long long &row0, long long &n_rows) -> bool {
+        ct = t % col_tiles;
+        const int rt = (t / col_tiles) % row_tiles;
+        f = t / (col_tiles * row_tiles);
+        n_rows = a.rows_fixed;
+        if (a.counts) {
+            const int N = a.counts[f * 4 + 0], K = a.counts[f * 4 + 1];
+            n_rows = a.rows_mode == 1 ? K + 1 : (a.rows_mode == 2 ? K + N : a.rows_fixed);
+        }
+        row0 = (long long)rt * kTM;
+        return row0 < n_rows;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), kProducerThreads + 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(accum_bar, 1);
+        mbar_init(tmem_empty_bar, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::kTmemPtr), "r"(2 * BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 8) {
+        // ================= A producers ===========================================================================
+        const int c = tid & 3, rsub = tid >> 2;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        int g = 0, cur_f = -1;  // global chunk counter of this CTA (ring position), frame whose BN coefficients are loaded
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            int f, ct;
+            long long row0, n_rows;
+            if (!decode(t, f, ct, row0, n_rows)) continue;
+            if (a.in_stats && f != cur_f) {  // BatchNorm coefficients of the producer layer for this frame
+                named_bar_sync(1, kProducerThreads);
+                const double Rstat = a.counts ? (double)a.counts[f * 4 + 0] * (double)a.T : (double)a.rows_fixed;
+                for (int cc = tid; cc < a.Cin; cc += kProducerThreads) {
+                    const double *st = a.in_stats + ((size_t)f * a.Cin + cc) * 2;
+                    const double m = st[0] / Rstat;
+                    double var = st[1] / Rstat - m * m;
+                    var = var < 0.0 ? 0.0 : var;
+                    s_mean[cc] = (float)m;
+                    s_rstd[cc] = (float)(1.0 / sqrt(var + a.eps));
+                }
+                named_bar_sync(1, kProducerThreads);
+            }
+            cur_f = f;
+            const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx + c * 4;
+            bool valid[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) valid[i] = row0 + rsub + 64 * i < n_rows;
+            auto load_chunk = [&](float4 (&buf)[4], int kc) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    buf[i] = valid[i] ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + kc * kBK)) : z4;
+            };
+            auto produce = [&](float4 (&buf)[4], int kc) {
+                float4 cur[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cur[i] = buf[i];
+                if (a.in_stats) {
+                    const int k = kc * kBK + c * 4;
+                    const float m0 = s_mean[k], m1 = s_mean[k + 1], m2 = s_mean[k + 2], m3 = s_mean[k + 3];
+                    const float r0 = s_rstd[k], r1 = s_rstd[k + 1], r2 = s_rstd[k + 2], r3 = s_rstd[k + 3];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (valid[i]) {
+                            cur[i].x = (cur[i].x - m0) * r0;
+                            cur[i].y = (cur[i].y - m1) * r1;
+                            cur[i].z = (cur[i].z - m2) * r2;
+                            cur[i].w = (cur[i].w - m3) * r3;
+                        }
+                    }
+                }
+                if (kc + 2 < nk) load_chunk(buf, kc + 2);
+                const int s = g % kStages;
+                const uint32_t ph = (g / kStages) & 1;
+                ++g;
+                if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);
+                __syncwarp();
+                uint8_t *stage = smem + (size_t)s * S::kStage;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 hi, lo;
+                    split_tf32(cur[i].x, hi.x, lo.x);
+                    split_tf32(cur[i].y, hi.y, lo.y);
+                    split_tf32(cur[i].z, hi.z, lo.z);
+                    split_tf32(cur[i].w, hi.w, lo.w);
+                    const uint32_t off = sw64_offset(rsub + 64 * i, c);
+                    *reinterpret_cast<float4 *>(stage + off) = hi;
+                    *reinterpret_cast<float4 *>(stage + S::kAHalf + off) = lo;
+                }
+                fence_async_smem();
+                mbar_arrive(full_bar(s));
+            };
+            float4 buf0[4], buf1[4];
+            load_chunk(buf0, 0);
+            if (nk > 1) load_chunk(buf1, 1);
+            for (int kc = 0; kc < nk; kc += 2) {
+                produce(buf0, kc);
+                if (kc + 1 < nk) produce(buf1, kc + 1);
+            }
+        }
+    } else if (warp == 8) {
+        // ================= B producer ============================================================================
+        if (lane == 0) {
+            int g = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                int f, ct;
+                long long row0, n_rows;
+                if (!decode(t, f, ct, row0, n_rows)) continue;
+                const float *src = wpack + (size_t)ct * nk * (2 * BN * kBK);
+                for (int kc = 0; kc < nk; ++kc, ++g) {
+                    const int s = g % kStages;
+                    const uint32_t ph = (g / kStages) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_arrive_expect_tx(full_bar(s), 2 * S::kBHalf);
+                    bulk_g2s(sbase + s * S::kStage + 2 * S::kAHalf, src + (size_t)kc * (2 * BN * kBK), 2 * S::kBHalf, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer ============================================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+            int g = 0, it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                int f, ct;
+                long long row0, n_rows;
+                if (!decode(t, f, ct, row0, n_rows)) continue;
+                mbar_wait(tmem_empty_bar, (it & 1) ^ 1);  // the epilogue has drained the previous tile's accumulators
+                tc_fence_after();
+                for (int kc = 0; kc < nk; ++kc, ++g) {
+                    const int s = g % kStages;
+                    const uint32_t ph = (g / kStages) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sA = sbase + s * S::kStage, sB = sA + 2 * S::kAHalf;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t d = tmem_base + h * BN;
+                        const uint32_t aoff = h * (128 * 64);
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint64_t a_hi = make_desc(sA + aoff + ks * 32), a_lo = make_desc(sA + S::kAHalf + aoff + ks * 32);
+                            const uint64_t b_hi = make_desc(sB + ks * 32), b_lo = make_desc(sB + S::kBHalf + ks * 32);
+                            mma_tf32(d, a_lo, b_hi, idesc, (kc | ks) != 0);
+                            mma_tf32(d, a_hi, b_lo, idesc, 1);
+                            mma_tf32(d, a_hi, b_hi, idesc, 1);
+                        }
+                    }
+                    mma_commit(empty_bar(s));
+                }
+                mma_commit(accum_bar);
+                ++it;
+            }
+        }
+    } else {
+        // ================= epilogue warps (10..13): TMEM lane quarter q = warp % 4 ================================
+        const int q = warp & 3, ew = warp - 10, et = tid - 10 * 32;  // et: 0..127
+        int it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            int f, ct;
+            long long row0, n_rows;
+            if (!decode(t, f, ct, row0, n_rows)) continue;
+            const int n0 = ct * BN;
+            double acc_s[BN / 32], acc_ss[BN / 32];
+#pragma unroll
+            for (int cb = 0; cb < BN / 32; ++cb) acc_s[cb] = 0.0, acc_ss[cb] = 0.0;
+            // zero the fp64 partials of the "heavy" rows (BN multiplicity != 1) before anybody adds to them
+            named_bar_sync(2, 128);  // previous tile's partial reads are done
+            for (int i = et; i < 4 * BN * 2; i += 128) s_part[i] = 0.0;
+            named_bar_sync(2, 128);
+            mbar_wait(accum_bar, it & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const long long r = row0 + h * 128 + q * 32 + lane;
+                const bool valid = r < n_rows;
+                const float w = valid ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + r] : 1.f) : 0.f;
+                const float m = w == 1.f ? 1.f : 0.f;         // ordinary rows go through the fp32 butterfly
+                const bool heavy = w != 0.f && w != 1.f;      // the weighted pad row: exact fp64 side path
+                float *yrow = a.Y ? a.Y + ((size_t)f * a.rowcap + r) * a.ldy + n0 : nullptr;
+#pragma unroll 1
+                for (int cb = 0; cb < BN / 32; ++cb) {
+                    float v[32], p2[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * BN + cb * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + n0 + cb * 32 + j));
+                        v[j] = fmaxf(v[j] + b4.x, 0.f);
+                        v[j + 1] = fmaxf(v[j + 1] + b4.y, 0.f);
+                        v[j + 2] = fmaxf(v[j + 2] + b4.z, 0.f);
+                        v[j + 3] = fmaxf(v[j + 3] + b4.w, 0.f);
+                    }
+                    if (yrow && valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(yrow + cb * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                    if (heavy) {
+                        for (int j = 0; j < 32; ++j) {
+                            const double y = (double)v[j], wy = (double)w * y;
+                            atomicAdd(&s_part[((size_t)ew * BN + cb * 32 + j) * 2], wy);
+                            atomicAdd(&s_part[((size_t)ew * BN + cb * 32 + j) * 2 + 1], wy * y);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] *= m;
+                        p2[j] = v[j] * v[j];
+                    }
+                    acc_s[cb] += (double)butterfly_colsum(v, lane);
+                    acc_ss[cb] += (double)butterfly_colsum(p2, lane);
+                }
+            }
+            // accumulators are drained: the MMA warp may start the next tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar);
+            // combine the four warps' column partials and publish one fp64 atomicAdd per column and quantity
+#pragma unroll
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                atomicAdd(&s_part[((size_t)ew * BN + cb * 32 + lane) * 2], acc_s[cb]);
+                atomicAdd(&s_part[((size_t)ew * BN + cb * 32 + lane) * 2 + 1], acc_ss[cb]);
+            }
+            named_bar_sync(2, 128);
+            for (int i = et; i < BN * 2; i += 128) {
+                const double s4 = s_part[i] + s_part[BN * 2 + i] + s_part[2 * BN * 2 + i] + s_part[3 * BN * 2 + i];
+                atomicAdd(a.out_stats + ((size_t)f * a.Cout + n0) * 2 + i, s4);
+            }
+            ++it;
+        }
+    }
+    __syncwarp();  // warps 8/9: lanes 1-31 wait here for their looping lane 0, so every warp reaches the barrier converged
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
+template <int BN>
+int launch_tc_persist(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
+    using S = PSmem<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        attr_set = true;
+    }
+    const int total = a.Cin * a.Cout;
+    pack_weights_kernel<BN><<<(total + 255) / 256, 256, 0, st>>>(a.Wt, a.Cin, a.Cout, wpack);
+    MVX_LAUNCH_CHECK();
+    const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
+    const int row_tiles = (int)ceil_div(max_rows, kTM), col_tiles = a.Cout / BN;
+    const long long slots = (long long)F * row_tiles * col_tiles;
+    const int grid = (int)(slots < kSMs ? slots : kSMs);
+    tc_layer_persist_kernel<BN><<<grid, kPThreads, S::kTotal, st>>>(a, wpack, F, row_tiles, col_tiles);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
 }  // namespace
+
+static int g_tc_persistent = 1;
+bool tc_persistent_enabled() { return g_tc_persistent != 0; }
+void set_tc_persistent(int on) { g_tc_persistent = on; }
 
 bool tc_layer_eligible(const LayerArgs &a) {
     return a.Cin % kBK == 0 && a.Cin <= 768 && a.Cout % 128 == 0 && a.ldx % 4 == 0 &&
@@ -427,6 +766,10 @@ int launch_layer_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     MVX_REQUIRE(tc_layer_eligible(a) && wpack, MVX_EINVAL, "layer not eligible for the tensor-core kernel");
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     if (max_rows <= 0) return MVX_OK;
+    if (a.vmax == nullptr && tc_persistent_enabled()) {  // persistent kernel with the overlapped register epilogue
+        if (a.Cout % 256 == 0) return launch_tc_persist<256>(a, F, wpack, st);
+        return launch_tc_persist<128>(a, F, wpack, st);
+    }
     if (a.Cout % 256 == 0) return launch_tc<256>(a, F, wpack, st);
     return launch_tc<128>(a, F, wpack, st);
 }

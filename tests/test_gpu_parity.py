@@ -192,13 +192,15 @@ def test_tensor_core_layer_is_fp32_accurate(mvx, R, cin, cout):
         with torch.no_grad():
             _lib.set_gemm_mode(0)
             y_simt = fcn(x)
-            _lib.set_gemm_mode(1)
+            _lib.set_gemm_mode(2)      # one tile per CTA
+            y_tc2 = fcn(x)
+            _lib.set_gemm_mode(1)      # persistent kernel, overlapped register epilogue (default)
             y_tc = fcn(x)
     finally:
         _lib.set_gemm_mode(1)
     y = torch.relu(x.double().reshape(-1, cin) @ fcn.fc.weight.double().t() + fcn.fc.bias.double())
     ref = (y - y.mean(0)) / torch.sqrt(y.var(0, unbiased=False) + 1e-6)
-    assert rel_err(y_tc, y_simt) < 2e-5
+    assert rel_err(y_tc, y_simt) < 2e-5 and rel_err(y_tc2, y_simt) < 2e-5
     assert rel_err(y_tc.reshape(-1, cout), ref) < 2e-5 and rel_err(y_simt.reshape(-1, cout), ref) < 2e-5
 
 
