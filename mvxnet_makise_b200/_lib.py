@@ -131,7 +131,8 @@ c_float = c_float  # re-export for callers building timing buffers
 
 
 def set_gemm_mode(mode: int):
-    """0 = exact-fp32 SIMT layers everywhere, 1 = tcgen05 3xTF32 tensor-core layers where eligible (default)."""
+    """0 = exact-fp32 SIMT layers everywhere, 1 = tcgen05 3xTF32 layers, one tile per CTA (default),
+    2 = tcgen05 3xTF32 layers, persistent variant with overlapped register epilogue (experimental)."""
     check(lib.mvx_set_gemm_mode(int(mode)), 'set_gemm_mode')
 
 

@@ -456,9 +456,9 @@ static int dense_layer(const float *x, int64_t R, int32_t T, int32_t Cin, const 
 }  // namespace mvx
 
 extern "C" int mvx_set_gemm_mode(int32_t mode) {
-    if (mode < 0 || mode > 2) return MVX_EINVAL;   // 2 = tensor cores, one tile per CTA (non-persistent variant)
-    mvx::g_gemm_mode = mode == 0 ? 0 : 1;
-    mvx::set_tc_persistent(mode == 1);
+    if (mode < 0 || mode > 2) return MVX_EINVAL;   // 2 = tensor cores, persistent 256x128 variant (measured slower: SS-mode
+    mvx::g_gemm_mode = mode == 0 ? 0 : 1;          //     MMAs at N=128 saturate shared-memory bandwidth); kept for experiments
+    mvx::set_tc_persistent(mode == 2);
     return MVX_OK;
 }
 

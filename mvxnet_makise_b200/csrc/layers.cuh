@@ -26,6 +26,7 @@ struct LayerArgs {
     long long rows_fixed;
     int rowcap, vcap, T;
     double eps;
+    int dbg;                 // experiments only (0 in production): bit 0 = skip the producer proxy fence
 };
 int launch_layer(const LayerArgs &a, int F, cudaStream_t st);            // exact-fp32 SIMT kernel
 
@@ -34,7 +35,7 @@ bool tc_layer_eligible(const LayerArgs &a);
 size_t tc_wpack_bytes(int Cin, int Cout);
 int launch_layer_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
 bool tc_persistent_enabled();
-void set_tc_persistent(int on);  // 1 = persistent kernel with overlapped epilogue (default), 0 = one tile per CTA
+void set_tc_persistent(int on);  // 0 = one 256 x BN tile per CTA (default), 1 = persistent 256 x 128 kernel with overlapped epilogue
 // dispatch by mvx_set_gemm_mode(): 0 = SIMT everywhere, 1 = tensor cores where eligible (default)
 int gemm_mode();
 int launch_layer_auto(const LayerArgs &a, int F, float *wpack, cudaStream_t st);

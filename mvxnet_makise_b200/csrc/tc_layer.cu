@@ -19,6 +19,8 @@
 // 1536 tensor cycles (31 B/cycle/SM), which the 148-SM L2 can sustain; a 128-row tile could not (53 B/cycle/SM).
 #include "layers.cuh"
 
+#include <cstdlib>
+
 namespace mvx {
 
 namespace {
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         auto load_chunk = [&](float4 (&buf)[4], int kc) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                buf[i] = valid[i] ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + kc * kBK)) : z4;
+                buf[i] = (valid[i] && !(a.dbg & 4)) ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + kc * kBK)) : z4;
         };
         // two chunks of raw activations are always in flight in registers (DRAM/L2 latency >> one chunk of MMA time)
         auto produce = [&](float4 (&buf)[4], int kc) {
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
                 *reinterpret_cast<float4 *>(stage + off) = hi;
                 *reinterpret_cast<float4 *>(stage + S::kAHalf + off) = lo;
             }
-            fence_async_smem();  // make the generic-proxy writes visible to the tensor core (async proxy)
+            if (!(a.dbg & 1)) fence_async_smem();  // make the generic-proxy writes visible to the tensor core (async proxy)
             mbar_arrive(full_bar(s));
         };
         float4 buf0[4], buf1[4];
@@ -321,9 +323,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
     __syncthreads();  // every stage buffer is idle now: reuse the tile memory for the output staging
     float *ytile = reinterpret_cast<float *>(smem);  // [2 halves][128 rows][kEpiLd]
     const int half = warp >> 2, q = warp & 3;        // accumulator, TMEM lane quarter
-    for (int pass = 0; pass < BN / kEpiCols; ++pass) {
+    for (int pass = 0; pass < ((a.dbg & 2) ? 0 : BN / kEpiCols); ++pass) {
         if (warp < 8) {
-            float *yrow = ytile + ((size_t)half * 128 + q * 32 + lane) * kEpiLd;
+            const int rloc = half * 128 + q * 32 + lane;
+            float *yrow = ytile + (size_t)rloc * kEpiLd;
 #pragma unroll 1
             for (int cb = 0; cb < kEpiCols / 32; ++cb) {
                 float v[32];
@@ -342,21 +345,35 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         }
         __syncthreads();
         if (tid < 256) {
-            // (a) weighted column sums in fp64: thread = (column, 128-row group); one load feeds both sums
+            // coalesced raw stores first (one warp per row, 32 lanes x 16 bytes = 128 columns): they drain while the sums run
+            if (a.Y) {
+                for (int r = warp; r < kTM; r += 8) {
+                    if (row0 + r >= n_rows) break;
+                    const float4 o = *reinterpret_cast<const float4 *>(ytile + (size_t)r * kEpiLd + lane * 4);
+                    *reinterpret_cast<float4 *>(a.Y + ((size_t)f * a.rowcap + row0 + r) * a.ldy + n0 + pass * kEpiCols + lane * 4) = o;
+                }
+            }
+            // weighted column sums: thread = (column, 128-row group). Ordinary rows (multiplicity 1) are summed in fp32
+            // over runs of 16 rows and the runs in fp64; the weighted pad row takes an exact fp64 side path.
             const int col = tid & 127, rg = tid >> 7;
             double sy = 0.0, syy = 0.0;
-#pragma unroll 4
-            for (int r = rg * 128; r < rg * 128 + 128; ++r) {
-                const float w = s_roww[r];
-                const double y = (double)ytile[(size_t)r * kEpiLd + col];
-                if (w == 1.f) {
-                    sy += y;
-                    syy = fma(y, y, syy);
-                } else if (w != 0.f) {
-                    const double wy = (double)w * y;
-                    sy += wy;
-                    syy = fma(wy, y, syy);
+            for (int r0 = rg * 128; r0 < rg * 128 + 128; r0 += 16) {
+                float ps = 0.f, pss = 0.f;
+#pragma unroll
+                for (int r = r0; r < r0 + 16; ++r) {
+                    const float w = s_roww[r];
+                    const float y = ytile[(size_t)r * kEpiLd + col];
+                    const float my = w == 1.f ? y : 0.f;
+                    ps += my;
+                    pss = fmaf(my, y, pss);
+                    if (w != 1.f && w != 0.f) {
+                        const double wy = (double)w * (double)y;
+                        sy += wy;
+                        syy = fma(wy, (double)y, syy);
+                    }
                 }
+                sy += (double)ps;
+                syy += (double)pss;
             }
             double *o = a.out_stats + ((size_t)f * a.Cout + n0 + pass * kEpiCols + col) * 2;
             atomicAdd(o, sy);
@@ -377,14 +394,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
                     }
                 }
                 if (cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
-            }
-            // (b) coalesced raw stores: one warp per row, 32 lanes x 16 bytes = 128 columns
-            if (a.Y) {
-                for (int r = warp; r < kTM; r += 8) {
-                    if (row0 + r >= n_rows) break;
-                    const float4 o = *reinterpret_cast<const float4 *>(ytile + (size_t)r * kEpiLd + lane * 4);
-                    *reinterpret_cast<float4 *>(a.Y + ((size_t)f * a.rowcap + row0 + r) * a.ldy + n0 + pass * kEpiCols + lane * 4) = o;
-                }
             }
         }
         __syncthreads();
@@ -425,18 +434,20 @@ int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
 //               transpose-reduction per 32x32 block (fp32 inside a warp's 32 rows, fp64 across warps/tiles/CTAs).
 // =====================================================================================================================
 constexpr int kPThreads = 14 * 32;
+constexpr int kPStages = 4;    // 48 KB per stage at BN = 128
+constexpr int kAccBufs = 2;    // TMEM accumulator ping-pong: 2 x (2 halves x BN columns) = 512 columns
 
 template <int BN>
 struct PSmem {
     static constexpr int kAHalf = kTM * kBK * 4;
     static constexpr int kBHalf = BN * kBK * 4;
     static constexpr int kStage = 2 * kAHalf + 2 * kBHalf;
-    static constexpr int kTiles = kStages * kStage;
+    static constexpr int kTiles = kPStages * kStage;
     static constexpr int kMean = kTiles;
     static constexpr int kRstd = kMean + 768 * 4;
     static constexpr int kPart = kRstd + 768 * 4;              // [4 warps][BN][2] fp64 column partials
-    static constexpr int kBars = kPart + 4 * BN * 2 * 8;       // full[3], empty[3], accum_full, tmem_empty
-    static constexpr int kTmemPtr = kBars + 8 * 8;
+    static constexpr int kBars = kPart + 4 * BN * 2 * 8;       // full[4], empty[4], accum_full[2], tmem_empty[2]
+    static constexpr int kTmemPtr = kBars + 8 * (2 * kPStages + 2 * kAccBufs);
     static constexpr int kTotal = kTmemPtr + 16 + 1024;
 };
 
@@ -471,8 +482,9 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
     double *s_part = reinterpret_cast<double *>(smem + S::kPart);
     const uint32_t bars = sbase + S::kBars;
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
-    const uint32_t accum_bar = bars + 8u * (2 * kStages), tmem_empty_bar = bars + 8u * (2 * kStages + 1);
+    auto empty_bar = [&](int s) { return bars + 8u * (kPStages + s); };
+    auto accum_bar = [&](int b) { return bars + 8u * (2 * kPStages + b); };
+    auto tmem_empty_bar = [&](int b) { return bars + 8u * (2 * kPStages + kAccBufs + b); };
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(smem + S::kTmemPtr);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nk = a.Cin / kBK;
@@ -493,16 +505,18 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
     };
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kPStages; ++s) {
             mbar_init(full_bar(s), kProducerThreads + 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(accum_bar, 1);
-        mbar_init(tmem_empty_bar, 4);
+        for (int b = 0; b < kAccBufs; ++b) {
+            mbar_init(accum_bar(b), 1);
+            mbar_init(tmem_empty_bar(b), 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::kTmemPtr), "r"(2 * BN)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::kTmemPtr), "r"(kAccBufs * 2 * BN)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -562,8 +576,8 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
                     }
                 }
                 if (kc + 2 < nk) load_chunk(buf, kc + 2);
-                const int s = g % kStages;
-                const uint32_t ph = (g / kStages) & 1;
+                const int s = g % kPStages;
+                const uint32_t ph = (g / kPStages) & 1;
                 ++g;
                 if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);
                 __syncwarp();
@@ -579,7 +593,7 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
                     *reinterpret_cast<float4 *>(stage + off) = hi;
                     *reinterpret_cast<float4 *>(stage + S::kAHalf + off) = lo;
                 }
-                fence_async_smem();
+                if (!(a.dbg & 1)) fence_async_smem();
                 mbar_arrive(full_bar(s));
             };
             float4 buf0[4], buf1[4];
@@ -600,8 +614,8 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
                 if (!decode(t, f, ct, row0, n_rows)) continue;
                 const float *src = wpack + (size_t)ct * nk * (2 * BN * kBK);
                 for (int kc = 0; kc < nk; ++kc, ++g) {
-                    const int s = g % kStages;
-                    const uint32_t ph = (g / kStages) & 1;
+                    const int s = g % kPStages;
+                    const uint32_t ph = (g / kPStages) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);
                     mbar_arrive_expect_tx(full_bar(s), 2 * S::kBHalf);
                     bulk_g2s(sbase + s * S::kStage + 2 * S::kAHalf, src + (size_t)kc * (2 * BN * kBK), 2 * S::kBHalf, full_bar(s));
@@ -617,17 +631,18 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
                 int f, ct;
                 long long row0, n_rows;
                 if (!decode(t, f, ct, row0, n_rows)) continue;
-                mbar_wait(tmem_empty_bar, (it & 1) ^ 1);  // the epilogue has drained the previous tile's accumulators
+                const int ab = it & 1;                              // accumulator buffer of this tile
+                mbar_wait(tmem_empty_bar(ab), ((it >> 1) & 1) ^ 1);  // the epilogue drained this buffer two tiles ago
                 tc_fence_after();
                 for (int kc = 0; kc < nk; ++kc, ++g) {
-                    const int s = g % kStages;
-                    const uint32_t ph = (g / kStages) & 1;
+                    const int s = g % kPStages;
+                    const uint32_t ph = (g / kPStages) & 1;
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t sA = sbase + s * S::kStage, sB = sA + 2 * S::kAHalf;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint32_t d = tmem_base + h * BN;
+                        const uint32_t d = tmem_base + ab * (2 * BN) + h * BN;
                         const uint32_t aoff = h * (128 * 64);
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
@@ -640,7 +655,7 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
                     }
                     mma_commit(empty_bar(s));
                 }
-                mma_commit(accum_bar);
+                mma_commit(accum_bar(ab));
                 ++it;
             }
         }
@@ -660,7 +675,8 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
             named_bar_sync(2, 128);  // previous tile's partial reads are done
             for (int i = et; i < 4 * BN * 2; i += 128) s_part[i] = 0.0;
             named_bar_sync(2, 128);
-            mbar_wait(accum_bar, it & 1);
+            const int ab = it & 1;
+            mbar_wait(accum_bar(ab), (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
@@ -673,7 +689,7 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
 #pragma unroll 1
                 for (int cb = 0; cb < BN / 32; ++cb) {
                     float v[32], p2[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * BN + cb * 32, v);
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * (2 * BN) + h * BN + cb * 32, v);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + n0 + cb * 32 + j));
@@ -706,7 +722,7 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
             // accumulators are drained: the MMA warp may start the next tile
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar);
+            if (lane == 0) mbar_arrive(tmem_empty_bar(ab));
             // combine the four warps' column partials and publish one fp64 atomicAdd per column and quantity
 #pragma unroll
             for (int cb = 0; cb < BN / 32; ++cb) {
@@ -725,7 +741,7 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
     tc_fence_before();
     __syncthreads();
     if (warp == 9) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAccBufs * 2 * BN) : "memory");
     }
 }
 
@@ -751,7 +767,7 @@ int launch_tc_persist(const LayerArgs &a, int F, float *wpack, cudaStream_t st) 
 
 }  // namespace
 
-static int g_tc_persistent = 1;
+static int g_tc_persistent = 0;
 bool tc_persistent_enabled() { return g_tc_persistent != 0; }
 void set_tc_persistent(int on) { g_tc_persistent = on; }
 
@@ -762,14 +778,14 @@ bool tc_layer_eligible(const LayerArgs &a) {
 
 size_t tc_wpack_bytes(int Cin, int Cout) { return (size_t)2 * Cin * Cout * sizeof(float); }
 
-int launch_layer_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
+int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st) {
+    LayerArgs a = a_in;
+    if (const char *e = getenv("MVX_DBG")) a.dbg = atoi(e);
     MVX_REQUIRE(tc_layer_eligible(a) && wpack, MVX_EINVAL, "layer not eligible for the tensor-core kernel");
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     if (max_rows <= 0) return MVX_OK;
-    if (a.vmax == nullptr && tc_persistent_enabled()) {  // persistent kernel with the overlapped register epilogue
-        if (a.Cout % 256 == 0) return launch_tc_persist<256>(a, F, wpack, st);
+    if (a.vmax == nullptr && tc_persistent_enabled())  // persistent kernel: 256 x 128 tiles, double-buffered accumulators
         return launch_tc_persist<128>(a, F, wpack, st);
-    }
     if (a.Cout % 256 == 0) return launch_tc<256>(a, F, wpack, st);
     return launch_tc<128>(a, F, wpack, st);
 }

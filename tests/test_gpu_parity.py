@@ -192,9 +192,9 @@ def test_tensor_core_layer_is_fp32_accurate(mvx, R, cin, cout):
         with torch.no_grad():
             _lib.set_gemm_mode(0)
             y_simt = fcn(x)
-            _lib.set_gemm_mode(2)      # one tile per CTA
+            _lib.set_gemm_mode(2)      # persistent variant, overlapped register epilogue
             y_tc2 = fcn(x)
-            _lib.set_gemm_mode(1)      # persistent kernel, overlapped register epilogue (default)
+            _lib.set_gemm_mode(1)      # one 256 x BN tile per CTA (default)
             y_tc = fcn(x)
     finally:
         _lib.set_gemm_mode(1)
