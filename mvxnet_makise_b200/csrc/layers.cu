@@ -410,8 +410,13 @@ int launch_layer(const LayerArgs &a, int F, cudaStream_t st) {
 static int g_gemm_mode = 1;
 int gemm_mode() { return g_gemm_mode; }
 
+static int g_tc_pair = 0;
+
 int launch_layer_auto(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
-    if (g_gemm_mode == 1 && wpack && tc_layer_eligible(a)) return launch_layer_tc(a, F, wpack, st);
+    if (g_gemm_mode == 1 && wpack) {
+        if (g_tc_pair && tc2_layer_eligible(a)) return launch_layer_tc2(a, F, wpack, st);
+        if (tc_layer_eligible(a)) return launch_layer_tc(a, F, wpack, st);
+    }
     return launch_layer(a, F, st);
 }
 
@@ -456,9 +461,10 @@ static int dense_layer(const float *x, int64_t R, int32_t T, int32_t Cin, const 
 }  // namespace mvx
 
 extern "C" int mvx_set_gemm_mode(int32_t mode) {
-    if (mode < 0 || mode > 2) return MVX_EINVAL;   // 2 = tensor cores, persistent 256x128 variant (measured slower: SS-mode
+    if (mode < 0 || mode > 3) return MVX_EINVAL;   // 3 = tensor cores, CTA-pair (cta_group::2) persistent kernel   // 2 = tensor cores, persistent 256x128 variant (measured slower: SS-mode
     mvx::g_gemm_mode = mode == 0 ? 0 : 1;          //     MMAs at N=128 saturate shared-memory bandwidth); kept for experiments
     mvx::set_tc_persistent(mode == 2);
+    mvx::g_tc_pair = mode == 3;
     return MVX_OK;
 }
 

@@ -34,6 +34,9 @@ int launch_layer(const LayerArgs &a, int F, cudaStream_t st);            // exac
 bool tc_layer_eligible(const LayerArgs &a);
 size_t tc_wpack_bytes(int Cin, int Cout);
 int launch_layer_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
+// CTA-pair (cta_group::2) persistent kernel with double-buffered accumulators (layers without a per-voxel max)
+bool tc2_layer_eligible(const LayerArgs &a);
+int launch_layer_tc2(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
 bool tc_persistent_enabled();
 void set_tc_persistent(int on);  // 0 = one 256 x BN tile per CTA (default), 1 = persistent 256 x 128 kernel with overlapped epilogue
 // dispatch by mvx_set_gemm_mode(): 0 = SIMT everywhere, 1 = tensor cores where eligible (default)

@@ -8,6 +8,7 @@ from mvxnet_makise_b200 import modules as M
 
 torch.manual_seed(0)
 dev = 'cuda'
+MODE = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 
 
 def ref64(x, w, b, eps=1e-6):
@@ -29,7 +30,7 @@ for (R, cin, cout) in [(1000, 768, 768), (5003, 768, 128), (777, 128, 128), (256
         _lib.set_gemm_mode(0)
         y0 = fcn(x)
         torch.cuda.synchronize()
-        _lib.set_gemm_mode(1)
+        _lib.set_gemm_mode(MODE)
         t0 = time.perf_counter()
         y1 = fcn(x)
         torch.cuda.synchronize()
