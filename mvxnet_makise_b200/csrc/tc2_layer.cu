@@ -8,12 +8,13 @@
 // stream per SM halves, and a 256-column accumulator leaves room for a second one.
 //
 // Per CTA (rank r of the pair), BK = 16 fp32 per stage, K-major SWIZZLE_64B operands, 3xTF32 split (see tc_layer.cu):
-//   warps 0-3  A producers (128 rows of the tile: coalesced loads two chunks ahead, BN of the producer layer, split,
-//              swizzled st.shared, fence.proxy.async, arrive on the local full barrier)
-//   warp 4     B producer: one cp.async.bulk per stage of this CTA's pre-packed N/2 x 16 [hi|lo] image
-//   warp 5     rank 0: MMA issuer (waits its own and the peer's stage, issues 6 MMAs, commits with multicast to both
+//   warps 0-7  A producers, two groups of four warps on alternate k-chunks (128 rows of the tile: coalesced loads two
+//              of the group's chunks ahead, BN of the producer layer, split, swizzled st.shared, fence.proxy.async,
+//              arrive on the local full barrier)
+//   warp 8     B producer: one cp.async.bulk per stage of this CTA's pre-packed N/2 x 16 [hi|lo] image
+//   warp 9     rank 0: MMA issuer (waits its own and the peer's stage, issues 6 MMAs, commits with multicast to both
 //              CTAs' empty barriers);  rank 1: relay (forwards "my stage is full" to rank 0's peer_full barrier)
-//   warps 6-9  epilogue from registers: tcgen05.ld -> bias/ReLU -> row stores, butterfly column sums (fp32 in a warp,
+//   warps 10-13 epilogue from registers: tcgen05.ld -> bias/ReLU -> row stores, butterfly column sums (fp32 in a warp,
 //              fp64 beyond), then a (remote) arrive on rank 0's tmem_empty barrier
 #include "layers.cuh"
 #include "tc_common.cuh"
@@ -25,8 +26,10 @@ namespace mvx {
 namespace {
 
 constexpr int kRowsPerCta = 128;
-constexpr int kThreads2 = 10 * 32;
-constexpr int kAProd = 128;
+constexpr int kThreads2 = 14 * 32;
+constexpr int kAProd = 128;       // threads that produce ONE chunk
+constexpr int kAGroups = 2;       // producer groups working on alternate chunks (a chunk's store->fence->arrive chain is
+                                  // ~1100 cycles, longer than the 768 tensor cycles a pair spends on it)
 
 template <int BN>
 struct Smem2 {
@@ -108,7 +111,7 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {  // same logical warp in both CTAs
+    if (warp == 9) {  // same logical warp in both CTAs
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::kTmemPtr), "r"(2 * BN)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -119,20 +122,24 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp < 4) {
+    const bool mma_only = (a.dbg & 8) != 0;
+    if (mma_only && warp != 9) {
+        // experiment: nobody but the MMA issuer works
+    } else if (warp < 4 * kAGroups) {
         // ================= A producers: this CTA's 128 rows of the pair tile ======================================
-        const int c = tid & 3, rsub = tid >> 2;  // rows rsub + 32*i
+        const int grp = warp >> 2, gt = tid & (kAProd - 1);
+        const int c = gt & 3, rsub = gt >> 2;  // rows rsub + 32*i
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        int g = 0, cur_f = -1;
+        int gbase = 0, cur_f = -1;               // ring position of the current tile's chunk 0
         for (int t = cluster_id; t < total; t += n_clusters) {
             int f, ct;
             long long row0, n_rows;
             if (!decode(t, f, ct, row0, n_rows)) continue;
             row0 += (long long)rank * kRowsPerCta;
             if (a.in_stats && f != cur_f) {
-                named_bar_sync(1, kAProd);
+                named_bar_sync(1, kAProd * kAGroups);
                 const double Rstat = a.counts ? (double)a.counts[f * 4 + 0] * (double)a.T : (double)a.rows_fixed;
-                for (int cc = tid; cc < a.Cin; cc += kAProd) {
+                for (int cc = tid; cc < a.Cin; cc += kAProd * kAGroups) {
                     const double *st = a.in_stats + ((size_t)f * a.Cin + cc) * 2;
                     const double m = st[0] / Rstat;
                     double var = st[1] / Rstat - m * m;
@@ -140,7 +147,7 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
                     s_mean[cc] = (float)m;
                     s_rstd[cc] = (float)(1.0 / sqrt(var + a.eps));
                 }
-                named_bar_sync(1, kAProd);
+                named_bar_sync(1, kAProd * kAGroups);
             }
             cur_f = f;
             const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx + c * 4;
@@ -150,7 +157,7 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
             auto load_chunk = [&](float4 (&buf)[4], int kc) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    buf[i] = valid[i] ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 32 * i) * a.ldx + kc * kBK)) : z4;
+                    buf[i] = (valid[i] && !(a.dbg & 4)) ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 32 * i) * a.ldx + kc * kBK)) : z4;
             };
             auto produce = [&](float4 (&buf)[4], int kc) {
                 float4 cur[4];
@@ -170,10 +177,10 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
                         }
                     }
                 }
-                if (kc + 2 < nk) load_chunk(buf, kc + 2);
+                if (kc + 2 * kAGroups < nk) load_chunk(buf, kc + 2 * kAGroups);
+                const int g = gbase + kc;
                 const int s = g % kStages;
                 const uint32_t ph = (g / kStages) & 1;
-                ++g;
                 if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);
                 __syncwarp();
                 uint8_t *stage = smem + (size_t)s * S::kStage;
@@ -191,15 +198,16 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
                 fence_async_smem();
                 mbar_arrive(full_bar(s));
             };
-            float4 buf0[4], buf1[4];
-            load_chunk(buf0, 0);
-            if (nk > 1) load_chunk(buf1, 1);
-            for (int kc = 0; kc < nk; kc += 2) {
+            float4 buf0[4], buf1[4];   // this group's chunks grp, grp + 2, grp + 4, ...
+            if (grp < nk) load_chunk(buf0, grp);
+            if (grp + kAGroups < nk) load_chunk(buf1, grp + kAGroups);
+            for (int kc = grp; kc < nk; kc += 2 * kAGroups) {
                 produce(buf0, kc);
-                if (kc + 1 < nk) produce(buf1, kc + 1);
+                if (kc + kAGroups < nk) produce(buf1, kc + kAGroups);
             }
+            gbase += nk;
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ================= B producer: this rank's half of every weight stage =======================================
         if (lane == 0) {
             int g = 0;
@@ -218,7 +226,7 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         if (lane == 0 && rank == 0) {
             // ================= MMA issuer (leader CTA) ================================================================
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((256u >> 4) << 24);
@@ -228,13 +236,16 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
                 long long row0, n_rows;
                 if (!decode(t, f, ct, row0, n_rows)) continue;
                 const int ab = it & 1;
-                mbar_wait_cluster(tmem_empty_bar(ab), ((it >> 1) & 1) ^ 1);  // both CTAs drained this accumulator buffer
+                if (!mma_only) mbar_wait(tmem_empty_bar(ab), ((it >> 1) & 1) ^ 1);  // both CTAs drained this accumulator buffer
                 tc_fence_after();
                 for (int kc = 0; kc < nk; ++kc, ++g) {
                     const int s = g % kStages;
                     const uint32_t ph = (g / kStages) & 1;
-                    mbar_wait(full_bar(s), ph);
-                    mbar_wait_cluster(peer_full_bar(s), ph);
+                    if (!mma_only) {
+                        mbar_wait(full_bar(s), ph);
+                        mbar_wait(peer_full_bar(s), ph);
+                    }   // plain (cta-scope) wait as CUTLASS's 2-SM pipelines do: the data is read by
+                                                       // the async proxy, ordered by the writers' fence.proxy.async + release.cluster arrive
                     tc_fence_after();
                     const uint32_t sA = sbase + s * S::kStage, sB = sA + 2 * S::kAHalf;
                     const uint32_t d = tmem_base + ab * BN;
@@ -251,24 +262,26 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
                 mma2_commit_multicast(accum_bar(ab), 3);
                 ++it;
             }
-        } else if (lane == 0) {
-            // ================= relay (peer CTA): tell the leader when this CTA's stage is full ===========================
-            int g = 0;
+        } else if (rank != 0 && lane < kStages && !mma_only) {
+            // ================= relay (peer CTA): lane L forwards "stage L is full" to the leader's peer_full[L] ==========
+            // one lane per stage, so the wake-up + remote-arrive latency of consecutive stages overlaps
+            int gbase = 0;
             for (int t = cluster_id; t < total; t += n_clusters) {
                 int f, ct;
                 long long row0, n_rows;
                 if (!decode(t, f, ct, row0, n_rows)) continue;
-                for (int kc = 0; kc < nk; ++kc, ++g) {
-                    const int s = g % kStages;
-                    const uint32_t ph = (g / kStages) & 1;
-                    mbar_wait(full_bar(s), ph);
-                    mbar_arrive_remote(map_to_cta(peer_full_bar(s), 0));
+                for (int kc = 0; kc < nk; ++kc) {
+                    const int g = gbase + kc;
+                    if (g % kStages != lane) continue;
+                    mbar_wait(full_bar(lane), (g / kStages) & 1);
+                    mbar_arrive_remote_relaxed(map_to_cta(peer_full_bar(lane), 0));
                 }
+                gbase += nk;
             }
         }
     } else {
-        // ================= epilogue warps 6..9: TMEM lane quarter q = warp % 4 =======================================
-        const int q = warp & 3, ew = warp - 6, et = tid - 6 * 32;
+        // ================= epilogue warps 10..13: TMEM lane quarter q = warp % 4 =====================================
+        const int q = warp & 3, ew = warp - 10, et = tid - 10 * 32;
         int it = 0;
         for (int t = cluster_id; t < total; t += n_clusters) {
             int f, ct;
@@ -291,7 +304,7 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
             const bool heavy = w != 0.f && w != 1.f;
             float *yrow = a.Y ? a.Y + ((size_t)f * a.rowcap + r) * a.ldy + n0 : nullptr;
 #pragma unroll 1
-            for (int cb = 0; cb < BN / 32; ++cb) {
+            for (int cb = 0; cb < ((a.dbg & 2) ? 0 : BN / 32); ++cb) {
                 float v[32], p2[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + cb * 32, v);
 #pragma unroll
@@ -302,11 +315,12 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
                     v[j + 2] = fmaxf(v[j + 2] + b4.z, 0.f);
                     v[j + 3] = fmaxf(v[j + 3] + b4.w, 0.f);
                 }
-                if (yrow && valid) {
+                if (yrow && valid && !(a.dbg & 16)) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         *reinterpret_cast<float4 *>(yrow + cb * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
+                if (a.dbg & 32) continue;
                 if (heavy) {
                     for (int j = 0; j < 32; ++j) {
                         const double y = (double)v[j], wy = (double)w * y;
@@ -345,7 +359,7 @@ tc2_layer_kernel(LayerArgs a, const float *__restrict__ wpack, int F, int row_ti
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // nobody leaves while the peer can still touch its barriers, shared memory or TMEM
-    if (warp == 5) {
+    if (warp == 9) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
     }
 }
@@ -379,6 +393,7 @@ bool tc2_layer_eligible(const LayerArgs &a) {
 
 int launch_layer_tc2(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st) {
     LayerArgs a = a_in;
+    if (const char *e = getenv("MVX_DBG")) a.dbg = atoi(e);
     MVX_REQUIRE(tc2_layer_eligible(a) && wpack, MVX_EINVAL, "layer not eligible for the CTA-pair tensor-core kernel");
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     if (max_rows <= 0) return MVX_OK;

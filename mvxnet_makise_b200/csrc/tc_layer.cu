@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp < 8) {
+    const bool mma_only = (a.dbg & 8) != 0;
+    if (mma_only && warp != 9) {
+    } else if (warp < 8) {
         // ================= A producers ===========================================================================
         const int c = tid & 3, rsub = tid >> 2;  // 16-byte chunk of the 64-byte k-chunk row; rows rsub + 64*i
         const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx + c * 4;
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % kStages;
                 const uint32_t ph = (kc / kStages) & 1;
-                mbar_wait(full_bar(s), ph);
+                if (!mma_only) mbar_wait(full_bar(s), ph);
                 tc_fence_after();
                 const uint32_t sA = sbase + s * S::kStage, sB = sA + 2 * S::kAHalf;
 #pragma unroll
