@@ -158,6 +158,11 @@ def algorithmic_work(seg: str, N, K, B, G):
     maps_b = 4.0 * 256 * (104 * 336 + 52 * 168 + 26 * 84)
     gemm = dict(fcn1=(768, 768, rowsA), conv1=(768, 128, rowsA), fcn2=(128, 128, rowsA), conv2=(128, 16, rowsA),
                 fcn3=(16, 16, rowsA), vfe1=(23, 16, rowsA), vfe2=(32, 64, rowsB), fcn=(128, 128, rowsB))
+    pixels = 104 * 336 + 52 * 168 + 26 * 84
+    if seg == 'pixel_gemm':      # pixel-first fcn1, tensor half: Z_l = F_l W1_l^T over every map pixel (3 launches)
+        return 'tensor', 2.0 * 256 * 768 * B * pixels
+    if seg == 'fcn1_combine':    # pixel-first fcn1, memory half: read Z once, 12-corner combine, write raw Y1 rows
+        return 'hbm', B * pixels * 768 * 4.0 + rowsA * (3072 + 16)
     if seg in gemm:
         cin, cout, rows = gemm[seg]
         return 'tensor', 2.0 * cin * cout * rows
@@ -198,7 +203,9 @@ def run_ours(args):
     maps_h = [torch.randn((B, 256, h, w), generator=g).pin_memory() for (h, w) in synth.fpn_shapes()]
     points_d, calib_d = points_h.to(dev), calib_h.to(dev)
     maps_d = [m.to(dev) for m in maps_h]
+    _lib.set_fusion_mode(args.fusion_mode)
     path = PointPath(synth.make_weights(0), synth.KITTI_GRID, device=dev)
+    path.host_chunk, path.host_streams = args.host_chunk, args.host_streams
 
     def barrier():
         if world > 1:
@@ -276,11 +283,13 @@ def run_ours(args):
                     traffic=traffic, peak_source=pk['src'], ms_per_launch=stages[dom], share_of_step=round(stages[dom] / (ms_total / args.steps), 4))
     # every memory-bound stage against the HBM roofline (the north star's per-stage report)
     per_stage = {}
-    for n in ('voxelize', 'maps_nhwc', 'gather', 'grid_fill'):
+    for n in ('voxelize', 'maps_nhwc', 'gather', 'fcn1_combine', 'grid_fill'):
         b, w = algorithmic_work(n, counts[:, 0], counts[:, 1], B, G)
         if stages.get(n, 0) > 0:
             per_stage[n] = dict(gbs=round(w / (stages[n] * 1e-3) / 1e9, 1), frac_hbm=round(w / (stages[n] * 1e-3) / 1e9 / pk['hbm'], 4))
-    for n in ('fcn1', 'conv1'):
+    for n in ('fcn1', 'pixel_gemm', 'conv1'):
+        if stages.get(n, 0) <= 0:
+            continue
         b, w = algorithmic_work(n, counts[:, 0], counts[:, 1], B, G)
         per_stage[n] = dict(tflops=round(w / (stages[n] * 1e-3) / 1e12, 2), frac_tensor=round(w / (stages[n] * 1e-3) / 1e12 / pk['tensor'], 4))
 
@@ -294,7 +303,7 @@ def run_ours(args):
                 clocks=clocks,
                 e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=int(path.h2d_bytes),
                          d2h_bytes_per_step=int(path.d2h_bytes), ms_per_step=ms_e2e / args.steps,
-                         note='PointPath.forward_host: pinned-host points+calib+FPN maps -> H2D -> fused path -> D2H counts + feature head'),
+                         note=f'PointPath.forward_host: pinned-host points+calib+FPN maps -> H2D -> fused path -> D2H counts + feature head; sub-batches of {args.host_chunk} frame(s), H2D of sub-batch j+1 on a copy stream overlaps the kernels of sub-batch j'),
                 gpu_launches=int(launches), roofline=roofline, stages_ms=stages, stage_rooflines=per_stage)
     if world == 1 and not args.no_cpu_baseline:
         t, st = cpu_reference_frame(0, os.cpu_count() or 1)
@@ -313,6 +322,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--host-streams', type=int, default=2, help='compute streams the sub-batches of the e2e leg alternate between')
+    ap.add_argument('--fusion-mode', type=int, default=1, help='1 = pixel-first fcn1 (default), 0 = row-first (gather + row GEMM)')
+    ap.add_argument('--host-chunk', type=int, default=1, help='frames per sub-batch of the host-buffer (e2e) leg')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -162,6 +162,14 @@ int mvx_pointpath_workspace_bytes(const mvx_pointpath_args_t *args, size_t *byte
 int mvx_pointpath_layout(const mvx_pointpath_args_t *args, int64_t *offsets /* [MVX_WS_REGIONS] */);
 const char *mvx_pointpath_layout_name(int32_t region);
 int mvx_pointpath_forward(const mvx_pointpath_args_t *args);
+/* How gather + fcn1 (Pipe.py:62-82 + Pipe.py:94) are evaluated inside the fused path. The 4-corner sample is linear in
+ * the map values, so fcn1 commutes with it:
+ *   1 (default) pixel-first: Z_l = F_l W1_l^T once per map pixel (tensor cores), then per point row
+ *               relu(b + sum of 12 weighted Z rows); the (K,768) gathered matrix is never materialised (6.7x fewer FLOPs);
+ *   0           row-first: gather the (K,768) matrix A1, then fcn1 over the point rows (the reference's order; the
+ *               layout the training-mode backward uses).  Timing segments "gather"/"fcn1" then mean
+ *               (pixel GEMMs, combine) in mode 1 and (gather, row GEMM) in mode 0. */
+int mvx_set_fusion_mode(int32_t mode);
 
 /* Optional per-kernel timing of mvx_pointpath_forward with CUDA events recorded on the launching stream
  * (bench.py's roofline leg). mvx_timing_enable(n) arms n event sets (one per forward call, n = 0 disables);

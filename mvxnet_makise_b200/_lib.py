@@ -28,6 +28,7 @@ EXPORTS = [
     'mvx_lidar2img', 'mvx_maps_nhwc_bytes', 'mvx_feature_mapping',
     'mvx_set_gemm_mode', 'mvx_layer_workspace_bytes', 'mvx_fcn_forward', 'mvx_vfe_forward', 'mvx_fcn_max_forward', 'mvx_set_grid_mode', 'mvx_scatter_dense',
     'mvx_pointpath_workspace_bytes', 'mvx_pointpath_layout', 'mvx_pointpath_layout_name', 'mvx_pointpath_forward',
+    'mvx_set_fusion_mode',
     'mvx_timing_enable', 'mvx_timing_read', 'mvx_timing_segment_name',
 ]
 
@@ -90,6 +91,7 @@ def _load():
     lib.mvx_pointpath_layout_name.argtypes = [i32]
     lib.mvx_pointpath_layout_name.restype = c_char_p
     lib.mvx_pointpath_forward.argtypes = [POINTER(PointPathArgs)]
+    lib.mvx_set_fusion_mode.argtypes = [i32]
     lib.mvx_timing_enable.argtypes = [i32]
     lib.mvx_timing_read.argtypes = [i32, POINTER(c_float)]
     lib.mvx_timing_segment_name.argtypes = [i32]
@@ -134,6 +136,12 @@ def set_gemm_mode(mode: int):
     """0 = exact-fp32 SIMT layers everywhere, 1 = tcgen05 3xTF32 layers, one tile per CTA (default),
     2 = tcgen05 3xTF32 layers, persistent variant with overlapped register epilogue (experimental)."""
     check(lib.mvx_set_gemm_mode(int(mode)), 'set_gemm_mode')
+
+
+def set_fusion_mode(mode: int):
+    """1 = pixel-first fcn1 (per-pixel tensor-core GEMM + 12-corner combine; default), 0 = row-first (gather the
+    (K,768) matrix, then fcn1 over the point rows)."""
+    check(lib.mvx_set_fusion_mode(int(mode)), 'set_fusion_mode')
 
 
 def launch_count() -> int:

@@ -198,7 +198,127 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(MapSet m, int capA, co
     }
 }
 
+
+// ---- pixel-first fcn1: per compact row, bias + 12 weighted rows of Z, ReLU, raw store, BatchNorm sums ------------
+// 256 threads = 4 row slots x 2 column halves: a warp owns 384 of the 768 output columns of one row at a time
+// (3 float4 per lane, every corner read is one contiguous 512-byte run), walks 32 consecutive rows (voxel-major
+// order: neighbouring rows share most of their corners, which L1 serves), and keeps fp32 column sums over runs of
+// 16 rows that are folded into fp64 shared accumulators, then one fp64 atomicAdd per column and CTA.
+constexpr int kCombRows = 128;   // rows per CTA
+constexpr int kCombCout = 768;
+
+__global__ void __launch_bounds__(256, 2) combine_rows_kernel(CombineArgs a) {
+    __shared__ double s_sum[kCombCout * 2];
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.counts[f * 4 + 1];
+    const int row_base = blockIdx.x * kCombRows;
+    if (row_base > K) return;
+    for (int i = tid; i < kCombCout * 2; i += 256) s_sum[i] = 0.0;
+    __syncthreads();
+    const int slot = warp >> 1, halfc = warp & 1;
+    const int col0 = halfc * 384 + lane * 4;           // this lane's columns: col0 + 128*j + {0..3}, j = 0..2
+    float4 bias[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) bias[j] = __ldg(reinterpret_cast<const float4 *>(a.bias + col0 + 128 * j));
+    float4 ps[3], pss[3];
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ps[j] = z4, pss[j] = z4;
+    auto flush = [&]() {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int c = col0 + 128 * j;
+            atomicAdd(&s_sum[(c + 0) * 2], (double)ps[j].x), atomicAdd(&s_sum[(c + 0) * 2 + 1], (double)pss[j].x);
+            atomicAdd(&s_sum[(c + 1) * 2], (double)ps[j].y), atomicAdd(&s_sum[(c + 1) * 2 + 1], (double)pss[j].y);
+            atomicAdd(&s_sum[(c + 2) * 2], (double)ps[j].z), atomicAdd(&s_sum[(c + 2) * 2 + 1], (double)pss[j].z);
+            atomicAdd(&s_sum[(c + 3) * 2], (double)ps[j].w), atomicAdd(&s_sum[(c + 3) * 2 + 1], (double)pss[j].w);
+            ps[j] = z4, pss[j] = z4;
+        }
+    };
+    for (int i = 0; i < 32; ++i) {
+        const int r = row_base + slot * 32 + i;
+        if (r > K) break;
+        const size_t ro = (size_t)f * a.capA + r;
+        const float4 xyz = __ldg(reinterpret_cast<const float4 *>(a.vox8 + ro * 8));
+        float4 acc[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[j] = bias[j];
+        if (r < K && !(xyz.x == 0.f && xyz.y == 0.f && xyz.z == 0.f)) {  // pad row / origin point: A1 row is zero
+            const float2 pr = __ldg(reinterpret_cast<const float2 *>(a.proj) + ro);
+#pragma unroll
+            for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+                // index math and (inverted) weights of Pipe.py:62-75, same fp32 order as gather_row_warp
+                const float q0 = __fsub_rn(__fdiv_rn(pr.x, a.rs_h[l]), a.eps);
+                const float q1 = __fsub_rn(__fdiv_rn(pr.y, a.rs_w[l]), a.eps);
+                const int i0 = (int)q0, i1 = (int)q1;
+                const float wa = __fsub_rn(q0, (float)i0), wb = __fsub_rn(q1, (float)i1);
+                const float wa_ = __fsub_rn(1.0f, wa), wb_ = __fsub_rn(1.0f, wb);
+                const int H = a.h[l], W = a.w[l];
+                const bool r0 = i0 >= 0 && i0 < H, r1 = i0 + 1 >= 0 && i0 + 1 < H;
+                const bool c0 = i1 >= 0 && i1 < W, c1 = i1 + 1 >= 0 && i1 + 1 < W;
+                const float w00 = (r0 && c0) ? wa * wb : 0.f, w10 = (r1 && c0) ? wa_ * wb : 0.f;
+                const float w01 = (r0 && c1) ? wa * wb_ : 0.f, w11 = (r1 && c1) ? wa_ * wb_ : 0.f;
+                // clamped addresses (weight 0 where the corner is the zero pad of Pipe.py:47-48)
+                const int y0 = min(max(i0, 0), H - 1), y1 = min(max(i0 + 1, 0), H - 1);
+                const int x0 = min(max(i1, 0), W - 1), x1 = min(max(i1 + 1, 0), W - 1);
+                const float *base = a.Z[l] + (size_t)f * a.frame_stride[l] + col0;
+                const float *p00 = base + ((size_t)y0 * W + x0) * kCombCout, *p10 = base + ((size_t)y1 * W + x0) * kCombCout;
+                const float *p01 = base + ((size_t)y0 * W + x1) * kCombCout, *p11 = base + ((size_t)y1 * W + x1) * kCombCout;
+                float4 v00[3], v10[3], v01[3], v11[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    v00[j] = __ldg(reinterpret_cast<const float4 *>(p00 + 128 * j));
+                    v10[j] = __ldg(reinterpret_cast<const float4 *>(p10 + 128 * j));
+                    v01[j] = __ldg(reinterpret_cast<const float4 *>(p01 + 128 * j));
+                    v11[j] = __ldg(reinterpret_cast<const float4 *>(p11 + 128 * j));
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+#define MVX_COMB(e) acc[j].e = fmaf(v11[j].e, w11, fmaf(v01[j].e, w01, fmaf(v10[j].e, w10, fmaf(v00[j].e, w00, acc[j].e))));
+                    MVX_COMB(x) MVX_COMB(y) MVX_COMB(z) MVX_COMB(w)
+#undef MVX_COMB
+                }
+            }
+        }
+        const float w = __ldg(a.row_w + ro);
+        float *yrow = a.Y1 + ro * kCombCout + col0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float4 y;
+            y.x = fmaxf(acc[j].x, 0.f), y.y = fmaxf(acc[j].y, 0.f), y.z = fmaxf(acc[j].z, 0.f), y.w = fmaxf(acc[j].w, 0.f);
+            *reinterpret_cast<float4 *>(yrow + 128 * j) = y;
+            if (w == 1.f) {
+                ps[j].x += y.x, ps[j].y += y.y, ps[j].z += y.z, ps[j].w += y.w;
+                pss[j].x = fmaf(y.x, y.x, pss[j].x), pss[j].y = fmaf(y.y, y.y, pss[j].y);
+                pss[j].z = fmaf(y.z, y.z, pss[j].z), pss[j].w = fmaf(y.w, y.w, pss[j].w);
+            } else if (w != 0.f) {   // the weighted pad row: exact fp64 side path
+                const int c = col0 + 128 * j;
+                const double wd = (double)w;
+                atomicAdd(&s_sum[(c + 0) * 2], wd * y.x), atomicAdd(&s_sum[(c + 0) * 2 + 1], wd * y.x * y.x);
+                atomicAdd(&s_sum[(c + 1) * 2], wd * y.y), atomicAdd(&s_sum[(c + 1) * 2 + 1], wd * y.y * y.y);
+                atomicAdd(&s_sum[(c + 2) * 2], wd * y.z), atomicAdd(&s_sum[(c + 2) * 2 + 1], wd * y.z * y.z);
+                atomicAdd(&s_sum[(c + 3) * 2], wd * y.w), atomicAdd(&s_sum[(c + 3) * 2 + 1], wd * y.w * y.w);
+            }
+        }
+        if ((i & 15) == 15) flush();
+    }
+    flush();
+    __syncthreads();
+    double *o = a.out_stats + (size_t)f * kCombCout * 2;
+    for (int i = tid; i < kCombCout * 2; i += 256) {
+        const double v = s_sum[i];
+        if (v != 0.0) atomicAdd(o + i, v);
+    }
+}
+
 }  // namespace
+
+int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st) {
+    dim3 grid((a.capA + kCombRows - 1) / kCombRows, B);
+    combine_rows_kernel<<<grid, 256, 0, st>>>(a);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
 
 int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, cudaStream_t st) {
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B);

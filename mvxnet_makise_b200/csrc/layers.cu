@@ -131,13 +131,14 @@ __global__ void __launch_bounds__(256) fcn_layer_kernel(LayerArgs a) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
         const int col = TN == 8 ? (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4)) : (TN == 4 ? tx * 4 + j : tx);
-        const float b = __ldg(a.bias + n0 + col);
+        const float b = a.plain ? 0.f : __ldg(a.bias + n0 + col);
+        const float floor_v = a.plain ? -INFINITY : 0.f;
         double s = 0.0, ss = 0.0;
         int cv = -1;
         float cm = 0.f;
 #pragma unroll
         for (int i = 0; i < kTM; ++i) {
-            const float y = fmaxf(acc[i][j] + b, 0.f);
+            const float y = fmaxf(acc[i][j] + b, floor_v);
             acc[i][j] = y;
             if (w[i] != 0.f) {
                 const double yd = (double)y, wd = (double)w[i];
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(256) fcn_layer_kernel(LayerArgs a) {
         }
     }
     __syncthreads();
-    if (tid < BN) {
+    if (tid < BN && !a.plain) {
         double s = 0.0, ss = 0.0;
 #pragma unroll
         for (int wv = 0; wv < 8; ++wv) {
@@ -414,7 +415,7 @@ static int g_tc_pair = 0;
 
 int launch_layer_auto(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     if (g_gemm_mode == 1 && wpack) {
-        if (g_tc_pair && tc2_layer_eligible(a)) return launch_layer_tc2(a, F, wpack, st);
+        if (g_tc_pair && !a.plain && tc2_layer_eligible(a)) return launch_layer_tc2(a, F, wpack, st);
         if (tc_layer_eligible(a)) return launch_layer_tc(a, F, wpack, st);
     }
     return launch_layer(a, F, st);

@@ -27,6 +27,7 @@ struct LayerArgs {
     int rowcap, vcap, T;
     double eps;
     int dbg;                 // experiments only (0 in production): bit 0 = skip the producer proxy fence
+    int plain;               // 1: Y = norm_in(X) W^T only (no bias, no ReLU, no statistics, no max) - the per-pixel half of fcn1
 };
 int launch_layer(const LayerArgs &a, int F, cudaStream_t st);            // exact-fp32 SIMT kernel
 

@@ -18,18 +18,24 @@ namespace mvx {
 enum Region {
     R_VOXWS = 0, R_VOX_COORD, R_VOX_CNT, R_VOX_ROW0, R_ROW_POINT, R_ROW_VOX, R_CELL2VID, R_NHWC0, R_NHWC1, R_NHWC2,
     R_VOX8, R_PROJ, R_ROWA_W, R_A1, R_Y1, R_Y2, R_Y3, R_Y4, R_Y5, R_X6, R_Y6, R_X7, R_Y7, R_ROWB_W, R_ROWB_V, R_X8,
-    R_VFEAT, R_STATS, R_VMAX6, R_VMAX7, R_VMAX8, R_WPACK, R_OCC, R_VFEAT_T, R_COUNT
+    R_VFEAT, R_STATS, R_VMAX6, R_VMAX7, R_VMAX8, R_WPACK, R_OCC, R_VFEAT_T, R_Z, R_COUNT
 };
 static_assert(R_COUNT <= MVX_WS_REGIONS, "too many regions");
 
 const char *kRegionNames[R_COUNT] = {
     "vox_ws", "vox_coord", "vox_cnt", "vox_row0", "row_point", "row_vox", "cell2vid", "nhwc0", "nhwc1", "nhwc2",
     "vox8", "proj", "rowA_w", "A1", "Y1", "Y2", "Y3", "Y4", "Y5", "X6", "Y6", "X7", "Y7", "rowB_w", "rowB_v", "X8",
-    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t"};
+    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t", "Z"};
 
 constexpr int kCin[MVX_NUM_LAYERS] = {768, 768, 128, 128, 16, 32, 32, 128};   // padded
 constexpr int kCout[MVX_NUM_LAYERS] = {768, 128, 128, 16, 16, 16, 64, 128};
 constexpr int kStatStride = 768 * 2;  // doubles per (layer, frame)
+
+// 1 (default): pixel-first fcn1 - one tensor-core GEMM per FPN level over the map pixels, then a 12-corner combine per
+// point row (gather.cuh CombineArgs); 0: materialise the gathered (K,768) matrix A1 and run fcn1 over the point rows
+// (the layout the training-mode backward needs: dW1 = dpre1^T A1).
+static int g_fusion_mode = 1;
+int fusion_mode() { return g_fusion_mode; }
 
 struct Layout {
     size_t off[R_COUNT];
@@ -89,6 +95,11 @@ int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
     take(R_WPACK, tc_wpack_bytes(768, 768));
     take(R_OCC, B * (size_t)(L.G / 32 + 1) * 4);
     take(R_VFEAT_T, B * cap * 128 * 4);
+    {   // per-pixel fcn1 products of the three FPN levels, (B, HW_l, 768) each
+        size_t px = 0;
+        for (int l = 0; l < MVX_NUM_LEVELS; ++l) px += (size_t)a->map_h[l] * a->map_w[l];
+        take(R_Z, B * px * 768 * 4);
+    }
     L.total = o;
     return MVX_OK;
 }
@@ -184,22 +195,54 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
     rp.vox8 = F32(R_VOX8), rp.proj = F32(R_PROJ), rp.rowA_w = F32(R_ROWA_W);
     rc = launch_rows_build(rp, st);
     if (rc) return rc;
+    const bool pixel_first = g_fusion_mode == 1 && gemm_mode() == 1;
+    double *stats = reinterpret_cast<double *>(ws + L.off[R_STATS]);
+    auto stat_of = [&](int layer) { return stats + (size_t)layer * B * kStatStride; };
+    // NOTE: stats are stored [F][Cout][2] with the layer's own Cout as the frame stride
     stamp.mark(S_GATHER);
-    rc = launch_gather_rows(m, B, L.capA, a->counts, F32(R_VOX8), F32(R_PROJ), a->gather_eps, F32(R_A1), st);
-    if (rc) return rc;
+    if (!pixel_first) {
+        rc = launch_gather_rows(m, B, L.capA, a->counts, F32(R_VOX8), F32(R_PROJ), a->gather_eps, F32(R_A1), st);
+        if (rc) return rc;
+    } else {
+        // Z_l = F_l W1[:, 256 l : 256 (l+1)]^T for every pixel of every frame (plain GEMM: no bias / ReLU / statistics)
+        size_t zoff = 0;
+        for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+            const long long px = (long long)B * a->map_h[l] * a->map_w[l];
+            LayerArgs la{};
+            la.X = m.nhwc[l], la.ldx = a->map_c, la.Cin = a->map_c;
+            la.Wt = a->wt[0] + (size_t)l * a->map_c * 768, la.bias = nullptr, la.Cout = 768;
+            la.Y = F32(R_Z) + zoff, la.ldy = 768;
+            la.rows_fixed = px, la.rows_mode = 0, la.rowcap = 0, la.T = 1, la.eps = a->bn_eps, la.plain = 1;
+            rc = launch_layer_auto(la, 1, F32(R_WPACK), st);
+            if (rc) return rc;
+            zoff += (size_t)px * 768;
+        }
+    }
 
     stamp.mark(S_CLEAR);
     // ---- stage 3 ----------------------------------------------------------------------------------------
-    double *stats = reinterpret_cast<double *>(ws + L.off[R_STATS]);
     MVX_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)MVX_NUM_LAYERS * B * kStatStride * 8, st));
     zero_vmax_kernel<<<dim3(kSMs, B), 256, 0, st>>>(a->counts, cap, I32(R_VMAX6), I32(R_VMAX7), I32(R_VMAX8));
     MVX_LAUNCH_CHECK();
-    auto stat_of = [&](int layer) { return stats + (size_t)layer * B * kStatStride; };
-    // NOTE: stats are stored [F][Cout][2] with the layer's own Cout as the frame stride
     const float *xin[5] = {F32(R_A1), F32(R_Y1), F32(R_Y2), F32(R_Y3), F32(R_Y4)};
     float *yout[5] = {F32(R_Y1), F32(R_Y2), F32(R_Y3), F32(R_Y4), F32(R_Y5)};
     for (int l = 0; l < 5; ++l) {  // fusion stack: fcn1 conv1 fcn2 conv2 fcn3 (Pipe.py:94-104)
         stamp.mark(S_FCN1 + l);
+        if (l == 0 && pixel_first) {
+            CombineArgs ca{};
+            size_t zoff = 0;
+            for (int lv = 0; lv < MVX_NUM_LEVELS; ++lv) {
+                ca.Z[lv] = F32(R_Z) + zoff;
+                ca.frame_stride[lv] = (size_t)a->map_h[lv] * a->map_w[lv] * 768;
+                ca.h[lv] = m.h[lv], ca.w[lv] = m.w[lv], ca.rs_h[lv] = m.rs_h[lv], ca.rs_w[lv] = m.rs_w[lv];
+                zoff += (size_t)B * a->map_h[lv] * a->map_w[lv] * 768;
+            }
+            ca.capA = L.capA, ca.counts = a->counts, ca.vox8 = F32(R_VOX8), ca.proj = F32(R_PROJ), ca.row_w = F32(R_ROWA_W);
+            ca.eps = a->gather_eps, ca.bias = a->bias[0], ca.Y1 = F32(R_Y1), ca.out_stats = stat_of(0);
+            rc = launch_combine_rows(ca, B, st);
+            if (rc) return rc;
+            continue;
+        }
         LayerArgs la{};
         la.X = xin[l], la.ldx = kCin[l], la.Cin = kCin[l], la.Wt = a->wt[l], la.bias = a->bias[l], la.Cout = kCout[l];
         la.Y = yout[l], la.ldy = kCout[l];
@@ -309,7 +352,12 @@ extern "C" int mvx_timing_read(int32_t call, float *ms) {
 }
 
 extern "C" const char *mvx_timing_segment_name(int32_t segment) {
-    return (segment >= 0 && segment < mvx::S_COUNT) ? mvx::kSegmentNames[segment] : nullptr;
+    if (segment < 0 || segment >= mvx::S_COUNT) return nullptr;
+    if (mvx::g_fusion_mode == 1 && mvx::gemm_mode() == 1) {  // pixel-first fcn1: the two segments change meaning
+        if (segment == mvx::S_GATHER) return "pixel_gemm";
+        if (segment == mvx::S_FCN1) return "fcn1_combine";
+    }
+    return mvx::kSegmentNames[segment];
 }
 
 extern "C" int mvx_pointpath_workspace_bytes(const mvx_pointpath_args_t *args, size_t *bytes) {
@@ -335,3 +383,9 @@ extern "C" const char *mvx_pointpath_layout_name(int32_t region) {
 }
 
 extern "C" int mvx_pointpath_forward(const mvx_pointpath_args_t *args) { return mvx::pointpath_forward(args); }
+
+extern "C" int mvx_set_fusion_mode(int32_t mode) {
+    if (mode != 0 && mode != 1) return MVX_EINVAL;
+    mvx::g_fusion_mode = mode;
+    return MVX_OK;
+}

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
             s_rstd[c] = (float)(1.0 / sqrt(var + a.eps));
         }
     }
-    for (int c = tid; c < BN; c += kThreads) s_bias[c] = a.bias[n0 + c];
+    for (int c = tid; c < BN; c += kThreads) s_bias[c] = a.plain ? 0.f : a.bias[n0 + c];
     for (int r = tid; r < kTM; r += kThreads) {
         const long long rr = row0 + r;
         const float w = rr < n_rows ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + rr] : 1.f) : 0.f;
@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
     __syncthreads();  // every stage buffer is idle now: reuse the tile memory for the output staging
     float *ytile = reinterpret_cast<float *>(smem);  // [2 halves][128 rows][kEpiLd]
     const int half = warp >> 2, q = warp & 3;        // accumulator, TMEM lane quarter
+    const float floor_v = a.plain ? -INFINITY : 0.f;  // plain mode: no ReLU (bias is zero)
     for (int pass = 0; pass < ((a.dbg & 2) ? 0 : BN / kEpiCols); ++pass) {
         if (warp < 8) {
             const int rloc = half * 128 + q * 32 + lane;
@@ -264,10 +265,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 o;
-                    o.x = fmaxf(v[j] + s_bias[col + j], 0.f);
-                    o.y = fmaxf(v[j + 1] + s_bias[col + j + 1], 0.f);
-                    o.z = fmaxf(v[j + 2] + s_bias[col + j + 2], 0.f);
-                    o.w = fmaxf(v[j + 3] + s_bias[col + j + 3], 0.f);
+                    o.x = fmaxf(v[j] + s_bias[col + j], floor_v);
+                    o.y = fmaxf(v[j + 1] + s_bias[col + j + 1], floor_v);
+                    o.z = fmaxf(v[j + 2] + s_bias[col + j + 2], floor_v);
+                    o.w = fmaxf(v[j + 3] + s_bias[col + j + 3], floor_v);
                     *reinterpret_cast<float4 *>(yrow + cb * 32 + j) = o;
                 }
             }
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
             // weighted column sums: thread = (column, 128-row group). Ordinary rows (multiplicity 1) are summed in fp32
             // over runs of 16 rows and the runs in fp64; the weighted pad row takes an exact fp64 side path.
             const int col = tid & 127, rg = tid >> 7;
+            if (!a.plain) {
             double sy = 0.0, syy = 0.0;
             for (int r0 = rg * 128; r0 < rg * 128 + 128; r0 += 16) {
                 float ps = 0.f, pss = 0.f;
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
                     }
                 }
                 if (cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
+            }
             }
         }
         __syncthreads();
@@ -694,7 +697,7 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
     MVX_REQUIRE(tc_layer_eligible(a) && wpack, MVX_EINVAL, "layer not eligible for the tensor-core kernel");
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     if (max_rows <= 0) return MVX_OK;
-    if (a.vmax == nullptr && tc_persistent_enabled())  // persistent kernel: 256 x 128 tiles, double-buffered accumulators
+    if (a.vmax == nullptr && !a.plain && tc_persistent_enabled())  // persistent kernel: 256 x 128 tiles, double-buffered accumulators
         return launch_tc_persist<128>(a, F, wpack, st);
     if (a.Cout % 256 == 0) return launch_tc<256>(a, F, wpack, st);
     return launch_tc<128>(a, F, wpack, st);

@@ -36,6 +36,10 @@ class PointPath:
         self._ws = None
         self._ws_key = None
         self._args = None
+        self._subs = None          # sub-batch contexts of the pipelined host entry (forward_host)
+        self._sub_chunk = 0
+        self.host_chunk = 1        # frames per sub-batch of forward_host: H2D of chunk j+1 overlaps compute of chunk j
+        self.host_streams = 2      # sub-batches alternate between this many compute streams (their kernels may overlap)
 
     def load_state_dict(self, sd):
         self.wt, self.bias = [], []
@@ -48,8 +52,8 @@ class PointPath:
             self.bias.append(b.detach().to(self.device, torch.float32).contiguous())
 
     # ------------------------------------------------------------------------------------------------
-    def _prepare(self, B: int, cap: int, map_hw):
-        key = (B, cap, tuple(map_hw))
+    def _prepare(self, B: int, cap: int, map_hw, own_outputs: bool = True):
+        key = (B, cap, tuple(map_hw), own_outputs)
         if self._ws_key == key:
             return
         a = _lib.PointPathArgs()
@@ -70,9 +74,14 @@ class PointPath:
         self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
         self._ws_key = key
         self.cap, self.B = cap, B
+        if own_outputs:
+            self._alloc_outputs(B)
+
+    def _alloc_outputs(self, B: int):
         nz, nx, ny = self.grid.shape[2], self.grid.shape[0], self.grid.shape[1]
-        self.grid_out = torch.empty((B, 128, nz, nx, ny), dtype=torch.float32, device=self.device)
-        self.counts = torch.empty((B, 4), dtype=torch.int32, device=self.device)
+        if getattr(self, 'grid_out', None) is None or self.grid_out.shape[0] != B:
+            self.grid_out = torch.empty((B, 128, nz, nx, ny), dtype=torch.float32, device=self.device)
+            self.counts = torch.empty((B, 4), dtype=torch.int32, device=self.device)
 
     def region(self, name: str, dtype, shape):
         """Typed view into a named workspace region (tests / diagnostics)."""
@@ -82,13 +91,19 @@ class PointPath:
 
     # ------------------------------------------------------------------------------------------------
     def forward_device(self, points: torch.Tensor, offsets: Sequence[int], calib32: torch.Tensor,
-                       maps: List[torch.Tensor], want_grid: bool = True, cap: int | None = None):
-        """points (sum P, stride>=4) fp32 CUDA, offsets host [B+1], calib32 (B,32) CUDA, maps 3 x (B,256,Hf,Wf) CUDA."""
+                       maps: List[torch.Tensor], want_grid: bool = True, cap: int | None = None,
+                       grid_out: torch.Tensor | None = None, counts: torch.Tensor | None = None):
+        """points (sum P, stride>=4) fp32 CUDA, offsets host [B+1], calib32 (B,32) CUDA, maps 3 x (B,256,Hf,Wf) CUDA.
+        grid_out / counts: optional caller-owned outputs ((B,128,nz,nx,ny) fp32, (B,4) int32, contiguous)."""
         B = len(offsets) - 1
         maxp = max(offsets[i + 1] - offsets[i] for i in range(B))
         cap = cap or max(128, (maxp + 127) // 128 * 128)
         map_hw = [(int(m.shape[-2]), int(m.shape[-1])) for m in maps]
-        self._prepare(B, cap, map_hw)
+        self._prepare(B, cap, map_hw, own_outputs=counts is None)
+        if counts is not None:
+            assert counts.is_contiguous() and counts.shape == (B, 4) and (grid_out is None or grid_out.is_contiguous())
+            self.grid_out, self.counts = grid_out, counts
+        self._subs_active = False
         a = _lib.PointPathArgs()
         a.grid = self.grid
         a.B, a.cap = B, cap
@@ -124,35 +139,82 @@ class PointPath:
         return self.forward_device(points, offsets, calib32, maps, want_grid)
 
     # ---- host-buffer entry: H2D of this batch's inputs, the fused path, D2H of the counts ---------------
+    def _child(self):
+        c = object.__new__(PointPath)
+        c.device, c.grid_spec, c.grid, c.imsize_hw, c.eps = self.device, self.grid_spec, self.grid, self.imsize_hw, self.eps
+        c.wt, c.bias = self.wt, self.bias          # shared weights
+        c._ws = c._ws_key = c._args = c._subs = None
+        c._sub_chunk, c.host_chunk = 0, 0
+        return c
+
     def forward_host(self, points_host: torch.Tensor, offsets: Sequence[int], calib32_host: torch.Tensor,
                      maps_host: List[torch.Tensor], want_grid: bool = True, head_rows: int = 1024):
         """Inputs in (ideally pinned) HOST memory: points (sum P, 4) fp32, calib32 (B,32), maps 3 x (B,256,Hf,Wf).
-        Copies them to persistent device buffers on the current stream, runs the fused path and reads back the
-        per-frame counts and the first `head_rows` voxel feature rows of frame 0 (the host-visible result).
+        Frames are independent, so the batch is cut into sub-batches of `self.host_chunk` frames: the H2D copy of
+        sub-batch j+1 (copy stream) overlaps the kernels of sub-batch j (current stream); each sub-batch has its own
+        input buffers and workspace and writes its slice of the batch outputs. Reads back the per-frame counts and
+        the first `head_rows` voxel feature rows of frame 0 (the host-visible result).
         Returns (grid on device, counts on host, head block on host); synchronises the stream."""
         dev = self.device
-        key = (tuple(points_host.shape), tuple(calib32_host.shape), tuple(tuple(m.shape) for m in maps_host))
+        B = len(offsets) - 1
+        chunk = max(1, min(int(self.host_chunk) or B, B))
+        key = (tuple(points_host.shape), tuple(int(o) for o in offsets), tuple(calib32_host.shape),
+               tuple(tuple(m.shape) for m in maps_host), chunk, head_rows)
         if getattr(self, '_in_key', None) != key:
-            self._in_points = torch.empty(points_host.shape, dtype=torch.float32, device=dev)
-            self._in_calib = torch.empty(calib32_host.shape, dtype=torch.float32, device=dev)
-            self._in_maps = [torch.empty(m.shape, dtype=torch.float32, device=dev) for m in maps_host]
-            self._out_counts = torch.empty((len(offsets) - 1, 4), dtype=torch.int32).pin_memory()
+            self._subs = []
+            for f0 in range(0, B, chunk):
+                f1 = min(B, f0 + chunk)
+                c = self._child()
+                c.f0, c.f1, c.p0, c.p1 = f0, f1, int(offsets[f0]), int(offsets[f1])
+                c.offsets = [int(o) - c.p0 for o in offsets[f0:f1 + 1]]
+                c.in_points = torch.empty((c.p1 - c.p0, points_host.shape[1]), dtype=torch.float32, device=dev)
+                c.in_calib = torch.empty((f1 - f0, 32), dtype=torch.float32, device=dev)
+                c.in_maps = [torch.empty((f1 - f0,) + tuple(m.shape[1:]), dtype=torch.float32, device=dev) for m in maps_host]
+                c.ev = torch.cuda.Event()
+                self._subs.append(c)
+            self._sub_chunk = chunk
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._out_counts = torch.empty((B, 4), dtype=torch.int32).pin_memory()
             self._out_head = torch.empty((head_rows, 128), dtype=torch.float32).pin_memory()
+            self._h2d_bytes = (points_host.numel() + calib32_host.numel() + sum(m.numel() for m in maps_host)) * 4
             self._in_key = key
-        self._in_points.copy_(points_host, non_blocking=True)
-        self._in_calib.copy_(calib32_host, non_blocking=True)
-        for d, h in zip(self._in_maps, maps_host):
-            d.copy_(h, non_blocking=True)
-        grid, counts = self.forward_device(self._in_points, offsets, self._in_calib, self._in_maps, want_grid)
-        self._out_counts.copy_(counts, non_blocking=True)
-        head = self.region('vfeat', torch.float32, (self.B, self.cap, 128))[0, :head_rows]
+        self._alloc_outputs(B)
+        self.B = B
+        cur = torch.cuda.current_stream()
+        cs = self._copy_stream
+        ns = max(1, min(int(self.host_streams), len(self._subs)))
+        if len(getattr(self, '_compute_streams', [])) != ns:
+            self._compute_streams = [torch.cuda.Stream(device=dev) for _ in range(ns)] if ns > 1 else [None]
+        cs.wait_stream(cur)                      # earlier work on the input buffers has been ordered before the copies
+        for s_ in self._compute_streams:
+            if s_ is not None:
+                s_.wait_stream(cur)
+        for j, c in enumerate(self._subs):
+            with torch.cuda.stream(cs):
+                c.in_points.copy_(points_host[c.p0:c.p1], non_blocking=True)
+                c.in_calib.copy_(calib32_host[c.f0:c.f1], non_blocking=True)
+                for d, h in zip(c.in_maps, maps_host):
+                    d.copy_(h[c.f0:c.f1], non_blocking=True)
+                c.ev.record(cs)
+            ks = self._compute_streams[j % ns] or cur
+            with torch.cuda.stream(ks):
+                ks.wait_event(c.ev)
+                c.forward_device(c.in_points, c.offsets, c.in_calib, c.in_maps, want_grid,
+                                 grid_out=self.grid_out[c.f0:c.f1] if want_grid else None, counts=self.counts[c.f0:c.f1])
+        for s_ in self._compute_streams:
+            if s_ is not None:
+                cur.wait_stream(s_)
+        self._subs_active = True
+        self._out_counts.copy_(self.counts, non_blocking=True)
+        c0 = self._subs[0]
+        head = c0.region('vfeat', torch.float32, (c0.B, c0.cap, 128))[0, :head_rows]
         self._out_head.copy_(head, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return grid, self._out_counts, self._out_head
+        cur.synchronize()
+        return (self.grid_out if want_grid else None), self._out_counts, self._out_head
 
     @property
     def h2d_bytes(self):
-        return (self._in_points.numel() + self._in_calib.numel() + sum(m.numel() for m in self._in_maps)) * 4
+        return self._h2d_bytes
 
     @property
     def d2h_bytes(self):
@@ -162,7 +224,11 @@ class PointPath:
     def voxel_features(self, f: int):
         """(N_f,128) fp32 features and (N_f,4) int64 idx [batch, ix, iy, iz] of frame f (after a forward)."""
         n = int(self.counts[f, 0].item())
-        vfeat = self.region('vfeat', torch.float32, (self.B, self.cap, 128))[f, :n]
-        coord = self.region('vox_coord', torch.int32, (self.B, self.cap, 4))[f, :n, :3].to(torch.int64)
+        src, fl = self, f
+        if getattr(self, '_subs_active', False):   # the last forward was the pipelined host entry: frame f lives in a sub-batch
+            src = self._subs[f // self._sub_chunk]
+            fl = f - src.f0
+        vfeat = src.region('vfeat', torch.float32, (src.B, src.cap, 128))[fl, :n]
+        coord = src.region('vox_coord', torch.int32, (src.B, src.cap, 4))[fl, :n, :3].to(torch.int64)
         idx = torch.cat([torch.full((n, 1), f, dtype=torch.int64, device=coord.device), coord], dim=1)
         return vfeat, idx

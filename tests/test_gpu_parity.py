@@ -239,8 +239,18 @@ def _check_frame(path, f, ref, ref64, counts, gold=None):
         _check_close(vfeat, gold['vfeat'], ref64['vfeat'], 'voxel features (reference golden)')
 
 
+@pytest.fixture
+def fusion_mode(request):
+    """1 = pixel-first fcn1 (default), 0 = row-first (gather the (K,768) matrix, then the row GEMM)."""
+    from mvxnet_makise_b200 import _lib
+    _lib.set_fusion_mode(request.param)
+    yield request.param
+    _lib.set_fusion_mode(1)
+
+
+@pytest.mark.parametrize('fusion_mode', [1, 0], indirect=True)
 @pytest.mark.parametrize('tag', ['path_a', 'path_b'])
-def test_fused_path_matches_reference_golden(mvx, golden_dir, tag):
+def test_fused_path_matches_reference_golden(mvx, golden_dir, tag, fusion_mode):
     g = np.load(os.path.join(golden_dir, tag + '.npz'))
     maps = small_maps(int(g['map_seed']))
     sd = synth.make_weights(int(g['weight_seed']))
@@ -277,6 +287,36 @@ def test_fused_path_matches_reference_golden(mvx, golden_dir, tag):
     assert rel_err(gcpu, ref64['grid'][0]) < TOL
 
 
+def test_pixel_first_fcn1_equals_row_first(mvx):
+    """fcn1 commutes with the (linear) 4-corner sample: relu(b + sum of 12 weighted rows of Z = F W1^T) must equal
+    relu(A1 W1^T + b) on the gathered matrix A1. Compared on the raw fcn1 activations Y1, the BatchNorm sums and the
+    final voxel features, for a batch with ragged frames (incl. points that sample the zero pad row/column)."""
+    from mvxnet_makise_b200 import _lib
+    sd = synth.make_weights(5)
+    calib = synth.kitti_calib()
+    frames = [synth.make_points(60 + f, P) for f, P in enumerate((1500, 700, 2300))]
+    maps = [torch.from_numpy(m) for m in small_maps(9, B=3)]
+    out = {}
+    try:
+        for mode in (0, 1):
+            _lib.set_fusion_mode(mode)
+            path = mvx.P.PointPath(sd, G)
+            _, counts = path(frames, [calib] * 3, maps, want_grid=False)
+            torch.cuda.synchronize()
+            c = counts.cpu().numpy()
+            capA = path.cap + 128
+            y1 = path.region('Y1', torch.float32, (3, capA, 768))
+            st = path.region('stats', torch.float64, (8, 3, 768, 2))[0]
+            out[mode] = ([y1[f, :c[f, 1] + 1].clone() for f in range(3)], st.clone(),
+                         [path.voxel_features(f)[0].clone() for f in range(3)])
+    finally:
+        _lib.set_fusion_mode(1)
+    for f in range(3):
+        assert rel_err(out[1][0][f], out[0][0][f]) < 1e-5, 'raw fcn1 activations'
+        assert rel_err(out[1][2][f], out[0][2][f]) < TOL / 2, 'voxel features'
+    assert rel_err(out[1][1], out[0][1]) < 1e-5, 'BatchNorm sums of fcn1'
+
+
 def test_fused_batch_equals_single_frames(mvx):
     """Batch = independent frames with per-frame BatchNorm statistics (SURVEY.md §7 hard part 6)."""
     sd = synth.make_weights(2)
@@ -300,6 +340,38 @@ def test_fused_batch_equals_single_frames(mvx):
         vf, idx = single.voxel_features(0)
         assert torch.equal(idx[:, 1:], batch[f][1][:, 1:])
         assert rel_err(vf, batch[f][0]) < 1e-6      # fp64 atomic accumulation order is the only difference
+
+
+@pytest.mark.parametrize('chunk', [1, 2, 8])
+def test_host_entry_pipelined_equals_device_entry(mvx, chunk):
+    """forward_host cuts the batch into sub-batches (H2D of chunk j+1 overlaps the kernels of chunk j): ragged last
+    chunk, per-chunk workspaces, outputs written into slices of the batch outputs. Same results as one batched call."""
+    from mvxnet_makise_b200.modules import pack_calib
+    sd = synth.make_weights(3)
+    calib = synth.kitti_calib()
+    frames = [synth.make_points(50 + f, P) for f, P in enumerate((900, 2000, 1311, 640, 1500))]
+    B = len(frames)
+    maps = [torch.from_numpy(m) for m in small_maps(5, B=B)]
+    ref_path = mvx.P.PointPath(sd, G)
+    grid_ref, counts_ref = ref_path(frames, [calib] * B, maps)
+    feats_ref = [tuple(t.clone() for t in ref_path.voxel_features(f)) for f in range(B)]
+    grid_ref, counts_ref = grid_ref.clone(), counts_ref.cpu()
+    offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in frames])]).tolist()
+    points_h = torch.from_numpy(np.concatenate(frames, 0)).pin_memory()
+    calib_h = torch.stack([pack_calib(calib) for _ in range(B)]).pin_memory()
+    maps_h = [m.pin_memory() for m in maps]
+    path = mvx.P.PointPath(sd, G)
+    path.host_chunk = chunk
+    for _ in range(2):                                    # second call reuses the buffers
+        grid, counts_h, head = path.forward_host(points_h, offsets, calib_h, maps_h, head_rows=64)
+    assert torch.equal(counts_h, counts_ref)
+    for f in range(B):
+        vf, idx = path.voxel_features(f)
+        assert torch.equal(idx, feats_ref[f][1])
+        assert rel_err(vf, feats_ref[f][0]) < 1e-6       # fp64 atomic accumulation order is the only difference
+    assert torch.equal(grid != 0, grid_ref != 0) and rel_err(grid, grid_ref) < 1e-6
+    assert rel_err(head, feats_ref[0][0][:64]) < 1e-6
+    assert path.h2d_bytes == (points_h.numel() + calib_h.numel() + sum(m.numel() for m in maps_h)) * 4
 
 
 def test_fused_path_full_size_properties(mvx):
