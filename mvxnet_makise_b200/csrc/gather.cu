@@ -3,6 +3,8 @@
 // corner read is a contiguous, coalesced run of channels (NCHW would cost one 32-byte sector per channel).
 #include "gather.cuh"
 
+#include <climits>
+
 namespace mvx {
 
 namespace {
@@ -200,112 +202,169 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(MapSet m, int capA, co
 
 
 // ---- pixel-first fcn1: per compact row, bias + 12 weighted rows of Z, ReLU, raw store, BatchNorm sums ------------
-// 256 threads = 4 row slots x 2 column halves: a warp owns 384 of the 768 output columns of one row at a time
-// (3 float4 per lane, every corner read is one contiguous 512-byte run), walks 32 consecutive rows (voxel-major
-// order: neighbouring rows share most of their corners, which L1 serves), and keeps fp32 column sums over runs of
-// 16 rows that are folded into fp64 shared accumulators, then one fp64 atomicAdd per column and CTA.
-constexpr int kCombRows = 128;   // rows per CTA
+// Rows are first sorted by the level-0 cell they sample (counting sort: histogram, scan, scatter), cells ordered in
+// 4x4 blocks with Morton order inside a block, so consecutive sorted rows share their level-0 cell and, almost always,
+// their level-1/level-2 cells. The combine kernel walks sorted rows; a warp keeps the 4 corner vectors of each level in
+// registers and re-loads them only when that level's cell changes (about every 5th / 17th / 60th row at KITTI
+// density), which cuts the corner traffic ~10x against a row-by-row gather. Output rows are written back to their
+// compact position (one contiguous 3 KB row per CTA step).
 constexpr int kCombCout = 768;
+constexpr int kCombWarps = 6;        // one warp per 128 output columns (one float4 per lane)
+constexpr int kCombRows = 128;       // sorted rows per CTA (<= threads per CTA)
 
-__global__ void __launch_bounds__(256, 2) combine_rows_kernel(CombineArgs a) {
+struct CellRef {
+    int i0, i1;
+    float wa, wb;
+};
+__device__ __forceinline__ CellRef cell_of(float prow, float pcol, float rs_h, float rs_w, float eps) {
+    // index math and (inverted) weights of Pipe.py:62-75, same fp32 order as gather_row_warp
+    const float q0 = __fsub_rn(__fdiv_rn(prow, rs_h), eps);
+    const float q1 = __fsub_rn(__fdiv_rn(pcol, rs_w), eps);
+    CellRef c;
+    c.i0 = (int)q0, c.i1 = (int)q1;
+    c.wa = __fsub_rn(q0, (float)c.i0), c.wb = __fsub_rn(q1, (float)c.i1);
+    return c;
+}
+__device__ __forceinline__ int combine_key(const CombineArgs &a, int f, int r, int K) {
+    const size_t ro = (size_t)f * a.capA + r;
+    const float4 xyz = __ldg(reinterpret_cast<const float4 *>(a.vox8 + ro * 8));
+    if (r >= K || (xyz.x == 0.f && xyz.y == 0.f && xyz.z == 0.f)) return a.nbins;  // pad row / origin point: no corners
+    const float2 pr = __ldg(reinterpret_cast<const float2 *>(a.proj) + ro);
+    const CellRef c = cell_of(pr.x, pr.y, a.rs_h[0], a.rs_w[0], a.eps);
+    const int y = min(max(c.i0, 0), a.h[0] - 1), x = min(max(c.i1, 0), a.w[0] - 1);
+    const int wb = (a.w[0] + 3) / 4;
+    const int inner = ((y & 2) << 2) | ((x & 2) << 1) | ((y & 1) << 1) | (x & 1);  // Morton order inside the 4x4 block
+    return ((y >> 2) * wb + (x >> 2)) * 16 + inner;
+}
+
+__global__ void __launch_bounds__(256) combine_hist_kernel(CombineArgs a) {
+    const int f = blockIdx.y, K = a.counts[f * 4 + 1];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > K) return;
+    atomicAdd(a.bin_count + (size_t)f * (a.nbins + 1) + combine_key(a, f, r, K), 1);
+}
+
+__global__ void __launch_bounds__(1024) combine_scan_kernel(CombineArgs a) {  // one CTA per frame
+    const int f = blockIdx.x, nb = a.nbins + 1;
+    int *cnt = a.bin_count + (size_t)f * nb, *start = a.bin_start + (size_t)f * (nb + 1);
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        const int v = b < nb ? cnt[b] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, &total);
+        if (b < nb) {
+            start[b] = carry + ex;
+            cnt[b] = 0;  // becomes the scatter cursor
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) start[nb] = carry;
+}
+
+__global__ void __launch_bounds__(256) combine_scatter_kernel(CombineArgs a) {
+    const int f = blockIdx.y, K = a.counts[f * 4 + 1];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > K) return;
+    const int nb = a.nbins + 1;
+    const int key = combine_key(a, f, r, K);
+    const int pos = a.bin_start[(size_t)f * (nb + 1) + key] + atomicAdd(a.bin_count + (size_t)f * nb + key, 1);
+    a.perm[(size_t)f * a.capA + pos] = r;
+}
+
+__global__ void __launch_bounds__(kCombWarps * 32) combine_rows_kernel(CombineArgs a) {
     __shared__ double s_sum[kCombCout * 2];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = a.counts[f * 4 + 1];
-    const int row_base = blockIdx.x * kCombRows;
-    if (row_base > K) return;
-    for (int i = tid; i < kCombCout * 2; i += 256) s_sum[i] = 0.0;
+    const int p0 = blockIdx.x * kCombRows;
+    if (p0 > K) return;
+    for (int i = tid; i < kCombCout * 2; i += kCombWarps * 32) s_sum[i] = 0.0;
     __syncthreads();
-    const int slot = warp >> 1, halfc = warp & 1;
-    const int col0 = halfc * 384 + lane * 4;           // this lane's columns: col0 + 128*j + {0..3}, j = 0..2
-    float4 bias[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) bias[j] = __ldg(reinterpret_cast<const float4 *>(a.bias + col0 + 128 * j));
-    float4 ps[3], pss[3];
+    const int col0 = warp * 128 + lane * 4;
+    const float4 bias = __ldg(reinterpret_cast<const float4 *>(a.bias + col0));
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ps = z4, pss = z4;
+    float4 v00[MVX_NUM_LEVELS], v10[MVX_NUM_LEVELS], v01[MVX_NUM_LEVELS], v11[MVX_NUM_LEVELS];
+    int ci0[MVX_NUM_LEVELS], ci1[MVX_NUM_LEVELS];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) ps[j] = z4, pss[j] = z4;
+    for (int l = 0; l < MVX_NUM_LEVELS; ++l) ci0[l] = ci1[l] = INT_MIN, v00[l] = v10[l] = v01[l] = v11[l] = z4;
     auto flush = [&]() {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int c = col0 + 128 * j;
-            atomicAdd(&s_sum[(c + 0) * 2], (double)ps[j].x), atomicAdd(&s_sum[(c + 0) * 2 + 1], (double)pss[j].x);
-            atomicAdd(&s_sum[(c + 1) * 2], (double)ps[j].y), atomicAdd(&s_sum[(c + 1) * 2 + 1], (double)pss[j].y);
-            atomicAdd(&s_sum[(c + 2) * 2], (double)ps[j].z), atomicAdd(&s_sum[(c + 2) * 2 + 1], (double)pss[j].z);
-            atomicAdd(&s_sum[(c + 3) * 2], (double)ps[j].w), atomicAdd(&s_sum[(c + 3) * 2 + 1], (double)pss[j].w);
-            ps[j] = z4, pss[j] = z4;
-        }
+        atomicAdd(&s_sum[(col0 + 0) * 2], (double)ps.x), atomicAdd(&s_sum[(col0 + 0) * 2 + 1], (double)pss.x);
+        atomicAdd(&s_sum[(col0 + 1) * 2], (double)ps.y), atomicAdd(&s_sum[(col0 + 1) * 2 + 1], (double)pss.y);
+        atomicAdd(&s_sum[(col0 + 2) * 2], (double)ps.z), atomicAdd(&s_sum[(col0 + 2) * 2 + 1], (double)pss.z);
+        atomicAdd(&s_sum[(col0 + 3) * 2], (double)ps.w), atomicAdd(&s_sum[(col0 + 3) * 2 + 1], (double)pss.w);
+        ps = z4, pss = z4;
     };
-    for (int i = 0; i < 32; ++i) {
-        const int r = row_base + slot * 32 + i;
-        if (r > K) break;
+    const int pend = min(p0 + kCombRows, K + 1);
+    // stage this CTA's row list (sorted position -> row, projection, BN multiplicity) in shared memory with one
+    // parallel round of gathers, so the row loop has no dependent global-load chain besides the corner re-loads
+    __shared__ int s_row[kCombRows];
+    __shared__ float2 s_proj[kCombRows];
+    __shared__ float s_w[kCombRows];
+    if (tid < pend - p0) {
+        const int r = a.perm[(size_t)f * a.capA + p0 + tid];
         const size_t ro = (size_t)f * a.capA + r;
         const float4 xyz = __ldg(reinterpret_cast<const float4 *>(a.vox8 + ro * 8));
-        float4 acc[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) acc[j] = bias[j];
-        if (r < K && !(xyz.x == 0.f && xyz.y == 0.f && xyz.z == 0.f)) {  // pad row / origin point: A1 row is zero
-            const float2 pr = __ldg(reinterpret_cast<const float2 *>(a.proj) + ro);
+        const bool none = r >= K || (xyz.x == 0.f && xyz.y == 0.f && xyz.z == 0.f);  // pad row / origin point: A1 row is zero
+        s_row[tid] = none ? ~r : r;
+        s_proj[tid] = __ldg(reinterpret_cast<const float2 *>(a.proj) + ro);
+        s_w[tid] = __ldg(a.row_w + ro);
+    }
+    __syncthreads();
+    for (int p = p0; p < pend; ++p) {
+        const int rr = s_row[p - p0];
+        const int r = rr < 0 ? ~rr : rr;
+        const float2 pr = s_proj[p - p0];
+        const size_t ro = (size_t)f * a.capA + r;
+        float4 acc = bias;
+        if (rr >= 0) {
 #pragma unroll
             for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
-                // index math and (inverted) weights of Pipe.py:62-75, same fp32 order as gather_row_warp
-                const float q0 = __fsub_rn(__fdiv_rn(pr.x, a.rs_h[l]), a.eps);
-                const float q1 = __fsub_rn(__fdiv_rn(pr.y, a.rs_w[l]), a.eps);
-                const int i0 = (int)q0, i1 = (int)q1;
-                const float wa = __fsub_rn(q0, (float)i0), wb = __fsub_rn(q1, (float)i1);
-                const float wa_ = __fsub_rn(1.0f, wa), wb_ = __fsub_rn(1.0f, wb);
+                const CellRef c = cell_of(pr.x, pr.y, a.rs_h[l], a.rs_w[l], a.eps);
                 const int H = a.h[l], W = a.w[l];
-                const bool r0 = i0 >= 0 && i0 < H, r1 = i0 + 1 >= 0 && i0 + 1 < H;
-                const bool c0 = i1 >= 0 && i1 < W, c1 = i1 + 1 >= 0 && i1 + 1 < W;
-                const float w00 = (r0 && c0) ? wa * wb : 0.f, w10 = (r1 && c0) ? wa_ * wb : 0.f;
-                const float w01 = (r0 && c1) ? wa * wb_ : 0.f, w11 = (r1 && c1) ? wa_ * wb_ : 0.f;
-                // clamped addresses (weight 0 where the corner is the zero pad of Pipe.py:47-48)
-                const int y0 = min(max(i0, 0), H - 1), y1 = min(max(i0 + 1, 0), H - 1);
-                const int x0 = min(max(i1, 0), W - 1), x1 = min(max(i1 + 1, 0), W - 1);
-                const float *base = a.Z[l] + (size_t)f * a.frame_stride[l] + col0;
-                const float *p00 = base + ((size_t)y0 * W + x0) * kCombCout, *p10 = base + ((size_t)y1 * W + x0) * kCombCout;
-                const float *p01 = base + ((size_t)y0 * W + x1) * kCombCout, *p11 = base + ((size_t)y1 * W + x1) * kCombCout;
-                float4 v00[3], v10[3], v01[3], v11[3];
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    v00[j] = __ldg(reinterpret_cast<const float4 *>(p00 + 128 * j));
-                    v10[j] = __ldg(reinterpret_cast<const float4 *>(p10 + 128 * j));
-                    v01[j] = __ldg(reinterpret_cast<const float4 *>(p01 + 128 * j));
-                    v11[j] = __ldg(reinterpret_cast<const float4 *>(p11 + 128 * j));
+                if (c.i0 != ci0[l] || c.i1 != ci1[l]) {  // warp-uniform: this level's cell changed, fetch its 4 corners
+                    ci0[l] = c.i0, ci1[l] = c.i1;
+                    const bool r0 = c.i0 >= 0 && c.i0 < H, r1 = c.i0 + 1 >= 0 && c.i0 + 1 < H;
+                    const bool c0 = c.i1 >= 0 && c.i1 < W, c1 = c.i1 + 1 >= 0 && c.i1 + 1 < W;
+                    const float *base = a.Z[l] + (size_t)f * a.frame_stride[l] + col0;
+                    // corners on the zero pad row/column of Pipe.py:47-48 read as zero
+                    v00[l] = (r0 && c0) ? __ldg(reinterpret_cast<const float4 *>(base + ((size_t)c.i0 * W + c.i1) * kCombCout)) : z4;
+                    v10[l] = (r1 && c0) ? __ldg(reinterpret_cast<const float4 *>(base + ((size_t)(c.i0 + 1) * W + c.i1) * kCombCout)) : z4;
+                    v01[l] = (r0 && c1) ? __ldg(reinterpret_cast<const float4 *>(base + ((size_t)c.i0 * W + c.i1 + 1) * kCombCout)) : z4;
+                    v11[l] = (r1 && c1) ? __ldg(reinterpret_cast<const float4 *>(base + ((size_t)(c.i0 + 1) * W + c.i1 + 1) * kCombCout)) : z4;
                 }
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-#define MVX_COMB(e) acc[j].e = fmaf(v11[j].e, w11, fmaf(v01[j].e, w01, fmaf(v10[j].e, w10, fmaf(v00[j].e, w00, acc[j].e))));
-                    MVX_COMB(x) MVX_COMB(y) MVX_COMB(z) MVX_COMB(w)
+                const float wa_ = __fsub_rn(1.0f, c.wa), wb_ = __fsub_rn(1.0f, c.wb);
+                const float w00 = c.wa * c.wb, w10 = wa_ * c.wb, w01 = c.wa * wb_, w11 = wa_ * wb_;
+#define MVX_COMB(e) acc.e = fmaf(v11[l].e, w11, fmaf(v01[l].e, w01, fmaf(v10[l].e, w10, fmaf(v00[l].e, w00, acc.e))));
+                MVX_COMB(x) MVX_COMB(y) MVX_COMB(z) MVX_COMB(w)
 #undef MVX_COMB
-                }
             }
         }
-        const float w = __ldg(a.row_w + ro);
-        float *yrow = a.Y1 + ro * kCombCout + col0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            float4 y;
-            y.x = fmaxf(acc[j].x, 0.f), y.y = fmaxf(acc[j].y, 0.f), y.z = fmaxf(acc[j].z, 0.f), y.w = fmaxf(acc[j].w, 0.f);
-            *reinterpret_cast<float4 *>(yrow + 128 * j) = y;
-            if (w == 1.f) {
-                ps[j].x += y.x, ps[j].y += y.y, ps[j].z += y.z, ps[j].w += y.w;
-                pss[j].x = fmaf(y.x, y.x, pss[j].x), pss[j].y = fmaf(y.y, y.y, pss[j].y);
-                pss[j].z = fmaf(y.z, y.z, pss[j].z), pss[j].w = fmaf(y.w, y.w, pss[j].w);
-            } else if (w != 0.f) {   // the weighted pad row: exact fp64 side path
-                const int c = col0 + 128 * j;
-                const double wd = (double)w;
-                atomicAdd(&s_sum[(c + 0) * 2], wd * y.x), atomicAdd(&s_sum[(c + 0) * 2 + 1], wd * y.x * y.x);
-                atomicAdd(&s_sum[(c + 1) * 2], wd * y.y), atomicAdd(&s_sum[(c + 1) * 2 + 1], wd * y.y * y.y);
-                atomicAdd(&s_sum[(c + 2) * 2], wd * y.z), atomicAdd(&s_sum[(c + 2) * 2 + 1], wd * y.z * y.z);
-                atomicAdd(&s_sum[(c + 3) * 2], wd * y.w), atomicAdd(&s_sum[(c + 3) * 2 + 1], wd * y.w * y.w);
-            }
+        float4 y;
+        y.x = fmaxf(acc.x, 0.f), y.y = fmaxf(acc.y, 0.f), y.z = fmaxf(acc.z, 0.f), y.w = fmaxf(acc.w, 0.f);
+        *reinterpret_cast<float4 *>(a.Y1 + ro * kCombCout + col0) = y;
+        const float w = s_w[p - p0];
+        if (w == 1.f) {
+            ps.x += y.x, ps.y += y.y, ps.z += y.z, ps.w += y.w;
+            pss.x = fmaf(y.x, y.x, pss.x), pss.y = fmaf(y.y, y.y, pss.y);
+            pss.z = fmaf(y.z, y.z, pss.z), pss.w = fmaf(y.w, y.w, pss.w);
+        } else if (w != 0.f) {   // the weighted pad row: exact fp64 side path
+            const double wd = (double)w;
+            atomicAdd(&s_sum[(col0 + 0) * 2], wd * y.x), atomicAdd(&s_sum[(col0 + 0) * 2 + 1], wd * y.x * y.x);
+            atomicAdd(&s_sum[(col0 + 1) * 2], wd * y.y), atomicAdd(&s_sum[(col0 + 1) * 2 + 1], wd * y.y * y.y);
+            atomicAdd(&s_sum[(col0 + 2) * 2], wd * y.z), atomicAdd(&s_sum[(col0 + 2) * 2 + 1], wd * y.z * y.z);
+            atomicAdd(&s_sum[(col0 + 3) * 2], wd * y.w), atomicAdd(&s_sum[(col0 + 3) * 2 + 1], wd * y.w * y.w);
         }
-        if ((i & 15) == 15) flush();
+        if (((p - p0) & 15) == 15) flush();
     }
     flush();
     __syncthreads();
     double *o = a.out_stats + (size_t)f * kCombCout * 2;
-    for (int i = tid; i < kCombCout * 2; i += 256) {
+    for (int i = tid; i < kCombCout * 2; i += kCombWarps * 32) {
         const double v = s_sum[i];
         if (v != 0.0) atomicAdd(o + i, v);
     }
@@ -314,8 +373,17 @@ __global__ void __launch_bounds__(256, 2) combine_rows_kernel(CombineArgs a) {
 }  // namespace
 
 int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st) {
+    MVX_REQUIRE(a.bin_count && a.bin_start && a.perm && a.nbins == combine_bins(a.h[0], a.w[0]), MVX_EINVAL, "combine: bad sort scratch");
+    MVX_CUDA_CHECK(cudaMemsetAsync(a.bin_count, 0, (size_t)B * (a.nbins + 1) * sizeof(int), st));
+    const dim3 rows_grid((a.capA + 255) / 256, B);
+    combine_hist_kernel<<<rows_grid, 256, 0, st>>>(a);
+    MVX_LAUNCH_CHECK();
+    combine_scan_kernel<<<B, 1024, 0, st>>>(a);
+    MVX_LAUNCH_CHECK();
+    combine_scatter_kernel<<<rows_grid, 256, 0, st>>>(a);
+    MVX_LAUNCH_CHECK();
     dim3 grid((a.capA + kCombRows - 1) / kCombRows, B);
-    combine_rows_kernel<<<grid, 256, 0, st>>>(a);
+    combine_rows_kernel<<<grid, kCombWarps * 32, 0, st>>>(a);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }

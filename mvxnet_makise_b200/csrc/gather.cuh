@@ -49,7 +49,15 @@ struct CombineArgs {
     const float *bias;      // (768)
     float *Y1;              // [B][capA][768] raw relu output
     double *out_stats;      // [B][768][2]
+    // rows sorted by their level-0 cell (4x4 cell blocks, Morton order inside a block) so that consecutive rows share
+    // their corners at all three levels and a warp re-loads a corner only when the cell changes
+    int *bin_count;         // [B][nbins + 1] scratch (zeroed by the launcher); bin nbins = rows without corners
+    int *bin_start;         // [B][nbins + 2] scratch
+    int *perm;              // [B][capA] sorted position -> compact row
+    int nbins;
 };
+// scratch sizes (ints per frame) for the level-0 extents of the call
+inline int combine_bins(int h0, int w0) { return ((h0 + 3) / 4) * ((w0 + 3) / 4) * 16; }
 int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st);
 
 }  // namespace mvx

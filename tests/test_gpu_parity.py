@@ -339,7 +339,7 @@ def test_fused_batch_equals_single_frames(mvx):
         single([frames[f]], [calib], [torch.from_numpy(m[f:f + 1]) for m in maps], want_grid=False)
         vf, idx = single.voxel_features(0)
         assert torch.equal(idx[:, 1:], batch[f][1][:, 1:])
-        assert rel_err(vf, batch[f][0]) < 1e-6      # fp64 atomic accumulation order is the only difference
+        assert rel_err(vf, batch[f][0]) < 1e-5      # accumulation order (fp64 atomics, fp32 16-row runs in sorted-row order) is the only difference
 
 
 @pytest.mark.parametrize('chunk', [1, 2, 8])
@@ -368,9 +368,9 @@ def test_host_entry_pipelined_equals_device_entry(mvx, chunk):
     for f in range(B):
         vf, idx = path.voxel_features(f)
         assert torch.equal(idx, feats_ref[f][1])
-        assert rel_err(vf, feats_ref[f][0]) < 1e-6       # fp64 atomic accumulation order is the only difference
-    assert torch.equal(grid != 0, grid_ref != 0) and rel_err(grid, grid_ref) < 1e-6
-    assert rel_err(head, feats_ref[0][0][:64]) < 1e-6
+        assert rel_err(vf, feats_ref[f][0]) < 1e-5       # accumulation order is the only difference
+    assert torch.equal(grid != 0, grid_ref != 0) and rel_err(grid, grid_ref) < 1e-5
+    assert rel_err(head, feats_ref[0][0][:64]) < 1e-5
     assert path.h2d_bytes == (points_h.numel() + calib_h.numel() + sum(m.numel() for m in maps_h)) * 4
 
 
