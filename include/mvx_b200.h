@@ -171,6 +171,25 @@ int mvx_pointpath_forward(const mvx_pointpath_args_t *args);
  *               (pixel GEMMs, combine) in mode 1 and (gather, row GEMM) in mode 0. */
 int mvx_set_fusion_mode(int32_t mode);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training mode (BASELINE.json configs[3]): forward that keeps every activation, then the backward of the 8 hot-path
+ * layers.  What loss.backward() does through modules/imhead/Pipe.py:84-104, modules/voxelnet/Pipe.py:5-29 and
+ * modules/voxelnet/VoxelNet.py:16-32 in train.py:140-166, for the parameters of SURVEY.md §8b.
+ *   mvx_pointpath_forward_train: same arguments and outputs as mvx_pointpath_forward; always row-first (keeps the
+ *     gathered matrix A1) and also keeps the raw output of the last FCN; args->workspace must hold `forward_bytes`.
+ *   mvx_pointpath_backward: call after forward_train with the SAME args (same workspace, weights, counts).
+ *     Upstream gradient: exactly one of d_vfeat (B, cap, 128: dLoss/d voxel features, reference voxel order, rows
+ *     >= N_f ignored) or d_grid (B,128,nz,nx,ny: dLoss/d dense grid; reindex's backward is an index select).
+ *     grad_flat: mvx_grad_floats() = 726 880 fp32, per layer [weight (Cout,Cin) | bias (Cout)] in checkpoint order
+ *     (fcn1 conv1 fcn2 conv2 fcn3 vfe1 vfe2 fcn) - the one flat bucket the NCCL all-reduce sums; gradients of all B
+ *     frames are summed into it (accumulate != 0: added to its current contents).
+ * ------------------------------------------------------------------------------------------------ */
+int mvx_pointpath_train_workspace_bytes(const mvx_pointpath_args_t *args, size_t *forward_bytes, size_t *backward_bytes);
+int mvx_pointpath_forward_train(const mvx_pointpath_args_t *args);
+int64_t mvx_grad_floats(void);
+int mvx_pointpath_backward(const mvx_pointpath_args_t *args, const float *d_vfeat, const float *d_grid, float *grad_flat,
+                           int32_t accumulate, void *backward_ws, size_t backward_ws_bytes);
+
 /* Optional per-kernel timing of mvx_pointpath_forward with CUDA events recorded on the launching stream
  * (bench.py's roofline leg). mvx_timing_enable(n) arms n event sets (one per forward call, n = 0 disables);
  * mvx_timing_read(call, ms) waits for that call's last event and returns MVX_NUM_SEGMENTS durations in ms, in the

@@ -10,39 +10,22 @@
 #include "layers.cuh"
 #include "scatter.cuh"
 #include "voxelize.cuh"
+#include "pointpath.cuh"
 
 #include <vector>
 
 namespace mvx {
 
-enum Region {
-    R_VOXWS = 0, R_VOX_COORD, R_VOX_CNT, R_VOX_ROW0, R_ROW_POINT, R_ROW_VOX, R_CELL2VID, R_NHWC0, R_NHWC1, R_NHWC2,
-    R_VOX8, R_PROJ, R_ROWA_W, R_A1, R_Y1, R_Y2, R_Y3, R_Y4, R_Y5, R_X6, R_Y6, R_X7, R_Y7, R_ROWB_W, R_ROWB_V, R_X8,
-    R_VFEAT, R_STATS, R_VMAX6, R_VMAX7, R_VMAX8, R_WPACK, R_OCC, R_VFEAT_T, R_Z, R_BINCNT, R_BINSTART, R_PERM, R_COUNT
-};
-static_assert(R_COUNT <= MVX_WS_REGIONS, "too many regions");
-
 const char *kRegionNames[R_COUNT] = {
     "vox_ws", "vox_coord", "vox_cnt", "vox_row0", "row_point", "row_vox", "cell2vid", "nhwc0", "nhwc1", "nhwc2",
     "vox8", "proj", "rowA_w", "A1", "Y1", "Y2", "Y3", "Y4", "Y5", "X6", "Y6", "X7", "Y7", "rowB_w", "rowB_v", "X8",
-    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t", "Z", "bin_count", "bin_start", "perm"};
-
-constexpr int kCin[MVX_NUM_LAYERS] = {768, 768, 128, 128, 16, 32, 32, 128};   // padded
-constexpr int kCout[MVX_NUM_LAYERS] = {768, 128, 128, 16, 16, 16, 64, 128};
-constexpr int kStatStride = 768 * 2;  // doubles per (layer, frame)
+    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t", "Z", "bin_count", "bin_start", "perm", "Y8"};
 
 // 1 (default): pixel-first fcn1 - one tensor-core GEMM per FPN level over the map pixels, then a 12-corner combine per
 // point row (gather.cuh CombineArgs); 0: materialise the gathered (K,768) matrix A1 and run fcn1 over the point rows
 // (the layout the training-mode backward needs: dW1 = dpre1^T A1).
 static int g_fusion_mode = 1;
 int fusion_mode() { return g_fusion_mode; }
-
-struct Layout {
-    size_t off[R_COUNT];
-    size_t total;
-    int capA, capB;
-    long long G;
-};
 
 int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
     MVX_REQUIRE(a, MVX_EINVAL, "null args");
@@ -105,6 +88,8 @@ int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
         take(R_PERM, B * capA * 4);
     }
     L.total = o;
+    take(R_Y8, B * capB * 128 * 4);   // last region: only present in a training workspace
+    L.total_train = o;
     return MVX_OK;
 }
 
@@ -149,11 +134,11 @@ __global__ void __launch_bounds__(256) zero_vmax_kernel(const int *__restrict__ 
     for (long long e = t0; e < N * 32; e += stride) p8[e] = z;
 }
 
-int pointpath_forward(const mvx_pointpath_args_t *a) {
+int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     Layout L;
     int rc = make_layout(a, L);
     if (rc) return rc;
-    MVX_REQUIRE(a->workspace && a->workspace_bytes >= L.total, MVX_ESPACE, "pointpath workspace too small");
+    MVX_REQUIRE(a->workspace && a->workspace_bytes >= (train ? L.total_train : L.total), MVX_ESPACE, "pointpath workspace too small");
     MVX_REQUIRE(a->points && a->pt_off_host && a->calib32 && a->counts, MVX_EINVAL, "null input pointer");
     MVX_REQUIRE(a->point_stride >= 4, MVX_EINVAL, "point_stride must be >= 4");
     for (int l = 0; l < MVX_NUM_LEVELS; ++l) MVX_REQUIRE(a->maps[l], MVX_EINVAL, "null FPN map");
@@ -199,7 +184,8 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
     rp.vox8 = F32(R_VOX8), rp.proj = F32(R_PROJ), rp.rowA_w = F32(R_ROWA_W);
     rc = launch_rows_build(rp, st);
     if (rc) return rc;
-    const bool pixel_first = g_fusion_mode == 1 && gemm_mode() == 1;
+    // training keeps the gathered matrix A1 (dW1 = dpre1^T A1), so it always runs row-first
+    const bool pixel_first = !train && g_fusion_mode == 1 && gemm_mode() == 1;
     double *stats = reinterpret_cast<double *>(ws + L.off[R_STATS]);
     auto stat_of = [&](int layer) { return stats + (size_t)layer * B * kStatStride; };
     // NOTE: stats are stored [F][Cout][2] with the layer's own Cout as the frame stride
@@ -305,7 +291,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a) {
         stamp.mark(S_FCN);
         LayerArgs la{};
         la.X = F32(R_X8), la.ldx = 128, la.Cin = 128, la.Wt = a->wt[7], la.bias = a->bias[7], la.Cout = 128;
-        la.Y = nullptr, la.ldy = 0, la.out_stats = stat_of(7), la.vmax = I32(R_VMAX8);
+        la.Y = train ? F32(R_Y8) : nullptr, la.ldy = train ? 128 : 0, la.out_stats = stat_of(7), la.vmax = I32(R_VMAX8);
         la.row_w = F32(R_ROWB_W), la.row_v = I32(R_ROWB_V), la.rowv_cap = L.capB, la.counts = a->counts, la.rows_mode = 2;
         la.rowcap = L.capB, la.vcap = cap, la.T = T, la.eps = a->bn_eps;
         rc = launch_layer_auto(la, B, F32(R_WPACK), st);
@@ -388,7 +374,7 @@ extern "C" const char *mvx_pointpath_layout_name(int32_t region) {
     return (region >= 0 && region < mvx::R_COUNT) ? mvx::kRegionNames[region] : nullptr;
 }
 
-extern "C" int mvx_pointpath_forward(const mvx_pointpath_args_t *args) { return mvx::pointpath_forward(args); }
+extern "C" int mvx_pointpath_forward(const mvx_pointpath_args_t *args) { return mvx::pointpath_forward(args, false); }
 
 extern "C" int mvx_set_fusion_mode(int32_t mode) {
     if (mode != 0 && mode != 1) return MVX_EINVAL;

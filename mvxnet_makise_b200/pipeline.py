@@ -52,8 +52,8 @@ class PointPath:
             self.bias.append(b.detach().to(self.device, torch.float32).contiguous())
 
     # ------------------------------------------------------------------------------------------------
-    def _prepare(self, B: int, cap: int, map_hw, own_outputs: bool = True):
-        key = (B, cap, tuple(map_hw), own_outputs)
+    def _prepare(self, B: int, cap: int, map_hw, own_outputs: bool = True, train: bool = False):
+        key = (B, cap, tuple(map_hw), own_outputs, train)
         if self._ws_key == key:
             return
         a = _lib.PointPathArgs()
@@ -71,6 +71,13 @@ class PointPath:
             n = lib.mvx_pointpath_layout_name(r)
             if n:
                 self.layout[n.decode()] = int(offs[r])
+        self._bws = None
+        if train:     # training workspace: + the raw output of the last FCN; backward scratch (gradient buffers)
+            fwd_b, bwd_b = ctypes.c_size_t(), ctypes.c_size_t()
+            check(lib.mvx_pointpath_train_workspace_bytes(ctypes.byref(a), ctypes.byref(fwd_b), ctypes.byref(bwd_b)),
+                  'pointpath_train_workspace_bytes')
+            nbytes = fwd_b
+            self._bws = torch.empty(bwd_b.value, dtype=torch.uint8, device=self.device)
         self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
         self._ws_key = key
         self.cap, self.B = cap, B
@@ -92,14 +99,15 @@ class PointPath:
     # ------------------------------------------------------------------------------------------------
     def forward_device(self, points: torch.Tensor, offsets: Sequence[int], calib32: torch.Tensor,
                        maps: List[torch.Tensor], want_grid: bool = True, cap: int | None = None,
-                       grid_out: torch.Tensor | None = None, counts: torch.Tensor | None = None):
+                       grid_out: torch.Tensor | None = None, counts: torch.Tensor | None = None, train: bool = False):
         """points (sum P, stride>=4) fp32 CUDA, offsets host [B+1], calib32 (B,32) CUDA, maps 3 x (B,256,Hf,Wf) CUDA.
-        grid_out / counts: optional caller-owned outputs ((B,128,nz,nx,ny) fp32, (B,4) int32, contiguous)."""
+        grid_out / counts: optional caller-owned outputs ((B,128,nz,nx,ny) fp32, (B,4) int32, contiguous).
+        train=True keeps every activation for `backward` (row-first fcn1; mvx_pointpath_forward_train)."""
         B = len(offsets) - 1
         maxp = max(offsets[i + 1] - offsets[i] for i in range(B))
         cap = cap or max(128, (maxp + 127) // 128 * 128)
         map_hw = [(int(m.shape[-2]), int(m.shape[-1])) for m in maps]
-        self._prepare(B, cap, map_hw, own_outputs=counts is None)
+        self._prepare(B, cap, map_hw, own_outputs=counts is None, train=train)
         if counts is not None:
             assert counts.is_contiguous() and counts.shape == (B, 4) and (grid_out is None or grid_out.is_contiguous())
             self.grid_out, self.counts = grid_out, counts
@@ -125,8 +133,54 @@ class PointPath:
         a.counts = self.counts.data_ptr()
         a.workspace, a.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
         a.stream = torch.cuda.current_stream().cuda_stream
-        check(lib.mvx_pointpath_forward(ctypes.byref(a)), 'pointpath_forward')
+        if train:
+            check(lib.mvx_pointpath_forward_train(ctypes.byref(a)), 'pointpath_forward_train')
+            self._train_args = (a, off, points, calib32, maps)      # kept alive for backward()
+        else:
+            check(lib.mvx_pointpath_forward(ctypes.byref(a)), 'pointpath_forward')
+            self._train_args = None
         return (self.grid_out if want_grid else None), self.counts
+
+    # ---- training mode -------------------------------------------------------------------------------------
+    def forward_train(self, points, offsets, calib32, maps, want_grid: bool = True, cap: int | None = None):
+        """Forward that keeps the activations the backward needs (BASELINE.json configs[3])."""
+        return self.forward_device(points, offsets, calib32, maps, want_grid, cap, train=True)
+
+    @staticmethod
+    def grad_layout():
+        """(name, offset, shape) of every parameter gradient inside the flat bucket: checkpoint names/order."""
+        out, o = [], 0
+        for name, cin, cout, is_conv in synth.HOT_LAYERS:
+            out.append((name + '.weight', o, (cout, cin, 1, 1) if is_conv else (cout, cin)))
+            o += cout * cin
+            out.append((name + '.bias', o, (cout,)))
+            o += cout
+        return out
+
+    def backward(self, d_vfeat: torch.Tensor | None = None, d_grid: torch.Tensor | None = None,
+                 grad_flat: torch.Tensor | None = None, accumulate: bool = False) -> torch.Tensor:
+        """Gradients of the 8 hot-path layers for the last forward_train call, summed over its frames, as ONE flat fp32
+        bucket (the message of the NCCL all-reduce; `grad_layout()` names its slices). Give dLoss/d voxel features
+        (B, cap, 128) or dLoss/d dense grid (B,128,nz,nx,ny)."""
+        if getattr(self, '_train_args', None) is None:
+            raise RuntimeError('backward() needs a preceding forward_train() on this PointPath')
+        a = self._train_args[0]
+        n = int(lib.mvx_grad_floats())
+        if grad_flat is None:
+            grad_flat = torch.empty(n, dtype=torch.float32, device=self.device)
+            accumulate = False
+        assert grad_flat.is_contiguous() and grad_flat.numel() == n and grad_flat.dtype == torch.float32
+        for t, shape in ((d_vfeat, (self.B, self.cap, 128)), (d_grid, tuple(self.grid_out.shape) if self.grid_out is not None else None)):
+            if t is not None:
+                assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and tuple(t.shape) == shape, (tuple(t.shape), shape)
+        a.stream = torch.cuda.current_stream().cuda_stream
+        check(lib.mvx_pointpath_backward(ctypes.byref(a), ptr(d_vfeat), ptr(d_grid), grad_flat.data_ptr(), int(bool(accumulate)),
+                                         self._bws.data_ptr(), self._bws.numel()), 'pointpath_backward')
+        return grad_flat
+
+    def grads(self, grad_flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Named views into a flat gradient bucket (reference state-dict names)."""
+        return {name: grad_flat[o:o + int(np.prod(shape))].view(*shape) for name, o, shape in self.grad_layout()}
 
     def __call__(self, points_list: List, calibs: List[dict], fpn_maps: List, want_grid: bool = True):
         """points_list: B arrays/tensors (P_f, >=4) [x,y,z,r]; calibs: B dicts of 4x4 matrices (Load.py:24-41);

@@ -266,3 +266,24 @@ def forward_frame(pcd4: np.ndarray, calib_np, fpn_maps: List[np.ndarray], sd_np,
     if stages is not None:
         stages.update(t)
     return out
+
+
+# --------------------------------------------------------------------------- training mode: gradients of the hot-path layers
+def backward_frame(pcd4: np.ndarray, calib_np, fpn_maps: List[np.ndarray], sd_np, grid, imsize_hw, d_vfeat: np.ndarray,
+                   eps: float = 1e-6, dtype: torch.dtype = torch.float64):
+    """What `loss.backward()` (train.py:140-166) leaves in `.grad` of the 8 hot-path layers for ONE frame, when the
+    gradient arriving at the voxel features (the input of `reindex`/CML, VoxelNet.py:33-36) is `d_vfeat` (N,128):
+    autograd through the dense reference chain featureMaping -> ImageFeatureFusion -> concat -> SVFE/FCN/max
+    (Pipe.py:84-104; MVXNet.py:25-26; voxelnet/Pipe.py:5-29; VoxelNet.py:27-32). The FPN maps are inputs (no gradient).
+    Returns (vfeat (N,128), {state-dict name: gradient})."""
+    params = {k: torch.from_numpy(np.asarray(v)).to(dtype).requires_grad_(True) for k, v in sd_np.items()}
+    pcd6 = points_with_proj(pcd4, calib_np)
+    voxel9, _ = group(pcd6, grid.velorange, grid.voxelsize, grid.T)
+    voxels = torch.Tensor(voxel9)
+    feats = [torch.from_numpy(m) for m in fpn_maps]
+    im768 = feature_mapping(voxels, feats, torch.Tensor(list(imsize_hw)), eps)
+    im16 = fusion(im768[None].to(dtype), params, eps)
+    x23 = torch.concat([voxels[None][..., :7].to(dtype), im16], dim=-1)
+    vfeat = voxel_features(x23, params, eps)
+    (vfeat * torch.from_numpy(np.asarray(d_vfeat)).to(dtype)).sum().backward()
+    return vfeat.detach(), {k: p.grad for k, p in params.items()}

@@ -43,7 +43,10 @@ def test_struct_layout_matches_header():
     names = [(_lib.lib.mvx_pointpath_layout_name(r) or b'').decode() for r in range(_lib.WS_REGIONS)]
     assert 'vfeat' in names and 'cell2vid' in names
     used = [offs[r] for r in range(_lib.WS_REGIONS) if names[r]]
-    assert used == sorted(used) and used[-1] < n.value
+    assert used == sorted(used) and names[len(used) - 1] == 'Y8' and used[-1] == n.value   # Y8: training-only tail region
+    fwd, bwd = ctypes.c_size_t(), ctypes.c_size_t()
+    assert _lib.lib.mvx_pointpath_train_workspace_bytes(ctypes.byref(a), ctypes.byref(fwd), ctypes.byref(bwd)) == 0
+    assert fwd.value > n.value and bwd.value > 0 and _lib.lib.mvx_grad_floats() == 726_880
     # the dense cell->voxel map must be there for both frames
     assert n.value > 2 * 352 * 400 * 10 * 4
 

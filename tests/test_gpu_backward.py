@@ -1,0 +1,148 @@
+"""Training mode (BASELINE.json configs[3]): gradients of the 8 hot-path layers from the CUDA backward (through the C ABI)
+against autograd through the oracle's dense restatement of the reference chain.
+
+The gradient of this path is only piecewise continuous in the activations (ReLU masks, the argmax of the max over T):
+forwards that agree to 1e-5 still disagree on a handful of near-tie decisions, each moving one O(1) gradient entry
+between rows - the fp32 reference's own autograd is 1e-2 .. 6e-2 (max-norm per tensor) from its fp64 evaluation. Parity
+is therefore pinned in two steps (oracle/compact_backward.py): (1) compact formulas == dense autograd in fp64 to 1e-9
+(CPU, tests/test_oracle.py); (2) here: CUDA kernels == those formulas evaluated in fp64 on the CUDA forward's own
+saved activations, every parameter gradient within TOL = 1e-4 (max|g - ref| / max|ref| per tensor). The end-to-end
+distance to the dense fp64 autograd is additionally bounded by the fp32 reference's own distance to it."""
+import numpy as np
+import pytest
+import torch
+
+from mvxnet_makise_b200 import synth
+from oracle import pointpath_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = synth.KITTI_GRID
+TOL = 1e-4
+SMALL_FPN = ((13, 42), (7, 21), (4, 11))
+
+
+def small_maps(seed, B=1):
+    rng = np.random.default_rng(seed)
+    return [rng.standard_normal((B, 256, h, w), dtype=np.float32) for (h, w) in SMALL_FPN]
+
+
+def rel_err(a, ref):
+    a = torch.as_tensor(a).double().cpu()
+    ref = torch.as_tensor(ref).double().cpu()
+    return ((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+def _device_inputs(frames, maps, calib):
+    from mvxnet_makise_b200.modules import pack_calib
+    offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in frames])]).tolist()
+    points = torch.from_numpy(np.concatenate(frames, 0)).cuda()
+    calib32 = torch.stack([pack_calib(calib) for _ in frames]).cuda()
+    return points, offsets, calib32, [torch.from_numpy(m).cuda() for m in maps]
+
+
+def _compact_reference(path, sd, d_vfeat):
+    """fp64 evaluation of the compact backward (oracle/compact_backward.py) on the activations the CUDA forward saved for
+    frame 0: same ReLU masks and argmax decisions as the implementation under test."""
+    import warnings
+    from oracle import compact_backward as CB
+    c = path.counts.cpu().numpy()[0]
+    N, K = int(c[0]), int(c[1])
+    cap, capA, capB = path.cap, path.cap + 128, 2 * path.cap
+    reg = lambda name, shape, n: path.region(name, torch.float32, (path.B,) + shape)[0, :n].double().cpu()
+    cnt = path.region('vox_cnt', torch.int32, (path.B, cap))[0, :N].cpu().numpy()
+    row_v = path.region('row_vox', torch.int32, (path.B, cap))[0, :K].long().cpu()
+    A1 = reg('A1', (capA, 768), K + 1)
+    vox7c = reg('vox8', (capA, 8), K + 1)[:, :7]
+    ys = {0: reg('Y1', (capA, 768), K + 1), 1: reg('Y2', (capA, 128), K + 1), 2: reg('Y3', (capA, 128), K + 1),
+          3: reg('Y4', (capA, 16), K + 1), 4: reg('Y5', (capA, 16), K + 1), 5: reg('Y6', (capA, 16), K + 1),
+          6: reg('Y7', (capB, 64), K + N), 7: reg('Y8', (capB, 128), K + N)}
+    sdt = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        out, st, aux = CB.compact_forward(A1, vox7c, sdt, cnt, row_v, G.T, y_given=ys)
+        grads = CB.compact_backward(st, aux, d_vfeat, row_v)
+    return out, grads
+
+
+@pytest.mark.parametrize('seed,P', [(11, 1200), (12, 2500)])
+def test_backward_matches_autograd(seed, P):
+    from mvxnet_makise_b200.pipeline import PointPath
+    sd = synth.make_weights(seed)
+    calib = synth.kitti_calib()
+    pts = synth.make_points(seed, P)
+    maps = small_maps(seed)
+    path = PointPath(sd, G)
+    points, offsets, calib32, dmaps = _device_inputs([pts], maps, calib)
+    grid, counts = path.forward_train(points, offsets, calib32, dmaps)
+    N = int(counts[0, 0].item())
+    rng = np.random.default_rng(seed + 100)
+    d_vfeat = rng.standard_normal((N, 128)).astype(np.float32)
+    dv = torch.zeros((1, path.cap, 128), dtype=torch.float32, device='cuda')
+    dv[0, :N] = torch.from_numpy(d_vfeat).cuda()
+    flat = path.backward(d_vfeat=dv)
+    torch.cuda.synchronize()
+    got = path.grads(flat)
+    vf, _ = path.voxel_features(0)
+
+    # (2) kernels vs the fp64 compact formulas on the SAME saved activations (same decisions): the parity bar
+    out_c, ref_c = _compact_reference(path, sd, d_vfeat)
+    assert rel_err(vf, out_c) < 1e-5
+    worst = {k: rel_err(got[k], ref_c[k].reshape(got[k].shape)) for k in ref_c}
+    assert set(got) == set(ref_c) and max(worst.values()) < TOL, worst
+
+    # end to end vs autograd through the dense reference chain. The forward agrees to TOL; the gradient is only
+    # piecewise continuous (ReLU masks, argmax of the max over T), so a few decisions taken on near-ties differ between
+    # any two forwards that are not bit-identical, each moving one O(1) entry. The fp32 reference is subject to the same
+    # effect: bound the distance to the fp64 autograd by the fp32 reference's own distance to it.
+    vfeat_ref, ref64 = O.backward_frame(pts, calib, [m[0:1] for m in maps], sd, G, synth.KITTI_IMSIZE_HW, d_vfeat)
+    _, ref32 = O.backward_frame(pts, calib, [m[0:1] for m in maps], sd, G, synth.KITTI_IMSIZE_HW, d_vfeat, dtype=torch.float32)
+    assert rel_err(vf, vfeat_ref) < TOL
+    for k in ref64:
+        assert tuple(got[k].shape) == tuple(ref64[k].shape), k
+    ours = max(rel_err(got[k], ref64[k]) for k in ref64)
+    noise = max(rel_err(ref32[k], ref64[k]) for k in ref64)
+    l2 = (sum(float(((got[k].double().cpu() - ref64[k]) ** 2).sum()) for k in ref64) / sum(float((ref64[k] ** 2).sum()) for k in ref64)) ** 0.5
+    l2_noise = (sum(float(((ref32[k].double() - ref64[k]) ** 2).sum()) for k in ref64) / sum(float((ref64[k] ** 2).sum()) for k in ref64)) ** 0.5
+    print(f'gradient vs fp64 autograd: ours max {ours:.3e} / L2 {l2:.3e}; fp32 reference max {noise:.3e} / L2 {l2_noise:.3e}')
+    assert ours <= 2 * noise + TOL and l2 <= 2 * l2_noise + TOL
+
+    # the same upstream gradient given on the dense grid (reindex backward = index select)
+    vfe, idx = path.voxel_features(0)
+    d_grid = torch.zeros_like(grid)
+    d_grid[0][:, idx[:, 3], idx[:, 1], idx[:, 2]] = torch.from_numpy(d_vfeat).cuda().T
+    flat2 = path.backward(d_grid=d_grid)
+    assert rel_err(flat2, flat) < 1e-6
+    # accumulate: a second backward into the same bucket doubles it
+    path.backward(d_vfeat=dv, grad_flat=flat2, accumulate=True)
+    assert rel_err(flat2, 2 * flat) < 1e-6
+
+
+def test_backward_batch_is_sum_of_frames():
+    """Frames are independent: the bucket of a batch is the sum of the single-frame buckets (what the all-reduce
+    across frame-sharded ranks then continues)."""
+    from mvxnet_makise_b200.pipeline import PointPath
+    sd = synth.make_weights(3)
+    calib = synth.kitti_calib()
+    frames = [synth.make_points(70 + f, P) for f, P in enumerate((900, 1700, 1300))]
+    maps = small_maps(21, B=3)
+    path = PointPath(sd, G)
+    points, offsets, calib32, dmaps = _device_inputs(frames, maps, calib)
+    _, counts = path.forward_train(points, offsets, calib32, dmaps, want_grid=False)
+    rng = torch.Generator(device='cuda').manual_seed(5)
+    dv = torch.randn((3, path.cap, 128), device='cuda', generator=rng)
+    flat = path.backward(d_vfeat=dv).clone()
+    total = torch.zeros_like(flat)
+    for f in range(3):
+        single = PointPath(sd, G)
+        p1, o1, c1, m1 = _device_inputs([frames[f]], [m[f:f + 1] for m in maps], calib)
+        single.forward_train(p1, o1, c1, m1, want_grid=False, cap=path.cap)
+        total += single.backward(d_vfeat=dv[f:f + 1].contiguous())
+    assert rel_err(flat, total) < 1e-5
+    assert torch.isfinite(flat).all() and float(flat.abs().max()) > 0
+
+
+def test_backward_requires_forward_train():
+    from mvxnet_makise_b200.pipeline import PointPath
+    path = PointPath(synth.make_weights(0), G)
+    with pytest.raises(RuntimeError, match='forward_train'):
+        path.backward(d_vfeat=torch.zeros((1, 128, 128), device='cuda'))

@@ -97,3 +97,34 @@ def test_oracle_empty_and_single_point():
     p = np.array([[1.0, 2.0, -1.0, 0.5]], np.float32)
     vox, (x, y, z), cnt = O.cpp_group(p, O.cell_index(p, G.velorange, G.voxelsize), 35)
     assert vox.shape == (1, 35, 7) and cnt[0] == 1 and (x[0], y[0], z[0]) == (5, 210, 5)
+
+
+def test_compact_backward_equals_dense_autograd():
+    """Step (1) of the gradient parity chain (oracle/compact_backward.py): the compact training-mode formulas (weighted
+    pad rows, first-argmax routing, batch-stat BatchNorm backward with multiplicities) reproduce autograd through the dense
+    restatement of the reference chain, in fp64."""
+    import warnings
+    from mvxnet_makise_b200 import synth
+    from oracle import compact_backward as CB
+    G = synth.KITTI_GRID
+    pts = synth.make_points(11, 700)
+    maps = [np.random.default_rng(1).standard_normal((1, 256, h, w), dtype=np.float32) for (h, w) in ((13, 42), (7, 21), (4, 11))]
+    sd_np = synth.make_weights(4)
+    sd = {k: torch.from_numpy(v) for k, v in sd_np.items()}
+    N = O.group_assign(O.cell_index(pts, G.velorange, G.voxelsize), G.T)[2].shape[0]
+    Gw = np.random.default_rng(2).standard_normal((N, 128))
+    vf, gref = O.backward_frame(pts, synth.kitti_calib(), maps, sd_np, G, synth.KITTI_IMSIZE_HW, Gw)
+    voxels = torch.Tensor(O.group(O.points_with_proj(pts, synth.kitti_calib()), G.velorange, G.voxelsize, G.T)[0])
+    im768 = O.feature_mapping(voxels, [torch.from_numpy(m) for m in maps], torch.Tensor(list(synth.KITTI_IMSIZE_HW))).double()
+    cnt, rows, row_v = CB.compact_rows(voxels, G.T)
+    A1 = torch.cat([im768.reshape(-1, 768)[rows], torch.zeros(1, 768, dtype=torch.float64)], 0)
+    vox7c = torch.cat([voxels[..., :7].double().reshape(-1, 7)[rows], torch.zeros(1, 7, dtype=torch.float64)], 0)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        out, st, aux = CB.compact_forward(A1, vox7c, sd, cnt, row_v, G.T)
+        grads = CB.compact_backward(st, aux, Gw, row_v)
+    assert (out - vf).abs().max().item() < 1e-9
+    assert set(grads) == set(gref)
+    for k in gref:
+        g = grads[k].reshape(gref[k].shape)
+        assert ((g - gref[k]).abs().max() / gref[k].abs().max()).item() < 1e-9, k

@@ -1,0 +1,106 @@
+"""Dev tool (GPU): checks each backward kernel against torch ops on the saved workspace regions."""
+import sys, os
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mvxnet_makise_b200 import synth, _lib
+from mvxnet_makise_b200.pipeline import PointPath
+from mvxnet_makise_b200.modules import pack_calib
+G = synth.KITTI_GRID
+seed, P = 11, 1200
+sd = synth.make_weights(seed); calib = synth.kitti_calib(); pts = synth.make_points(seed, P)
+rng = np.random.default_rng(seed)
+maps = [torch.from_numpy(rng.standard_normal((1, 256, h, w), dtype=np.float32)).cuda() for (h, w) in ((13, 42), (7, 21), (4, 11))]
+path = PointPath(sd, G)
+points = torch.from_numpy(pts).cuda(); calib32 = pack_calib(calib)[None].cuda()
+_, counts = path.forward_train(points, [0, P], calib32, maps, want_grid=False)
+N, K = int(counts[0, 0]), int(counts[0, 1]); cap = path.cap; capA, capB = cap + 128, 2 * cap; T = G.T
+dv = torch.zeros((1, cap, 128), device='cuda'); dv[0, :N] = torch.randn(N, 128, device='cuda')
+flat = path.backward(d_vfeat=dv); torch.cuda.synchronize()
+g = path.grads(flat)
+reg = path.region
+Y8 = reg('Y8', torch.float32, (1, capB, 128))[0, :K + N].double()
+X8 = reg('X8', torch.float32, (1, capB, 128))[0, :K + N].double()
+wB = reg('rowB_w', torch.float32, (1, capB))[0, :K + N].double()
+st = reg('stats', torch.float64, (8, 1, 768, 2))
+row0 = reg('vox_row0', torch.int32, (1, cap + 1))[0, :N + 1].long(); cnt = reg('vox_cnt', torch.int32, (1, cap))[0, :N].long()
+R = N * T
+def coef(l, C):
+    s = st[l, 0, :C]; m = s[:, 0] / R; var = (s[:, 1] / R - m * m).clamp_min(0); return m, 1 / torch.sqrt(var + 1e-6)
+# reference dz8 by routing
+m8, r8 = coef(7, 128)
+dz = torch.zeros(K + N, 128, dtype=torch.float64, device='cuda')
+Yc = Y8.cpu(); dvc = dv[0, :N].double().cpu(); dzc = dz.cpu()
+for v in range(N):
+    rows = list(range(int(row0[v]), int(row0[v]) + int(cnt[v])))
+    yr = Yc[rows]                      # (cnt,128)
+    mreal, arg = yr.max(0)
+    # first argmax
+    first = (yr == mreal[None]).float().argmax(0)
+    ypad = Yc[K + v]
+    pw = (int(cnt[v]) < T) & (ypad > mreal)
+    for c in range(128):
+        if pw[c]: dzc[K + v, c] = dvc[v, c]
+        else: dzc[rows[int(first[c])], c] = dvc[v, c]
+dz = dzc.cuda()
+z = (Y8 - m8) * r8
+S1 = dz.sum(0); S2 = (dz * z).sum(0)
+dpre = r8 * (dz - wB[:, None] * S1 / R - wB[:, None] * z * S2 / R) * (Y8 > 0)
+# what the kernels produced: G8 lives in the backward workspace; recompute via bucket
+W7 = torch.from_numpy(sd['backbone.fcn.fc.weight']).cuda().double()
+print('db7 rel', ((g['backbone.fcn.fc.bias'].double() - dpre.sum(0)).abs().max() / dpre.sum(0).abs().max()).item())
+dW = dpre.T @ X8
+print('dW7 rel', ((g['backbone.fcn.fc.weight'].double() - dW).abs().max() / dW.abs().max()).item())
+# read G8 from backward ws: offsets unknown in python; print norms instead
+print('N', N, 'K', K, 'cap', cap)
+
+# ---- oracle dense autograd with hooks on the last FCN's pre-activation ------------------------------------------
+from oracle import pointpath_oracle as O
+import torch.nn.functional as F
+maps_np = [m.cpu().numpy() for m in maps]
+params = {k: torch.from_numpy(np.asarray(v)).double().requires_grad_(True) for k, v in sd.items()}
+pcd6 = O.points_with_proj(pts, calib)
+voxel9, _ = O.group(pcd6, G.velorange, G.voxelsize, G.T)
+voxels = torch.Tensor(voxel9)
+im768 = O.feature_mapping(voxels, [torch.from_numpy(m) for m in maps_np], torch.Tensor(list(synth.KITTI_IMSIZE_HW)), 1e-6)
+im16 = O.fusion(im768[None].double(), params, 1e-6)
+x23 = torch.concat([voxels[None][..., :7].double(), im16], dim=-1)
+x = O.vfe(x23, params['backbone.svfe.vfe1.fcn.fc.weight'], params['backbone.svfe.vfe1.fcn.fc.bias'])
+x8 = O.vfe(x, params['backbone.svfe.vfe2.fcn.fc.weight'], params['backbone.svfe.vfe2.fcn.fc.bias'])
+x8.retain_grad()
+pre8 = F.linear(x8, params['backbone.fcn.fc.weight'], params['backbone.fcn.fc.bias'])
+pre8.retain_grad()
+y8 = F.relu(pre8).permute(0, 3, 1, 2)
+z8 = F.batch_norm(y8, None, None, None, None, True, 0.0, 1e-6).permute(0, 2, 3, 1)
+vf = torch.max(z8, dim=2)[0].reshape(-1, 128)
+(vf * dv[0, :N].double().cpu()).sum().backward()
+cntc = cnt.cpu()
+# compact the dense tensors: real rows then one pad row per voxel (sum of pad slots for grads)
+rows = torch.cat([v * T + torch.arange(int(cntc[v])) for v in range(N)])
+def compact_grad(d):   # (1,N,T,C)
+    d = d[0]
+    real = d.reshape(N * T, -1)[rows]
+    pad = torch.stack([d[v, int(cntc[v]):].sum(0) for v in range(N)])
+    return torch.cat([real, pad], 0)
+def compact_val(d):
+    d = d[0]
+    real = d.reshape(N * T, -1)[rows]
+    pad = torch.stack([d[v, T - 1] for v in range(N)])
+    return torch.cat([real, pad], 0)
+dpre_o = compact_grad(pre8.grad)
+x8_o = compact_val(x8.detach())
+print('X8 vs oracle (rel)', ((X8.cpu() - x8_o).abs().max() / x8_o.abs().max()).item())
+full = (cntc == T)
+mask = torch.ones(K + N, dtype=torch.bool); mask[K:][full] = False      # pad rows of full voxels are not in the dense tensor
+e = (dpre.cpu() - dpre_o).abs()
+e[~mask] = 0
+print('dpre8 formula(GPU activations) vs oracle: max abs', e.max().item(), 'ref max', dpre_o.abs().max().item())
+r, c = divmod(int(e.argmax()), 128)
+print('worst at row', r, 'col', c, 'is pad row' if r >= K else 'real', dpre[r, c].item(), dpre_o[r, c].item(), 'w', wB[r].item())
+print('rows with err > 1e-4*max:', int((e.max(1)[0] > 1e-4 * dpre_o.abs().max()).sum()), 'of', K + N)
+bad = (e.max(1)[0] > 1e-4 * dpre_o.abs().max()).nonzero().flatten().tolist()
+y8_o = compact_val(F.relu(pre8.detach()))
+for r in bad:
+    c = int(e[r].argmax())
+    v = r - K if r >= K else int(reg('row_vox', torch.int32, (1, cap))[0, r])
+    r0, n = int(row0[v]), int(cntc[v])
+    print(f'row {r} col {c} voxel {v} cnt {n}: GPU y real {Yc[r0:r0+n, c].tolist()} pad {Yc[K+v, c].item():.9g} | oracle y real {y8_o[r0:r0+n, c].tolist()} pad {y8_o[K+v, c].item():.9g}')
