@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(MapSet m, int capA, co
 // compact position (one contiguous 3 KB row per CTA step).
 constexpr int kCombCout = 768;
 constexpr int kCombWarps = 6;        // one warp per 128 output columns (one float4 per lane)
-constexpr int kCombRows = 128;       // sorted rows per CTA (<= threads per CTA)
+constexpr int kCombRows = 256;       // sorted rows per CTA
 
 struct CellRef {
     int i0, i1;
@@ -276,97 +276,107 @@ __global__ void __launch_bounds__(256) combine_scatter_kernel(CombineArgs a) {
     a.perm[(size_t)f * a.capA + pos] = r;
 }
 
+// per-row, per-level sampling record, computed once per row by one thread (the six column warps only read it)
+struct CombRec {
+    int cell;        // x0 | y0 << 12 | dx << 24 | dy << 25 : clamped corner coordinates; also the cache tag
+    float w[4];      // w00, w10, w01, w11 (0 where the corner lies on the zero pad row/column of Pipe.py:47-48)
+};
+
 __global__ void __launch_bounds__(kCombWarps * 32) combine_rows_kernel(CombineArgs a) {
-    __shared__ double s_sum[kCombCout * 2];
+    __shared__ int s_row[kCombRows];                     // compact row; ~row for rows without corners
+    __shared__ float s_w[kCombRows];                     // BatchNorm multiplicity
+    __shared__ CombRec s_rec[kCombRows][MVX_NUM_LEVELS];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = a.counts[f * 4 + 1];
     const int p0 = blockIdx.x * kCombRows;
     if (p0 > K) return;
-    for (int i = tid; i < kCombCout * 2; i += kCombWarps * 32) s_sum[i] = 0.0;
+    const int pend = min(p0 + kCombRows, K + 1);
+    // stage this CTA's rows: sorted position -> row, weights and corner coordinates of the three levels. One parallel
+    // round of gathers and ONE evaluation of the index math per row, instead of one per column warp.
+    for (int i = tid; i < pend - p0; i += kCombWarps * 32) {
+        const int r = a.perm[(size_t)f * a.capA + p0 + i];
+        const size_t ro = (size_t)f * a.capA + r;
+        const float4 xyz = __ldg(reinterpret_cast<const float4 *>(a.vox8 + ro * 8));
+        const bool none = r >= K || (xyz.x == 0.f && xyz.y == 0.f && xyz.z == 0.f);  // pad row / origin point: A1 row is zero
+        s_row[i] = none ? ~r : r;
+        s_w[i] = __ldg(a.row_w + ro);
+        const float2 pr = __ldg(reinterpret_cast<const float2 *>(a.proj) + ro);
+#pragma unroll
+        for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+            const CellRef c = cell_of(pr.x, pr.y, a.rs_h[l], a.rs_w[l], a.eps);
+            const int H = a.h[l], W = a.w[l];
+            const bool r0 = c.i0 >= 0 && c.i0 < H, r1 = c.i0 + 1 >= 0 && c.i0 + 1 < H;
+            const bool c0 = c.i1 >= 0 && c.i1 < W, c1 = c.i1 + 1 >= 0 && c.i1 + 1 < W;
+            const float wa_ = __fsub_rn(1.0f, c.wa), wb_ = __fsub_rn(1.0f, c.wb);
+            CombRec rec;
+            rec.w[0] = (r0 && c0) ? c.wa * c.wb : 0.f, rec.w[1] = (r1 && c0) ? wa_ * c.wb : 0.f;
+            rec.w[2] = (r0 && c1) ? c.wa * wb_ : 0.f, rec.w[3] = (r1 && c1) ? wa_ * wb_ : 0.f;
+            const int y0 = min(max(c.i0, 0), H - 1), y1 = min(max(c.i0 + 1, 0), H - 1);
+            const int x0 = min(max(c.i1, 0), W - 1), x1 = min(max(c.i1 + 1, 0), W - 1);
+            rec.cell = x0 | (y0 << 12) | ((x1 - x0) << 24) | ((y1 - y0) << 25);
+            s_rec[i][l] = rec;
+        }
+    }
     __syncthreads();
     const int col0 = warp * 128 + lane * 4;
     const float4 bias = __ldg(reinterpret_cast<const float4 *>(a.bias + col0));
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 ps = z4, pss = z4;
+    float4 ps = z4, pss = z4;                  // fp32 column sums over runs of 16 rows
+    double ds[4] = {0, 0, 0, 0}, dss[4] = {0, 0, 0, 0};   // this lane owns its 4 columns within the CTA: fp64 in registers
     float4 v00[MVX_NUM_LEVELS], v10[MVX_NUM_LEVELS], v01[MVX_NUM_LEVELS], v11[MVX_NUM_LEVELS];
-    int ci0[MVX_NUM_LEVELS], ci1[MVX_NUM_LEVELS];
+    int tag[MVX_NUM_LEVELS];
 #pragma unroll
-    for (int l = 0; l < MVX_NUM_LEVELS; ++l) ci0[l] = ci1[l] = INT_MIN, v00[l] = v10[l] = v01[l] = v11[l] = z4;
-    auto flush = [&]() {
-        atomicAdd(&s_sum[(col0 + 0) * 2], (double)ps.x), atomicAdd(&s_sum[(col0 + 0) * 2 + 1], (double)pss.x);
-        atomicAdd(&s_sum[(col0 + 1) * 2], (double)ps.y), atomicAdd(&s_sum[(col0 + 1) * 2 + 1], (double)pss.y);
-        atomicAdd(&s_sum[(col0 + 2) * 2], (double)ps.z), atomicAdd(&s_sum[(col0 + 2) * 2 + 1], (double)pss.z);
-        atomicAdd(&s_sum[(col0 + 3) * 2], (double)ps.w), atomicAdd(&s_sum[(col0 + 3) * 2 + 1], (double)pss.w);
+    for (int l = 0; l < MVX_NUM_LEVELS; ++l) tag[l] = -1, v00[l] = v10[l] = v01[l] = v11[l] = z4;
+    auto fold = [&]() {
+        ds[0] += (double)ps.x, ds[1] += (double)ps.y, ds[2] += (double)ps.z, ds[3] += (double)ps.w;
+        dss[0] += (double)pss.x, dss[1] += (double)pss.y, dss[2] += (double)pss.z, dss[3] += (double)pss.w;
         ps = z4, pss = z4;
     };
-    const int pend = min(p0 + kCombRows, K + 1);
-    // stage this CTA's row list (sorted position -> row, projection, BN multiplicity) in shared memory with one
-    // parallel round of gathers, so the row loop has no dependent global-load chain besides the corner re-loads
-    __shared__ int s_row[kCombRows];
-    __shared__ float2 s_proj[kCombRows];
-    __shared__ float s_w[kCombRows];
-    if (tid < pend - p0) {
-        const int r = a.perm[(size_t)f * a.capA + p0 + tid];
-        const size_t ro = (size_t)f * a.capA + r;
-        const float4 xyz = __ldg(reinterpret_cast<const float4 *>(a.vox8 + ro * 8));
-        const bool none = r >= K || (xyz.x == 0.f && xyz.y == 0.f && xyz.z == 0.f);  // pad row / origin point: A1 row is zero
-        s_row[tid] = none ? ~r : r;
-        s_proj[tid] = __ldg(reinterpret_cast<const float2 *>(a.proj) + ro);
-        s_w[tid] = __ldg(a.row_w + ro);
-    }
-    __syncthreads();
     for (int p = p0; p < pend; ++p) {
-        const int rr = s_row[p - p0];
+        const int i = p - p0;
+        const int rr = s_row[i];
         const int r = rr < 0 ? ~rr : rr;
-        const float2 pr = s_proj[p - p0];
-        const size_t ro = (size_t)f * a.capA + r;
         float4 acc = bias;
         if (rr >= 0) {
 #pragma unroll
             for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
-                const CellRef c = cell_of(pr.x, pr.y, a.rs_h[l], a.rs_w[l], a.eps);
-                const int H = a.h[l], W = a.w[l];
-                if (c.i0 != ci0[l] || c.i1 != ci1[l]) {  // warp-uniform: this level's cell changed, fetch its 4 corners
-                    ci0[l] = c.i0, ci1[l] = c.i1;
-                    const bool r0 = c.i0 >= 0 && c.i0 < H, r1 = c.i0 + 1 >= 0 && c.i0 + 1 < H;
-                    const bool c0 = c.i1 >= 0 && c.i1 < W, c1 = c.i1 + 1 >= 0 && c.i1 + 1 < W;
-                    const float *base = a.Z[l] + (size_t)f * a.frame_stride[l] + col0;
-                    // corners on the zero pad row/column of Pipe.py:47-48 read as zero
-                    v00[l] = (r0 && c0) ? __ldg(reinterpret_cast<const float4 *>(base + ((size_t)c.i0 * W + c.i1) * kCombCout)) : z4;
-                    v10[l] = (r1 && c0) ? __ldg(reinterpret_cast<const float4 *>(base + ((size_t)(c.i0 + 1) * W + c.i1) * kCombCout)) : z4;
-                    v01[l] = (r0 && c1) ? __ldg(reinterpret_cast<const float4 *>(base + ((size_t)c.i0 * W + c.i1 + 1) * kCombCout)) : z4;
-                    v11[l] = (r1 && c1) ? __ldg(reinterpret_cast<const float4 *>(base + ((size_t)(c.i0 + 1) * W + c.i1 + 1) * kCombCout)) : z4;
+                const CombRec rec = s_rec[i][l];
+                if (rec.cell != tag[l]) {  // warp-uniform: this level's cell changed, fetch its 4 corner vectors
+                    tag[l] = rec.cell;
+                    const int W = a.w[l];
+                    const int x0 = rec.cell & 0xFFF, y0 = (rec.cell >> 12) & 0xFFF, dx = (rec.cell >> 24) & 1, dy = (rec.cell >> 25) & 1;
+                    const float *b00 = a.Z[l] + (size_t)f * a.frame_stride[l] + ((size_t)y0 * W + x0) * kCombCout + col0;
+                    v00[l] = __ldg(reinterpret_cast<const float4 *>(b00));
+                    v10[l] = __ldg(reinterpret_cast<const float4 *>(b00 + (size_t)dy * W * kCombCout));
+                    v01[l] = __ldg(reinterpret_cast<const float4 *>(b00 + (size_t)dx * kCombCout));
+                    v11[l] = __ldg(reinterpret_cast<const float4 *>(b00 + ((size_t)dy * W + dx) * kCombCout));
                 }
-                const float wa_ = __fsub_rn(1.0f, c.wa), wb_ = __fsub_rn(1.0f, c.wb);
-                const float w00 = c.wa * c.wb, w10 = wa_ * c.wb, w01 = c.wa * wb_, w11 = wa_ * wb_;
-#define MVX_COMB(e) acc.e = fmaf(v11[l].e, w11, fmaf(v01[l].e, w01, fmaf(v10[l].e, w10, fmaf(v00[l].e, w00, acc.e))));
+#define MVX_COMB(e) acc.e = fmaf(v11[l].e, rec.w[3], fmaf(v01[l].e, rec.w[2], fmaf(v10[l].e, rec.w[1], fmaf(v00[l].e, rec.w[0], acc.e))));
                 MVX_COMB(x) MVX_COMB(y) MVX_COMB(z) MVX_COMB(w)
 #undef MVX_COMB
             }
         }
         float4 y;
         y.x = fmaxf(acc.x, 0.f), y.y = fmaxf(acc.y, 0.f), y.z = fmaxf(acc.z, 0.f), y.w = fmaxf(acc.w, 0.f);
-        *reinterpret_cast<float4 *>(a.Y1 + ro * kCombCout + col0) = y;
-        const float w = s_w[p - p0];
+        *reinterpret_cast<float4 *>(a.Y1 + ((size_t)f * a.capA + r) * kCombCout + col0) = y;
+        const float w = s_w[i];
         if (w == 1.f) {
             ps.x += y.x, ps.y += y.y, ps.z += y.z, ps.w += y.w;
             pss.x = fmaf(y.x, y.x, pss.x), pss.y = fmaf(y.y, y.y, pss.y);
             pss.z = fmaf(y.z, y.z, pss.z), pss.w = fmaf(y.w, y.w, pss.w);
         } else if (w != 0.f) {   // the weighted pad row: exact fp64 side path
             const double wd = (double)w;
-            atomicAdd(&s_sum[(col0 + 0) * 2], wd * y.x), atomicAdd(&s_sum[(col0 + 0) * 2 + 1], wd * y.x * y.x);
-            atomicAdd(&s_sum[(col0 + 1) * 2], wd * y.y), atomicAdd(&s_sum[(col0 + 1) * 2 + 1], wd * y.y * y.y);
-            atomicAdd(&s_sum[(col0 + 2) * 2], wd * y.z), atomicAdd(&s_sum[(col0 + 2) * 2 + 1], wd * y.z * y.z);
-            atomicAdd(&s_sum[(col0 + 3) * 2], wd * y.w), atomicAdd(&s_sum[(col0 + 3) * 2 + 1], wd * y.w * y.w);
+            ds[0] += wd * y.x, ds[1] += wd * y.y, ds[2] += wd * y.z, ds[3] += wd * y.w;
+            dss[0] += wd * y.x * y.x, dss[1] += wd * y.y * y.y, dss[2] += wd * y.z * y.z, dss[3] += wd * y.w * y.w;
         }
-        if (((p - p0) & 15) == 15) flush();
+        if ((i & 15) == 15) fold();
     }
-    flush();
-    __syncthreads();
-    double *o = a.out_stats + (size_t)f * kCombCout * 2;
-    for (int i = tid; i < kCombCout * 2; i += kCombWarps * 32) {
-        const double v = s_sum[i];
-        if (v != 0.0) atomicAdd(o + i, v);
+    fold();
+    double *o = a.out_stats + ((size_t)f * kCombCout + col0) * 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        atomicAdd(o + 2 * j, ds[j]);
+        atomicAdd(o + 2 * j + 1, dss[j]);
     }
 }
 
