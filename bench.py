@@ -315,6 +315,95 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ training workload
+def run_train(args):
+    """BASELINE.json configs[3]: training step through the fused VFE/fusion layers, 16 frames per GPU - forward_train,
+    CUDA backward into one flat gradient bucket, NCCL all-reduce of the bucket, AdamW. Not the headline metric (that is
+    the forward path above); run with `--workload train`."""
+    import torch
+    import torch.distributed as dist
+    from mvxnet_makise_b200 import synth, _lib
+    from mvxnet_makise_b200.training import HotPathTrainer
+    from mvxnet_makise_b200.modules import pack_calib
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', os.devnull)
+        dist.init_process_group('nccl', device_id=dev)
+    B = args.train_frames
+    frames = [synth.make_points(rank * B + f, POINTS) for f in range(B)]
+    offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in frames])]).tolist()
+    points = torch.from_numpy(np.concatenate(frames, 0)).to(dev)
+    calib = torch.stack([pack_calib(synth.kitti_calib()) for _ in range(B)]).to(dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    maps = [torch.randn((B, 256, h, w), generator=g, device=dev) for (h, w) in synth.fpn_shapes()]
+    tr = HotPathTrainer(synth.make_weights(0), synth.KITTI_GRID, device=dev)
+    cap = max(128, (POINTS + 127) // 128 * 128)
+    d_vfeat = torch.randn((B, cap, 128), generator=g, device=dev) * 1e-3      # stand-in for dLoss/d(voxel features) from CML/RPN
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        tr.step(points, offsets, calib, maps, d_vfeat=d_vfeat)
+    barrier()
+    launches0 = _lib.launch_count()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if sampler:
+        sampler.begin()
+    e0.record()
+    for s_ in range(args.steps):
+        ev[s_][0].record()
+        tr.path.forward_train(points, offsets, calib, maps, True)
+        ev[s_][1].record()
+        tr.path.backward(d_vfeat=d_vfeat, grad_flat=tr.grad)
+        ev[s_][2].record()
+        tr.opt.reduce_and_step(tr.grad, B)
+        tr._push_weights()
+        ev[s_][3].record()
+    e1.record()
+    barrier()
+    if sampler:
+        sampler.end()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    phases = [sum(ev[s_][i].elapsed_time(ev[s_][i + 1]) for s_ in range(args.steps)) / args.steps for i in range(3)]
+    launches = _lib.launch_count() - launches0
+    counts = tr.path.counts.cpu().numpy()
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    if rank == 0:
+        K = float(counts[:, 1].sum())
+        flops_fwd = 2.0 * 706816 * (K + B) + 2.0 * 18800 * (K + B + float(counts[:, 0].sum()))
+        line = dict(metric='frames/sec training step (forward + backward of the fused VFE/fusion layers, gradient all-reduce, AdamW)',
+                    value=world * B * args.steps / (ms_total * 1e-3), unit='frames/s', n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak',
+                    vs_baseline=None, dtype='f32', data='synthetic',
+                    config=dict(workload=f'configs[3]: training step, {B} synthetic KITTI-shaped frames per GPU (P={POINTS}), forward_train '
+                                         '(row-first fcn1, activations kept) + backward of the 8 hot-path layers into one flat fp32 bucket '
+                                         '(726 880 floats) + NCCL all-reduce of the bucket + AdamW; upstream gradient dLoss/d(voxel features) synthetic',
+                                frames_per_gpu=B, points_per_frame=POINTS, parallelism=f'frame-sharded x{world}; one all-reduce of 2.9 MB per step',
+                                l2='no flush: activations (A1/Y1: 5.9 GB each at 16 frames) exceed the 126 MB L2'),
+                    clocks=clocks, gpu_launches=int(launches),
+                    phases_ms=dict(forward_train=round(phases[0], 3), backward=round(phases[1], 3), allreduce_adamw=round(phases[2], 3)),
+                    algorithmic_tflops=dict(forward=round(flops_fwd / (phases[0] * 1e-3) / 1e12, 2),
+                                            backward=round((2.0 * flops_fwd - 2.0 * 768 * 768 * (K + B)) / (phases[1] * 1e-3) / 1e12, 2)))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -324,10 +413,14 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--host-streams', type=int, default=2, help='compute streams the sub-batches of the e2e leg alternate between')
     ap.add_argument('--fusion-mode', type=int, default=1, help='1 = pixel-first fcn1 (default), 0 = row-first (gather + row GEMM)')
-    ap.add_argument('--host-chunk', type=int, default=1, help='frames per sub-batch of the host-buffer (e2e) leg')
+    ap.add_argument('--workload', default='forward', choices=['forward', 'train'], help="'train' = BASELINE configs[3] (not the headline metric)")
+    ap.add_argument('--train-frames', type=int, default=16)
+    ap.add_argument('--host-chunk', type=int, default=2, help='frames per sub-batch of the host-buffer (e2e) leg')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'train':
+        run_train(args)
     else:
         run_ours(args)
 

@@ -243,13 +243,14 @@ class PointPath:
         for s_ in self._compute_streams:
             if s_ is not None:
                 s_.wait_stream(cur)
-        for j, c in enumerate(self._subs):
-            with torch.cuda.stream(cs):
+        with torch.cuda.stream(cs):              # every copy is queued up front: the copy engine never waits for the CPU
+            for c in self._subs:
                 c.in_points.copy_(points_host[c.p0:c.p1], non_blocking=True)
                 c.in_calib.copy_(calib32_host[c.f0:c.f1], non_blocking=True)
                 for d, h in zip(c.in_maps, maps_host):
                     d.copy_(h[c.f0:c.f1], non_blocking=True)
                 c.ev.record(cs)
+        for j, c in enumerate(self._subs):
             ks = self._compute_streams[j % ns] or cur
             with torch.cuda.stream(ks):
                 ks.wait_event(c.ev)

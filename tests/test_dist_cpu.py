@@ -74,3 +74,43 @@ def test_single_process_paths():
     b = mdist.GradBucket(lin.parameters())
     b.allreduce(global_frames=2)
     assert torch.allclose(lin.weight.grad, torch.full_like(lin.weight, 0.5)) and lin.bias.grad is not None
+
+
+def _opt_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    mdist.init('gloo')
+    from mvxnet_makise_b200.training import FlatAdamW
+    torch.manual_seed(0)
+    params = torch.randn(1000)
+    p0 = params.clone()
+    opt = FlatAdamW(params)
+    frames_per_rank = 3
+    for step in range(2):
+        g = torch.full((1000,), float(rank + 1 + step))      # this rank's bucket: sum over its 3 frames
+        opt.reduce_and_step(g, frames_per_rank)
+    q.put((rank, p0, params.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_adamw_allreduce_gloo():
+    """The training step's exchange: ONE all-reduce of the flat gradient bucket, averaged over the global frame count,
+    then AdamW on the flat parameter vector - identical parameters on every rank, equal to torch.optim.AdamW fed the
+    averaged gradient."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_opt_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert torch.equal(res[0][2], res[1][2])
+    ref = torch.nn.Parameter(res[0][1].clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, eps=1e-6)
+    for step in range(2):
+        ref.grad = torch.full((1000,), ((1 + step) + (2 + step)) / 6.0)     # (rank0 + rank1 buckets) / 6 global frames
+        opt.step()
+    assert torch.allclose(res[0][2], ref.detach(), rtol=1e-6, atol=1e-7)
