@@ -11,7 +11,7 @@ namespace {
 
 // ---- NCHW -> NHWC ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int C,
-                                                           int HW) {
+                                                           int HW, int *__restrict__ rowmax) {
     __shared__ float tile[32][33];
     const size_t fb = (size_t)blockIdx.z * C * HW;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -26,6 +26,12 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restri
     for (int k = 0; k < 4; ++k) {
         const int p = p0 + ty + k * 8, c = c0 + tx;
         if (c < C && p < HW) out[fb + (size_t)p * C + c] = tile[tx][ty + k * 8];
+    }
+    if (rowmax && threadIdx.x < 32 && p0 + tx < HW) {   // max |x| of each pixel row (as float bits), for the fp16 row scaling of the pixel GEMM
+        float m = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) m = fmaxf(m, fabsf(tile[c][tx]));
+        atomicMax(rowmax + (size_t)blockIdx.z * HW + p0 + tx, __float_as_int(m));
     }
 }
 
@@ -398,9 +404,10 @@ int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st) {
     return MVX_OK;
 }
 
-int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, cudaStream_t st) {
+int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, float *rowmax, cudaStream_t st) {
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
-    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(in, out, C, HW);
+    if (rowmax) MVX_CUDA_CHECK(cudaMemsetAsync(rowmax, 0, (size_t)B * HW * sizeof(float), st));
+    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(in, out, C, HW, reinterpret_cast<int *>(rowmax));
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }
@@ -460,7 +467,7 @@ extern "C" int mvx_feature_mapping(float *voxels, int64_t R, const float *const 
         m.rs_w[l] = imsize_w / (float)map_w[l];
         m.nhwc[l] = ws;
         m.frame_stride[l] = 0;
-        int rc = mvx::launch_nchw_to_nhwc(maps[l], ws, 1, C, map_h[l] * map_w[l], st);
+        int rc = mvx::launch_nchw_to_nhwc(maps[l], ws, 1, C, map_h[l] * map_w[l], nullptr, st);
         if (rc) return rc;
         ws += (size_t)map_h[l] * map_w[l] * C;
     }

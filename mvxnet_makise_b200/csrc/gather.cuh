@@ -13,7 +13,8 @@ struct MapSet {
 };
 
 // NCHW (B,C,H,W) -> NHWC (B,H,W,C)
-int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, cudaStream_t st);
+// rowmax (optional): [B][HW] max |x| over the C channels of every pixel (float; zeroed and filled here)
+int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, float *rowmax, cudaStream_t st);
 
 struct RowsParams {
     int B, cap, capA, T;

@@ -412,6 +412,7 @@ static int g_gemm_mode = 1;
 int gemm_mode() { return g_gemm_mode; }
 
 static int g_tc_pair = 0;
+static int g_dense_f16 = 0;
 
 int launch_layer_auto(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     if (g_gemm_mode == 1 && wpack) {
@@ -456,13 +457,16 @@ static int dense_layer(const float *x, int64_t R, int32_t T, int32_t Cin, const 
     a.X = x, a.ldx = Cin, a.Cin = Cin, a.Wt = wt, a.bias = bias, a.Cout = Cout, a.Y = y, a.ldy = ldy;
     a.out_stats = stats, a.vmax = vmax, a.rows_mode = 0, a.rows_fixed = R, a.rowcap = 0, a.vcap = 0, a.T = T > 0 ? T : 1;
     a.eps = eps;
+    a.f16_ok = g_dense_f16;   // arbitrary caller data: 3xTF32 unless mode 5 promises O(1) inputs
     return launch_layer_auto(a, 1, wpack, st);
 }
 
 }  // namespace mvx
 
 extern "C" int mvx_set_gemm_mode(int32_t mode) {
-    if (mode < 0 || mode > 3) return MVX_EINVAL;   // 3 = tensor cores, CTA-pair (cta_group::2) persistent kernel   // 2 = tensor cores, persistent 256x128 variant (measured slower: SS-mode
+    if (mode < 0 || mode > 5) return MVX_EINVAL;   // 4 = tensor cores, 3xTF32 everywhere (no fp16 operands)
+    mvx::set_tc_f16(mode != 4);                    // 5 = like 1, and the dense layer API (mvx_fcn_forward ...) also uses fp16
+    mvx::g_dense_f16 = mode == 5;                  //     operands: the caller promises inputs of O(1) magnitude (tests)   // 3 = tensor cores, CTA-pair (cta_group::2) persistent kernel   // 2 = tensor cores, persistent 256x128 variant (measured slower: SS-mode
     mvx::g_gemm_mode = mode == 0 ? 0 : 1;          //     MMAs at N=128 saturate shared-memory bandwidth); kept for experiments
     mvx::set_tc_persistent(mode == 2);
     mvx::g_tc_pair = mode == 3;

@@ -27,6 +27,9 @@ struct LayerArgs {
     int rowcap, vcap, T;
     double eps;
     int dbg;                 // experiments only (0 in production): bit 0 = skip the producer proxy fence
+    int f16_ok;              // 1: the tensor-core kernel may use fp16 operands (3xFP16): inputs are BatchNorm-ed (in_stats, or
+                             // stored normalised) or row_max is given; 0 keeps 3xTF32 (arbitrary input range)
+    const float *row_max;    // [F][rowcap] max|x| of each input row for the fp16 row scaling, or NULL (scale 1)
     int plain;               // 1: Y = norm_in(X) W^T only (no bias, no ReLU, no statistics, no max) - the per-pixel half of fcn1
 };
 int launch_layer(const LayerArgs &a, int F, cudaStream_t st);            // exact-fp32 SIMT kernel
@@ -39,6 +42,8 @@ int launch_layer_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
 bool tc2_layer_eligible(const LayerArgs &a);
 int launch_layer_tc2(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
 bool tc_persistent_enabled();
+bool tc_f16_enabled();
+void set_tc_f16(int on);   // 1 (default): 3xFP16 where LayerArgs::f16_ok, 0: 3xTF32 everywhere
 void set_tc_persistent(int on);  // 0 = one 256 x BN tile per CTA (default), 1 = persistent 256 x 128 kernel with overlapped epilogue
 // dispatch by mvx_set_gemm_mode(): 0 = SIMT everywhere, 1 = tensor cores where eligible (default)
 int gemm_mode();

@@ -19,7 +19,7 @@ namespace mvx {
 const char *kRegionNames[R_COUNT] = {
     "vox_ws", "vox_coord", "vox_cnt", "vox_row0", "row_point", "row_vox", "cell2vid", "nhwc0", "nhwc1", "nhwc2",
     "vox8", "proj", "rowA_w", "A1", "Y1", "Y2", "Y3", "Y4", "Y5", "X6", "Y6", "X7", "Y7", "rowB_w", "rowB_v", "X8",
-    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t", "Z", "bin_count", "bin_start", "perm", "Y8"};
+    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t", "Z", "bin_count", "bin_start", "perm", "rowmax", "Y8"};
 
 // 1 (default): pixel-first fcn1 - one tensor-core GEMM per FPN level over the map pixels, then a 12-corner combine per
 // point row (gather.cuh CombineArgs); 0: materialise the gathered (K,768) matrix A1 and run fcn1 over the point rows
@@ -86,6 +86,7 @@ int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
         take(R_BINCNT, B * (nb + 1) * 4);
         take(R_BINSTART, B * (nb + 2) * 4);
         take(R_PERM, B * capA * 4);
+        take(R_ROWMAX, B * px * 4);
     }
     L.total = o;
     take(R_Y8, B * capB * 128 * 4);   // last region: only present in a training workspace
@@ -164,6 +165,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     // ---- stage 2 ----------------------------------------------------------------------------------------
     MapSet m{};
     m.C = a->map_c;
+    size_t rowmax_off = 0;
     for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
         const int HW = a->map_h[l] * a->map_w[l];
         m.h[l] = a->map_h[l], m.w[l] = a->map_w[l];
@@ -171,8 +173,9 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         m.rs_w[l] = a->imsize_w / (float)a->map_w[l];
         m.nhwc[l] = F32((Region)(R_NHWC0 + l));
         m.frame_stride[l] = (size_t)HW * a->map_c;
-        rc = launch_nchw_to_nhwc(a->maps[l], F32((Region)(R_NHWC0 + l)), B, a->map_c, HW, st);
+        rc = launch_nchw_to_nhwc(a->maps[l], F32((Region)(R_NHWC0 + l)), B, a->map_c, HW, F32(R_ROWMAX) + rowmax_off, st);
         if (rc) return rc;
+        rowmax_off += (size_t)B * HW;
     }
     stamp.mark(S_ROWS);
     RowsParams rp{};
@@ -203,6 +206,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
             la.Wt = a->wt[0] + (size_t)l * a->map_c * 768, la.bias = nullptr, la.Cout = 768;
             la.Y = F32(R_Z) + zoff, la.ldy = 768;
             la.rows_fixed = px, la.rows_mode = 0, la.rowcap = 0, la.T = 1, la.eps = a->bn_eps, la.plain = 1;
+            la.f16_ok = 1, la.row_max = F32(R_ROWMAX) + zoff / 768;   // raw FPN features: per-pixel power-of-two scaling
             rc = launch_layer_auto(la, 1, F32(R_WPACK), st);
             if (rc) return rc;
             zoff += (size_t)px * 768;
@@ -242,6 +246,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         la.out_stats = stat_of(l);
         la.row_w = F32(R_ROWA_W), la.counts = a->counts, la.rows_mode = 1, la.rowcap = L.capA, la.vcap = cap, la.T = T;
         la.eps = a->bn_eps;
+        la.f16_ok = l > 0;   // BatchNorm-ed inputs; fcn1 row-first reads raw features of arbitrary range: 3xTF32
         rc = launch_layer_auto(la, B, F32(R_WPACK), st);
         if (rc) return rc;
     }
@@ -294,6 +299,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         la.Y = train ? F32(R_Y8) : nullptr, la.ldy = train ? 128 : 0, la.out_stats = stat_of(7), la.vmax = I32(R_VMAX8);
         la.row_w = F32(R_ROWB_W), la.row_v = I32(R_ROWB_V), la.rowv_cap = L.capB, la.counts = a->counts, la.rows_mode = 2;
         la.rowcap = L.capB, la.vcap = cap, la.T = T, la.eps = a->bn_eps;
+        la.f16_ok = 1;       // X8 is stored BatchNorm-ed
         rc = launch_layer_auto(la, B, F32(R_WPACK), st);
         if (rc) return rc;
     }

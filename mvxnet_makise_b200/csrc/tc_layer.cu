@@ -20,6 +20,8 @@
 #include "layers.cuh"
 #include "tc_common.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 namespace mvx {
@@ -47,7 +49,9 @@ struct Smem {
     static constexpr int kBias = kRstd + 768 * 4;
     static constexpr int kRowW = kBias + BN * 4;
     static constexpr int kRowV = kRowW + kTM * 4;      // voxel id of each row (per-voxel max), -1 = none
-    static constexpr int kBars = kRowV + kTM * 4;      // full[3], empty[3], accum
+    static constexpr int kRowInv = kRowV + kTM * 4;    // fp16 variant: inverse row scales
+    static constexpr int kColInv = kRowInv + kTM * 4;  // fp16 variant: inverse column scales
+    static constexpr int kBars = kColInv + BN * 4;     // full[3], empty[3], accum
     static constexpr int kTmemPtr = kBars + 8 * 8;
     static constexpr int kTotal = kTmemPtr + 16 + 1024;  // + slack for the 1024-byte alignment of the base
 };
@@ -67,9 +71,77 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
     out[blob + BN * kBK + off] = lo;
 }
 
+// ---- fp16 operand variant ("3xFP16") ---------------------------------------------------------------------------
+// Same three-product split, but hi/lo are IEEE fp16 (11 significant bits, like TF32) fed to kind::f16 MMAs, which run
+// at twice the TF32 rate and read half the shared-memory bytes per MAC. fp16 has a 5-bit exponent, so operands are
+// first scaled by an exact power of two: every weight column (output channel) by 2^-e with max|w| in [0.5,1), activation
+// rows by a per-row power of two when the caller supplies row maxima (raw FPN features) and by 1 for BatchNorm-ed
+// inputs (|z| <= sqrt(R) << 65504). The epilogue multiplies the accumulator by the inverse scales (exact). With hi =
+// rn16(x) and lo = rn16(x - hi) the representation error is max(2^-23 |x|, 2^-25) per element (lo may be subnormal),
+// i.e. fp32-level relative to the row scale; products of two fp16 values are exact in the fp32 accumulator.
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a, high half = b
+    return r;
+}
+__device__ __forceinline__ void split_f16_pair(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    hi = pack_half2(x0, x1);
+    const __half2 h = *reinterpret_cast<const __half2 *>(&hi);
+    const float2 hf = __half22float2(h);
+    lo = pack_half2(x0 - hf.x, x1 - hf.y);
+}
+// power of two s with max * s in [0.5, 1) (1 when max is 0 or not finite)
+__device__ __forceinline__ float pow2_scale(float mx) {
+    if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
+    int e;
+    frexpf(mx, &e);            // mx = m * 2^e, m in [0.5, 1)
+    e = max(-100, min(100, e));
+    return exp2f((float)-e);
+}
+
+// W^T (Cin, Cout) -> per (column tile, 32-k chunk) the shared-memory image [hi | lo] in fp16, columns pre-scaled;
+// colinv[n] = 1 / scale_n. One CTA per output column.
 template <int BN>
+__global__ void __launch_bounds__(256) pack_weights_f16_kernel(const float *__restrict__ Wt, int Cin, int Cout, uint8_t *__restrict__ out,
+                                                               float *__restrict__ colinv) {
+    __shared__ float s_max[256];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    float mx = 0.f;
+    for (int k = tid; k < Cin; k += 256) mx = fmaxf(mx, fabsf(Wt[(size_t)k * Cout + n]));
+    s_max[tid] = mx;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) s_max[tid] = fmaxf(s_max[tid], s_max[tid + s]);
+        __syncthreads();
+    }
+    const float sc = pow2_scale(s_max[0]);
+    if (tid == 0) colinv[n] = 1.f / sc;
+    const int ct = n / BN, nl = n - ct * BN;
+    for (int k = tid; k < Cin; k += 256) {
+        const int kc = k >> 5, kl = k & 31;
+        const float v = Wt[(size_t)k * Cout + n] * sc;
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn(v - __half2float(h));
+        const size_t blob = ((size_t)ct * (Cin / 32) + kc) * (2 * BN * 64);  // bytes
+        const uint32_t off = sw64_offset(nl, kl >> 3) + (kl & 7) * 2;
+        *reinterpret_cast<__half *>(out + blob + off) = h;
+        *reinterpret_cast<__half *>(out + blob + BN * 64 + off) = l;
+    }
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int BN, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, const float *__restrict__ wpack) {
     using S = Smem<BN>;
+    constexpr int KB = F16 ? 32 : kBK;   // k per pipeline stage: one 64-byte swizzle row of fp16 / tf32
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // keep the pointer in the shared address space (pointer arithmetic only, no integer round trip): STS/LDS, not ST.E/LD.E
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -97,7 +169,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
     }
     const long long row0 = (long long)blockIdx.y * kTM;  // column tiles of one row tile are launch-adjacent: A hits L2
     if (row0 >= n_rows) return;  // uniform for the CTA, before any barrier / TMEM allocation
-    const int nk = a.Cin / kBK;
+    const int nk = a.Cin / KB;
+    float *s_rowinv = reinterpret_cast<float *>(smem + S::kRowInv);   // F16: 1 / (power-of-two scale of each row)
+    float *s_colinv = reinterpret_cast<float *>(smem + S::kColInv);   // F16: 1 / (power-of-two scale of each output column)
 
     // ---- one-time setup ------------------------------------------------------------------------------------
     if (a.in_stats) {
@@ -111,6 +185,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         }
     }
     for (int c = tid; c < BN; c += kThreads) s_bias[c] = a.plain ? 0.f : a.bias[n0 + c];
+    if constexpr (F16) {
+        const float *colinv = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(wpack) + (size_t)a.Cin * a.Cout * 4);
+        for (int c = tid; c < BN; c += kThreads) s_colinv[c] = colinv[n0 + c];
+        for (int r = tid; r < kTM; r += kThreads) {
+            const long long rr = row0 + r;
+            s_rowinv[r] = (a.row_max && rr < n_rows) ? 1.f / pow2_scale(a.row_max[(size_t)f * a.rowcap + rr]) : 1.f;
+        }
+    }
     for (int r = tid; r < kTM; r += kThreads) {
         const long long rr = row0 + r;
         const float w = rr < n_rows ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + rr] : 1.f) : 0.f;
@@ -142,6 +224,72 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
 
     const bool mma_only = (a.dbg & 8) != 0;
     if (mma_only && warp != 9) {
+    } else if (warp < 8 && F16) {
+        // ================= A producers, fp16 operands: a thread owns 8 k (one 16-byte chunk of fp16) of 4 rows ======
+        const int c = tid & 3, rsub = tid >> 2;
+        const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx + c * 8;
+        bool valid[4];
+        float rs[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            valid[i] = row0 + rsub + 64 * i < n_rows;
+            rs[i] = 1.f / s_rowinv[rsub + 64 * i];   // power of two: exact
+        }
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load_chunk = [&](float4 (&buf)[8], int kc) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 *p = reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + kc * KB);
+                buf[2 * i] = valid[i] ? __ldg(p) : z4;
+                buf[2 * i + 1] = valid[i] ? __ldg(p + 1) : z4;
+            }
+        };
+        auto produce = [&](float4 (&buf)[8], int kc) {
+            float4 cur[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = buf[i];
+            if (a.in_stats) {
+                const int k = kc * KB + c * 8;
+                const float4 m0 = *reinterpret_cast<const float4 *>(s_mean + k), m1 = *reinterpret_cast<const float4 *>(s_mean + k + 4);
+                const float4 r0 = *reinterpret_cast<const float4 *>(s_rstd + k), r1 = *reinterpret_cast<const float4 *>(s_rstd + k + 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (valid[i]) {
+                        cur[2 * i].x = (cur[2 * i].x - m0.x) * r0.x, cur[2 * i].y = (cur[2 * i].y - m0.y) * r0.y;
+                        cur[2 * i].z = (cur[2 * i].z - m0.z) * r0.z, cur[2 * i].w = (cur[2 * i].w - m0.w) * r0.w;
+                        cur[2 * i + 1].x = (cur[2 * i + 1].x - m1.x) * r1.x, cur[2 * i + 1].y = (cur[2 * i + 1].y - m1.y) * r1.y;
+                        cur[2 * i + 1].z = (cur[2 * i + 1].z - m1.z) * r1.z, cur[2 * i + 1].w = (cur[2 * i + 1].w - m1.w) * r1.w;
+                    }
+                }
+            }
+            if (kc + 2 < nk) load_chunk(buf, kc + 2);
+            const int s = kc % kStages;
+            const uint32_t ph = (kc / kStages) & 1;
+            if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);
+            __syncwarp();
+            uint8_t *stage = smem + (size_t)s * S::kStage;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float sc = rs[i];
+                uint4 hi, lo;
+                split_f16_pair(cur[2 * i].x * sc, cur[2 * i].y * sc, hi.x, lo.x);
+                split_f16_pair(cur[2 * i].z * sc, cur[2 * i].w * sc, hi.y, lo.y);
+                split_f16_pair(cur[2 * i + 1].x * sc, cur[2 * i + 1].y * sc, hi.z, lo.z);
+                split_f16_pair(cur[2 * i + 1].z * sc, cur[2 * i + 1].w * sc, hi.w, lo.w);
+                const uint32_t off = sw64_offset(rsub + 64 * i, c);
+                *reinterpret_cast<uint4 *>(stage + off) = hi;
+                *reinterpret_cast<uint4 *>(stage + S::kAHalf + off) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(full_bar(s));
+        };
+        float4 buf0[8], buf1[8];
+        load_chunk(buf0, 0);
+        if (nk > 1) load_chunk(buf1, 1);
+        for (int kc = 0; kc < nk; kc += 2) {
+            produce(buf0, kc);
+            if (kc + 1 < nk) produce(buf1, kc + 1);
+        }
     } else if (warp < 8) {
         // ================= A producers ===========================================================================
         const int c = tid & 3, rsub = tid >> 2;  // 16-byte chunk of the 64-byte k-chunk row; rows rsub + 64*i
@@ -216,8 +364,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
     } else {
         // ================= MMA issuer (one thread) ================================================================
         if (lane == 0) {
-            // D fp32, A/B TF32, K-major both, N = BN, M = 128
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+            // D fp32, A/B TF32 (format 2) or F16 (format 0), K-major both, N = BN, M = 128
+            constexpr uint32_t fmt = F16 ? 0u : 2u;
+            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % kStages;
                 const uint32_t ph = (kc / kStages) & 1;
@@ -229,12 +378,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
                     const uint32_t d = tmem_base + h * BN;
                     const uint32_t aoff = h * (128 * 64);
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {   // two K=8 steps per 16-k chunk: +32 bytes inside the swizzle atom
+                    for (int ks = 0; ks < 2; ++ks) {   // two MMA K-steps (8 tf32 / 16 fp16 = 32 bytes) per stage row: +32 bytes inside the swizzle atom
                         const uint64_t a_hi = make_desc(sA + aoff + ks * 32), a_lo = make_desc(sA + S::kAHalf + aoff + ks * 32);
                         const uint64_t b_hi = make_desc(sB + ks * 32), b_lo = make_desc(sB + S::kBHalf + ks * 32);
-                        mma_tf32(d, a_lo, b_hi, idesc, (kc | ks) != 0);
-                        mma_tf32(d, a_hi, b_lo, idesc, 1);
-                        mma_tf32(d, a_hi, b_hi, idesc, 1);
+                        if constexpr (F16) {
+                            mma_f16(d, a_lo, b_hi, idesc, (kc | ks) != 0);
+                            mma_f16(d, a_hi, b_lo, idesc, 1);
+                            mma_f16(d, a_hi, b_hi, idesc, 1);
+                        } else {
+                            mma_tf32(d, a_lo, b_hi, idesc, (kc | ks) != 0);
+                            mma_tf32(d, a_hi, b_lo, idesc, 1);
+                            mma_tf32(d, a_hi, b_hi, idesc, 1);
+                        }
                     }
                 }
                 mma_commit(empty_bar(s));  // frees the stage when the MMAs above have read it
@@ -257,11 +412,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         if (warp < 8) {
             const int rloc = half * 128 + q * 32 + lane;
             float *yrow = ytile + (size_t)rloc * kEpiLd;
+            const float rinv = F16 ? s_rowinv[rloc] : 1.f;
 #pragma unroll 1
             for (int cb = 0; cb < kEpiCols / 32; ++cb) {
                 float v[32];
                 const int col = pass * kEpiCols + cb * 32;
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + half * BN + col, v);
+                if constexpr (F16) {   // undo the power-of-two operand scales (exact)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= rinv * s_colinv[col + j];
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 o;
@@ -337,20 +497,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
     }
 }
 
-template <int BN>
+template <int BN, bool F16>
 int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     using S = Smem<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         attr_set = true;
     }
     const int total = a.Cin * a.Cout;
-    pack_weights_kernel<BN><<<(total + 255) / 256, 256, 0, st>>>(a.Wt, a.Cin, a.Cout, wpack);
+    if (F16) {   // [fp16 hi|lo images: Cin*Cout*4 bytes][inverse column scales: Cout floats]
+        uint8_t *blob = reinterpret_cast<uint8_t *>(wpack);
+        pack_weights_f16_kernel<BN><<<a.Cout, 256, 0, st>>>(a.Wt, a.Cin, a.Cout, blob, reinterpret_cast<float *>(blob + (size_t)total * 4));
+    } else {
+        pack_weights_kernel<BN><<<(total + 255) / 256, 256, 0, st>>>(a.Wt, a.Cin, a.Cout, wpack);
+    }
     MVX_LAUNCH_CHECK();
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     dim3 grid(a.Cout / BN, (unsigned)ceil_div(max_rows, kTM), F);
-    tc_layer_kernel<BN><<<grid, kThreads, S::kTotal, st>>>(a, wpack);
+    tc_layer_kernel<BN, F16><<<grid, kThreads, S::kTotal, st>>>(a, wpack);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }
@@ -680,6 +845,10 @@ int launch_tc_persist(const LayerArgs &a, int F, float *wpack, cudaStream_t st) 
 
 }  // namespace
 
+static int g_tc_f16 = 1;
+bool tc_f16_enabled() { return g_tc_f16 != 0; }
+void set_tc_f16(int on) { g_tc_f16 = on; }
+
 static int g_tc_persistent = 0;
 bool tc_persistent_enabled() { return g_tc_persistent != 0; }
 void set_tc_persistent(int on) { g_tc_persistent = on; }
@@ -699,8 +868,12 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
     if (max_rows <= 0) return MVX_OK;
     if (a.vmax == nullptr && !a.plain && tc_persistent_enabled())  // persistent kernel: 256 x 128 tiles, double-buffered accumulators
         return launch_tc_persist<128>(a, F, wpack, st);
-    if (a.Cout % 256 == 0) return launch_tc<256>(a, F, wpack, st);
-    return launch_tc<128>(a, F, wpack, st);
+    if (a.f16_ok && tc_f16_enabled() && a.Cin % 32 == 0) {   // 3xFP16: half the tensor cycles and operand bytes of 3xTF32
+        if (a.Cout % 256 == 0) return launch_tc<256, true>(a, F, wpack, st);
+        return launch_tc<128, true>(a, F, wpack, st);
+    }
+    if (a.Cout % 256 == 0) return launch_tc<256, false>(a, F, wpack, st);
+    return launch_tc<128, false>(a, F, wpack, st);
 }
 
 }  // namespace mvx

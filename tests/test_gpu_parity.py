@@ -194,13 +194,16 @@ def test_tensor_core_layer_is_fp32_accurate(mvx, R, cin, cout):
             y_simt = fcn(x)
             _lib.set_gemm_mode(2)      # persistent variant, overlapped register epilogue
             y_tc2 = fcn(x)
-            _lib.set_gemm_mode(1)      # one 256 x BN tile per CTA (default)
+            _lib.set_gemm_mode(5)      # fp16 hi/lo operands (3xFP16), the default of the fused path's BatchNorm-ed layers
+            y_f16 = fcn(x)
+            _lib.set_gemm_mode(1)      # one 256 x BN tile per CTA (default), 3xTF32 for the dense API
             y_tc = fcn(x)
     finally:
         _lib.set_gemm_mode(1)
     y = torch.relu(x.double().reshape(-1, cin) @ fcn.fc.weight.double().t() + fcn.fc.bias.double())
     ref = (y - y.mean(0)) / torch.sqrt(y.var(0, unbiased=False) + 1e-6)
-    assert rel_err(y_tc, y_simt) < 2e-5 and rel_err(y_tc2, y_simt) < 2e-5
+    assert rel_err(y_tc, y_simt) < 2e-5 and rel_err(y_tc2, y_simt) < 2e-5 and rel_err(y_f16, y_simt) < 2e-5
+    assert rel_err(y_f16.reshape(-1, cout), ref) < 2e-5
     assert rel_err(y_tc.reshape(-1, cout), ref) < 2e-5 and rel_err(y_simt.reshape(-1, cout), ref) < 2e-5
 
 
