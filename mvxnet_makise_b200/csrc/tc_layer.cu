@@ -20,6 +20,7 @@
 #include "layers.cuh"
 #include "tc_common.cuh"
 
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -90,6 +91,11 @@ __device__ __forceinline__ void split_f16_pair(float x0, float x1, uint32_t &hi,
     const float2 hf = __half22float2(h);
     lo = pack_half2(x0 - hf.x, x1 - hf.y);
 }
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));  // low half = a, high half = b
+    return r;
+}
 // power of two s with max * s in [0.5, 1) (1 when max is 0 or not finite)
 __device__ __forceinline__ float pow2_scale(float mx) {
     if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
@@ -101,7 +107,7 @@ __device__ __forceinline__ float pow2_scale(float mx) {
 
 // W^T (Cin, Cout) -> per (column tile, 32-k chunk) the shared-memory image [hi | lo] in fp16, columns pre-scaled;
 // colinv[n] = 1 / scale_n. One CTA per output column.
-template <int BN>
+template <int BN, bool BF1>
 __global__ void __launch_bounds__(256) pack_weights_f16_kernel(const float *__restrict__ Wt, int Cin, int Cout, uint8_t *__restrict__ out,
                                                                float *__restrict__ colinv) {
     __shared__ float s_max[256];
@@ -114,18 +120,22 @@ __global__ void __launch_bounds__(256) pack_weights_f16_kernel(const float *__re
         if (tid < s) s_max[tid] = fmaxf(s_max[tid], s_max[tid + s]);
         __syncthreads();
     }
-    const float sc = pow2_scale(s_max[0]);
+    const float sc = BF1 ? 1.f : pow2_scale(s_max[0]);
     if (tid == 0) colinv[n] = 1.f / sc;
     const int ct = n / BN, nl = n - ct * BN;
     for (int k = tid; k < Cin; k += 256) {
         const int kc = k >> 5, kl = k & 31;
         const float v = Wt[(size_t)k * Cout + n] * sc;
-        const __half h = __float2half_rn(v);
-        const __half l = __float2half_rn(v - __half2float(h));
         const size_t blob = ((size_t)ct * (Cin / 32) + kc) * (2 * BN * 64);  // bytes
         const uint32_t off = sw64_offset(nl, kl >> 3) + (kl & 7) * 2;
-        *reinterpret_cast<__half *>(out + blob + off) = h;
-        *reinterpret_cast<__half *>(out + blob + BN * 64 + off) = l;
+        if constexpr (BF1) {
+            *reinterpret_cast<__nv_bfloat16 *>(out + blob + off) = __float2bfloat16_rn(v);
+        } else {
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn(v - __half2float(h));
+            *reinterpret_cast<__half *>(out + blob + off) = h;
+            *reinterpret_cast<__half *>(out + blob + BN * 64 + off) = l;
+        }
     }
 }
 
@@ -138,8 +148,11 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
         : "memory");
 }
 
-template <int BN, bool F16>
+// BF1: single-pass bf16 operands (no lo parts, one MMA per K-step, no scaling: bf16 has the fp32 exponent range) - the
+// reduced-precision mode whose tolerance is stated separately (tests/test_gpu_parity.py::test_bf16_mode_tolerance).
+template <int BN, bool F16, bool BF1 = false>
 __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, const float *__restrict__ wpack) {
+    static_assert(!BF1 || F16, "the bf16 variant shares the 16-bit operand path");
     using S = Smem<BN>;
     constexpr int KB = F16 ? 32 : kBK;   // k per pipeline stage: one 64-byte swizzle row of fp16 / tf32
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         for (int c = tid; c < BN; c += kThreads) s_colinv[c] = colinv[n0 + c];
         for (int r = tid; r < kTM; r += kThreads) {
             const long long rr = row0 + r;
-            s_rowinv[r] = (a.row_max && rr < n_rows) ? 1.f / pow2_scale(a.row_max[(size_t)f * a.rowcap + rr]) : 1.f;
+            s_rowinv[r] = (!BF1 && a.row_max && rr < n_rows) ? 1.f / pow2_scale(a.row_max[(size_t)f * a.rowcap + rr]) : 1.f;
         }
     }
     for (int r = tid; r < kTM; r += kThreads) {
@@ -270,15 +283,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
             uint8_t *stage = smem + (size_t)s * S::kStage;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float sc = rs[i];
-                uint4 hi, lo;
-                split_f16_pair(cur[2 * i].x * sc, cur[2 * i].y * sc, hi.x, lo.x);
-                split_f16_pair(cur[2 * i].z * sc, cur[2 * i].w * sc, hi.y, lo.y);
-                split_f16_pair(cur[2 * i + 1].x * sc, cur[2 * i + 1].y * sc, hi.z, lo.z);
-                split_f16_pair(cur[2 * i + 1].z * sc, cur[2 * i + 1].w * sc, hi.w, lo.w);
                 const uint32_t off = sw64_offset(rsub + 64 * i, c);
-                *reinterpret_cast<uint4 *>(stage + off) = hi;
-                *reinterpret_cast<uint4 *>(stage + S::kAHalf + off) = lo;
+                if constexpr (BF1) {
+                    uint4 hi;
+                    hi.x = pack_bf16x2(cur[2 * i].x, cur[2 * i].y), hi.y = pack_bf16x2(cur[2 * i].z, cur[2 * i].w);
+                    hi.z = pack_bf16x2(cur[2 * i + 1].x, cur[2 * i + 1].y), hi.w = pack_bf16x2(cur[2 * i + 1].z, cur[2 * i + 1].w);
+                    *reinterpret_cast<uint4 *>(stage + off) = hi;
+                } else {
+                    const float sc = rs[i];
+                    uint4 hi, lo;
+                    split_f16_pair(cur[2 * i].x * sc, cur[2 * i].y * sc, hi.x, lo.x);
+                    split_f16_pair(cur[2 * i].z * sc, cur[2 * i].w * sc, hi.y, lo.y);
+                    split_f16_pair(cur[2 * i + 1].x * sc, cur[2 * i + 1].y * sc, hi.z, lo.z);
+                    split_f16_pair(cur[2 * i + 1].z * sc, cur[2 * i + 1].w * sc, hi.w, lo.w);
+                    *reinterpret_cast<uint4 *>(stage + off) = hi;
+                    *reinterpret_cast<uint4 *>(stage + S::kAHalf + off) = lo;
+                }
             }
             fence_async_smem();
             mbar_arrive(full_bar(s));
@@ -365,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         // ================= MMA issuer (one thread) ================================================================
         if (lane == 0) {
             // D fp32, A/B TF32 (format 2) or F16 (format 0), K-major both, N = BN, M = 128
-            constexpr uint32_t fmt = F16 ? 0u : 2u;
+            constexpr uint32_t fmt = BF1 ? 1u : (F16 ? 0u : 2u);   // kind::f16: 0 = fp16, 1 = bf16; kind::tf32: 2 = tf32
             constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % kStages;
@@ -381,7 +401,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
                     for (int ks = 0; ks < 2; ++ks) {   // two MMA K-steps (8 tf32 / 16 fp16 = 32 bytes) per stage row: +32 bytes inside the swizzle atom
                         const uint64_t a_hi = make_desc(sA + aoff + ks * 32), a_lo = make_desc(sA + S::kAHalf + aoff + ks * 32);
                         const uint64_t b_hi = make_desc(sB + ks * 32), b_lo = make_desc(sB + S::kBHalf + ks * 32);
-                        if constexpr (F16) {
+                        if constexpr (BF1) {
+                            mma_f16(d, a_hi, b_hi, idesc, (kc | ks) != 0);
+                        } else if constexpr (F16) {
                             mma_f16(d, a_lo, b_hi, idesc, (kc | ks) != 0);
                             mma_f16(d, a_hi, b_lo, idesc, 1);
                             mma_f16(d, a_hi, b_hi, idesc, 1);
@@ -497,25 +519,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
     }
 }
 
-template <int BN, bool F16>
+template <int BN, bool F16, bool BF1 = false>
 int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     using S = Smem<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN, F16, BF1>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         attr_set = true;
     }
     const int total = a.Cin * a.Cout;
     if (F16) {   // [fp16 hi|lo images: Cin*Cout*4 bytes][inverse column scales: Cout floats]
         uint8_t *blob = reinterpret_cast<uint8_t *>(wpack);
-        pack_weights_f16_kernel<BN><<<a.Cout, 256, 0, st>>>(a.Wt, a.Cin, a.Cout, blob, reinterpret_cast<float *>(blob + (size_t)total * 4));
+        pack_weights_f16_kernel<BN, BF1><<<a.Cout, 256, 0, st>>>(a.Wt, a.Cin, a.Cout, blob, reinterpret_cast<float *>(blob + (size_t)total * 4));
     } else {
         pack_weights_kernel<BN><<<(total + 255) / 256, 256, 0, st>>>(a.Wt, a.Cin, a.Cout, wpack);
     }
     MVX_LAUNCH_CHECK();
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     dim3 grid(a.Cout / BN, (unsigned)ceil_div(max_rows, kTM), F);
-    tc_layer_kernel<BN, F16><<<grid, kThreads, S::kTotal, st>>>(a, wpack);
+    tc_layer_kernel<BN, F16, BF1><<<grid, kThreads, S::kTotal, st>>>(a, wpack);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }
@@ -845,6 +867,8 @@ int launch_tc_persist(const LayerArgs &a, int F, float *wpack, cudaStream_t st) 
 
 }  // namespace
 
+static int g_tc_bf16 = 0;
+void set_tc_bf16(int on) { g_tc_bf16 = on; }
 static int g_tc_f16 = 1;
 bool tc_f16_enabled() { return g_tc_f16 != 0; }
 void set_tc_f16(int on) { g_tc_f16 = on; }
@@ -868,6 +892,10 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
     if (max_rows <= 0) return MVX_OK;
     if (a.vmax == nullptr && !a.plain && tc_persistent_enabled())  // persistent kernel: 256 x 128 tiles, double-buffered accumulators
         return launch_tc_persist<128>(a, F, wpack, st);
+    if (a.f16_ok && g_tc_bf16 && a.Cin % 32 == 0) {          // reduced precision: one bf16 product per K-step
+        if (a.Cout % 256 == 0) return launch_tc<256, true, true>(a, F, wpack, st);
+        return launch_tc<128, true, true>(a, F, wpack, st);
+    }
     if (a.f16_ok && tc_f16_enabled() && a.Cin % 32 == 0) {   // 3xFP16: half the tensor cycles and operand bytes of 3xTF32
         if (a.Cout % 256 == 0) return launch_tc<256, true>(a, F, wpack, st);
         return launch_tc<128, true>(a, F, wpack, st);
