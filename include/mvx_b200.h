@@ -157,7 +157,7 @@ typedef struct {
 } mvx_pointpath_args_t;
 
 /* byte offsets of named workspace regions, for tests/diagnostics (names in mvx_pointpath_layout_name) */
-#define MVX_WS_REGIONS 40
+#define MVX_WS_REGIONS 64
 int mvx_pointpath_workspace_bytes(const mvx_pointpath_args_t *args, size_t *bytes);
 int mvx_pointpath_layout(const mvx_pointpath_args_t *args, int64_t *offsets /* [MVX_WS_REGIONS] */);
 const char *mvx_pointpath_layout_name(int32_t region);

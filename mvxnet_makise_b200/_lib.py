@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_PKG, 'libmvx_b200.so')
 
 NUM_LAYERS = 8
 NUM_LEVELS = 3
-WS_REGIONS = 40
+WS_REGIONS = 64
 NUM_SEGMENTS = 20
 
 # every symbol include/mvx_b200.h declares (tests check that the .so exports all of them)

@@ -13,6 +13,7 @@
 // tools/compact_backward_proto.py validates these formulas against autograd through the dense oracle chain.
 #include "layers.cuh"
 #include "pointpath.cuh"
+#include "tc_common.cuh"
 
 #include <algorithm>
 
@@ -43,6 +44,8 @@ struct BnArgs {
     float *dbias;          // (C) slice of the flat gradient bucket
     double eps;
     RowSet rs;
+    int *dmax;             // [B][C] max |dpre| per column as float bits (zeroed by the caller), or NULL: the power-of-two
+                           // column scales of the tensor-core dW; the frame pad row of mode 1 (huge multiplicity) is excluded
 };
 
 constexpr int kBnRows = 512;  // rows per CTA
@@ -118,6 +121,8 @@ __global__ void __launch_bounds__(256) bn_back_apply_kernel(BnArgs a) {
         m1[j] = bs[0] / R, m2[j] = bs[1] / R;
     }
     double sb[4] = {0, 0, 0, 0};
+    float mx[4] = {0.f, 0.f, 0.f, 0.f};
+    const int pad_row = a.rs.mode == 1 ? a.rs.counts[f * 4 + 1] : -1;
     const int rend = min(row0 + kBnRows, n_rows);
     for (int r = row0 + rg; r < rend; r += rpp) {
         const size_t ro = (size_t)f * a.rs.rowcap + r;
@@ -134,11 +139,15 @@ __global__ void __launch_bounds__(256) bn_back_apply_kernel(BnArgs a) {
             const float d = (float)(rstd[j] * ((double)gv[j] - wd * m1[j] - wd * z * m2[j]));
             o[j] = yv[j] > 0.f ? d : 0.f;
             sb[j] += (double)o[j];
+            if (r != pad_row) mx[j] = fmaxf(mx[j], fabsf(o[j]));
         }
         *gp = make_float4(o[0], o[1], o[2], o[3]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(&s_acc[c + j], sb[j]);
+    for (int j = 0; j < 4; ++j) {
+        atomicAdd(&s_acc[c + j], sb[j]);
+        if (a.dmax && mx[j] > 0.f) atomicMax(a.dmax + (size_t)f * C + c + j, __float_as_int(mx[j]));
+    }
     __syncthreads();
     for (int i = tid; i < C; i += blockDim.x) atomicAdd(a.dbias + i, (float)s_acc[i]);
 }
@@ -153,6 +162,8 @@ struct DwArgs {
     float *dW;             // (Cout, CinTrue) slice of the flat gradient bucket
     int chunk_rows;
     RowSet rs;
+    const int *dmax;       // tensor-core path: [B][Cout] max |dpre| per column (float bits)
+    const int *xmax;       // tensor-core path: [B][Cin] max |x| per column (float bits) or NULL (BatchNorm-ed input: scale 1)
 };
 
 template <int TN, int TK>
@@ -256,7 +267,256 @@ int launch_dw(const DwArgs &a_in, int B, cudaStream_t st) {
     return MVX_OK;
 }
 
+// ---- dW on the tensor cores -----------------------------------------------------------------------------------------
+// dW[n][k] += sum_r D[r][n] * X[r][k]: both operands are row-major with the REDUCTION index r as the slow dimension, i.e.
+// "MN-major" for tcgen05. They are staged in the no-swizzle MN-major canonical layout (8 (r) x 16-byte core matrices,
+// 128 contiguous bytes each): a producer lane loads 8 consecutive columns of one row (two float4), applies BatchNorm of
+// the producer layer (X), scales by a per-COLUMN power of two (the sum runs over rows, so only column scales factor
+// out), splits into fp16 hi/lo and writes one 16-byte core-matrix row; a warp writes 4 whole core matrices (512
+// contiguous bytes) per store. One CTA owns a (MH*128) x TK tile of dW for one row chunk of one frame: MH M=128
+// accumulators of TK fp32 columns in TMEM, 32 rows per pipeline stage, three products per K=16 step (3xFP16), and the
+// epilogue adds acc / (scale_n * scale_k) into the flat bucket with fp32 atomics. The frame pad row of the fusion stack
+// (multiplicity ~N*T) is orders of magnitude larger than ordinary rows and would eat the fp16 dynamic range of its
+// columns: it is left out here and added as an exact fp32 rank-1 update by dw_pad_row_kernel.
+constexpr int kDwStages = 3;
+constexpr int kDwRows = 32;                 // rows (K extent) per stage = two K=16 MMA steps
+constexpr int kDwProducers = 256;
+constexpr int kDwThreads = kDwProducers + 32;
+
+template <int MH, int TK>
+struct DwSmem {
+    static constexpr int kMT = MH * 128;
+    static constexpr int kAPart = kMT * kDwRows * 2;      // bytes of the hi (or lo) image of the D tile
+    static constexpr int kBPart = TK * kDwRows * 2;
+    static constexpr int kStage = 2 * kAPart + 2 * kBPart;
+    static constexpr int kTiles = kDwStages * kStage;
+    static constexpr int kMean = kTiles;                   // [TK]
+    static constexpr int kRstd = kMean + TK * 4;
+    static constexpr int kDScale = kRstd + TK * 4;         // [kMT] forward scales of the D columns
+    static constexpr int kXScale = kDScale + kMT * 4;      // [TK]
+    static constexpr int kBars = kXScale + TK * 4;         // full[3], empty[3], accum
+    static constexpr int kTmemPtr = kBars + 8 * 8;
+    static constexpr int kTotal = kTmemPtr + 16 + 1024;
+};
+
+template <int MH, int TK>
+__global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(DwArgs a) {
+    using S = DwSmem<MH, TK>;
+    constexpr int MT = S::kMT;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    float *s_mean = reinterpret_cast<float *>(smem + S::kMean), *s_rstd = reinterpret_cast<float *>(smem + S::kRstd);
+    float *s_dscale = reinterpret_cast<float *>(smem + S::kDScale), *s_xscale = reinterpret_cast<float *>(smem + S::kXScale);
+    const uint32_t bars = sbase + S::kBars;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kDwStages + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * kDwStages);
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(smem + S::kTmemPtr);
+
+    const int f = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_k = a.Cin / TK;
+    const int n0 = (blockIdx.x / tiles_k) * MT, k0 = (blockIdx.x % tiles_k) * TK;
+    const int n_rows = rows_of(a.rs, f);
+    const int row0 = blockIdx.y * a.chunk_rows;
+    if (row0 >= n_rows) return;
+    const int rend = min(row0 + a.chunk_rows, n_rows);
+    const int pad_row = a.rs.mode == 1 ? a.rs.counts[f * 4 + 1] : -1;   // handled by dw_pad_row_kernel
+    const int nst = (rend - row0 + kDwRows - 1) / kDwRows;
+
+    for (int k = tid; k < TK; k += kDwThreads) {
+        float m = 0.f, r = 1.f;
+        if (a.in_stats) {
+            const double R = (double)a.rs.counts[f * 4 + 0] * (double)a.rs.T;
+            const double *st = a.in_stats + ((size_t)f * a.Cin + k0 + k) * 2;
+            const double mu = st[0] / R;
+            double var = st[1] / R - mu * mu;
+            var = var < 0.0 ? 0.0 : var;
+            m = (float)mu, r = (float)(1.0 / sqrt(var + a.eps));
+        }
+        s_mean[k] = m, s_rstd[k] = r;
+        s_xscale[k] = a.xmax ? pow2_scale(__int_as_float(a.xmax[(size_t)f * a.Cin + k0 + k])) : 1.f;
+    }
+    for (int n = tid; n < MT; n += kDwThreads) s_dscale[n] = pow2_scale(__int_as_float(a.dmax[(size_t)f * a.Cout + n0 + n]));
+    if (tid == 0) {
+        for (int s = 0; s < kDwStages; ++s) {
+            mbar_init(full_bar(s), kDwProducers);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::kTmemPtr), "r"(MH * TK) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 8) {
+        // ================= producers: granule = 8 rows x 32 columns of D or X; lane = (row lane&7, 8-column block lane>>3) ====
+        constexpr int GD = 4 * (MT / 32), GX = 4 * (TK / 32), G = GD + GX, GPW = G / 8;   // granules per stage / per warp
+        static_assert(G % 8 == 0, "granules must divide over the 8 producer warps");
+        const int lr = lane & 7, lb = lane >> 3;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t < nst; ++t) {
+            const int r0 = row0 + t * kDwRows;
+            float4 v[GPW][2];
+#pragma unroll
+            for (int q = 0; q < GPW; ++q) {        // all loads of this warp's granules first (memory-level parallelism)
+                const int g = warp + 8 * q;
+                const bool isx = g >= GD;
+                const int gg = isx ? g - GD : g;
+                const int cgs = isx ? TK / 32 : MT / 32;
+                const int j = gg / cgs, cg = gg - j * cgs;
+                const int r = r0 + 8 * j + lr, col = cg * 32 + lb * 8;
+                const bool ok = r < rend && r != pad_row;
+                const float *src = isx ? a.X + ((size_t)f * a.rs.rowcap + r) * a.ldx + k0 + col
+                                       : a.D + ((size_t)f * a.rs.rowcap + r) * a.Cout + n0 + col;
+                v[q][0] = ok ? __ldg(reinterpret_cast<const float4 *>(src)) : z4;
+                v[q][1] = ok ? __ldg(reinterpret_cast<const float4 *>(src) + 1) : z4;
+            }
+            const int s = t % kDwStages;
+            const uint32_t ph = (t / kDwStages) & 1;
+            if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);
+            __syncwarp();
+            uint8_t *stage = smem + (size_t)s * S::kStage;
+#pragma unroll
+            for (int q = 0; q < GPW; ++q) {
+                const int g = warp + 8 * q;
+                const bool isx = g >= GD;
+                const int gg = isx ? g - GD : g;
+                const int cgs = isx ? TK / 32 : MT / 32;
+                const int j = gg / cgs, cg = gg - j * cgs;
+                const int col = cg * 32 + lb * 8;
+                const int r = r0 + 8 * j + lr;
+                const bool ok = r < rend && r != pad_row;
+                float x[8] = {v[q][0].x, v[q][0].y, v[q][0].z, v[q][0].w, v[q][1].x, v[q][1].y, v[q][1].z, v[q][1].w};
+                const float *sc = (isx ? s_xscale : s_dscale) + col;
+                if (isx && ok) {                    // BatchNorm of the producer layer (absent rows stay zero)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] = (x[e] - s_mean[col + e]) * s_rstd[col + e];
+                }
+                uint4 hi, lo;
+                split_f16_pair(x[0] * sc[0], x[1] * sc[1], hi.x, lo.x);
+                split_f16_pair(x[2] * sc[2], x[3] * sc[3], hi.y, lo.y);
+                split_f16_pair(x[4] * sc[4], x[5] * sc[5], hi.z, lo.z);
+                split_f16_pair(x[6] * sc[6], x[7] * sc[7], hi.w, lo.w);
+                const uint32_t part = isx ? 2 * S::kAPart : 0, psz = isx ? S::kBPart : S::kAPart;
+                const uint32_t off = part + (uint32_t)((j * cgs * 4 + cg * 4 + lb) * 128 + lr * 16);
+                *reinterpret_cast<uint4 *>(stage + off) = hi;
+                *reinterpret_cast<uint4 *>(stage + off + psz) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(full_bar(s));
+        }
+    } else if (lane == 0) {
+        // ================= MMA issuer: D fp32, A/B fp16, both MN-major, M = 128, N = TK =============================
+        constexpr uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(TK >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr uint32_t lboA = (MT / 8) * 128, lboB = (TK / 8) * 128;
+        for (int t = 0; t < nst; ++t) {
+            const int s = t % kDwStages;
+            const uint32_t ph = (t / kDwStages) & 1;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t sA = sbase + s * S::kStage, sB = sA + 2 * S::kAPart;
+#pragma unroll
+            for (int h = 0; h < MH; ++h) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {   // K = 16 rows = two groups of 8
+                    const uint64_t a_hi = make_desc_mn(sA + h * 16 * 128 + ks * 2 * lboA, lboA, 128);
+                    const uint64_t a_lo = make_desc_mn(sA + S::kAPart + h * 16 * 128 + ks * 2 * lboA, lboA, 128);
+                    const uint64_t b_hi = make_desc_mn(sB + ks * 2 * lboB, lboB, 128);
+                    const uint64_t b_lo = make_desc_mn(sB + S::kBPart + ks * 2 * lboB, lboB, 128);
+                    const uint32_t d = tmem_base + h * TK;
+                    mma_f16(d, a_lo, b_hi, idesc, (t | ks) != 0);
+                    mma_f16(d, a_hi, b_lo, idesc, 1);
+                    mma_f16(d, a_hi, b_hi, idesc, 1);
+                }
+            }
+            mma_commit(empty_bar(s));
+        }
+        mma_commit(accum_bar);
+    }
+
+    // ================= epilogue: TMEM -> unscale -> fp32 atomics into the flat bucket ===================================
+    __syncwarp();
+    if (warp < 4 * MH) {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int h = warp >> 2, q = warp & 3;
+        const int n = h * 128 + q * 32 + lane;           // accumulator row = output channel
+        const float dinv = 1.f / s_dscale[n];
+        float *orow = a.dW + (size_t)(n0 + n) * a.CinTrue + k0;
+#pragma unroll 1
+        for (int cb = 0; cb < TK / 32; ++cb) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * TK + cb * 32, v);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const int k = cb * 32 + e;
+                const float g = v[e] * dinv / s_xscale[k];
+                if (k0 + k < a.CinTrue && g != 0.f) atomicAdd(orow + k, g);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(MH * TK) : "memory");
+}
+
+// the frame pad row of a mode-1 layer, exact fp32: dW[n][k] += D[K][n] * xhat[K][k]
+__global__ void __launch_bounds__(256) dw_pad_row_kernel(DwArgs a) {
+    const int f = blockIdx.y, n = blockIdx.x, K = a.rs.counts[f * 4 + 1];
+    const float d = a.D[((size_t)f * a.rs.rowcap + K) * a.Cout + n];
+    if (d == 0.f) return;
+    const double R = (double)a.rs.counts[f * 4 + 0] * (double)a.rs.T;
+    for (int k = threadIdx.x; k < a.CinTrue; k += blockDim.x) {
+        float x = a.X[((size_t)f * a.rs.rowcap + K) * a.ldx + k];
+        if (a.in_stats) {
+            const double *st = a.in_stats + ((size_t)f * a.Cin + k) * 2;
+            const double mu = st[0] / R;
+            double var = st[1] / R - mu * mu;
+            var = var < 0.0 ? 0.0 : var;
+            x = (x - (float)mu) * (float)(1.0 / sqrt(var + a.eps));
+        }
+        const float g = d * x;
+        if (g != 0.f) atomicAdd(a.dW + (size_t)n * a.CinTrue + k, g);
+    }
+}
+
+template <int MH, int TK>
+int launch_dw_tc(const DwArgs &a_in, int B, cudaStream_t st) {
+    using S = DwSmem<MH, TK>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(dw_tc_kernel<MH, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        attr_set = true;
+    }
+    DwArgs a = a_in;
+    const int tiles = (a.Cout / (MH * 128)) * (a.Cin / TK);
+    const long long per = (long long)tiles * B;
+    const int chunks = (int)std::max<long long>(1, std::min<long long>(ceil_div(a.rs.rowcap, 2048), (kSMs + per / 2) / per));
+    a.chunk_rows = (int)round_up(ceil_div(a.rs.rowcap, chunks), kDwRows);
+    dw_tc_kernel<MH, TK><<<dim3(tiles, (unsigned)ceil_div(a.rs.rowcap, a.chunk_rows), B), kDwThreads, S::kTotal, st>>>(a);
+    MVX_LAUNCH_CHECK();
+    if (a.rs.mode == 1) {
+        dw_pad_row_kernel<<<dim3(a.Cout, B), 256, 0, st>>>(a);
+        MVX_LAUNCH_CHECK();
+    }
+    return MVX_OK;
+}
+
+static int g_dw_tc = 1;   // 1: tensor-core dW where eligible, 0: SIMT everywhere (mvx_set_gemm_mode(0) also selects SIMT)
+
 int launch_dw_auto(const DwArgs &a, int B, cudaStream_t st) {
+    if (g_dw_tc && gemm_mode() == 1 && a.dmax && a.Cout % 128 == 0 && a.Cin % 128 == 0) {
+        if (a.Cout % 256 == 0 && a.Cin % 256 == 0) return launch_dw_tc<2, 256>(a, B, st);
+        if (a.Cin % 256 == 0) return launch_dw_tc<1, 256>(a, B, st);
+        return launch_dw_tc<1, 128>(a, B, st);
+    }
     if (a.Cout % 128 == 0 && a.Cin % 128 == 0) return launch_dw<128, 128>(a, B, st);
     if (a.Cout == 64 && a.Cin == 32) return launch_dw<64, 32>(a, B, st);
     if (a.Cout == 16 && a.Cin % 128 == 0) return launch_dw<16, 128>(a, B, st);
@@ -360,7 +620,7 @@ __global__ void __launch_bounds__(256) grid_grad_gather_kernel(const float *__re
     dv[((size_t)f * cap + v) * 128 + c] = dgrid[((size_t)f * 128 + c) * G + cell];
 }
 
-enum BRegion { BR_G1 = 0, BR_G2, BR_G3, BR_G4, BR_G5, BR_DX6, BR_G6, BR_DX7, BR_G7, BR_DX8, BR_G8, BR_BSTATS, BR_WT, BR_DVFEAT, BR_COUNT };
+enum BRegion { BR_G1 = 0, BR_G2, BR_G3, BR_G4, BR_G5, BR_DX6, BR_G6, BR_DX7, BR_G7, BR_DX8, BR_G8, BR_BSTATS, BR_WT, BR_DVFEAT, BR_DMAX, BR_COUNT };
 
 struct BLayout {
     size_t off[BR_COUNT];
@@ -394,6 +654,7 @@ void make_blayout(const mvx_pointpath_args_t *a, const Layout &L, BLayout &BL) {
     }
     take(BR_WT, w * 4);
     take(BR_DVFEAT, B * cap * 128 * 4);
+    take(BR_DMAX, (size_t)MVX_NUM_LAYERS * B * 768 * 4);
     BL.total = o;
 }
 
@@ -436,6 +697,9 @@ int pointpath_backward(const mvx_pointpath_args_t *a, const float *d_vfeat, cons
     }
     if (!accumulate) MVX_CUDA_CHECK(cudaMemsetAsync(grad_flat, 0, o * sizeof(float), st));
     MVX_CUDA_CHECK(cudaMemsetAsync(bstats, 0, (size_t)MVX_NUM_LAYERS * B * kStatStride * 8, st));
+    int *dmax = reinterpret_cast<int *>(bws + BL.off[BR_DMAX]);
+    MVX_CUDA_CHECK(cudaMemsetAsync(dmax, 0, (size_t)MVX_NUM_LAYERS * B * 768 * 4, st));
+    auto dmax_of = [&](int l) { return dmax + (size_t)l * B * 768; };   // [B][Cout_l] inside
     float *wT = BF(BR_WT);
     for (int l = 1; l < MVX_NUM_LAYERS; ++l) {   // fcn1 needs no dx (the FPN maps are inputs of the path)
         const int n = kCin[l] * kCout[l];
@@ -454,14 +718,17 @@ int pointpath_backward(const mvx_pointpath_args_t *a, const float *d_vfeat, cons
     auto layer_back = [&](int l, float *G, const float *Y, const RowSet &rs, const float *X, int ldx, const double *in_stats,
                           float *dX) -> int {
         const int C = kCout[l];
-        BnArgs bn{G, Y, C, stat_of(l), bstat_of(l), grad_flat + b_off[l], a->bn_eps, rs};
+        BnArgs bn{G, Y, C, stat_of(l), bstat_of(l), grad_flat + b_off[l], a->bn_eps, rs, dmax_of(l)};
         const int threads = C == 768 ? 192 : 256;
         const dim3 grid((unsigned)ceil_div(rs.rowcap, kBnRows), B);
         bn_back_reduce_kernel<<<grid, threads, 0, st>>>(bn);
         MVX_LAUNCH_CHECK();
         bn_back_apply_kernel<<<grid, threads, 0, st>>>(bn);
         MVX_LAUNCH_CHECK();
-        DwArgs dw{G, X, ldx, kCin[l], kCinTrue[l], C, in_stats, a->bn_eps, grad_flat + w_off[l], 0, rs};
+        // column maxima for the fp16 scaling of the tensor-core dW: dpre from bn_back_apply; X is BatchNorm-ed (scale 1)
+        // except fcn1's gathered features, bounded per column by the channel maxima of the FPN maps (convex combination)
+        DwArgs dw{G, X, ldx, kCin[l], kCinTrue[l], C, in_stats, a->bn_eps, grad_flat + w_off[l], 0, rs, dmax_of(l),
+                  l == 0 ? I32(R_CHMAX) : nullptr};
         int r = launch_dw_auto(dw, B, st);
         if (r) return r;
         if (dX) {

@@ -11,7 +11,7 @@ namespace {
 
 // ---- NCHW -> NHWC ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int C,
-                                                           int HW, int *__restrict__ rowmax) {
+                                                           int HW, int *__restrict__ rowmax, int *__restrict__ chmax, int chmax_stride) {
     __shared__ float tile[32][33];
     const size_t fb = (size_t)blockIdx.z * C * HW;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -32,6 +32,11 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restri
 #pragma unroll
         for (int c = 0; c < 32; ++c) m = fmaxf(m, fabsf(tile[c][tx]));
         atomicMax(rowmax + (size_t)blockIdx.z * HW + p0 + tx, __float_as_int(m));
+    }
+    if (chmax && threadIdx.x >= 32 && threadIdx.x < 64 && c0 + tx < C) {   // max |x| of each channel over the frame (training:
+        float m = 0.f;                                                      // column bound of the gathered matrix for the dW scaling)
+        for (int p = 0; p < 32; ++p) m = fmaxf(m, fabsf(tile[tx][p]));     // pixels beyond HW were loaded as 0
+        atomicMax(chmax + (size_t)blockIdx.z * chmax_stride + c0 + tx, __float_as_int(m));
     }
 }
 
@@ -404,10 +409,10 @@ int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st) {
     return MVX_OK;
 }
 
-int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, float *rowmax, cudaStream_t st) {
+int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, float *rowmax, int *chmax, int chmax_stride, cudaStream_t st) {
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
     if (rowmax) MVX_CUDA_CHECK(cudaMemsetAsync(rowmax, 0, (size_t)B * HW * sizeof(float), st));
-    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(in, out, C, HW, reinterpret_cast<int *>(rowmax));
+    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(in, out, C, HW, reinterpret_cast<int *>(rowmax), chmax, chmax_stride);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }
@@ -467,7 +472,7 @@ extern "C" int mvx_feature_mapping(float *voxels, int64_t R, const float *const 
         m.rs_w[l] = imsize_w / (float)map_w[l];
         m.nhwc[l] = ws;
         m.frame_stride[l] = 0;
-        int rc = mvx::launch_nchw_to_nhwc(maps[l], ws, 1, C, map_h[l] * map_w[l], nullptr, st);
+        int rc = mvx::launch_nchw_to_nhwc(maps[l], ws, 1, C, map_h[l] * map_w[l], nullptr, nullptr, 0, st);
         if (rc) return rc;
         ws += (size_t)map_h[l] * map_w[l] * C;
     }

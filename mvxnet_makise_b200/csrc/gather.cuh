@@ -14,7 +14,8 @@ struct MapSet {
 
 // NCHW (B,C,H,W) -> NHWC (B,H,W,C)
 // rowmax (optional): [B][HW] max |x| over the C channels of every pixel (float; zeroed and filled here)
-int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, float *rowmax, cudaStream_t st);
+// chmax (optional): [B][chmax_stride] ints (float bits, zeroed by the caller): max |x| of every channel over the frame's pixels
+int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, float *rowmax, int *chmax, int chmax_stride, cudaStream_t st);
 
 struct RowsParams {
     int B, cap, capA, T;

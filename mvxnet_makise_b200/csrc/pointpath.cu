@@ -19,7 +19,7 @@ namespace mvx {
 const char *kRegionNames[R_COUNT] = {
     "vox_ws", "vox_coord", "vox_cnt", "vox_row0", "row_point", "row_vox", "cell2vid", "nhwc0", "nhwc1", "nhwc2",
     "vox8", "proj", "rowA_w", "A1", "Y1", "Y2", "Y3", "Y4", "Y5", "X6", "Y6", "X7", "Y7", "rowB_w", "rowB_v", "X8",
-    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t", "Z", "bin_count", "bin_start", "perm", "rowmax", "Y8"};
+    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t", "Z", "bin_count", "bin_start", "perm", "rowmax", "chmax", "Y8"};
 
 // 1 (default): pixel-first fcn1 - one tensor-core GEMM per FPN level over the map pixels, then a 12-corner combine per
 // point row (gather.cuh CombineArgs); 0: materialise the gathered (K,768) matrix A1 and run fcn1 over the point rows
@@ -87,6 +87,7 @@ int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
         take(R_BINSTART, B * (nb + 2) * 4);
         take(R_PERM, B * capA * 4);
         take(R_ROWMAX, B * px * 4);
+        take(R_CHMAX, B * 768 * 4);
     }
     L.total = o;
     take(R_Y8, B * capB * 128 * 4);   // last region: only present in a training workspace
@@ -151,6 +152,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     auto I32 = [&](Region r) { return reinterpret_cast<int *>(ws + L.off[r]); };
 
     const Stamp stamp(st);
+    if (train) MVX_CUDA_CHECK(cudaMemsetAsync(I32(R_CHMAX), 0, (size_t)B * 768 * 4, st));
     stamp.mark(S_VOXELIZE);
     // ---- stage 1 ----------------------------------------------------------------------------------------
     mvx_voxel_out_t vo{};
@@ -173,7 +175,8 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         m.rs_w[l] = a->imsize_w / (float)a->map_w[l];
         m.nhwc[l] = F32((Region)(R_NHWC0 + l));
         m.frame_stride[l] = (size_t)HW * a->map_c;
-        rc = launch_nchw_to_nhwc(a->maps[l], F32((Region)(R_NHWC0 + l)), B, a->map_c, HW, F32(R_ROWMAX) + rowmax_off, st);
+        rc = launch_nchw_to_nhwc(a->maps[l], F32((Region)(R_NHWC0 + l)), B, a->map_c, HW, F32(R_ROWMAX) + rowmax_off,
+                                 train ? I32(R_CHMAX) + l * a->map_c : nullptr, MVX_NUM_LEVELS * a->map_c, st);
         if (rc) return rc;
         rowmax_off += (size_t)B * HW;
     }

@@ -2,6 +2,9 @@
 #pragma once
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 namespace mvx {
 namespace {
 
@@ -147,6 +150,49 @@ __device__ __forceinline__ void mma2_commit_multicast(uint32_t bar, uint16_t cta
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                  "h"(cta_mask)
                  : "memory");
+}
+
+
+// ---- 16-bit operand helpers (3xFP16 / bf16 variants) ---------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a, high half = b
+    return r;
+}
+__device__ __forceinline__ void split_f16_pair(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    hi = pack_half2(x0, x1);
+    const __half2 h = *reinterpret_cast<const __half2 *>(&hi);
+    const float2 hf = __half22float2(h);
+    lo = pack_half2(x0 - hf.x, x1 - hf.y);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));  // low half = a, high half = b
+    return r;
+}
+// power of two s with max * s in [0.5, 1) (1 when max is 0 or not finite)
+__device__ __forceinline__ float pow2_scale(float mx) {
+    if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
+    int e;
+    frexpf(mx, &e);            // mx = m * 2^e, m in [0.5, 1)
+    e = max(-100, min(100, e));
+    return exp2f((float)-e);
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+
+// MN-major, no-swizzle ("interleave") canonical layout: 8 (k) x 16-byte core matrices of 128 contiguous bytes;
+// SBO = byte stride between core matrices along M/N, LBO = byte stride between groups of 8 along K.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
 
 }  // namespace

@@ -20,8 +20,6 @@
 #include "layers.cuh"
 #include "tc_common.cuh"
 
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -80,31 +78,6 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
 // inputs (|z| <= sqrt(R) << 65504). The epilogue multiplies the accumulator by the inverse scales (exact). With hi =
 // rn16(x) and lo = rn16(x - hi) the representation error is max(2^-23 |x|, 2^-25) per element (lo may be subnormal),
 // i.e. fp32-level relative to the row scale; products of two fp16 values are exact in the fp32 accumulator.
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    uint32_t r;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a, high half = b
-    return r;
-}
-__device__ __forceinline__ void split_f16_pair(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-    hi = pack_half2(x0, x1);
-    const __half2 h = *reinterpret_cast<const __half2 *>(&hi);
-    const float2 hf = __half22float2(h);
-    lo = pack_half2(x0 - hf.x, x1 - hf.y);
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));  // low half = a, high half = b
-    return r;
-}
-// power of two s with max * s in [0.5, 1) (1 when max is 0 or not finite)
-__device__ __forceinline__ float pow2_scale(float mx) {
-    if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
-    int e;
-    frexpf(mx, &e);            // mx = m * 2^e, m in [0.5, 1)
-    e = max(-100, min(100, e));
-    return exp2f((float)-e);
-}
-
 // W^T (Cin, Cout) -> per (column tile, 32-k chunk) the shared-memory image [hi | lo] in fp16, columns pre-scaled;
 // colinv[n] = 1 / scale_n. One CTA per output column.
 template <int BN, bool BF1>
@@ -137,15 +110,6 @@ __global__ void __launch_bounds__(256) pack_weights_f16_kernel(const float *__re
             *reinterpret_cast<__half *>(out + blob + BN * 64 + off) = l;
         }
     }
-}
-
-__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 
 // BF1: single-pass bf16 operands (no lo parts, one MMA per K-step, no scaling: bf16 has the fp32 exponent range) - the
