@@ -30,6 +30,14 @@ struct LayerArgs {
     int f16_ok;              // 1: the tensor-core kernel may use fp16 operands (3xFP16): inputs are BatchNorm-ed (in_stats, or
                              // stored normalised) or row_max is given; 0 keeps 3xTF32 (arbitrary input range)
     const float *row_max;    // [F][rowcap] max|x| of each input row for the fp16 row scaling, or NULL (scale 1)
+    // fused concat (16-bit tensor-core producer only): input columns [Cin - x2_cols, Cin) of row r come from
+    // X2[f][v(r)][0:x2_cols] (float bits, e.g. the per-voxel max of the producer layer) instead of X, with
+    // v(r) = r >= K_f ? r - K_f : cat_row_vox[f][r]; both parts are normalised with the same in_stats (in_C channels)
+    const int *X2;           // [F][vcap][x2_cols] or NULL
+    int x2_cols;
+    const int *cat_row_vox;  // [F][cat_rowv_cap] voxel of the rows below K_f
+    int cat_rowv_cap;
+    int in_C;                // channels of in_stats (0: Cin)
     int plain;               // 1: Y = norm_in(X) W^T only (no bias, no ReLU, no statistics, no max) - the per-pixel half of fcn1
 };
 int launch_layer(const LayerArgs &a, int F, cudaStream_t st);            // exact-fp32 SIMT kernel

@@ -293,12 +293,21 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         if (rc) return rc;
     }
     stamp.mark(S_PREP3);
-    rc = launch_prep_fcn(vp, st);
-    if (rc) return rc;
+    // inference: the concat [norm7(Y7) | norm7(max7)] that prep_fcn materialises as X8 is built by the FCN's own
+    // A-producer instead (16-bit tensor-core kernel); training keeps X8 (dW8 = dpre8^T X8)
+    const bool fuse_cat = !train && gemm_mode() == 1 && tc_f16_enabled();
+    if (!fuse_cat) {
+        rc = launch_prep_fcn(vp, st);
+        if (rc) return rc;
+    }
     {  // FCN(128,128) + max over T (VoxelNet.py:27-32): only the per-voxel max and the statistics are kept
         stamp.mark(S_FCN);
         LayerArgs la{};
         la.X = F32(R_X8), la.ldx = 128, la.Cin = 128, la.Wt = a->wt[7], la.bias = a->bias[7], la.Cout = 128;
+        if (fuse_cat) {
+            la.X = F32(R_Y7), la.ldx = 64, la.in_stats = stat_of(6), la.in_C = 64;
+            la.X2 = I32(R_VMAX7), la.x2_cols = 64, la.cat_row_vox = vo.row_vox, la.cat_rowv_cap = cap;
+        }
         la.Y = train ? F32(R_Y8) : nullptr, la.ldy = train ? 128 : 0, la.out_stats = stat_of(7), la.vmax = I32(R_VMAX8);
         la.row_w = F32(R_ROWB_W), la.row_v = I32(R_ROWB_V), la.rowv_cap = L.capB, la.counts = a->counts, la.rows_mode = 2;
         la.rowcap = L.capB, la.vcap = cap, la.T = T, la.eps = a->bn_eps;

@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
 
     // ---- one-time setup ------------------------------------------------------------------------------------
     if (a.in_stats) {
+        const int inC = a.in_C > 0 ? a.in_C : a.Cin;   // fused concat: both parts share the producer layer's statistics
         for (int c = tid; c < a.Cin; c += kThreads) {
-            const double *st = a.in_stats + ((size_t)f * a.Cin + c) * 2;
+            const double *st = a.in_stats + ((size_t)f * inC + c % inC) * 2;
             const double m = st[0] / Rstat;
             double var = st[1] / Rstat - m * m;
             var = var < 0.0 ? 0.0 : var;
@@ -207,16 +208,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx + c * 8;
         bool valid[4];
         float rs[4];
+        const float *x2row[4];   // fused concat: this row's source for the trailing x2_cols input columns
+        const int split = a.X2 ? a.Cin - a.x2_cols : a.Cin;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            valid[i] = row0 + rsub + 64 * i < n_rows;
+            const long long rr = row0 + rsub + 64 * i;
+            valid[i] = rr < n_rows;
             rs[i] = 1.f / s_rowinv[rsub + 64 * i];   // power of two: exact
+            x2row[i] = nullptr;
+            if (a.X2 && valid[i]) {
+                const int v = rr >= Kf ? (int)(rr - Kf) : a.cat_row_vox[(size_t)f * a.cat_rowv_cap + rr];
+                x2row[i] = reinterpret_cast<const float *>(a.X2) + ((size_t)f * a.vcap + v) * a.x2_cols + c * 8;
+            }
         }
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         auto load_chunk = [&](float4 (&buf)[8], int kc) {
+            const bool second = kc * KB >= split;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float4 *p = reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + kc * KB);
+                const float4 *p = second ? reinterpret_cast<const float4 *>(x2row[i] + (kc * KB - split))
+                                         : reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + kc * KB);
                 buf[2 * i] = valid[i] ? __ldg(p) : z4;
                 buf[2 * i + 1] = valid[i] ? __ldg(p + 1) : z4;
             }
@@ -854,8 +865,10 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
     MVX_REQUIRE(tc_layer_eligible(a) && wpack, MVX_EINVAL, "layer not eligible for the tensor-core kernel");
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     if (max_rows <= 0) return MVX_OK;
-    if (a.vmax == nullptr && !a.plain && tc_persistent_enabled())  // persistent kernel: 256 x 128 tiles, double-buffered accumulators
+    if (a.vmax == nullptr && !a.plain && !a.X2 && tc_persistent_enabled())  // persistent kernel: 256 x 128 tiles, double-buffered accumulators
         return launch_tc_persist<128>(a, F, wpack, st);
+    MVX_REQUIRE(!a.X2 || (a.f16_ok && (g_tc_bf16 || tc_f16_enabled()) && a.Cin % 32 == 0 && a.x2_cols % 32 == 0 && a.counts),
+                MVX_EINVAL, "fused concat input needs the 16-bit tensor-core producer");
     if (a.f16_ok && g_tc_bf16 && a.Cin % 32 == 0) {          // reduced precision: one bf16 product per K-step
         if (a.Cout % 256 == 0) return launch_tc<256, true, true>(a, F, wpack, st);
         return launch_tc<128, true, true>(a, F, wpack, st);
