@@ -168,7 +168,9 @@ int mvx_pointpath_forward(const mvx_pointpath_args_t *args);
  *               relu(b + sum of 12 weighted Z rows); the (K,768) gathered matrix is never materialised (6.7x fewer FLOPs);
  *   0           row-first: gather the (K,768) matrix A1, then fcn1 over the point rows (the reference's order; the
  *               layout the training-mode backward uses).  Timing segments "gather"/"fcn1" then mean
- *               (pixel GEMMs, combine) in mode 1 and (gather, row GEMM) in mode 0. */
+ *               (pixel GEMMs, combine) in mode 1 and (gather, row GEMM) in mode 0.
+ *   2           pixel-first like 1 but without running the map branch (channels-last copy + pixel GEMMs) on a side stream
+ *               concurrently with the point branch (voxelization, row build, row sort) - for per-stage profiling. */
 int mvx_set_fusion_mode(int32_t mode);
 
 /* ------------------------------------------------------------------------------------------------

@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kCombWarps * 32) combine_rows_kernel(CombineAr
 
 }  // namespace
 
-int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st) {
+int launch_combine_sort(const CombineArgs &a, int B, cudaStream_t st) {
     MVX_REQUIRE(a.bin_count && a.bin_start && a.perm && a.nbins == combine_bins(a.h[0], a.w[0]), MVX_EINVAL, "combine: bad sort scratch");
     MVX_CUDA_CHECK(cudaMemsetAsync(a.bin_count, 0, (size_t)B * (a.nbins + 1) * sizeof(int), st));
     const dim3 rows_grid((a.capA + 255) / 256, B);
@@ -403,6 +403,10 @@ int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st) {
     MVX_LAUNCH_CHECK();
     combine_scatter_kernel<<<rows_grid, 256, 0, st>>>(a);
     MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st) {
     dim3 grid((a.capA + kCombRows - 1) / kCombRows, B);
     combine_rows_kernel<<<grid, kCombWarps * 32, 0, st>>>(a);
     MVX_LAUNCH_CHECK();

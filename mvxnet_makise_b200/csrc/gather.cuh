@@ -60,6 +60,7 @@ struct CombineArgs {
 };
 // scratch sizes (ints per frame) for the level-0 extents of the call
 inline int combine_bins(int h0, int w0) { return ((h0 + 3) / 4) * ((w0 + 3) / 4) * 16; }
-int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st);
+int launch_combine_sort(const CombineArgs &a, int B, cudaStream_t st);   // counting sort of the rows (needs vox8 / proj only)
+int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st);   // the combine itself (needs Z and the sort)
 
 }  // namespace mvx

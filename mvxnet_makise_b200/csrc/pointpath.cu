@@ -26,6 +26,7 @@ const char *kRegionNames[R_COUNT] = {
 // (the layout the training-mode backward needs: dW1 = dpre1^T A1).
 static int g_fusion_mode = 1;
 int fusion_mode() { return g_fusion_mode; }
+static int g_overlap = 1;   // 1: run the map branch of the pixel-first path on a side stream (mvx_set_fusion_mode(2) = pixel-first, serial)
 
 int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
     MVX_REQUIRE(a, MVX_EINVAL, "null args");
@@ -105,21 +106,61 @@ const char *kSegmentNames[S_COUNT] = {"voxelize", "maps_nhwc", "rows_build", "ga
                                       "conv2", "fcn3", "prep_vfe1", "vfe1", "prep_vfe2", "vfe2", "prep_fcn", "fcn",
                                       "finalize_vfeat", "grid_fill"};
 struct Timing {
-    std::vector<cudaEvent_t> ev;  // [calls][S_COUNT + 1]
+    std::vector<cudaEvent_t> ev;      // [calls][S_COUNT][2]: begin / end of every segment, recorded on the stream it runs on
+    std::vector<unsigned> recorded;   // [calls] bit i: segment i was timed in this call
     int max_calls = 0, next = 0;
 };
 static Timing g_timing;
 
 struct Stamp {
     cudaEvent_t *ev = nullptr;
+    unsigned *rec = nullptr;
     cudaStream_t st;
+    mutable int cur = -1;
     explicit Stamp(cudaStream_t s) : st(s) {
-        if (g_timing.max_calls > 0 && g_timing.next < g_timing.max_calls) ev = &g_timing.ev[(size_t)g_timing.next++ * (S_COUNT + 1)];
+        if (g_timing.max_calls > 0 && g_timing.next < g_timing.max_calls) {
+            rec = &g_timing.recorded[g_timing.next];
+            *rec = 0;
+            ev = &g_timing.ev[(size_t)g_timing.next++ * (S_COUNT * 2)];
+        }
     }
+    void begin(int i, cudaStream_t s) const {
+        if (ev) cudaEventRecord(ev[2 * i], s), *rec |= 1u << i;
+    }
+    void end(int i, cudaStream_t s) const {
+        if (ev) cudaEventRecord(ev[2 * i + 1], s);
+    }
+    // main-stream segments are back to back: mark(i) closes the running one and opens segment i (S_COUNT: just close)
     void mark(int i) const {
-        if (ev) cudaEventRecord(ev[i], st);
+        if (!ev) return;
+        if (cur >= 0) end(cur, st);
+        cur = -1;
+        if (i < S_COUNT) begin(i, st), cur = i;
     }
 };
+
+// the map branch (channels-last copy + per-pixel GEMM) does not depend on the point branch (voxelization, row build, row
+// sort): it runs on a side stream, forked from and joined back into the caller's stream with events
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int device = -1;
+};
+static int side_stream(SideStream **out) {
+    static SideStream per_device[64];
+    int dev = 0;
+    MVX_CUDA_CHECK(cudaGetDevice(&dev));
+    MVX_REQUIRE(dev >= 0 && dev < 64, MVX_EINVAL, "device ordinal out of range");
+    SideStream &s = per_device[dev];
+    if (!s.stream) {
+        MVX_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        MVX_CUDA_CHECK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        MVX_CUDA_CHECK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+        s.device = dev;
+    }
+    *out = &s;
+    return MVX_OK;
+}
 
 // zero vmax rows [0, N_f) of each frame (bounded by the device-side voxel count, not by cap)
 __global__ void __launch_bounds__(256) zero_vmax_kernel(const int *__restrict__ counts, int cap, int *__restrict__ v6,
@@ -153,8 +194,67 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
 
     const Stamp stamp(st);
     if (train) MVX_CUDA_CHECK(cudaMemsetAsync(I32(R_CHMAX), 0, (size_t)B * 768 * 4, st));
+    // training keeps the gathered matrix A1 (dW1 = dpre1^T A1), so it always runs row-first
+    const bool pixel_first = !train && g_fusion_mode == 1 && gemm_mode() == 1;
+    double *stats = reinterpret_cast<double *>(ws + L.off[R_STATS]);
+    auto stat_of = [&](int layer) { return stats + (size_t)layer * B * kStatStride; };
+    // NOTE: stats are stored [F][Cout][2] with the layer's own Cout as the frame stride
+
+    // ---- map branch (independent of the points): channels-last copy, then in pixel-first mode Z_l = F_l W1_l^T ----------
+    // forked onto a side stream so that the latency-bound point branch below (voxelization, row build, row sort) hides
+    // under it; joined before the first kernel that needs both
+    cudaStream_t ms = st;
+    SideStream *side = nullptr;
+    if (pixel_first && g_overlap) {
+        rc = side_stream(&side);
+        if (rc) return rc;
+        ms = side->stream;
+        MVX_CUDA_CHECK(cudaEventRecord(side->fork, st));
+        MVX_CUDA_CHECK(cudaStreamWaitEvent(ms, side->fork, 0));
+    }
+    auto map_branch = [&](MapSet &m) -> int {
+        stamp.begin(S_NHWC, ms);
+        size_t rowmax_off = 0;
+        for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+            const int HW = a->map_h[l] * a->map_w[l];
+            m.h[l] = a->map_h[l], m.w[l] = a->map_w[l];
+            m.rs_h[l] = a->imsize_h / (float)a->map_h[l];
+            m.rs_w[l] = a->imsize_w / (float)a->map_w[l];
+            m.nhwc[l] = F32((Region)(R_NHWC0 + l));
+            m.frame_stride[l] = (size_t)HW * a->map_c;
+            int r = launch_nchw_to_nhwc(a->maps[l], F32((Region)(R_NHWC0 + l)), B, a->map_c, HW, F32(R_ROWMAX) + rowmax_off,
+                                        train ? I32(R_CHMAX) + l * a->map_c : nullptr, MVX_NUM_LEVELS * a->map_c, ms);
+            if (r) return r;
+            rowmax_off += (size_t)B * HW;
+        }
+        stamp.end(S_NHWC, ms);
+        if (!pixel_first) return MVX_OK;
+        // Z_l = F_l W1[:, 256 l : 256 (l+1)]^T for every pixel of every frame (plain GEMM: no bias / ReLU / statistics)
+        stamp.begin(S_GATHER, ms);
+        size_t zoff = 0;
+        for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+            const long long px = (long long)B * a->map_h[l] * a->map_w[l];
+            LayerArgs la{};
+            la.X = m.nhwc[l], la.ldx = a->map_c, la.Cin = a->map_c;
+            la.Wt = a->wt[0] + (size_t)l * a->map_c * 768, la.bias = nullptr, la.Cout = 768;
+            la.Y = F32(R_Z) + zoff, la.ldy = 768;
+            la.rows_fixed = px, la.rows_mode = 0, la.rowcap = 0, la.T = 1, la.eps = a->bn_eps, la.plain = 1;
+            la.f16_ok = 1, la.row_max = F32(R_ROWMAX) + zoff / 768;   // raw FPN features: per-pixel power-of-two scaling
+            int r = launch_layer_auto(la, 1, F32(R_WPACK), ms);
+            if (r) return r;
+            zoff += (size_t)px * 768;
+        }
+        stamp.end(S_GATHER, ms);
+        return MVX_OK;
+    };
+    MapSet m{};
+    m.C = a->map_c;
+    rc = map_branch(m);
+    if (rc) return rc;
+    if (side) MVX_CUDA_CHECK(cudaEventRecord(side->join, ms));
+
+    // ---- point branch: stage 1 (voxelization), compact rows, clears, row sort -----------------------------------------------
     stamp.mark(S_VOXELIZE);
-    // ---- stage 1 ----------------------------------------------------------------------------------------
     mvx_voxel_out_t vo{};
     vo.counts = a->counts;
     vo.vox_coord = I32(R_VOX_COORD), vo.vox_cnt = I32(R_VOX_CNT), vo.vox_row0 = I32(R_VOX_ROW0);
@@ -162,24 +262,6 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     rc = vox_run(&a->grid, B, cap, a->points, a->point_stride, a->pt_off_host, nullptr, T, &vo, ws + L.off[R_VOXWS],
                  vox_workspace_bytes(B, cap), st);
     if (rc) return rc;
-
-    stamp.mark(S_NHWC);
-    // ---- stage 2 ----------------------------------------------------------------------------------------
-    MapSet m{};
-    m.C = a->map_c;
-    size_t rowmax_off = 0;
-    for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
-        const int HW = a->map_h[l] * a->map_w[l];
-        m.h[l] = a->map_h[l], m.w[l] = a->map_w[l];
-        m.rs_h[l] = a->imsize_h / (float)a->map_h[l];
-        m.rs_w[l] = a->imsize_w / (float)a->map_w[l];
-        m.nhwc[l] = F32((Region)(R_NHWC0 + l));
-        m.frame_stride[l] = (size_t)HW * a->map_c;
-        rc = launch_nchw_to_nhwc(a->maps[l], F32((Region)(R_NHWC0 + l)), B, a->map_c, HW, F32(R_ROWMAX) + rowmax_off,
-                                 train ? I32(R_CHMAX) + l * a->map_c : nullptr, MVX_NUM_LEVELS * a->map_c, st);
-        if (rc) return rc;
-        rowmax_off += (size_t)B * HW;
-    }
     stamp.mark(S_ROWS);
     RowsParams rp{};
     rp.B = B, rp.cap = cap, rp.capA = L.capA, rp.T = T;
@@ -190,54 +272,41 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     rp.vox8 = F32(R_VOX8), rp.proj = F32(R_PROJ), rp.rowA_w = F32(R_ROWA_W);
     rc = launch_rows_build(rp, st);
     if (rc) return rc;
-    // training keeps the gathered matrix A1 (dW1 = dpre1^T A1), so it always runs row-first
-    const bool pixel_first = !train && g_fusion_mode == 1 && gemm_mode() == 1;
-    double *stats = reinterpret_cast<double *>(ws + L.off[R_STATS]);
-    auto stat_of = [&](int layer) { return stats + (size_t)layer * B * kStatStride; };
-    // NOTE: stats are stored [F][Cout][2] with the layer's own Cout as the frame stride
-    stamp.mark(S_GATHER);
-    if (!pixel_first) {
-        rc = launch_gather_rows(m, B, L.capA, a->counts, F32(R_VOX8), F32(R_PROJ), a->gather_eps, F32(R_A1), st);
-        if (rc) return rc;
-    } else {
-        // Z_l = F_l W1[:, 256 l : 256 (l+1)]^T for every pixel of every frame (plain GEMM: no bias / ReLU / statistics)
-        size_t zoff = 0;
-        for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
-            const long long px = (long long)B * a->map_h[l] * a->map_w[l];
-            LayerArgs la{};
-            la.X = m.nhwc[l], la.ldx = a->map_c, la.Cin = a->map_c;
-            la.Wt = a->wt[0] + (size_t)l * a->map_c * 768, la.bias = nullptr, la.Cout = 768;
-            la.Y = F32(R_Z) + zoff, la.ldy = 768;
-            la.rows_fixed = px, la.rows_mode = 0, la.rowcap = 0, la.T = 1, la.eps = a->bn_eps, la.plain = 1;
-            la.f16_ok = 1, la.row_max = F32(R_ROWMAX) + zoff / 768;   // raw FPN features: per-pixel power-of-two scaling
-            rc = launch_layer_auto(la, 1, F32(R_WPACK), st);
-            if (rc) return rc;
-            zoff += (size_t)px * 768;
-        }
-    }
 
     stamp.mark(S_CLEAR);
-    // ---- stage 3 ----------------------------------------------------------------------------------------
     MVX_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)MVX_NUM_LAYERS * B * kStatStride * 8, st));
     zero_vmax_kernel<<<dim3(kSMs, B), 256, 0, st>>>(a->counts, cap, I32(R_VMAX6), I32(R_VMAX7), I32(R_VMAX8));
     MVX_LAUNCH_CHECK();
+    CombineArgs ca{};
+    if (pixel_first) {
+        size_t zoff = 0;
+        for (int lv = 0; lv < MVX_NUM_LEVELS; ++lv) {
+            ca.Z[lv] = F32(R_Z) + zoff;
+            ca.frame_stride[lv] = (size_t)a->map_h[lv] * a->map_w[lv] * 768;
+            ca.h[lv] = m.h[lv], ca.w[lv] = m.w[lv], ca.rs_h[lv] = m.rs_h[lv], ca.rs_w[lv] = m.rs_w[lv];
+            zoff += (size_t)B * a->map_h[lv] * a->map_w[lv] * 768;
+        }
+        ca.capA = L.capA, ca.counts = a->counts, ca.vox8 = F32(R_VOX8), ca.proj = F32(R_PROJ), ca.row_w = F32(R_ROWA_W);
+        ca.eps = a->gather_eps, ca.bias = a->bias[0], ca.Y1 = F32(R_Y1), ca.out_stats = stat_of(0);
+        ca.bin_count = I32(R_BINCNT), ca.bin_start = I32(R_BINSTART), ca.perm = I32(R_PERM);
+        ca.nbins = combine_bins(a->map_h[0], a->map_w[0]);
+        rc = launch_combine_sort(ca, B, st);      // needs only the projections: still part of the point branch
+        if (rc) return rc;
+    }
+    stamp.mark(S_COUNT);   // close the running segment before the join wait (it must not absorb the map branch's time)
+    if (side) MVX_CUDA_CHECK(cudaStreamWaitEvent(st, side->join, 0));   // ---- join: both branches done ----
+
+    // ---- stage 2b / 3 -------------------------------------------------------------------------------------------------------
+    if (!pixel_first) {
+        stamp.mark(S_GATHER);
+        rc = launch_gather_rows(m, B, L.capA, a->counts, F32(R_VOX8), F32(R_PROJ), a->gather_eps, F32(R_A1), st);
+        if (rc) return rc;
+    }
     const float *xin[5] = {F32(R_A1), F32(R_Y1), F32(R_Y2), F32(R_Y3), F32(R_Y4)};
     float *yout[5] = {F32(R_Y1), F32(R_Y2), F32(R_Y3), F32(R_Y4), F32(R_Y5)};
     for (int l = 0; l < 5; ++l) {  // fusion stack: fcn1 conv1 fcn2 conv2 fcn3 (Pipe.py:94-104)
         stamp.mark(S_FCN1 + l);
         if (l == 0 && pixel_first) {
-            CombineArgs ca{};
-            size_t zoff = 0;
-            for (int lv = 0; lv < MVX_NUM_LEVELS; ++lv) {
-                ca.Z[lv] = F32(R_Z) + zoff;
-                ca.frame_stride[lv] = (size_t)a->map_h[lv] * a->map_w[lv] * 768;
-                ca.h[lv] = m.h[lv], ca.w[lv] = m.w[lv], ca.rs_h[lv] = m.rs_h[lv], ca.rs_w[lv] = m.rs_w[lv];
-                zoff += (size_t)B * a->map_h[lv] * a->map_w[lv] * 768;
-            }
-            ca.capA = L.capA, ca.counts = a->counts, ca.vox8 = F32(R_VOX8), ca.proj = F32(R_PROJ), ca.row_w = F32(R_ROWA_W);
-            ca.eps = a->gather_eps, ca.bias = a->bias[0], ca.Y1 = F32(R_Y1), ca.out_stats = stat_of(0);
-            ca.bin_count = I32(R_BINCNT), ca.bin_start = I32(R_BINSTART), ca.perm = I32(R_PERM);
-            ca.nbins = combine_bins(a->map_h[0], a->map_w[0]);
             rc = launch_combine_rows(ca, B, st);
             if (rc) return rc;
             continue;
@@ -343,9 +412,11 @@ extern "C" int mvx_timing_enable(int32_t max_calls) {
     auto &t = mvx::g_timing;
     for (cudaEvent_t e : t.ev) cudaEventDestroy(e);
     t.ev.clear();
+    t.recorded.clear();
     t.max_calls = 0, t.next = 0;
     if (max_calls <= 0) return MVX_OK;
-    t.ev.resize((size_t)max_calls * (mvx::S_COUNT + 1));
+    t.ev.resize((size_t)max_calls * mvx::S_COUNT * 2);
+    t.recorded.assign(max_calls, 0u);
     for (auto &e : t.ev) MVX_CUDA_CHECK(cudaEventCreate(&e));
     t.max_calls = max_calls;
     return MVX_OK;
@@ -354,10 +425,13 @@ extern "C" int mvx_timing_enable(int32_t max_calls) {
 extern "C" int mvx_timing_read(int32_t call, float *ms) {
     auto &t = mvx::g_timing;
     MVX_REQUIRE(ms && call >= 0 && call < t.next, MVX_EINVAL, "no timing recorded for this call");
-    cudaEvent_t *ev = &t.ev[(size_t)call * (mvx::S_COUNT + 1)];
-    MVX_CUDA_CHECK(cudaEventSynchronize(ev[mvx::S_COUNT]));
+    cudaEvent_t *ev = &t.ev[(size_t)call * mvx::S_COUNT * 2];
     for (int i = 0; i < MVX_NUM_SEGMENTS; ++i) ms[i] = 0.f;
-    for (int i = 0; i < mvx::S_COUNT; ++i) MVX_CUDA_CHECK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    for (int i = 0; i < mvx::S_COUNT; ++i) {
+        if (!(t.recorded[call] >> i & 1u)) continue;
+        MVX_CUDA_CHECK(cudaEventSynchronize(ev[2 * i + 1]));
+        MVX_CUDA_CHECK(cudaEventElapsedTime(&ms[i], ev[2 * i], ev[2 * i + 1]));
+    }
     return MVX_OK;
 }
 
@@ -395,7 +469,8 @@ extern "C" const char *mvx_pointpath_layout_name(int32_t region) {
 extern "C" int mvx_pointpath_forward(const mvx_pointpath_args_t *args) { return mvx::pointpath_forward(args, false); }
 
 extern "C" int mvx_set_fusion_mode(int32_t mode) {
-    if (mode != 0 && mode != 1) return MVX_EINVAL;
-    mvx::g_fusion_mode = mode;
+    if (mode < 0 || mode > 2) return MVX_EINVAL;   // 2 = pixel-first without the side stream (serial, for per-stage profiling)
+    mvx::g_fusion_mode = mode == 0 ? 0 : 1;
+    mvx::g_overlap = mode != 2;
     return MVX_OK;
 }
