@@ -80,6 +80,21 @@ int mvx_group_emit9(const float *points, int32_t point_stride, int32_t V, int32_
                     float *out_f32, double *uidx_f64, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Before the path — `crop` (modules/data/Preprocessing.py:12-17) and `cropToSight`
+ * (Preprocessing.py:26-55; callers modules/data/Load.py:59,73, cropdata.py:32-65) with an order-preserving
+ * compaction, batched over B frames (pt_off_host[B+1] HOST offsets into `points`, which may start at a non-zero
+ * offset). range6 = velorange (lo xyz, hi xyz) or NULL (no range filter); calib32 = device [B][32]
+ * (R0@Tr | P2) or NULL (no sight filter); imsize as (w, h) like the reference. The kept points of frame f are
+ * written, in input order and with all `point_stride` columns, to out_points starting at row pt_off_host[f];
+ * out_counts[f] (device) = how many. Decisions are the reference's: fp32 coordinates promoted to fp64 against the
+ * fp64 range, camera z > 0, 0 <= (u, v) and (double)(u, v) < imsize - 1e-3.
+ * ------------------------------------------------------------------------------------------------ */
+int mvx_crop_workspace_bytes(int32_t B, int64_t total_points, int64_t max_points, size_t *bytes);
+int mvx_crop_points(const float *points, int32_t point_stride, int32_t B, const int32_t *pt_off_host, const double *range6,
+                    const float *calib32, double imsize_w, double imsize_h, float *out_points, int32_t *out_counts,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stage 2a — projection.  Replaces modules/utils/Calib.py:47-70 (`lidar2Img(pcd, calib, True)`).
  * calib32 (device, 32 floats): M = R0_rect @ Tr_velo_to_cam (row-major 4x4, host-multiplied like the
  * reference does) followed by P2.  out_uv (P,2) = (u,v) = (width, height) coordinates.

@@ -25,6 +25,7 @@ NUM_SEGMENTS = 20
 EXPORTS = [
     'mvx_last_error', 'mvx_version', 'mvx_launch_count',
     'mvx_voxelize_workspace_bytes', 'mvx_voxelize', 'mvx_group_emit7', 'mvx_group_emit9',
+    'mvx_crop_workspace_bytes', 'mvx_crop_points',
     'mvx_lidar2img', 'mvx_maps_nhwc_bytes', 'mvx_feature_mapping',
     'mvx_set_gemm_mode', 'mvx_layer_workspace_bytes', 'mvx_fcn_forward', 'mvx_vfe_forward', 'mvx_fcn_max_forward', 'mvx_set_grid_mode', 'mvx_scatter_dense',
     'mvx_pointpath_workspace_bytes', 'mvx_pointpath_layout', 'mvx_pointpath_layout_name', 'mvx_pointpath_forward',
@@ -76,6 +77,8 @@ def _load():
     lib.mvx_voxelize.argtypes = [POINTER(Grid), i32, i32, vp, i32, POINTER(i32), vp, i32, POINTER(VoxelOut), vp, c_size_t, vp]
     lib.mvx_group_emit7.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mvx_group_emit9.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.mvx_crop_workspace_bytes.argtypes = [i32, i64, i64, POINTER(c_size_t)]
+    lib.mvx_crop_points.argtypes = [vp, i32, i32, POINTER(i32), POINTER(c_double), vp, c_double, c_double, vp, vp, vp, c_size_t, vp]
     lib.mvx_lidar2img.argtypes = [vp, i32, i64, vp, vp, vp]
     lib.mvx_maps_nhwc_bytes.argtypes = [POINTER(i32), POINTER(i32), i32, POINTER(c_size_t)]
     lib.mvx_feature_mapping.argtypes = [vp, i64, POINTER(vp), POINTER(i32), POINTER(i32), i32, c_float, c_float, c_float,

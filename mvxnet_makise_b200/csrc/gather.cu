@@ -2,6 +2,7 @@
 // (modules/imhead/Pipe.py:23-82).  The FPN maps are re-laid out channels-last once per call so that every
 // corner read is a contiguous, coalesced run of channels (NCHW would cost one 32-byte sector per channel).
 #include "gather.cuh"
+#include "project.cuh"
 
 #include <climits>
 
@@ -38,33 +39,6 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restri
         for (int p = 0; p < 32; ++p) m = fmaxf(m, fabsf(tile[tx][p]));     // pixels beyond HW were loaded as 0
         atomicMax(chmax + (size_t)blockIdx.z * chmax_stride + c0 + tx, __float_as_int(m));
     }
-}
-
-// ---- projection: (R0@Tr) @ [x y z 1], then P2 @ ., then divide (Calib.py:65-70) -----------------------
-// Accumulation order = sequential FMA over k (what torch's CPU sgemm does for a 4x4 operand; pinned by
-// tests/test_gpu_parity.py on the reference-generated golden projections).
-__device__ __forceinline__ void project_point(const float *__restrict__ c32, float x, float y, float z, float &u,
-                                              float &v) {
-    float cam[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float a = __fmul_rn(c32[i * 4 + 0], x);
-        a = __fmaf_rn(c32[i * 4 + 1], y, a);
-        a = __fmaf_rn(c32[i * 4 + 2], z, a);
-        a = __fmaf_rn(c32[i * 4 + 3], 1.0f, a);
-        cam[i] = a;
-    }
-    float img[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        float a = __fmul_rn(c32[16 + i * 4 + 0], cam[0]);
-        a = __fmaf_rn(c32[16 + i * 4 + 1], cam[1], a);
-        a = __fmaf_rn(c32[16 + i * 4 + 2], cam[2], a);
-        a = __fmaf_rn(c32[16 + i * 4 + 3], cam[3], a);
-        img[i] = a;
-    }
-    u = __fdiv_rn(img[0], img[2]);
-    v = __fdiv_rn(img[1], img[2]);
 }
 
 __global__ void __launch_bounds__(256) lidar2img_kernel(const float *__restrict__ pts, int stride, long long P,

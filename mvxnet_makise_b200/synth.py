@@ -129,6 +129,20 @@ def make_points(frame_id: int, P: int = 120_000, grid: GridSpec = KITTI_GRID, be
     return np.ascontiguousarray(out, dtype=np.float32)
 
 
+def make_raw_sweep(frame_id: int, P: int = 120_000, beams: int = 64) -> np.ndarray:
+    """(P,4) fp32 UNcropped 360-degree sweep (what a raw KITTI .bin holds, Load.py:57): returns behind the camera, beyond the
+    velo range and outside the image are all present - the input of `crop` / `cropToSight`."""
+    rng = np.random.default_rng(1000 * frame_id + 13)
+    az = np.deg2rad(rng.uniform(-180.0, 180.0, P))
+    el = np.deg2rad(np.linspace(-24.8, 4.0, beams))[rng.integers(0, beams, P)]
+    with np.errstate(divide='ignore'):
+        rg = np.where(el < 0, 1.73 / np.sin(-el), 150.0)
+    rg = np.where(rng.uniform(0.0, 1.0, P) < 0.4, np.minimum(rg, rng.uniform(2.0, 120.0, P)), rg)
+    rg = rg + rng.normal(0.0, 0.02, P)
+    pcd = np.stack([rg * np.cos(el) * np.cos(az), rg * np.cos(el) * np.sin(az), rg * np.sin(el), rng.uniform(0.0, 1.0, P)], axis=1)
+    return np.ascontiguousarray(pcd, dtype=np.float32)
+
+
 def make_fpn_maps(frame_id: int, imsize_hw: Sequence[int] = KITTI_IMSIZE_HW, channels: int = FPN_CHANNELS):
     """Random stand-ins for FPN levels '0','1','2' (NCHW fp32, batch 1) for stage-isolated runs."""
     rng = np.random.default_rng(1000 * frame_id + 11)

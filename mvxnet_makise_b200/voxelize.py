@@ -3,6 +3,7 @@
 Mirrors (same names, argument meaning and return types):
   * ``cpp._group``                     — cpp/voxelutil.cpp:325-360 via modules/Extension.py:1-3
   * ``group`` (numba) / ``group_``     — modules/data/Preprocessing.py:75-116 / :57-73
+  * ``crop`` / ``cropTensor`` / ``cropToSight`` — modules/data/Preprocessing.py:12-55 (the step before the path)
 The in-function shuffle of ``group``/``group_`` is kept (``shuffle=True`` default); parity is defined on the
 post-shuffle order, so tests call with ``shuffle=False`` (SURVEY.md trap 3).
 """
@@ -149,6 +150,67 @@ def group(pcd: np.ndarray, range: Sequence[float], size: Sequence[float], sample
     check(lib.mvx_group_emit9(ptr(pts), pts.shape[1], V, T, ptr(vb.vox_coord), ptr(vb.vox_cnt), ptr(vb.vox_row0),
                               ptr(vb.row_point), ptr(v64), None, ptr(u64), stream_ptr()), 'group_emit9')
     return v64.cpu().numpy(), u64.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Before the path: range crop and field-of-view crop with order-preserving compaction (Preprocessing.py:12-55)
+def crop_frames(points: torch.Tensor, offsets: Sequence[int], range6: Sequence[float] | None = None,
+                calib32: torch.Tensor | None = None, imsize_wh: Sequence[float] | None = None):
+    """Batched device entry. points (sum P, C>=3) fp32 CUDA, offsets host [B+1]; range6 = velorange or None;
+    calib32 (B,32) CUDA ([R0@Tr | P2], `modules.pack_calib`) + imsize (w, h) or None. Returns (out, counts): `out` has
+    the layout of `points` with the kept points of frame f compacted, in input order, at rows offsets[f] ..
+    offsets[f] + counts[f]; counts (B,) int32 CUDA."""
+    _lib.require_cuda()
+    assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous() and points.dim() == 2
+    B = len(offsets) - 1
+    off = (ctypes.c_int32 * (B + 1))(*[int(o) for o in offsets])
+    maxp = max([offsets[i + 1] - offsets[i] for i in range(B)] + [0])
+    nbytes = ctypes.c_size_t()
+    check(lib.mvx_crop_workspace_bytes(B, int(offsets[-1]), int(maxp), ctypes.byref(nbytes)), 'crop_workspace_bytes')
+    ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=points.device)
+    out = torch.empty_like(points)
+    counts = torch.empty(B, dtype=torch.int32, device=points.device)
+    rng = (ctypes.c_double * 6)(*[float(v) for v in range6]) if range6 is not None else None
+    w, h = (float(imsize_wh[0]), float(imsize_wh[1])) if imsize_wh is not None else (0.0, 0.0)
+    if calib32 is not None:
+        assert calib32.is_cuda and calib32.dtype == torch.float32 and calib32.is_contiguous() and tuple(calib32.shape) == (B, 32)
+        assert imsize_wh is not None
+    check(lib.mvx_crop_points(ptr(points), points.shape[1], B, off, rng, ptr(calib32), w, h, ptr(out), ptr(counts), ptr(ws),
+                              ws.numel(), stream_ptr()), 'crop_points')
+    return out, counts
+
+
+def _crop_one(pcd, range6, calib, imsize):
+    from .modules import pack_calib
+    as_numpy = isinstance(pcd, np.ndarray)
+    assert pcd.ndim == 2
+    x = _to_cuda_f32(np.ascontiguousarray(pcd, dtype=np.float32) if as_numpy else pcd)
+    c32 = pack_calib(calib)[None].to(x.device) if calib is not None else None
+    out, counts = crop_frames(x, [0, x.shape[0]], range6, c32, imsize)
+    kept = out[:int(counts[0].item())]
+    if as_numpy:
+        return kept.cpu().numpy().astype(pcd.dtype, copy=False)
+    return kept.to(pcd.dtype)
+
+
+def crop(pcd, range: Sequence[float]):
+    """`crop(pcd, range)` — Preprocessing.py:12-17: points with low <= xyz < high, input order kept. numpy in -> numpy out,
+    torch in -> torch (CUDA) out (`cropTensor`, Preprocessing.py:19-24, is the same filter)."""
+    return _crop_one(pcd, list(range), None, None)
+
+
+cropTensor = crop
+
+
+def cropToSight(pcd, calib: dict, imsize: Sequence[int]):
+    """`cropToSight(pcd, calib, imsize)` — Preprocessing.py:26-55: points in front of the camera whose projection falls
+    inside the image (imsize is (w, h), minus the reference's 1e-3 fudge), input order kept."""
+    return _crop_one(pcd, None, calib, imsize)
+
+
+def cropFrame(pcd, range: Sequence[float], calib: dict, imsize: Sequence[int]):
+    """crop + cropToSight in one pass (what Load.py:59,73 / cropdata.py:32-65 do back to back)."""
+    return _crop_one(pcd, list(range), calib, imsize)
 
 
 class VoxelUtil:

@@ -121,6 +121,32 @@ def group(pcd6: np.ndarray, velorange, voxelsize, T: int):
     return voxel, coords.astype(np.float64)
 
 
+# --------------------------------------------------------------------------- before the path: crop / cropToSight
+def crop(pcd: np.ndarray, velorange: Sequence[float]) -> np.ndarray:
+    """`crop(pcd, range)` — modules/data/Preprocessing.py:12-17 (fp32 coordinates compared against fp64 bounds)."""
+    low = np.array(velorange[0:3])
+    high = np.array(velorange[3:6])
+    roi = pcd[:, :3]
+    return pcd[np.all((low <= roi) & (roi < high), axis=1)]
+
+
+def crop_to_sight(pcd: np.ndarray, calib: Dict[str, np.ndarray], imsize_wh: Sequence[int]) -> np.ndarray:
+    """numpy branch of `cropToSight(pcd, calib, imsize)` — modules/data/Preprocessing.py:26-55 (imsize is (w, h))."""
+    imsize = np.array(imsize_wh) - 1e-3
+    points = np.empty((4, pcd.shape[0]), dtype='float32')
+    points[:3] = pcd.T[:3]
+    points[3] = 1
+    points = calib['R0_rect'] @ calib['Tr_velo_to_cam'] @ points
+    f = points[2] > 0
+    pcd = pcd[f]
+    points = points[:, f]
+    points = calib['P2'] @ points
+    points[:2] = points[:2] / points[2]
+    points = points[:2].T
+    f = np.all(points >= 0, axis=1) & np.all(points < imsize, axis=1)
+    return pcd[f]
+
+
 # --------------------------------------------------------------------------- stage 2a: projection
 def lidar2img(pcd: torch.Tensor, calib: Dict[str, torch.Tensor]) -> torch.Tensor:
     """`lidar2Img(pcd, calib, uncheck=True)` — modules/utils/Calib.py:47-70. Returns (P,2) (u,v)."""

@@ -47,6 +47,53 @@ def mvx():
     return type('NS', (), dict(V=V, M=M, P=P))
 
 
+# ------------------------------------------------------------------------------------------- before the path (§8f rank 1)
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_crop_matches_reference_golden(mvx, golden_dir, tag):
+    """On-GPU `crop` / `cropToSight` (Preprocessing.py:12-55): the same points, in the same order, as the unmodified
+    reference selects - including points exactly on the range bounds and their fp32 neighbours."""
+    g = np.load(os.path.join(golden_dir, 'crop_a.npz'))
+    raw = g[f'raw_{tag}']
+    tagged = raw.copy()
+    tagged[:, 3] = np.arange(raw.shape[0], dtype=np.float32)
+    calib = synth.kitti_calib()
+    wh = (synth.KITTI_IMSIZE_HW[1], synth.KITTI_IMSIZE_HW[0])
+    c = mvx.V.crop(tagged, synth.KITTI_VELORANGE)
+    assert isinstance(c, np.ndarray) and c.dtype == np.float32 and np.array_equal(c[:, 3].astype(np.int32), g[f'crop_{tag}'])
+    assert np.array_equal(c, tagged[g[f'crop_{tag}']])                        # whole rows, untouched
+    s_ = mvx.V.cropToSight(tagged, calib, wh)
+    assert np.array_equal(s_[:, 3].astype(np.int32), g[f'sight_{tag}'])
+    both = mvx.V.cropFrame(tagged, synth.KITTI_VELORANGE, calib, wh)
+    assert np.array_equal(both[:, 3].astype(np.int32), g[f'both_{tag}'])
+    t = mvx.V.cropTensor(torch.from_numpy(tagged).cuda(), synth.KITTI_VELORANGE)  # torch in -> CUDA tensor out
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), c)
+
+
+def test_crop_batched_ragged_and_feeds_the_path(mvx):
+    """Batched device entry with ragged frames (one empty), vs the oracle per frame; the cropped sweep is a valid input of
+    the fused path (every point inside the grid and the image)."""
+    from mvxnet_makise_b200.modules import pack_calib
+    calib = synth.kitti_calib()
+    wh = (synth.KITTI_IMSIZE_HW[1], synth.KITTI_IMSIZE_HW[0])
+    frames = [synth.make_raw_sweep(80, 5000), np.zeros((0, 4), np.float32), synth.make_raw_sweep(81, 1), synth.make_raw_sweep(82, 33333)]
+    offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in frames])]).tolist()
+    pts = torch.from_numpy(np.concatenate(frames, 0)).cuda()
+    c32 = torch.stack([pack_calib(calib) for _ in frames]).cuda()
+    out, counts = mvx.V.crop_frames(pts, offsets, synth.KITTI_VELORANGE, c32, wh)
+    counts = counts.cpu().numpy()
+    kept = []
+    for f, p in enumerate(frames):
+        ref = O.crop_to_sight(O.crop(p, synth.KITTI_VELORANGE), calib, wh)
+        got = out[offsets[f]:offsets[f] + counts[f]].cpu().numpy()
+        assert counts[f] == ref.shape[0] and np.array_equal(got, ref), f
+        kept.append(got)
+    path = mvx.P.PointPath(synth.make_weights(1), G)
+    maps = [torch.from_numpy(m) for m in small_maps(3, B=2)]
+    _, cnt = path([kept[0], kept[3]], [calib, calib], maps, want_grid=False)
+    cnt = cnt.cpu().numpy()
+    assert (cnt[:, 2] == 0).all() and cnt[0, 1] <= kept[0].shape[0] and cnt[1, 0] > 0
+
+
 # ------------------------------------------------------------------------------------------- stage 1
 @pytest.mark.parametrize('tag', ['vox_a', 'vox_b'])
 def test_group_matches_reference_golden(mvx, golden_dir, tag):

@@ -128,3 +128,19 @@ def test_compact_backward_equals_dense_autograd():
     for k in gref:
         g = grads[k].reshape(gref[k].shape)
         assert ((g - gref[k]).abs().max() / gref[k].abs().max()).item() < 1e-9, k
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_crop_oracle_matches_reference_golden(golden_dir, tag):
+    """`crop` / `cropToSight` restatements vs the unmodified reference's selections (tests/golden/make_golden_crop.py)."""
+    from mvxnet_makise_b200 import synth
+    g = np.load(os.path.join(golden_dir, 'crop_a.npz'))
+    raw = g[f'raw_{tag}']
+    tagged = raw.copy()
+    tagged[:, 3] = np.arange(raw.shape[0], dtype=np.float32)
+    calib = synth.kitti_calib()
+    wh = (synth.KITTI_IMSIZE_HW[1], synth.KITTI_IMSIZE_HW[0])
+    c = O.crop(tagged, synth.KITTI_VELORANGE)
+    assert np.array_equal(c[:, 3].astype(np.int32), g[f'crop_{tag}'])
+    assert np.array_equal(O.crop_to_sight(tagged, calib, wh)[:, 3].astype(np.int32), g[f'sight_{tag}'])
+    assert np.array_equal(O.crop_to_sight(c, calib, wh)[:, 3].astype(np.int32), g[f'both_{tag}'])
