@@ -34,13 +34,13 @@ constexpr int kThreads = kProducerThreads + 64;
 constexpr int kEpiCols = 128;   // columns per epilogue pass
 constexpr int kEpiLd = kEpiCols + 4;
 
-template <int BN>
+template <int BN, int STAGES = kStages, bool HALF_EPI = false>
 struct Smem {
     static constexpr int kAHalf = kTM * kBK * 4;      // 16 KB: A_hi (then A_lo)
     static constexpr int kBHalf = BN * kBK * 4;       // B_hi (then B_lo)
     static constexpr int kStage = 2 * kAHalf + 2 * kBHalf;
-    static constexpr int kTiles = kStages * kStage;
-    static constexpr int kEpi = 2 * 128 * kEpiLd * 4;  // two 128-row halves of one 128-column pass
+    static constexpr int kTiles = STAGES * kStage;
+    static constexpr int kEpi = (HALF_EPI ? 1 : 2) * 128 * kEpiLd * 4;  // 128-row halves of one 128-column pass (one at a time if HALF_EPI)
     static constexpr int kMain = kTiles > kEpi ? kTiles : kEpi;
     // after the tiles: mean[768], rstd[768], bias[BN], row_w[256], barriers, tmem pointer
     static constexpr int kMean = kMain;
@@ -114,10 +114,14 @@ __global__ void __launch_bounds__(256) pack_weights_f16_kernel(const float *__re
 
 // BF1: single-pass bf16 operands (no lo parts, one MMA per K-step, no scaling: bf16 has the fp32 exponent range) - the
 // reduced-precision mode whose tolerance is stated separately (tests/test_gpu_parity.py::test_bf16_mode_tolerance).
-template <int BN, bool F16, bool BF1 = false>
-__global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, const float *__restrict__ wpack) {
+// TWO: two CTAs per SM (BN = 128, 16-bit operands): 2 pipeline stages, the epilogue staged one 128-row half at a time (96 KB of
+// shared memory, 256 TMEM columns, <= 102 registers), so one CTA's epilogue overlaps the other's main loop.
+template <int BN, bool F16, bool BF1 = false, bool TWO = false>
+__global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerArgs a, const float *__restrict__ wpack) {
     static_assert(!BF1 || F16, "the bf16 variant shares the 16-bit operand path");
-    using S = Smem<BN>;
+    static_assert(!TWO || (F16 && BN == 128), "the two-CTA variant is the 16-bit, 128-column kernel");
+    constexpr int STAGES = TWO ? 2 : kStages;
+    using S = Smem<BN, STAGES, TWO>;
     constexpr int KB = F16 ? 32 : kBK;   // k per pipeline stage: one 64-byte swizzle row of fp16 / tf32
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // keep the pointer in the shared address space (pointer arithmetic only, no integer round trip): STS/LDS, not ST.E/LD.E
@@ -130,8 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
     int *s_rowv = reinterpret_cast<int *>(smem + S::kRowV);
     const uint32_t bars = sbase + S::kBars;
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
-    const uint32_t accum_bar = bars + 8u * (2 * kStages);
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * STAGES);
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(smem + S::kTmemPtr);
 
     const int f = blockIdx.z, ctile = blockIdx.x, n0 = ctile * BN, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         s_rowv[r] = v;
     }
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), kProducerThreads + 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -222,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
             }
         }
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int PF = TWO ? 1 : 2;   // chunks of raw activations in flight in registers
         auto load_chunk = [&](float4 (&buf)[8], int kc) {
             const bool second = kc * KB >= split;
 #pragma unroll
@@ -250,9 +255,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
                     }
                 }
             }
-            if (kc + 2 < nk) load_chunk(buf, kc + 2);
-            const int s = kc % kStages;
-            const uint32_t ph = (kc / kStages) & 1;
+            if (kc + PF < nk) load_chunk(buf, kc + PF);
+            const int s = kc % STAGES;
+            const uint32_t ph = (kc / STAGES) & 1;
             if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);
             __syncwarp();
             uint8_t *stage = smem + (size_t)s * S::kStage;
@@ -278,12 +283,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
             fence_async_smem();
             mbar_arrive(full_bar(s));
         };
-        float4 buf0[8], buf1[8];
-        load_chunk(buf0, 0);
-        if (nk > 1) load_chunk(buf1, 1);
-        for (int kc = 0; kc < nk; kc += 2) {
-            produce(buf0, kc);
-            if (kc + 1 < nk) produce(buf1, kc + 1);
+        if constexpr (TWO) {   // one chunk in flight per thread (register budget of two CTAs per SM; 16 producer warps per SM)
+            float4 buf0[8];
+            load_chunk(buf0, 0);
+            for (int kc = 0; kc < nk; ++kc) produce(buf0, kc);
+        } else {
+            float4 buf0[8], buf1[8];
+            load_chunk(buf0, 0);
+            if (nk > 1) load_chunk(buf1, 1);
+            for (int kc = 0; kc < nk; kc += 2) {
+                produce(buf0, kc);
+                if (kc + 1 < nk) produce(buf1, kc + 1);
+            }
         }
     } else if (warp < 8) {
         // ================= A producers ===========================================================================
@@ -318,8 +329,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
                 }
             }
             if (kc + 2 < nk) load_chunk(buf, kc + 2);
-            const int s = kc % kStages;
-            const uint32_t ph = (kc / kStages) & 1;
+            const int s = kc % STAGES;
+            const uint32_t ph = (kc / STAGES) & 1;
             if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);  // one poller per warp
             __syncwarp();
             uint8_t *stage = smem + (size_t)s * S::kStage;
@@ -349,8 +360,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         if (lane == 0) {
             const float *src = wpack + (size_t)ctile * nk * (2 * BN * kBK);
             for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % kStages;
-                const uint32_t ph = (kc / kStages) & 1;
+                const int s = kc % STAGES;
+                const uint32_t ph = (kc / STAGES) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
                 mbar_arrive_expect_tx(full_bar(s), 2 * S::kBHalf);
                 bulk_g2s(sbase + s * S::kStage + 2 * S::kAHalf, src + (size_t)kc * (2 * BN * kBK), 2 * S::kBHalf, full_bar(s));
@@ -363,8 +374,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
             constexpr uint32_t fmt = BF1 ? 1u : (F16 ? 0u : 2u);   // kind::f16: 0 = fp16, 1 = bf16; kind::tf32: 2 = tf32
             constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
             for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % kStages;
-                const uint32_t ph = (kc / kStages) & 1;
+                const int s = kc % STAGES;
+                const uint32_t ph = (kc / STAGES) & 1;
                 if (!mma_only) mbar_wait(full_bar(s), ph);
                 tc_fence_after();
                 const uint32_t sA = sbase + s * S::kStage, sB = sA + 2 * S::kAHalf;
@@ -402,90 +413,101 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
         tc_fence_after();
     }
     __syncthreads();  // every stage buffer is idle now: reuse the tile memory for the output staging
-    float *ytile = reinterpret_cast<float *>(smem);  // [2 halves][128 rows][kEpiLd]
-    const int half = warp >> 2, q = warp & 3;        // accumulator, TMEM lane quarter
+    float *ytile = reinterpret_cast<float *>(smem);  // [2 halves (TWO: 1)][128 rows][kEpiLd]
+    const int q = warp & 3;                          // TMEM lane quarter of this warp
     const float floor_v = a.plain ? -INFINITY : 0.f;  // plain mode: no ReLU (bias is zero)
+    constexpr int HP = TWO ? 2 : 1;                  // half passes: TWO stages one 128-row accumulator at a time
+    constexpr int TR = TWO ? 128 : kTM;              // rows in the staging tile
     for (int pass = 0; pass < ((a.dbg & 2) ? 0 : BN / kEpiCols); ++pass) {
-        if (warp < 8) {
-            const int rloc = half * 128 + q * 32 + lane;
-            float *yrow = ytile + (size_t)rloc * kEpiLd;
-            const float rinv = F16 ? s_rowinv[rloc] : 1.f;
 #pragma unroll 1
-            for (int cb = 0; cb < kEpiCols / 32; ++cb) {
-                float v[32];
-                const int col = pass * kEpiCols + cb * 32;
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + half * BN + col, v);
-                if constexpr (F16) {   // undo the power-of-two operand scales (exact)
+        for (int hp = 0; hp < HP; ++hp) {
+            if (warp < 8) {
+                // TWO: all 8 warps drain accumulator `hp`, warps w and w+4 share a lane quarter and split the 128 columns;
+                // otherwise warps 0-3 drain accumulator 0 and warps 4-7 accumulator 1
+                const int half = TWO ? hp : (warp >> 2);
+                const int cpart = TWO ? (warp >> 2) * 64 : 0, ncb = TWO ? 2 : kEpiCols / 32;
+                const int rloc = half * 128 + q * 32 + lane;          // row inside the 256-row CTA tile
+                float *yrow = ytile + (size_t)(TWO ? q * 32 + lane : rloc) * kEpiLd + cpart;
+                const float rinv = F16 ? s_rowinv[rloc] : 1.f;
+#pragma unroll 1
+                for (int cb = 0; cb < ncb; ++cb) {
+                    float v[32];
+                    const int col = pass * kEpiCols + cpart + cb * 32;
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + half * BN + col, v);
+                    if constexpr (F16) {   // undo the power-of-two operand scales (exact)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= rinv * s_colinv[col + j];
-                }
+                        for (int j = 0; j < 32; ++j) v[j] *= rinv * s_colinv[col + j];
+                    }
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    o.x = fmaxf(v[j] + s_bias[col + j], floor_v);
-                    o.y = fmaxf(v[j + 1] + s_bias[col + j + 1], floor_v);
-                    o.z = fmaxf(v[j + 2] + s_bias[col + j + 2], floor_v);
-                    o.w = fmaxf(v[j + 3] + s_bias[col + j + 3], floor_v);
-                    *reinterpret_cast<float4 *>(yrow + cb * 32 + j) = o;
-                }
-            }
-        }
-        __syncthreads();
-        if (tid < 256) {
-            // coalesced raw stores first (one warp per row, 32 lanes x 16 bytes = 128 columns): they drain while the sums run
-            if (a.Y) {
-                for (int r = warp; r < kTM; r += 8) {
-                    if (row0 + r >= n_rows) break;
-                    const float4 o = *reinterpret_cast<const float4 *>(ytile + (size_t)r * kEpiLd + lane * 4);
-                    *reinterpret_cast<float4 *>(a.Y + ((size_t)f * a.rowcap + row0 + r) * a.ldy + n0 + pass * kEpiCols + lane * 4) = o;
-                }
-            }
-            // weighted column sums: thread = (column, 128-row group). Ordinary rows (multiplicity 1) are summed in fp32
-            // over runs of 16 rows and the runs in fp64; the weighted pad row takes an exact fp64 side path.
-            const int col = tid & 127, rg = tid >> 7;
-            if (!a.plain) {
-            double sy = 0.0, syy = 0.0;
-            for (int r0 = rg * 128; r0 < rg * 128 + 128; r0 += 16) {
-                float ps = 0.f, pss = 0.f;
-#pragma unroll
-                for (int r = r0; r < r0 + 16; ++r) {
-                    const float w = s_roww[r];
-                    const float y = ytile[(size_t)r * kEpiLd + col];
-                    const float my = w == 1.f ? y : 0.f;
-                    ps += my;
-                    pss = fmaf(my, y, pss);
-                    if (w != 1.f && w != 0.f) {
-                        const double wy = (double)w * (double)y;
-                        sy += wy;
-                        syy = fma(wy, (double)y, syy);
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        o.x = fmaxf(v[j] + s_bias[col + j], floor_v);
+                        o.y = fmaxf(v[j + 1] + s_bias[col + j + 1], floor_v);
+                        o.z = fmaxf(v[j + 2] + s_bias[col + j + 2], floor_v);
+                        o.w = fmaxf(v[j + 3] + s_bias[col + j + 3], floor_v);
+                        *reinterpret_cast<float4 *>(yrow + cb * 32 + j) = o;
                     }
                 }
-                sy += (double)ps;
-                syy += (double)pss;
             }
-            double *o = a.out_stats + ((size_t)f * a.Cout + n0 + pass * kEpiCols + col) * 2;
-            atomicAdd(o, sy);
-            atomicAdd(o + 1, syy);
-            if (a.vmax) {  // per-voxel max of the raw (>= 0) activations: rows of a voxel are consecutive
-                int *vm = a.vmax + (size_t)f * a.vcap * a.Cout + n0 + pass * kEpiCols + col;
-                int cv = -1;
-                float cm = 0.f;
-                for (int r = rg * 128; r < rg * 128 + 128; ++r) {
-                    const int v = s_rowv[r];
-                    const float y = ytile[(size_t)r * kEpiLd + col];
-                    if (v != cv) {
+            __syncthreads();
+            if (tid < 256) {
+                const int rbase = TWO ? hp * 128 : 0;    // first CTA-tile row of the staging tile
+                // coalesced raw stores first (one warp per row, 32 lanes x 16 bytes = 128 columns): they drain while the sums run
+                if (a.Y) {
+                    for (int r = warp; r < TR; r += 8) {
+                        if (row0 + rbase + r >= n_rows) break;
+                        const float4 o = *reinterpret_cast<const float4 *>(ytile + (size_t)r * kEpiLd + lane * 4);
+                        *reinterpret_cast<float4 *>(a.Y + ((size_t)f * a.rowcap + row0 + rbase + r) * a.ldy + n0 + pass * kEpiCols + lane * 4) = o;
+                    }
+                }
+                // weighted column sums: thread = (column, row group). Ordinary rows (multiplicity 1) are summed in fp32
+                // over runs of 16 rows and the runs in fp64; the weighted pad row takes an exact fp64 side path.
+                const int col = tid & 127, rg = tid >> 7;
+                constexpr int RG = TR / 2;               // rows per group
+                if (!a.plain) {
+                    double sy = 0.0, syy = 0.0;
+                    for (int r0 = rg * RG; r0 < rg * RG + RG; r0 += 16) {
+                        float ps = 0.f, pss = 0.f;
+#pragma unroll
+                        for (int r = r0; r < r0 + 16; ++r) {
+                            const float w = s_roww[rbase + r];
+                            const float y = ytile[(size_t)r * kEpiLd + col];
+                            const float my = w == 1.f ? y : 0.f;
+                            ps += my;
+                            pss = fmaf(my, y, pss);
+                            if (w != 1.f && w != 0.f) {
+                                const double wy = (double)w * (double)y;
+                                sy += wy;
+                                syy = fma(wy, (double)y, syy);
+                            }
+                        }
+                        sy += (double)ps;
+                        syy += (double)pss;
+                    }
+                    double *o = a.out_stats + ((size_t)f * a.Cout + n0 + pass * kEpiCols + col) * 2;
+                    atomicAdd(o, sy);
+                    atomicAdd(o + 1, syy);
+                    if (a.vmax) {  // per-voxel max of the raw (>= 0) activations: rows of a voxel are consecutive
+                        int *vm = a.vmax + (size_t)f * a.vcap * a.Cout + n0 + pass * kEpiCols + col;
+                        int cv = -1;
+                        float cm = 0.f;
+                        for (int r = rg * RG; r < rg * RG + RG; ++r) {
+                            const int v = s_rowv[rbase + r];
+                            const float y = ytile[(size_t)r * kEpiLd + col];
+                            if (v != cv) {
+                                if (cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
+                                cv = v;
+                                cm = y;
+                            } else {
+                                cm = fmaxf(cm, y);
+                            }
+                        }
                         if (cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
-                        cv = v;
-                        cm = y;
-                    } else {
-                        cm = fmaxf(cm, y);
                     }
                 }
-                if (cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
             }
-            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     tc_fence_before();
     __syncthreads();
@@ -494,12 +516,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(LayerArgs a, cons
     }
 }
 
-template <int BN, bool F16, bool BF1 = false>
+template <int BN, bool F16, bool BF1 = false, bool TWO = false>
 int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
-    using S = Smem<BN>;
+    using S = Smem<BN, TWO ? 2 : kStages, TWO>;
     static bool attr_set = false;
     if (!attr_set) {
-        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN, F16, BF1>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN, F16, BF1, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        if (TWO) MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN, F16, BF1, TWO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
     const int total = a.Cin * a.Cout;
@@ -512,7 +535,7 @@ int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     MVX_LAUNCH_CHECK();
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     dim3 grid(a.Cout / BN, (unsigned)ceil_div(max_rows, kTM), F);
-    tc_layer_kernel<BN, F16, BF1><<<grid, kThreads, S::kTotal, st>>>(a, wpack);
+    tc_layer_kernel<BN, F16, BF1, TWO><<<grid, kThreads, S::kTotal, st>>>(a, wpack);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }
@@ -842,6 +865,9 @@ int launch_tc_persist(const LayerArgs &a, int F, float *wpack, cudaStream_t st) 
 
 }  // namespace
 
+static int g_tc_two = 0;        // MVX_TC_TWO=1: 128-column 16-bit layers run as two CTAs per SM (measured slower for conv1/fcn2: 0.99 vs 0.86 ms, 0.42 vs 0.35 ms;
+                                // 1-deep prefetch and a 2-stage ring cost more than the overlapped epilogue gains) - experimental
+static int g_tc_two_wide = 0;   // 1: also split 256-column tiles (the pixel GEMM) into 128-column two-CTA tiles (MVX_TC_TWO=2)
 static int g_tc_bf16 = 0;
 void set_tc_bf16(int on) { g_tc_bf16 = on; }
 static int g_tc_f16 = 1;
@@ -862,6 +888,11 @@ size_t tc_wpack_bytes(int Cin, int Cout) { return (size_t)2 * Cin * Cout * sizeo
 int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st) {
     LayerArgs a = a_in;
     if (const char *e = getenv("MVX_DBG")) a.dbg = atoi(e);
+    static const bool env_read = [] {
+        if (const char *e = getenv("MVX_TC_TWO")) g_tc_two = atoi(e) != 0, g_tc_two_wide = atoi(e) == 2;
+        return true;
+    }();
+    (void)env_read;
     MVX_REQUIRE(tc_layer_eligible(a) && wpack, MVX_EINVAL, "layer not eligible for the tensor-core kernel");
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     if (max_rows <= 0) return MVX_OK;
@@ -870,11 +901,13 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
     MVX_REQUIRE(!a.X2 || (a.f16_ok && (g_tc_bf16 || tc_f16_enabled()) && a.Cin % 32 == 0 && a.x2_cols % 32 == 0 && a.counts),
                 MVX_EINVAL, "fused concat input needs the 16-bit tensor-core producer");
     if (a.f16_ok && g_tc_bf16 && a.Cin % 32 == 0) {          // reduced precision: one bf16 product per K-step
-        if (a.Cout % 256 == 0) return launch_tc<256, true, true>(a, F, wpack, st);
+        if (a.Cout % 256 == 0 && !g_tc_two_wide) return launch_tc<256, true, true>(a, F, wpack, st);
+        if (g_tc_two) return launch_tc<128, true, true, true>(a, F, wpack, st);
         return launch_tc<128, true, true>(a, F, wpack, st);
     }
     if (a.f16_ok && tc_f16_enabled() && a.Cin % 32 == 0) {   // 3xFP16: half the tensor cycles and operand bytes of 3xTF32
-        if (a.Cout % 256 == 0) return launch_tc<256, true>(a, F, wpack, st);
+        if (a.Cout % 256 == 0 && !g_tc_two_wide) return launch_tc<256, true>(a, F, wpack, st);
+        if (g_tc_two) return launch_tc<128, true, false, true>(a, F, wpack, st);   // two CTAs per SM: epilogue of one overlaps the main loop of the other
         return launch_tc<128, true>(a, F, wpack, st);
     }
     if (a.Cout % 256 == 0) return launch_tc<256, false>(a, F, wpack, st);
