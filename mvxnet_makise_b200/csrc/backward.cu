@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) bn_back_reduce_kernel(BnArgs a) {
     }
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     const int rend = min(row0 + kBnRows, n_rows);
-    for (int r = row0 + rg; r < rend; r += rpp) {
+#pragma unroll 4
+    for (int r = row0 + rg; r < rend; r += rpp) {   // unrolled: four rows of loads in flight per thread
         const size_t o = ((size_t)f * a.rs.rowcap + r) * C + c;
         const float4 g = *reinterpret_cast<const float4 *>(a.G + o);
         const float4 y = *reinterpret_cast<const float4 *>(a.Y + o);
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(256) bn_back_apply_kernel(BnArgs a) {
     float mx[4] = {0.f, 0.f, 0.f, 0.f};
     const int pad_row = a.rs.mode == 1 ? a.rs.counts[f * 4 + 1] : -1;
     const int rend = min(row0 + kBnRows, n_rows);
+#pragma unroll 4
     for (int r = row0 + rg; r < rend; r += rpp) {
         const size_t ro = (size_t)f * a.rs.rowcap + r;
         const float w = a.rs.row_w[ro];
@@ -361,16 +363,21 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(DwArgs a) {
         static_assert(G % 8 == 0, "granules must divide over the 8 producer warps");
         const int lr = lane & 7, lb = lane >> 3;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int t = 0; t < nst; ++t) {
+        // granule q of this warp: operand (D or X), 8-row group j, 32-column group cg
+        auto geom = [&](int q, bool &isx, int &cgs, int &j, int &cg) {
+            const int g = warp + 8 * q;
+            isx = g >= GD;
+            const int gg = isx ? g - GD : g;
+            cgs = isx ? TK / 32 : MT / 32;
+            j = gg / cgs, cg = gg - j * cgs;
+        };
+        auto load_stage = [&](float4 (&v)[GPW][2], int t) {   // all loads of a stage first (memory-level parallelism)
             const int r0 = row0 + t * kDwRows;
-            float4 v[GPW][2];
 #pragma unroll
-            for (int q = 0; q < GPW; ++q) {        // all loads of this warp's granules first (memory-level parallelism)
-                const int g = warp + 8 * q;
-                const bool isx = g >= GD;
-                const int gg = isx ? g - GD : g;
-                const int cgs = isx ? TK / 32 : MT / 32;
-                const int j = gg / cgs, cg = gg - j * cgs;
+            for (int q = 0; q < GPW; ++q) {
+                bool isx;
+                int cgs, j, cg;
+                geom(q, isx, cgs, j, cg);
                 const int r = r0 + 8 * j + lr, col = cg * 32 + lb * 8;
                 const bool ok = r < rend && r != pad_row;
                 const float *src = isx ? a.X + ((size_t)f * a.rs.rowcap + r) * a.ldx + k0 + col
@@ -378,6 +385,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(DwArgs a) {
                 v[q][0] = ok ? __ldg(reinterpret_cast<const float4 *>(src)) : z4;
                 v[q][1] = ok ? __ldg(reinterpret_cast<const float4 *>(src) + 1) : z4;
             }
+        };
+        auto store_stage = [&](float4 (&v)[GPW][2], int t) {
+            const int r0 = row0 + t * kDwRows;
             const int s = t % kDwStages;
             const uint32_t ph = (t / kDwStages) & 1;
             if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);
@@ -385,11 +395,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(DwArgs a) {
             uint8_t *stage = smem + (size_t)s * S::kStage;
 #pragma unroll
             for (int q = 0; q < GPW; ++q) {
-                const int g = warp + 8 * q;
-                const bool isx = g >= GD;
-                const int gg = isx ? g - GD : g;
-                const int cgs = isx ? TK / 32 : MT / 32;
-                const int j = gg / cgs, cg = gg - j * cgs;
+                bool isx;
+                int cgs, j, cg;
+                geom(q, isx, cgs, j, cg);
                 const int col = cg * 32 + lb * 8;
                 const int r = r0 + 8 * j + lr;
                 const bool ok = r < rend && r != pad_row;
@@ -411,6 +419,17 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(DwArgs a) {
             }
             fence_async_smem();
             mbar_arrive(full_bar(s));
+        };
+        // the raw rows of the next stage are already in flight in registers while this stage is converted and stored
+        float4 va[GPW][2], vb[GPW][2];
+        load_stage(va, 0);
+        for (int t = 0; t < nst; t += 2) {
+            if (t + 1 < nst) load_stage(vb, t + 1);
+            store_stage(va, t);
+            if (t + 1 < nst) {
+                if (t + 2 < nst) load_stage(va, t + 2);
+                store_stage(vb, t + 1);
+            }
         }
     } else if (lane == 0) {
         // ================= MMA issuer: D fp32, A/B fp16, both MN-major, M = 128, N = TK =============================

@@ -57,9 +57,11 @@ __global__ void __launch_bounds__(256) lidar2img_kernel(const float *__restrict_
 // ---- the 4-corner weighted gather of one row, one warp, all levels ------------------------------------
 // Index math and the (inverted) weights are those of Pipe.py:62-75, evaluated in the same fp32 order with no
 // FMA contraction, so the result is bit-identical to the reference's eager ops for the same `proj`.
+// returns this lane's max |value| over the row (for the fp16 row scaling of a tensor-core consumer)
 template <bool kStreaming>
-__device__ __forceinline__ void gather_row_warp(const MapSet &m, int f, float prow, float pcol, float eps, int lane,
-                                                float *__restrict__ out_row) {
+__device__ __forceinline__ float gather_row_warp(const MapSet &m, int f, float prow, float pcol, float eps, int lane,
+                                                 float *__restrict__ out_row) {
+    float amax = 0.f;
 #pragma unroll
     for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
         const float q0 = __fsub_rn(__fdiv_rn(prow, m.rs_h[l]), eps);
@@ -92,8 +94,10 @@ __device__ __forceinline__ void gather_row_warp(const MapSet &m, int f, float pr
 #undef MVX_CORNERS
             float4 *dst = reinterpret_cast<float4 *>(out_row + (size_t)l * C) + c4;
             if (kStreaming) st_cs_f4(dst, g); else *dst = g;
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(g.x), fabsf(g.y))), fmaxf(fabsf(g.z), fabsf(g.w)));
         }
     }
+    return amax;
 }
 
 template <bool kStreaming>
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(256) rows_build_kernel(RowsParams p) {
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(MapSet m, int capA, const int *__restrict__ counts,
                                                           const float *__restrict__ vox8, const float *__restrict__ proj,
-                                                          float eps, float *__restrict__ A1) {
+                                                          float eps, float *__restrict__ A1, float *__restrict__ rowmax) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int K = counts[f * 4 + 1];
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -179,9 +183,15 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(MapSet m, int capA, co
     float *orow = A1 + ro * 3 * m.C;
     if (xyz.x == 0.f && xyz.y == 0.f && xyz.z == 0.f) {
         zero_row_warp<false>(3 * m.C, lane, orow);
+        if (rowmax && lane == 0) rowmax[ro] = 0.f;
     } else {
         const float2 pr = reinterpret_cast<const float2 *>(proj)[ro];
-        gather_row_warp<false>(m, f, pr.x, pr.y, eps, lane, orow);
+        float amax = gather_row_warp<false>(m, f, pr.x, pr.y, eps, lane, orow);
+        if (rowmax) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
+            if (lane == 0) rowmax[ro] = amax;
+        }
     }
 }
 
@@ -403,9 +413,9 @@ int launch_rows_build(const RowsParams &p, cudaStream_t st) {
 }
 
 int launch_gather_rows(const MapSet &m, int B, int capA, const int *counts, const float *vox8, const float *proj, float eps,
-                       float *A1, cudaStream_t st) {
+                       float *A1, float *rowmax, cudaStream_t st) {
     dim3 grid((capA + 7) / 8, B);
-    gather_rows_kernel<<<grid, 256, 0, st>>>(m, capA, counts, vox8, proj, eps, A1);
+    gather_rows_kernel<<<grid, 256, 0, st>>>(m, capA, counts, vox8, proj, eps, A1, rowmax);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }

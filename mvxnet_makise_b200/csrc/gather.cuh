@@ -32,8 +32,9 @@ struct RowsParams {
 int launch_rows_build(const RowsParams &p, cudaStream_t st);
 
 // compact gather: A1[f][r][0:3C] for r <= K_f (row K_f is the all-zero pad row)
+// rowmax (optional): [B][capA] max |A1[r][:]| of every row
 int launch_gather_rows(const MapSet &m, int B, int capA, const int *counts, const float *vox8, const float *proj,
-                       float eps, float *A1, cudaStream_t st);
+                       float eps, float *A1, float *rowmax, cudaStream_t st);
 
 // Pixel-first form of gather + fcn1. The 4-corner sample is linear in the map values, so
 //   relu(A1[r] W^T + b) = relu(b + sum_l sum_corner wgt(r,l,corner) * Z_l[pixel(r,l,corner)]),   Z_l = F_l W_l^T

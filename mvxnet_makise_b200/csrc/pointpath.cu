@@ -19,7 +19,7 @@ namespace mvx {
 const char *kRegionNames[R_COUNT] = {
     "vox_ws", "vox_coord", "vox_cnt", "vox_row0", "row_point", "row_vox", "cell2vid", "nhwc0", "nhwc1", "nhwc2",
     "vox8", "proj", "rowA_w", "A1", "Y1", "Y2", "Y3", "Y4", "Y5", "X6", "Y6", "X7", "Y7", "rowB_w", "rowB_v", "X8",
-    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t", "Z", "bin_count", "bin_start", "perm", "rowmax", "chmax", "Y8"};
+    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t", "Z", "bin_count", "bin_start", "perm", "rowmax", "chmax", "A1max", "Y8"};
 
 // 1 (default): pixel-first fcn1 - one tensor-core GEMM per FPN level over the map pixels, then a 12-corner combine per
 // point row (gather.cuh CombineArgs); 0: materialise the gathered (K,768) matrix A1 and run fcn1 over the point rows
@@ -89,6 +89,7 @@ int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
         take(R_PERM, B * capA * 4);
         take(R_ROWMAX, B * px * 4);
         take(R_CHMAX, B * 768 * 4);
+        take(R_A1MAX, B * capA * 4);
     }
     L.total = o;
     take(R_Y8, B * capB * 128 * 4);   // last region: only present in a training workspace
@@ -299,7 +300,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     // ---- stage 2b / 3 -------------------------------------------------------------------------------------------------------
     if (!pixel_first) {
         stamp.mark(S_GATHER);
-        rc = launch_gather_rows(m, B, L.capA, a->counts, F32(R_VOX8), F32(R_PROJ), a->gather_eps, F32(R_A1), st);
+        rc = launch_gather_rows(m, B, L.capA, a->counts, F32(R_VOX8), F32(R_PROJ), a->gather_eps, F32(R_A1), F32(R_A1MAX), st);
         if (rc) return rc;
     }
     const float *xin[5] = {F32(R_A1), F32(R_Y1), F32(R_Y2), F32(R_Y3), F32(R_Y4)};
@@ -318,7 +319,8 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         la.out_stats = stat_of(l);
         la.row_w = F32(R_ROWA_W), la.counts = a->counts, la.rows_mode = 1, la.rowcap = L.capA, la.vcap = cap, la.T = T;
         la.eps = a->bn_eps;
-        la.f16_ok = l > 0;   // BatchNorm-ed inputs; fcn1 row-first reads raw features of arbitrary range: 3xTF32
+        la.f16_ok = 1;       // BatchNorm-ed inputs; fcn1 row-first reads raw gathered features: per-row power-of-two scaling
+        if (l == 0) la.row_max = F32(R_A1MAX);
         rc = launch_layer_auto(la, B, F32(R_WPACK), st);
         if (rc) return rc;
     }
