@@ -89,10 +89,21 @@ __global__ void __launch_bounds__(256) bn_back_reduce_kernel(BnArgs a) {
             s2[j] += (double)gv[j] * z;
         }
     }
+    // narrow layers put 32 / tpr lanes of a warp on the same columns: combine them with shuffles first (64 threads
+    // CAS-looping on one shared fp64 address cost 0.8 ms per 16-column layer)
+    for (int d = 16; d >= tpr; d >>= 1) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        atomicAdd(&s_acc[(c + j) * 2], s1[j]);
-        atomicAdd(&s_acc[(c + j) * 2 + 1], s2[j]);
+        for (int j = 0; j < 4; ++j) {
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], d);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], d);
+        }
+    }
+    if (tpr >= 32 || (tid & 31) < tpr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&s_acc[(c + j) * 2], s1[j]);
+            atomicAdd(&s_acc[(c + j) * 2 + 1], s2[j]);
+        }
     }
     __syncthreads();
     for (int i = tid; i < C * 2; i += blockDim.x) atomicAdd(a.bstats + (size_t)f * C * 2 + i, s_acc[i]);
@@ -145,10 +156,19 @@ __global__ void __launch_bounds__(256) bn_back_apply_kernel(BnArgs a) {
         }
         *gp = make_float4(o[0], o[1], o[2], o[3]);
     }
+    for (int d = 16; d >= tpr; d >>= 1) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        atomicAdd(&s_acc[c + j], sb[j]);
-        if (a.dmax && mx[j] > 0.f) atomicMax(a.dmax + (size_t)f * C + c + j, __float_as_int(mx[j]));
+        for (int j = 0; j < 4; ++j) {
+            sb[j] += __shfl_xor_sync(0xffffffffu, sb[j], d);
+            mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], d));
+        }
+    }
+    if (tpr >= 32 || (tid & 31) < tpr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&s_acc[c + j], sb[j]);
+            if (a.dmax && mx[j] > 0.f) atomicMax(a.dmax + (size_t)f * C + c + j, __float_as_int(mx[j]));
+        }
     }
     __syncthreads();
     for (int i = tid; i < C; i += blockDim.x) atomicAdd(a.dbias + i, (float)s_acc[i]);

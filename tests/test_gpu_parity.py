@@ -367,6 +367,39 @@ def test_pixel_first_fcn1_equals_row_first(mvx):
     assert rel_err(out[1][1], out[0][1]) < 1e-5, 'BatchNorm sums of fcn1'
 
 
+@pytest.mark.parametrize('scale', [3e4, 1e-5])
+@pytest.mark.parametrize('fusion_mode', [1, 0], indirect=True)
+def test_fp16_operands_survive_extreme_feature_ranges(mvx, scale, fusion_mode):
+    """The 3xFP16 tensor-core layers scale raw inputs by exact powers of two (per pixel row for the pixel GEMM, per gathered
+    row for the row-first fcn1, per weight column): FPN features far outside fp16's range (values up to ~1e5, or ~1e-5)
+    must give the same fp32-level agreement with the fp64 oracle as O(1) features."""
+    sd = synth.make_weights(8)
+    calib = synth.kitti_calib()
+    pts = synth.make_points(90, 1800)
+    maps = [m * np.float32(scale) for m in small_maps(13)]
+    path = mvx.P.PointPath(sd, G)
+    if fusion_mode == 0:
+        from mvxnet_makise_b200.modules import pack_calib
+        pd = torch.from_numpy(pts).cuda()
+        path.forward_train(pd, [0, pts.shape[0]], pack_calib(calib)[None].cuda(), [torch.from_numpy(m).cuda() for m in maps],
+                           want_grid=False)                      # row-first fcn1 in 3xFP16 (per-row scale from the gather)
+    else:
+        path([pts], [calib], [torch.from_numpy(m) for m in maps], want_grid=False)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref64 = O.forward_frame(pts, calib, maps, sd, G, synth.KITTI_IMSIZE_HW, dtype=torch.float64, want_grid=False)
+        ref32 = O.forward_frame(pts, calib, maps, sd, G, synth.KITTI_IMSIZE_HW, want_grid=False)
+    vf, idx = path.voxel_features(0)
+    assert np.array_equal(idx.cpu().numpy()[:, 1:], ref64['idx'].numpy()[:, 1:])
+    # tiny features ride on an O(1e-2) bias: y = relu(b + delta) stored in fp32 keeps delta to ~1e-3 relative in ANY fp32
+    # implementation, the reference included, so the bar is TOL on top of the fp32 oracle's own distance to fp64
+    noise = rel_err(ref32['vfeat'], ref64['vfeat'])
+    e = rel_err(vf, ref64['vfeat'])
+    assert torch.isfinite(vf).all() and e < TOL + 2 * noise, (e, noise)
+    if scale > 1:
+        assert e < TOL
+
+
 BF16_TOL = 8e-2
 
 
