@@ -183,7 +183,8 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     int rc = make_layout(a, L);
     if (rc) return rc;
     MVX_REQUIRE(a->workspace && a->workspace_bytes >= (train ? L.total_train : L.total), MVX_ESPACE, "pointpath workspace too small");
-    MVX_REQUIRE(a->points && a->pt_off_host && a->calib32 && a->counts, MVX_EINVAL, "null input pointer");
+    MVX_REQUIRE(a->pt_off_host && a->calib32 && a->counts, MVX_EINVAL, "null input pointer");
+    MVX_REQUIRE(a->points || a->pt_off_host[a->B] == a->pt_off_host[0], MVX_EINVAL, "null points pointer");   // an all-empty batch may pass NULL
     MVX_REQUIRE(a->point_stride >= 4, MVX_EINVAL, "point_stride must be >= 4");
     for (int l = 0; l < MVX_NUM_LEVELS; ++l) MVX_REQUIRE(a->maps[l], MVX_EINVAL, "null FPN map");
     for (int l = 0; l < MVX_NUM_LAYERS; ++l) MVX_REQUIRE(a->wt[l] && a->bias[l], MVX_EINVAL, "null layer weights");

@@ -115,6 +115,8 @@ class PointPath:
         a = _lib.PointPathArgs()
         a.grid = self.grid
         a.B, a.cap = B, cap
+        if points.shape[0] == 0:     # all-empty batch: the kernels read no point, but the ABI wants a valid pointer
+            points = torch.zeros((1, max(4, points.shape[1])), dtype=torch.float32, device=self.device)
         a.points, a.point_stride = points.data_ptr(), points.shape[1]
         off = (ctypes.c_int32 * (B + 1))(*[int(o) for o in offsets])
         a.pt_off_host = off

@@ -491,6 +491,32 @@ def test_host_entry_pipelined_equals_device_entry(mvx, chunk):
     assert path.h2d_bytes == (points_h.numel() + calib_h.numel() + sum(m.numel() for m in maps_h)) * 4
 
 
+def test_fused_path_empty_and_tiny_frames(mvx):
+    """Ragged batch with an empty frame and a one-point frame, and an all-empty batch: no NaNs, zero grid for empty frames,
+    the one-point frame equals the oracle."""
+    sd = synth.make_weights(1)
+    calib = synth.kitti_calib()
+    maps = small_maps(2, B=3)
+    frames = [synth.make_points(1, 700), np.zeros((0, 4), np.float32), synth.make_points(2, 1)]
+    path = mvx.P.PointPath(sd, G)
+    grid, counts = path(frames, [calib] * 3, [torch.from_numpy(m) for m in maps])
+    torch.cuda.synchronize()
+    c = counts.cpu().numpy()
+    assert c[:, 0].tolist() == [c[0, 0], 0, 1] and c[:, 1].tolist() == [700, 0, 1] and c[0, 0] > 0
+    assert torch.isfinite(grid).all() and float(grid[1].abs().sum()) == 0.0
+    for f in (0, 2):
+        with torch.no_grad():
+            ref64 = O.forward_frame(frames[f], calib, [m[f:f + 1] for m in maps], sd, G, synth.KITTI_IMSIZE_HW, dtype=torch.float64)
+        vf, idx = path.voxel_features(f)
+        assert np.array_equal(idx.cpu().numpy()[:, 1:], ref64['idx'].numpy()[:, 1:])
+        assert rel_err(vf, ref64['vfeat']) < TOL and rel_err(grid[f], ref64['grid'][0]) < TOL
+    assert path.voxel_features(1)[0].shape == (0, 128)
+    empty = mvx.P.PointPath(sd, G)
+    g2, c2 = empty([np.zeros((0, 4), np.float32)], [calib], [torch.from_numpy(m[:1]) for m in maps])
+    torch.cuda.synchronize()
+    assert c2.cpu().numpy().tolist() == [[0, 0, 0, 0]] and float(g2.abs().sum()) == 0.0
+
+
 def test_fused_path_full_size_properties(mvx):
     """BASELINE-size frame (P = 120 000, real FPN shapes): size-independent properties."""
     sd = synth.make_weights(0)
