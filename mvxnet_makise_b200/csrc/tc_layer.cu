@@ -30,7 +30,7 @@ namespace {
 constexpr int kTM = 256;        // rows per CTA
 constexpr int kStages = 3;
 constexpr int kProducerThreads = 256;
-constexpr int kThreads = kProducerThreads + 64;
+constexpr int kThreads = kProducerThreads + 64;   // (tcgen05 TF32 kernels; the 16-bit one-CTA variant runs 16 producer warps)
 constexpr int kEpiCols = 128;   // columns per epilogue pass
 constexpr int kEpiLd = kEpiCols + 4;
 
@@ -116,8 +116,14 @@ __global__ void __launch_bounds__(256) pack_weights_f16_kernel(const float *__re
 // reduced-precision mode whose tolerance is stated separately (tests/test_gpu_parity.py::test_bf16_mode_tolerance).
 // TWO: two CTAs per SM (BN = 128, 16-bit operands): 2 pipeline stages, the epilogue staged one 128-row half at a time (96 KB of
 // shared memory, 256 TMEM columns, <= 102 registers), so one CTA's epilogue overlaps the other's main loop.
+// producer warps: the 16-bit producers are instruction-latency bound with 8 warps (ncu: ~1.8 warp instructions per cycle
+// and SM, conv1 at 2.7k cycles per stage against 0.8k of MMA), so the one-CTA-per-SM variant runs 16 of them (2 rows of
+// a stage per thread instead of 4)
+__host__ __device__ constexpr int tc_producer_warps(bool f16, bool two) { return (f16 && !two) ? 16 : 8; }
+
 template <int BN, bool F16, bool BF1 = false, bool TWO = false>
-__global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerArgs a, const float *__restrict__ wpack) {
+__global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2 : 1) tc_layer_kernel(LayerArgs a, const float *__restrict__ wpack) {
+    constexpr int PW = tc_producer_warps(F16, TWO), PT = PW * 32, NT = PT + 64;   // producer warps / threads, CTA threads
     static_assert(!BF1 || F16, "the bf16 variant shares the 16-bit operand path");
     static_assert(!TWO || (F16 && BN == 128), "the two-CTA variant is the 16-bit, 128-column kernel");
     constexpr int STAGES = TWO ? 2 : kStages;
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerAr
     // ---- one-time setup ------------------------------------------------------------------------------------
     if (a.in_stats) {
         const int inC = a.in_C > 0 ? a.in_C : a.Cin;   // fused concat: both parts share the producer layer's statistics
-        for (int c = tid; c < a.Cin; c += kThreads) {
+        for (int c = tid; c < a.Cin; c += NT) {
             const double *st = a.in_stats + ((size_t)f * inC + c % inC) * 2;
             const double m = st[0] / Rstat;
             double var = st[1] / Rstat - m * m;
@@ -166,16 +172,16 @@ __global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerAr
             s_rstd[c] = (float)(1.0 / sqrt(var + a.eps));
         }
     }
-    for (int c = tid; c < BN; c += kThreads) s_bias[c] = a.plain ? 0.f : a.bias[n0 + c];
+    for (int c = tid; c < BN; c += NT) s_bias[c] = a.plain ? 0.f : a.bias[n0 + c];
     if constexpr (F16) {
         const float *colinv = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(wpack) + (size_t)a.Cin * a.Cout * 4);
-        for (int c = tid; c < BN; c += kThreads) s_colinv[c] = colinv[n0 + c];
-        for (int r = tid; r < kTM; r += kThreads) {
+        for (int c = tid; c < BN; c += NT) s_colinv[c] = colinv[n0 + c];
+        for (int r = tid; r < kTM; r += NT) {
             const long long rr = row0 + r;
             s_rowinv[r] = (!BF1 && a.row_max && rr < n_rows) ? 1.f / pow2_scale(a.row_max[(size_t)f * a.rowcap + rr]) : 1.f;
         }
     }
-    for (int r = tid; r < kTM; r += kThreads) {
+    for (int r = tid; r < kTM; r += NT) {
         const long long rr = row0 + r;
         const float w = rr < n_rows ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + rr] : 1.f) : 0.f;
         s_roww[r] = w;
@@ -188,13 +194,13 @@ __global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerAr
     }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), kProducerThreads + 1);
+            mbar_init(full_bar(s), PT + 1);
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {  // TMEM: 2*BN fp32 accumulator columns (power of two >= 32)
+    if (warp == PW + 1) {  // TMEM: 2*BN fp32 accumulator columns (power of two >= 32)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::kTmemPtr), "r"(2 * BN)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -205,20 +211,21 @@ __global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerAr
     const uint32_t tmem_base = *tmem_ptr;
 
     const bool mma_only = (a.dbg & 8) != 0;
-    if (mma_only && warp != 9) {
-    } else if (warp < 8 && F16) {
+    if (mma_only && warp != PW + 1) {
+    } else if (warp < PW && F16) {
         // ================= A producers, fp16 operands: a thread owns 8 k (one 16-byte chunk of fp16) of 4 rows ======
+        constexpr int RS = PT / 4, RPT = kTM / RS;   // row stride between a thread's rows, rows per thread (4 or 2)
         const int c = tid & 3, rsub = tid >> 2;
         const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx + c * 8;
-        bool valid[4];
-        float rs[4];
-        const float *x2row[4];   // fused concat: this row's source for the trailing x2_cols input columns
+        bool valid[RPT];
+        float rs[RPT];
+        const float *x2row[RPT];   // fused concat: this row's source for the trailing x2_cols input columns
         const int split = a.X2 ? a.Cin - a.x2_cols : a.Cin;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long long rr = row0 + rsub + 64 * i;
+        for (int i = 0; i < RPT; ++i) {
+            const long long rr = row0 + rsub + RS * i;
             valid[i] = rr < n_rows;
-            rs[i] = 1.f / s_rowinv[rsub + 64 * i];   // power of two: exact
+            rs[i] = 1.f / s_rowinv[rsub + RS * i];   // power of two: exact
             x2row[i] = nullptr;
             if (a.X2 && valid[i]) {
                 const int v = rr >= Kf ? (int)(rr - Kf) : a.cat_row_vox[(size_t)f * a.cat_rowv_cap + rr];
@@ -227,26 +234,26 @@ __global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerAr
         }
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         constexpr int PF = TWO ? 1 : 2;   // chunks of raw activations in flight in registers
-        auto load_chunk = [&](float4 (&buf)[8], int kc) {
+        auto load_chunk = [&](float4 (&buf)[2 * RPT], int kc) {
             const bool second = kc * KB >= split;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RPT; ++i) {
                 const float4 *p = second ? reinterpret_cast<const float4 *>(x2row[i] + (kc * KB - split))
-                                         : reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + kc * KB);
+                                         : reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + RS * i) * a.ldx + kc * KB);
                 buf[2 * i] = valid[i] ? __ldg(p) : z4;
                 buf[2 * i + 1] = valid[i] ? __ldg(p + 1) : z4;
             }
         };
-        auto produce = [&](float4 (&buf)[8], int kc) {
-            float4 cur[8];
+        auto produce = [&](float4 (&buf)[2 * RPT], int kc) {
+            float4 cur[2 * RPT];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cur[i] = buf[i];
+            for (int i = 0; i < 2 * RPT; ++i) cur[i] = buf[i];
             if (a.in_stats) {
                 const int k = kc * KB + c * 8;
                 const float4 m0 = *reinterpret_cast<const float4 *>(s_mean + k), m1 = *reinterpret_cast<const float4 *>(s_mean + k + 4);
                 const float4 r0 = *reinterpret_cast<const float4 *>(s_rstd + k), r1 = *reinterpret_cast<const float4 *>(s_rstd + k + 4);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < RPT; ++i) {
                     if (valid[i]) {
                         cur[2 * i].x = (cur[2 * i].x - m0.x) * r0.x, cur[2 * i].y = (cur[2 * i].y - m0.y) * r0.y;
                         cur[2 * i].z = (cur[2 * i].z - m0.z) * r0.z, cur[2 * i].w = (cur[2 * i].w - m0.w) * r0.w;
@@ -262,8 +269,8 @@ __global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerAr
             __syncwarp();
             uint8_t *stage = smem + (size_t)s * S::kStage;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t off = sw64_offset(rsub + 64 * i, c);
+            for (int i = 0; i < RPT; ++i) {
+                const uint32_t off = sw64_offset(rsub + RS * i, c);
                 if constexpr (BF1) {
                     uint4 hi;
                     hi.x = pack_bf16x2(cur[2 * i].x, cur[2 * i].y), hi.y = pack_bf16x2(cur[2 * i].z, cur[2 * i].w);
@@ -284,11 +291,11 @@ __global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerAr
             mbar_arrive(full_bar(s));
         };
         if constexpr (TWO) {   // one chunk in flight per thread (register budget of two CTAs per SM; 16 producer warps per SM)
-            float4 buf0[8];
+            float4 buf0[2 * RPT];
             load_chunk(buf0, 0);
             for (int kc = 0; kc < nk; ++kc) produce(buf0, kc);
         } else {
-            float4 buf0[8], buf1[8];
+            float4 buf0[2 * RPT], buf1[2 * RPT];
             load_chunk(buf0, 0);
             if (nk > 1) load_chunk(buf1, 1);
             for (int kc = 0; kc < nk; kc += 2) {
@@ -296,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerAr
                 if (kc + 1 < nk) produce(buf1, kc + 1);
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < PW) {
         // ================= A producers ===========================================================================
         const int c = tid & 3, rsub = tid >> 2;  // 16-byte chunk of the 64-byte k-chunk row; rows rsub + 64*i
         const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx + c * 4;
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerAr
             produce(buf0, kc);
             if (kc + 1 < nk) produce(buf1, kc + 1);
         }
-    } else if (warp == 8) {
+    } else if (warp == PW) {
         // ================= B producer: one bulk copy per stage ===================================================
         if (lane == 0) {
             const float *src = wpack + (size_t)ctile * nk * (2 * BN * kBK);
@@ -511,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, TWO ? 2 : 1) tc_layer_kernel(LayerAr
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == PW + 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
     }
 }
@@ -535,7 +542,7 @@ int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     MVX_LAUNCH_CHECK();
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     dim3 grid(a.Cout / BN, (unsigned)ceil_div(max_rows, kTM), F);
-    tc_layer_kernel<BN, F16, BF1, TWO><<<grid, kThreads, S::kTotal, st>>>(a, wpack);
+    tc_layer_kernel<BN, F16, BF1, TWO><<<grid, tc_producer_warps(F16, TWO) * 32 + 64, S::kTotal, st>>>(a, wpack);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }
