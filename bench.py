@@ -115,6 +115,49 @@ def cpu_reference_frame(frame_id: int, threads: int):
     return time.perf_counter() - t0, stages
 
 
+def gpu_eager_reference_frame(frame_id: int, device):
+    """Second comparison line of SURVEY.md §8d: the reference's GPU half (featureMaping -> ImageFeatureFusion -> concat ->
+    SVFE/FCN/max -> reindex, MVXNet.py:21-27 on cfg.device='cuda') as torch-eager ops on THIS GPU, through the oracle port;
+    the CPU half (lidar2Img + group, train.py:26-49) is timed separately on the host like the reference runs it."""
+    import torch
+    from mvxnet_makise_b200 import synth
+    from oracle import pointpath_oracle as O
+    pts = synth.make_points(frame_id, POINTS)
+    maps = synth.make_fpn_maps(frame_id)
+    sd = {k: torch.from_numpy(np.asarray(v)).to(device) for k, v in synth.make_weights(0).items()}
+    t0 = time.perf_counter()
+    pcd6 = O.points_with_proj(pts, synth.kitti_calib())
+    voxel9, uidx = O.group(pcd6, synth.KITTI_GRID.velorange, synth.KITTI_GRID.voxelsize, synth.KITTI_GRID.T)
+    t_cpu = time.perf_counter() - t0
+    feats = [torch.from_numpy(m).to(device) for m in maps]
+    imsize = torch.Tensor(list(synth.KITTI_IMSIZE_HW)).to(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times = []
+    with torch.no_grad():
+        for it in range(4):
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            voxels = torch.Tensor(voxel9).to(device)                              # train.py:125-128 (H2D of the dense tensor)
+            idx = torch.LongTensor(np.concatenate([np.zeros((uidx.shape[0], 1)), uidx], axis=1)).to(device)
+            e0.record()
+            im768 = O.feature_mapping(voxels, feats, imsize, 1e-6)
+            im16 = O.fusion(im768[None], sd, 1e-6)
+            x23 = torch.concat([voxels[None][..., :7], im16], dim=-1)
+            vfeat = O.voxel_features(x23, sd, 1e-6)
+            grid = O.reindex(vfeat, idx, synth.KITTI_GRID.voxelshape)
+            e1.record()
+            torch.cuda.synchronize()
+            if it:
+                times.append((e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t1))
+            del im768, im16, x23, vfeat, grid
+    gpu_s = sum(t[0] for t in times) / len(times)
+    wall_s = sum(t[1] for t in times) / len(times)
+    return dict(gpu_half_ms=round(gpu_s * 1e3, 2), gpu_half_with_h2d_ms=round(wall_s * 1e3, 2), cpu_half_ms=round(t_cpu * 1e3, 2),
+                value=round(1.0 / (wall_s + t_cpu), 3), unit='frames/s', kind='port',
+                sample=f'1 full-size frame (P={POINTS}), dense (N,T,.) formulation like the reference: CPU lidar2Img+group on the host, '
+                       'then featureMaping .. reindex as torch-eager CUDA ops (oracle/pointpath_oracle.py); 3 timed repeats after 1 warm-up')
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -325,6 +368,13 @@ def run_ours(args):
         line['cpu_baseline'] = dict(value=1.0 / t, unit='frames/s', cores=os.cpu_count() or 1, kind='port',
                                     sample=f'1 full-size frame (P={POINTS}) of the batch through oracle/pointpath_oracle.py (numpy + torch CPU fp32)',
                                     stages_s={k: round(v, 3) for k, v in st.items()})
+        if not args.no_gpu_eager_baseline:
+            try:
+                del path
+                torch.cuda.empty_cache()
+                line['gpu_eager_baseline'] = gpu_eager_reference_frame(0, dev)
+            except Exception as exc:   # a context line only: never let it take the bench line down
+                line['gpu_eager_baseline'] = dict(error=f'{type(exc).__name__}: {exc}'[:200])
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -426,6 +476,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-eager-baseline', action='store_true', help='skip the torch-eager-on-this-GPU context line')
     ap.add_argument('--host-streams', type=int, default=2, help='compute streams the sub-batches of the e2e leg alternate between')
     ap.add_argument('--fusion-mode', type=int, default=1, help='1 = pixel-first fcn1 (default), 0 = row-first (gather + row GEMM)')
     ap.add_argument('--workload', default='forward', choices=['forward', 'train'], help="'train' = BASELINE configs[3] (not the headline metric)")

@@ -174,7 +174,7 @@ def feature_mapping(voxels: torch.Tensor, features: List[torch.Tensor], imsize: 
     voxels (N,T,9) fp32 is MUTATED like the reference does (pad slots zeroed); features are the
     un-padded NCHW maps (this function pads a copy, it does not mutate the list). Returns (N,T,768)."""
     feats = [F.pad(f, (0, 1, 0, 1)) for f in features]                     # Pipe.py:47-48
-    region = [imsize / torch.Tensor([*f.shape[-2:]]) for f in features]    # Pipe.py:41-45
+    region = [imsize / torch.Tensor([*f.shape[-2:]]).to(imsize.device) for f in features]    # Pipe.py:41-45
     v = voxels
     origshape = v.shape[:-1]
     xyz = v[..., :3].reshape((-1, 3))
@@ -244,7 +244,7 @@ def voxel_features(x23: torch.Tensor, sd, eps=1e-6) -> torch.Tensor:
 # --------------------------------------------------------------------------- stage 4: scatter
 def reindex(x: torch.Tensor, idx: torch.Tensor, voxelshape) -> torch.Tensor:
     """`VoxelNet.reindex` — modules/voxelnet/VoxelNet.py:16-22. idx (N,4) int64 [batch,ix,iy,iz]."""
-    res = torch.zeros((1, x.shape[1], voxelshape[2], voxelshape[0], voxelshape[1]), dtype=x.dtype)
+    res = torch.zeros((1, x.shape[1], voxelshape[2], voxelshape[0], voxelshape[1]), dtype=x.dtype, device=x.device)   # VoxelNet.py:19 (cfg.device)
     res[idx[:, 0], :, idx[:, 3], idx[:, 1], idx[:, 2]] = x
     return res
 
