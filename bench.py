@@ -193,7 +193,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def algorithmic_work(seg: str, N, K, B, G):
+def algorithmic_work(seg: str, N, K, B, G, npts=POINTS):
     """(bound, work per launch) for a timed segment: bytes for HBM-bound kernels, flops for the GEMM layers
     (SURVEY.md §8d minimal figures: kept rows + weighted pad rows only)."""
     sumK, sumN = float(sum(K)), float(sum(N))
@@ -216,7 +216,7 @@ def algorithmic_work(seg: str, N, K, B, G):
     if seg == 'maps_nhwc':
         return 'hbm', 2 * B * maps_b
     if seg == 'voxelize':
-        return 'hbm', B * POINTS * 16.0 + sumK * 8 + sumN * 32 + B * G * 4
+        return 'hbm', B * npts * 16.0 + sumK * 8 + sumN * 32 + B * G * 4
     return 'hbm', 0.0
 
 
@@ -235,10 +235,13 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault('NCCL_DEBUG_FILE', os.devnull)   # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
-    B, G = FRAMES_PER_GPU, synth.KITTI_GRID.cells
+    dense = args.workload == 'dense'       # BASELINE.json configs[4]: 128-beam-like frames on the larger 512x512x10 grid
+    grid_spec = synth.DENSE_GRID if dense else synth.KITTI_GRID
+    npts = 250_000 if dense else POINTS
+    B, G = FRAMES_PER_GPU, grid_spec.cells
 
     # ---- synthetic inputs for THIS rank's frames (frame ids are global: weak scaling, frames sharded by rank)
-    frames = [synth.make_points(rank * B + f, POINTS) for f in range(B)]
+    frames = [synth.make_points(rank * B + f, npts, grid=grid_spec, beams=128 if dense else 64) for f in range(B)]
     offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in frames])]).tolist()
     points_h = torch.from_numpy(np.concatenate(frames, 0)).pin_memory()
     calib_h = torch.stack([pack_calib(synth.kitti_calib()) for _ in range(B)]).pin_memory()
@@ -247,7 +250,7 @@ def run_ours(args):
     points_d, calib_d = points_h.to(dev), calib_h.to(dev)
     maps_d = [m.to(dev) for m in maps_h]
     _lib.set_fusion_mode(args.fusion_mode)
-    path = PointPath(synth.make_weights(0), synth.KITTI_GRID, device=dev)
+    path = PointPath(synth.make_weights(0), grid_spec, device=dev)
     path.host_chunk, path.host_streams = args.host_chunk, args.host_streams
 
     def barrier():
@@ -326,7 +329,7 @@ def run_ours(args):
     names = [(_lib.lib.mvx_timing_segment_name(i) or b'').decode() for i in range(_lib.NUM_SEGMENTS)]
     stages = {n: round(float(ms), 4) for n, ms in zip(names, seg_ms) if n}
     dom = max(stages, key=stages.get)
-    bound, work = algorithmic_work(dom, counts[:, 0], counts[:, 1], B, G)
+    bound, work = algorithmic_work(dom, counts[:, 0], counts[:, 1], B, G, npts)
     dur_s = stages[dom] * 1e-3
     if bound == 'tensor':
         achieved, peak, unit = work / dur_s / 1e12, pk['tensor'], 'TFLOP/s'
@@ -334,14 +337,14 @@ def run_ours(args):
         achieved, peak, unit = work / dur_s / 1e9, pk['hbm'], 'GB/s'
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and not dense:      # the ncu capture was taken on the headline (KITTI) configuration
         traffic = json.load(open(tpath)).get(dom)
     roofline = dict(kernel=dom, bound=bound, achieved=round(achieved, 3), peak=peak, unit=unit, frac=round(achieved / peak, 4),
                     traffic=traffic, peak_source=pk['src'], ms_per_launch=stages[dom], share_of_step=round(stages[dom] / ms_serial, 4))
     # every memory-bound stage against the HBM roofline (the north star's per-stage report)
     per_stage = {}
     for n in ('voxelize', 'maps_nhwc', 'gather', 'fcn1_combine', 'grid_fill'):
-        b, w = algorithmic_work(n, counts[:, 0], counts[:, 1], B, G)
+        b, w = algorithmic_work(n, counts[:, 0], counts[:, 1], B, G, npts)
         if stages.get(n, 0) > 0:
             per_stage[n] = dict(gbs=round(w / (stages[n] * 1e-3) / 1e9, 1), frac_hbm=round(w / (stages[n] * 1e-3) / 1e9 / pk['hbm'], 4))
     for n in ('fcn1', 'pixel_gemm', 'conv1'):
@@ -353,9 +356,12 @@ def run_ours(args):
     line = dict(metric=METRIC, value=world * B * args.steps / (ms_total * 1e-3), unit='frames/s', n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload=WORKLOAD, frames_per_gpu=B, points_per_frame=POINTS,
+                config=dict(workload=(WORKLOAD if not dense else
+                                      'configs[4]: batch-8 dense 128-beam-like synthetic frames per GPU (P=250000 pts/frame, velorange [0,-51.2,-3,102.4,51.2,1], '
+                                      'grid 512x512x10 = 1.34 GB dense output per frame, same FPN maps / layers): NOT the headline configuration'),
+                            frames_per_gpu=B, points_per_frame=npts,
                             voxels_per_frame=int(counts[:, 0].mean()), kept_points_per_frame=int(counts[:, 1].mean()),
-                            l2='no flush: per step the inputs (376 MB FPN maps) and outputs (5.8 GB grid) exceed the 126 MB L2',
+                            l2=f'no flush: per step the inputs (376 MB FPN maps) and outputs ({B * 128 * G * 4 / 1e9:.1f} GB grid) exceed the 126 MB L2',
                             parallelism=f'frame-sharded x{world}, no forward collective'),
                 clocks=clocks,
                 e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=int(path.h2d_bytes),
@@ -363,7 +369,7 @@ def run_ours(args):
                          note=f'PointPath.forward_host: pinned-host points+calib+FPN maps -> H2D -> fused path -> D2H counts + feature head; sub-batches of {args.host_chunk} frame(s), H2D of sub-batch j+1 on a copy stream overlaps the kernels of sub-batch j'),
                 gpu_launches=int(launches), roofline=roofline, stages_ms=stages, stage_rooflines=per_stage,
                 stages_note=f'per-stage CUDA events from a separate pass of {n_stage} steps with the map branch serialised (fusion mode 2, {ms_serial:.3f} ms/step); the timed region runs it on a side stream concurrently with the point branch')
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not dense:
         t, st = cpu_reference_frame(0, os.cpu_count() or 1)
         line['cpu_baseline'] = dict(value=1.0 / t, unit='frames/s', cores=os.cpu_count() or 1, kind='port',
                                     sample=f'1 full-size frame (P={POINTS}) of the batch through oracle/pointpath_oracle.py (numpy + torch CPU fp32)',
@@ -479,7 +485,8 @@ def main():
     ap.add_argument('--no-gpu-eager-baseline', action='store_true', help='skip the torch-eager-on-this-GPU context line')
     ap.add_argument('--host-streams', type=int, default=2, help='compute streams the sub-batches of the e2e leg alternate between')
     ap.add_argument('--fusion-mode', type=int, default=1, help='1 = pixel-first fcn1 (default), 0 = row-first (gather + row GEMM)')
-    ap.add_argument('--workload', default='forward', choices=['forward', 'train'], help="'train' = BASELINE configs[3] (not the headline metric)")
+    ap.add_argument('--workload', default='forward', choices=['forward', 'train', 'dense'],
+                    help="'train' = BASELINE configs[3], 'dense' = configs[4] (128-beam-like frames, 512x512x10 grid); neither is the headline metric")
     ap.add_argument('--train-frames', type=int, default=16)
     ap.add_argument('--host-chunk', type=int, default=2, help='frames per sub-batch of the host-buffer (e2e) leg')
     args = ap.parse_args()
