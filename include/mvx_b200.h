@@ -207,6 +207,19 @@ int64_t mvx_grad_floats(void);
 int mvx_pointpath_backward(const mvx_pointpath_args_t *args, const float *d_vfeat, const float *d_grid, float *grad_flat,
                            int32_t accumulate, void *backward_ws, size_t backward_ws_bytes);
 
+/* ------------------------------------------------------------------------------------------------
+ * After the path — sparse hand-off to the first middle-layer convolution.
+ * Replaces `CML.conv1` = CRB3d(128, 64, 3, (2,1,1), (1,1,1)) (modules/voxelnet/Pipe.py:31-43; Blocks.py CRB3d:
+ * relu(Conv3d) then batch-statistic BatchNorm3d) applied to the dense grid of VoxelNet.reindex, WITHOUT the dense grid:
+ * call after mvx_pointpath_forward with the SAME args (the voxel features and the cell -> voxel map are read from
+ * args->workspace; args->grid_out may be NULL in that forward). conv_w (64,128,3,3,3), conv_b (64) device fp32 in
+ * torch's Conv3d layout; out (B, 64, (nz+1)/2, nx, ny) fp32 fully written; per-frame statistics like the batch-1
+ * reference. ws: mvx_cml_conv1_workspace_bytes() of scratch.
+ * ------------------------------------------------------------------------------------------------ */
+int mvx_cml_conv1_workspace_bytes(const mvx_pointpath_args_t *args, size_t *bytes);
+int mvx_cml_conv1_sparse(const mvx_pointpath_args_t *args, const float *conv_w, const float *conv_b, double eps, float *out,
+                         void *ws, size_t ws_bytes);
+
 /* Optional per-kernel timing of mvx_pointpath_forward with CUDA events recorded on the launching stream
  * (bench.py's roofline leg). mvx_timing_enable(n) arms n event sets (one per forward call, n = 0 disables);
  * mvx_timing_read(call, ms) waits for that call's last event and returns MVX_NUM_SEGMENTS durations in ms, in the

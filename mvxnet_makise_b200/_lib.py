@@ -30,7 +30,7 @@ EXPORTS = [
     'mvx_set_gemm_mode', 'mvx_layer_workspace_bytes', 'mvx_fcn_forward', 'mvx_vfe_forward', 'mvx_fcn_max_forward', 'mvx_set_grid_mode', 'mvx_scatter_dense',
     'mvx_pointpath_workspace_bytes', 'mvx_pointpath_layout', 'mvx_pointpath_layout_name', 'mvx_pointpath_forward',
     'mvx_set_fusion_mode', 'mvx_pointpath_train_workspace_bytes', 'mvx_pointpath_forward_train', 'mvx_grad_floats',
-    'mvx_pointpath_backward',
+    'mvx_pointpath_backward', 'mvx_cml_conv1_workspace_bytes', 'mvx_cml_conv1_sparse',
     'mvx_timing_enable', 'mvx_timing_read', 'mvx_timing_segment_name',
 ]
 
@@ -99,6 +99,8 @@ def _load():
     lib.mvx_pointpath_train_workspace_bytes.argtypes = [POINTER(PointPathArgs), POINTER(c_size_t), POINTER(c_size_t)]
     lib.mvx_pointpath_forward_train.argtypes = [POINTER(PointPathArgs)]
     lib.mvx_grad_floats.restype = i64
+    lib.mvx_cml_conv1_workspace_bytes.argtypes = [POINTER(PointPathArgs), POINTER(c_size_t)]
+    lib.mvx_cml_conv1_sparse.argtypes = [POINTER(PointPathArgs), vp, vp, c_double, vp, vp, c_size_t]
     lib.mvx_pointpath_backward.argtypes = [POINTER(PointPathArgs), vp, vp, vp, i32, vp, c_size_t]
     lib.mvx_timing_enable.argtypes = [i32]
     lib.mvx_timing_read.argtypes = [i32, POINTER(c_float)]

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) fcn_layer_kernel(LayerArgs a) {
     if (a.counts) {
         const int N = a.counts[f * 4 + 0];
         K = a.counts[f * 4 + 1];
-        n_rows = a.rows_mode == 1 ? K + 1 : (a.rows_mode == 2 ? K + N : a.rows_fixed);
+        n_rows = a.rows_mode == 1 ? K + 1 : (a.rows_mode == 2 ? K + N : (a.rows_mode == 3 ? N : a.rows_fixed));
         Rstat = (double)N * (double)a.T;
     }
     const long long row0 = (long long)blockIdx.x * kBM;
@@ -416,7 +416,7 @@ static int g_dense_f16 = 0;
 
 int launch_layer_auto(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     if (g_gemm_mode == 1 && wpack) {
-        if (g_tc_pair && !a.plain && tc2_layer_eligible(a)) return launch_layer_tc2(a, F, wpack, st);
+        if (g_tc_pair && !a.plain && a.rows_mode != 3 && tc2_layer_eligible(a)) return launch_layer_tc2(a, F, wpack, st);
         if (tc_layer_eligible(a)) return launch_layer_tc(a, F, wpack, st);
     }
     return launch_layer(a, F, st);

@@ -22,7 +22,7 @@ struct LayerArgs {
                              // pad row (r == K_f) belongs to no voxel
     int rowv_cap;            // frame stride of row_v
     const int *counts;       // [F][4] device (N_f, K_f, ..), or NULL
-    int rows_mode;           // 0: rows_fixed rows; 1: K_f + 1 rows; 2: K_f + N_f rows
+    int rows_mode;           // 0: rows_fixed rows; 1: K_f + 1 rows; 2: K_f + N_f rows; 3: N_f rows (one per voxel)
     long long rows_fixed;
     int rowcap, vcap, T;
     double eps;

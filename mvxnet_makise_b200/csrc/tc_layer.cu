@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
     if (a.counts) {
         const int N = a.counts[f * 4 + 0];
         Kf = a.counts[f * 4 + 1];
-        n_rows = a.rows_mode == 1 ? Kf + 1 : (a.rows_mode == 2 ? Kf + N : a.rows_fixed);
+        n_rows = a.rows_mode == 1 ? Kf + 1 : (a.rows_mode == 2 ? Kf + N : (a.rows_mode == 3 ? N : a.rows_fixed));
         Rstat = (double)N * (double)a.T;
     }
     const long long row0 = (long long)blockIdx.y * kTM;  // column tiles of one row tile are launch-adjacent: A hits L2
@@ -903,7 +903,7 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
     MVX_REQUIRE(tc_layer_eligible(a) && wpack, MVX_EINVAL, "layer not eligible for the tensor-core kernel");
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     if (max_rows <= 0) return MVX_OK;
-    if (a.vmax == nullptr && !a.plain && !a.X2 && tc_persistent_enabled())  // persistent kernel: 256 x 128 tiles, double-buffered accumulators
+    if (a.vmax == nullptr && !a.plain && !a.X2 && a.rows_mode != 3 && tc_persistent_enabled())  // persistent kernel: 256 x 128 tiles, double-buffered accumulators
         return launch_tc_persist<128>(a, F, wpack, st);
     MVX_REQUIRE(!a.X2 || (a.f16_ok && (g_tc_bf16 || tc_f16_enabled()) && a.Cin % 32 == 0 && a.x2_cols % 32 == 0 && a.counts),
                 MVX_EINVAL, "fused concat input needs the 16-bit tensor-core producer");

@@ -141,7 +141,31 @@ class PointPath:
         else:
             check(lib.mvx_pointpath_forward(ctypes.byref(a)), 'pointpath_forward')
             self._train_args = None
+        self._last_args = (a, off, points, calib32, maps)           # kept alive for cml_conv1()
         return (self.grid_out if want_grid else None), self.counts
+
+    # ---- after the path: sparse hand-off to CML.conv1 -------------------------------------
+    def cml_conv1(self, weight: torch.Tensor, bias: torch.Tensor, eps: float | None = None) -> torch.Tensor:
+        """`backbone.cml.conv1` = CRB3d(128, 64, 3, (2,1,1), (1,1,1)) (voxelnet/Pipe.py:31-43) of the dense grid of the LAST
+        forward, computed sparsely from the voxel features (the forward may have run with want_grid=False).
+        weight (64,128,3,3,3), bias (64) as in the reference checkpoint (`backbone.cml.conv1.conv.*`).
+        Returns (B, 64, (nz+1)//2, nx, ny) fp32 on the GPU, per-frame BatchNorm statistics like the batch-1 reference."""
+        if getattr(self, '_last_args', None) is None or getattr(self, '_subs_active', False):
+            raise RuntimeError('cml_conv1() needs a preceding forward (device entry) on this PointPath')
+        a = self._last_args[0]
+        w = weight.detach().to(self.device, torch.float32).contiguous()
+        b = bias.detach().to(self.device, torch.float32).contiguous()
+        assert tuple(w.shape) == (64, 128, 3, 3, 3) and tuple(b.shape) == (64,)
+        nz, nx, ny = self.grid.shape[2], self.grid.shape[0], self.grid.shape[1]
+        nbytes = ctypes.c_size_t()
+        check(lib.mvx_cml_conv1_workspace_bytes(ctypes.byref(a), ctypes.byref(nbytes)), 'cml_conv1_workspace_bytes')
+        if getattr(self, '_cml_ws', None) is None or self._cml_ws.numel() < nbytes.value:
+            self._cml_ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        out = torch.empty((self.B, 64, (nz + 2 - 3) // 2 + 1, nx, ny), dtype=torch.float32, device=self.device)
+        a.stream = torch.cuda.current_stream().cuda_stream
+        check(lib.mvx_cml_conv1_sparse(ctypes.byref(a), ptr(w), ptr(b), float(self.eps if eps is None else eps), ptr(out),
+                                       ptr(self._cml_ws), self._cml_ws.numel()), 'cml_conv1_sparse')
+        return out
 
     # ---- training mode -------------------------------------------------------------------------------------
     def forward_train(self, points, offsets, calib32, maps, want_grid: bool = True, cap: int | None = None):

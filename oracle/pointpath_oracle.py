@@ -249,6 +249,15 @@ def reindex(x: torch.Tensor, idx: torch.Tensor, voxelshape) -> torch.Tensor:
     return res
 
 
+# --------------------------------------------------------------------------- after the path: CML.conv1
+def cml_conv1(grid: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """`CML.conv1` = CRB3d(128, 64, 3, (2,1,1), (1,1,1)) — modules/voxelnet/Pipe.py:31-43; CRB3d (modules/layers/Blocks.py):
+    bn(relu(Conv3d(x))) with BatchNorm3d(affine=False, track_running_stats=False) i.e. batch statistics, biased variance.
+    grid (1,128,nz,nx,ny) -> (1,64,(nz+1)//2,nx,ny)."""
+    y = F.relu(F.conv3d(grid, w, b, stride=(2, 1, 1), padding=(1, 1, 1)))
+    return F.batch_norm(y, None, None, None, None, True, 0.0, eps)
+
+
 # --------------------------------------------------------------------------- whole path, one frame
 def forward_frame(pcd4: np.ndarray, calib_np, fpn_maps: List[np.ndarray], sd_np, grid, imsize_hw,
                   eps: float = 1e-6, want_grid: bool = True, stages: dict | None = None,

@@ -517,6 +517,34 @@ def test_fused_path_empty_and_tiny_frames(mvx):
     assert c2.cpu().numpy().tolist() == [[0, 0, 0, 0]] and float(g2.abs().sum()) == 0.0
 
 
+def test_sparse_cml_conv1_matches_dense_reference(mvx):
+    """§8f rank 2: `CML.conv1` (Conv3d 128->64, k 3, stride (2,1,1), pad 1, + ReLU + batch-stat BatchNorm3d) computed
+    sparsely from the voxel features equals the dense reference ops applied to the dense grid (small grid so the dense
+    fp64 convolution runs in seconds on the CPU). Two frames with different occupancy, per-frame statistics."""
+    small = synth.GridSpec((0.0, -4.8, -3.0, 8.0, 4.8, 1.0), (40, 48, 10), 35)
+    sd = synth.make_weights(6)
+    calib = synth.kitti_calib()
+    frames = [synth.make_points(120 + f, P, grid=small) for f, P in enumerate((700, 350))]
+    assert all(p.shape[0] > 100 for p in frames)
+    maps = small_maps(14, B=2)
+    rng = np.random.default_rng(3)
+    w = (rng.standard_normal((64, 128, 3, 3, 3)) / np.sqrt(128 * 27)).astype(np.float32)
+    b = (rng.standard_normal(64) * 0.1).astype(np.float32)
+    path = mvx.P.PointPath(sd, small)
+    grid, counts = path(frames, [calib] * 2, [torch.from_numpy(m) for m in maps])
+    out = path.cml_conv1(torch.from_numpy(w), torch.from_numpy(b))
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (2, 64, 5, 40, 48) and torch.isfinite(out).all()
+    for f in range(2):
+        with torch.no_grad():
+            ref = O.cml_conv1(grid[f:f + 1].double().cpu(), torch.from_numpy(w).double(), torch.from_numpy(b).double())
+        assert rel_err(out[f], ref[0]) < TOL, f
+    # the dense grid is not needed for it
+    path2 = mvx.P.PointPath(sd, small)
+    path2(frames, [calib] * 2, [torch.from_numpy(m) for m in maps], want_grid=False)
+    assert rel_err(path2.cml_conv1(torch.from_numpy(w), torch.from_numpy(b)), out) < 1e-5
+
+
 def test_fused_path_full_size_properties(mvx):
     """BASELINE-size frame (P = 120 000, real FPN shapes): size-independent properties."""
     sd = synth.make_weights(0)
