@@ -260,8 +260,13 @@ def run_ours(args):
 
     # ---- device-resident leg (`value`) ----------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
+    def step():
+        if args.device_split > 1:
+            return path.forward_device_split(points_d, offsets, calib_d, maps_d, True, args.device_split)
+        return path.forward_device(points_d, offsets, calib_d, maps_d)
+
     for _ in range(max(args.warmup, 3)):
-        path.forward_device(points_d, offsets, calib_d, maps_d)
+        step()
     barrier()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -270,7 +275,7 @@ def run_ours(args):
         sampler.begin()
     e0.record()
     for _ in range(args.steps):
-        path.forward_device(points_d, offsets, calib_d, maps_d)
+        step()
     e1.record()
     barrier()
     if sampler:
@@ -488,6 +493,7 @@ def main():
     ap.add_argument('--workload', default='forward', choices=['forward', 'train', 'dense'],
                     help="'train' = BASELINE configs[3], 'dense' = configs[4] (128-beam-like frames, 512x512x10 grid); neither is the headline metric")
     ap.add_argument('--train-frames', type=int, default=16)
+    ap.add_argument('--device-split', type=int, default=1, help='run the device-resident leg as this many concurrent sub-batches (streams)')
     ap.add_argument('--host-chunk', type=int, default=2, help='frames per sub-batch of the host-buffer (e2e) leg')
     args = ap.parse_args()
     if args.impl == 'reference':

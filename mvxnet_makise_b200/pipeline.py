@@ -208,6 +208,40 @@ class PointPath:
         """Named views into a flat gradient bucket (reference state-dict names)."""
         return {name: grad_flat[o:o + int(np.prod(shape))].view(*shape) for name, o, shape in self.grad_layout()}
 
+    def forward_device_split(self, points: torch.Tensor, offsets: Sequence[int], calib32: torch.Tensor,
+                             maps: List[torch.Tensor], want_grid: bool = True, n_split: int = 2):
+        """Same inputs/outputs as forward_device, but the batch is cut into `n_split` sub-batches that run CONCURRENTLY on
+        their own streams and workspaces (frames are independent): the memory-bound kernels of one sub-batch (grid fill,
+        combine) overlap the tensor-core kernels of the other. Joins back into the current stream."""
+        B = len(offsets) - 1
+        n_split = max(1, min(int(n_split), B))
+        if n_split == 1:
+            return self.forward_device(points, offsets, calib32, maps, want_grid)
+        key = (B, n_split)
+        if getattr(self, '_split_key', None) != key:
+            bounds = [round(i * B / n_split) for i in range(n_split + 1)]
+            self._split = []
+            for i in range(n_split):
+                c = self._child()
+                c.f0, c.f1 = bounds[i], bounds[i + 1]
+                c.stream = torch.cuda.Stream(device=self.device)
+                self._split.append(c)
+            self._split_key = key
+        self._alloc_outputs(B)
+        self.B = B
+        cur = torch.cuda.current_stream()
+        for c in self._split:
+            p0, p1 = int(offsets[c.f0]), int(offsets[c.f1])
+            c.stream.wait_stream(cur)
+            with torch.cuda.stream(c.stream):
+                c.forward_device(points[p0:p1], [int(o) - p0 for o in offsets[c.f0:c.f1 + 1]], calib32[c.f0:c.f1],
+                                 [m[c.f0:c.f1] for m in maps], want_grid,
+                                 grid_out=self.grid_out[c.f0:c.f1] if want_grid else None, counts=self.counts[c.f0:c.f1])
+        for c in self._split:
+            cur.wait_stream(c.stream)
+        self._subs, self._sub_chunk, self._subs_active = self._split, None, True
+        return (self.grid_out if want_grid else None), self.counts
+
     def __call__(self, points_list: List, calibs: List[dict], fpn_maps: List, want_grid: bool = True):
         """points_list: B arrays/tensors (P_f, >=4) [x,y,z,r]; calibs: B dicts of 4x4 matrices (Load.py:24-41);
         fpn_maps: 3 tensors (B,256,Hf,Wf) (FPN levels '0','1','2')."""
@@ -306,8 +340,8 @@ class PointPath:
         """(N_f,128) fp32 features and (N_f,4) int64 idx [batch, ix, iy, iz] of frame f (after a forward)."""
         n = int(self.counts[f, 0].item())
         src, fl = self, f
-        if getattr(self, '_subs_active', False):   # the last forward was the pipelined host entry: frame f lives in a sub-batch
-            src = self._subs[f // self._sub_chunk]
+        if getattr(self, '_subs_active', False):   # the last forward ran in sub-batches: frame f lives in one of them
+            src = next(c for c in self._subs if c.f0 <= f < c.f1)
             fl = f - src.f0
         vfeat = src.region('vfeat', torch.float32, (src.B, src.cap, 128))[fl, :n]
         coord = src.region('vox_coord', torch.int32, (src.B, src.cap, 4))[fl, :n, :3].to(torch.int64)

@@ -545,6 +545,30 @@ def test_sparse_cml_conv1_matches_dense_reference(mvx):
     assert rel_err(path2.cml_conv1(torch.from_numpy(w), torch.from_numpy(b)), out) < 1e-5
 
 
+@pytest.mark.parametrize('n_split', [2, 3])
+def test_device_split_equals_single_call(mvx, n_split):
+    """forward_device_split: sub-batches on concurrent streams with their own workspaces give the batched call's results."""
+    from mvxnet_makise_b200.modules import pack_calib
+    sd = synth.make_weights(9)
+    calib = synth.kitti_calib()
+    frames = [synth.make_points(140 + f, P) for f, P in enumerate((800, 1200, 500, 1500, 950))]
+    B = len(frames)
+    offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in frames])]).tolist()
+    pts = torch.from_numpy(np.concatenate(frames, 0)).cuda()
+    c32 = torch.stack([pack_calib(calib) for _ in range(B)]).cuda()
+    maps = [torch.from_numpy(m).cuda() for m in small_maps(15, B=B)]
+    ref = mvx.P.PointPath(sd, G)
+    g_ref, c_ref = ref.forward_device(pts, offsets, c32, maps)
+    feats = [tuple(t.clone() for t in ref.voxel_features(f)) for f in range(B)]
+    path = mvx.P.PointPath(sd, G)
+    g, c = path.forward_device_split(pts, offsets, c32, maps, True, n_split)
+    torch.cuda.synchronize()
+    assert torch.equal(c, c_ref) and torch.equal(g != 0, g_ref != 0) and rel_err(g, g_ref) < 1e-5
+    for f in range(B):
+        vf, idx = path.voxel_features(f)
+        assert torch.equal(idx, feats[f][1]) and rel_err(vf, feats[f][0]) < 1e-5
+
+
 def test_fused_path_full_size_properties(mvx):
     """BASELINE-size frame (P = 120 000, real FPN shapes): size-independent properties."""
     sd = synth.make_weights(0)
