@@ -5,6 +5,7 @@
 #include "project.cuh"
 
 #include <climits>
+#include <cuda_fp16.h>
 
 namespace mvx {
 
@@ -52,6 +53,73 @@ __global__ void __launch_bounds__(256) lidar2img_kernel(const float *__restrict_
     float u, v;
     project_point(c32, q[0], q[1], q[2], u, v);
     reinterpret_cast<float2 *>(out_uv)[i] = make_float2(u, v);
+}
+
+// ---- NCHW fp32 maps -> pre-packed fp16 hi/lo A operand of the pixel GEMM -------------------------------------------------
+// Row R = f * HW + p of the GEMM is pixel p of frame f. Per (256-row tile, 32-channel chunk) the output holds the exact
+// shared-memory image of the tensor-core kernel: [hi: 256 rows x 64 B, SWIZZLE_64B | lo: same], so the GEMM fetches a
+// stage of A with ONE bulk copy and has no register producers. A CTA owns 32 pixels x all C = 256 channels, finds each
+// pixel's max |x| (power-of-two scale into [0.5,1)), splits and stores; rowinv[R] = 1 / scale.
+__device__ __forceinline__ uint32_t pk_half2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ void pk_split(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    hi = pk_half2(x0, x1);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+    lo = pk_half2(x0 - hf.x, x1 - hf.y);
+}
+__global__ void __launch_bounds__(256) pack_maps_f16_kernel(const float *__restrict__ in, int C, int HW, uint8_t *__restrict__ apack,
+                                                            float *__restrict__ rowinv) {
+    __shared__ float tile[256][33];
+    __shared__ float s_max[8][32];
+    __shared__ float s_scale[32];
+    const int f = blockIdx.y, p0 = blockIdx.x * 32, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const float *src = in + (size_t)f * C * HW;
+    float mx = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {
+        const int c = ty + 8 * k;
+        const float v = (p0 + tx < HW) ? __ldg(src + (size_t)c * HW + p0 + tx) : 0.f;
+        tile[c][tx] = v;
+        mx = fmaxf(mx, fabsf(v));
+    }
+    s_max[ty][tx] = mx;
+    __syncthreads();
+    if (tid < 32) {
+        float m = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m = fmaxf(m, s_max[q][tid]);
+        float sc = 1.f;
+        if (m > 0.f && isfinite(m)) {
+            int e;
+            frexpf(m, &e);
+            e = max(-100, min(100, e));
+            sc = exp2f((float)-e);
+        }
+        s_scale[tid] = sc;
+        if (p0 + tid < HW) rowinv[(size_t)f * HW + p0 + tid] = 1.f / sc;
+    }
+    __syncthreads();
+    const int nkc = C / 32;
+    for (int q = tid; q < nkc * 128; q += 256) {   // one 16-byte piece (8 channels of one pixel) of hi and of lo per iteration
+        const int kc = q >> 7, rem = q & 127, r = rem >> 2, c16 = rem & 3;
+        if (p0 + r >= HW) continue;
+        const float sc = s_scale[r];
+        const int ch = kc * 32 + c16 * 8;
+        uint4 hi, lo;
+        pk_split(tile[ch][r] * sc, tile[ch + 1][r] * sc, hi.x, lo.x);
+        pk_split(tile[ch + 2][r] * sc, tile[ch + 3][r] * sc, hi.y, lo.y);
+        pk_split(tile[ch + 4][r] * sc, tile[ch + 5][r] * sc, hi.z, lo.z);
+        pk_split(tile[ch + 6][r] * sc, tile[ch + 7][r] * sc, hi.w, lo.w);
+        const size_t R = (size_t)f * HW + p0 + r;
+        const size_t t = R >> 8;
+        const uint32_t rr = (uint32_t)(R & 255);
+        uint8_t *dst = apack + (t * nkc + kc) * 32768 + rr * 64u + ((c16 ^ ((rr >> 1) & 3u)) << 4);
+        *reinterpret_cast<uint4 *>(dst) = hi;
+        *reinterpret_cast<uint4 *>(dst + 16384) = lo;
+    }
 }
 
 // ---- the 4-corner weighted gather of one row, one warp, all levels ------------------------------------
@@ -393,6 +461,13 @@ int launch_combine_sort(const CombineArgs &a, int B, cudaStream_t st) {
 int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st) {
     dim3 grid((a.capA + kCombRows - 1) / kCombRows, B);
     combine_rows_kernel<<<grid, kCombWarps * 32, 0, st>>>(a);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+int launch_pack_maps_f16(const float *in, void *apack, float *rowinv, int B, int C, int HW, cudaStream_t st) {
+    MVX_REQUIRE(C == 256, MVX_EINVAL, "pack_maps: C must be 256");
+    pack_maps_f16_kernel<<<dim3((HW + 31) / 32, B), 256, 0, st>>>(in, C, HW, static_cast<uint8_t *>(apack), rowinv);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }

@@ -17,6 +17,10 @@ struct MapSet {
 // chmax (optional): [B][chmax_stride] ints (float bits, zeroed by the caller): max |x| of every channel over the frame's pixels
 int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, float *rowmax, int *chmax, int chmax_stride, cudaStream_t st);
 
+// NCHW (B,C,HW) fp32 -> pre-packed fp16 hi/lo A operand of the pixel GEMM (rows R = f*HW + p), rowinv[R] = 1 / row scale.
+// apack must hold round_up(B*HW, 256) * C * 4 bytes; rows beyond B*HW are never read back (their outputs are not stored).
+int launch_pack_maps_f16(const float *in, void *apack, float *rowinv, int B, int C, int HW, cudaStream_t st);
+
 struct RowsParams {
     int B, cap, capA, T;
     const float *points;

@@ -30,6 +30,11 @@ struct LayerArgs {
     int f16_ok;              // 1: the tensor-core kernel may use fp16 operands (3xFP16): inputs are BatchNorm-ed (in_stats, or
                              // stored normalised) or row_max is given; 0 keeps 3xTF32 (arbitrary input range)
     const float *row_max;    // [F][rowcap] max|x| of each input row for the fp16 row scaling, or NULL (scale 1)
+    // pre-packed A (rows_mode 0 only): the producing kernel already wrote the fp16 hi/lo shared-memory images of every
+    // (256-row tile, 32-k chunk) [hi 16 KB | lo 16 KB]; the layer kernel then has no register producers at all, the A tiles
+    // arrive by bulk copy like the weights. a_rowinv[r] = 1 / (power-of-two scale the packer applied to row r).
+    const void *a_pack;
+    const float *a_rowinv;
     // fused concat (16-bit tensor-core producer only): input columns [Cin - x2_cols, Cin) of row r come from
     // X2[f][v(r)][0:x2_cols] (float bits, e.g. the per-voxel max of the producer layer) instead of X, with
     // v(r) = r >= K_f ? r - K_f : cat_row_vox[f][r]; both parts are normalised with the same in_stats (in_C channels)
@@ -51,6 +56,7 @@ bool tc2_layer_eligible(const LayerArgs &a);
 int launch_layer_tc2(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
 bool tc_persistent_enabled();
 bool tc_f16_enabled();
+bool tc_bf16_enabled();
 void set_tc_bf16(int on);  // 1: single-pass bf16 operands where LayerArgs::f16_ok (reduced precision, tolerance stated in the tests)
 void set_tc_f16(int on);   // 1 (default): 3xFP16 where LayerArgs::f16_ok, 0: 3xTF32 everywhere
 void set_tc_persistent(int on);  // 0 = one 256 x BN tile per CTA (default), 1 = persistent 256 x 128 kernel with overlapped epilogue

@@ -12,6 +12,7 @@
 #include "voxelize.cuh"
 #include "pointpath.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 namespace mvx {
@@ -26,6 +27,7 @@ const char *kRegionNames[R_COUNT] = {
 // (the layout the training-mode backward needs: dW1 = dpre1^T A1).
 static int g_fusion_mode = 1;
 int fusion_mode() { return g_fusion_mode; }
+static int g_apack = 1;     // MVX_APACK=0: channels-last fp32 copy + register producers for the pixel GEMM (A/B comparison)
 static int g_overlap = 1;   // 1: run the map branch of the pixel-first path on a side stream (mvx_set_fusion_mode(2) = pixel-first, serial)
 
 int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
@@ -52,7 +54,7 @@ int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
     take(R_CELL2VID, B * (size_t)L.G * 4);
     for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
         MVX_REQUIRE(a->map_h[l] > 0 && a->map_w[l] > 0, MVX_EINVAL, "bad FPN map extent");
-        take((Region)(R_NHWC0 + l), B * (size_t)a->map_h[l] * a->map_w[l] * a->map_c * 4);
+        take((Region)(R_NHWC0 + l), (size_t)round_up((int64_t)B * a->map_h[l] * a->map_w[l], 256) * a->map_c * 4);   // NHWC fp32, or the packed fp16 hi/lo image
     }
     const size_t capA = L.capA, capB = L.capB;
     take(R_VOX8, B * capA * 8 * 4);
@@ -194,6 +196,11 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     auto F32 = [&](Region r) { return reinterpret_cast<float *>(ws + L.off[r]); };
     auto I32 = [&](Region r) { return reinterpret_cast<int *>(ws + L.off[r]); };
 
+    static const bool env_read = [] {
+        if (const char *e = getenv("MVX_APACK")) g_apack = atoi(e);
+        return true;
+    }();
+    (void)env_read;
     const Stamp stamp(st);
     if (train) MVX_CUDA_CHECK(cudaMemsetAsync(I32(R_CHMAX), 0, (size_t)B * 768 * 4, st));
     // training keeps the gathered matrix A1 (dW1 = dpre1^T A1), so it always runs row-first
@@ -214,6 +221,8 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         MVX_CUDA_CHECK(cudaEventRecord(side->fork, st));
         MVX_CUDA_CHECK(cudaStreamWaitEvent(ms, side->fork, 0));
     }
+    // pixel-first with 3xFP16: the maps are written directly as the pre-packed A operand of the pixel GEMM (no NHWC copy)
+    const bool apack = pixel_first && tc_f16_enabled() && !tc_bf16_enabled() && g_apack;
     auto map_branch = [&](MapSet &m) -> int {
         stamp.begin(S_NHWC, ms);
         size_t rowmax_off = 0;
@@ -224,6 +233,12 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
             m.rs_w[l] = a->imsize_w / (float)a->map_w[l];
             m.nhwc[l] = F32((Region)(R_NHWC0 + l));
             m.frame_stride[l] = (size_t)HW * a->map_c;
+            if (apack) {
+                int r = launch_pack_maps_f16(a->maps[l], ws + L.off[R_NHWC0 + l], F32(R_ROWMAX) + rowmax_off, B, a->map_c, HW, ms);
+                if (r) return r;
+                rowmax_off += (size_t)B * HW;
+                continue;
+            }
             int r = launch_nchw_to_nhwc(a->maps[l], F32((Region)(R_NHWC0 + l)), B, a->map_c, HW, F32(R_ROWMAX) + rowmax_off,
                                         train ? I32(R_CHMAX) + l * a->map_c : nullptr, MVX_NUM_LEVELS * a->map_c, ms);
             if (r) return r;
@@ -242,6 +257,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
             la.Y = F32(R_Z) + zoff, la.ldy = 768;
             la.rows_fixed = px, la.rows_mode = 0, la.rowcap = 0, la.T = 1, la.eps = a->bn_eps, la.plain = 1;
             la.f16_ok = 1, la.row_max = F32(R_ROWMAX) + zoff / 768;   // raw FPN features: per-pixel power-of-two scaling
+            if (apack) la.a_pack = ws + L.off[R_NHWC0 + l], la.a_rowinv = F32(R_ROWMAX) + zoff / 768, la.row_max = nullptr;
             int r = launch_layer_auto(la, 1, F32(R_WPACK), ms);
             if (r) return r;
             zoff += (size_t)px * 768;

@@ -121,8 +121,10 @@ __global__ void __launch_bounds__(256) pack_weights_f16_kernel(const float *__re
 // a stage per thread instead of 4)
 __host__ __device__ constexpr int tc_producer_warps(bool f16, bool two) { return (f16 && !two) ? 16 : 8; }
 
-template <int BN, bool F16, bool BF1 = false, bool TWO = false>
+// APK: the A operand arrives pre-packed (LayerArgs::a_pack): no register producers, one bulk copy of 32 KB per stage.
+template <int BN, bool F16, bool BF1 = false, bool TWO = false, bool APK = false>
 __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2 : 1) tc_layer_kernel(LayerArgs a, const float *__restrict__ wpack) {
+    static_assert(!APK || (F16 && !BF1 && !TWO), "pre-packed A is the 3xFP16 one-CTA variant");
     constexpr int PW = tc_producer_warps(F16, TWO), PT = PW * 32, NT = PT + 64;   // producer warps / threads, CTA threads
     static_assert(!BF1 || F16, "the bf16 variant shares the 16-bit operand path");
     static_assert(!TWO || (F16 && BN == 128), "the two-CTA variant is the 16-bit, 128-column kernel");
@@ -178,7 +180,8 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
         for (int c = tid; c < BN; c += NT) s_colinv[c] = colinv[n0 + c];
         for (int r = tid; r < kTM; r += NT) {
             const long long rr = row0 + r;
-            s_rowinv[r] = (!BF1 && a.row_max && rr < n_rows) ? 1.f / pow2_scale(a.row_max[(size_t)f * a.rowcap + rr]) : 1.f;
+            if constexpr (APK) s_rowinv[r] = rr < n_rows ? a.a_rowinv[rr] : 1.f;
+            else s_rowinv[r] = (!BF1 && a.row_max && rr < n_rows) ? 1.f / pow2_scale(a.row_max[(size_t)f * a.rowcap + rr]) : 1.f;
         }
     }
     for (int r = tid; r < kTM; r += NT) {
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
     }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), PT + 1);
+            mbar_init(full_bar(s), APK ? 1 : PT + 1);   // APK: only the bulk-copy thread's expect_tx arrive
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(accum_bar, 1);
@@ -212,6 +215,8 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
 
     const bool mma_only = (a.dbg & 8) != 0;
     if (mma_only && warp != PW + 1) {
+    } else if (warp < PW && APK) {
+        // pre-packed A: nothing to produce (these warps run the epilogue)
     } else if (warp < PW && F16) {
         // ================= A producers, fp16 operands: a thread owns 8 k (one 16-byte chunk of fp16) of 4 rows ======
         constexpr int RS = PT / 4, RPT = kTM / RS;   // row stride between a thread's rows, rows per thread (4 or 2)
@@ -370,7 +375,13 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
                 const int s = kc % STAGES;
                 const uint32_t ph = (kc / STAGES) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_arrive_expect_tx(full_bar(s), 2 * S::kBHalf);
+                if constexpr (APK) {
+                    mbar_arrive_expect_tx(full_bar(s), 2 * S::kAHalf + 2 * S::kBHalf);
+                    const uint8_t *asrc = static_cast<const uint8_t *>(a.a_pack) + ((size_t)blockIdx.y * nk + kc) * (2 * S::kAHalf);
+                    bulk_g2s(sbase + s * S::kStage, asrc, 2 * S::kAHalf, full_bar(s));
+                } else {
+                    mbar_arrive_expect_tx(full_bar(s), 2 * S::kBHalf);
+                }
                 bulk_g2s(sbase + s * S::kStage + 2 * S::kAHalf, src + (size_t)kc * (2 * BN * kBK), 2 * S::kBHalf, full_bar(s));
             }
         }
@@ -523,13 +534,13 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
     }
 }
 
-template <int BN, bool F16, bool BF1 = false, bool TWO = false>
+template <int BN, bool F16, bool BF1 = false, bool TWO = false, bool APK = false>
 int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     using S = Smem<BN, TWO ? 2 : kStages, TWO>;
     static bool attr_set = false;
     if (!attr_set) {
-        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN, F16, BF1, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-        if (TWO) MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN, F16, BF1, TWO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN, F16, BF1, TWO, APK>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        if (TWO) MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_kernel<BN, F16, BF1, TWO, APK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
     const int total = a.Cin * a.Cout;
@@ -542,7 +553,7 @@ int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     MVX_LAUNCH_CHECK();
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     dim3 grid(a.Cout / BN, (unsigned)ceil_div(max_rows, kTM), F);
-    tc_layer_kernel<BN, F16, BF1, TWO><<<grid, tc_producer_warps(F16, TWO) * 32 + 64, S::kTotal, st>>>(a, wpack);
+    tc_layer_kernel<BN, F16, BF1, TWO, APK><<<grid, tc_producer_warps(F16, TWO) * 32 + 64, S::kTotal, st>>>(a, wpack);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }
@@ -877,6 +888,7 @@ static int g_tc_two = 0;        // MVX_TC_TWO=1: 128-column 16-bit layers run as
 static int g_tc_two_wide = 0;   // 1: also split 256-column tiles (the pixel GEMM) into 128-column two-CTA tiles (MVX_TC_TWO=2)
 static int g_tc_bf16 = 0;
 void set_tc_bf16(int on) { g_tc_bf16 = on; }
+bool tc_bf16_enabled() { return g_tc_bf16 != 0; }
 static int g_tc_f16 = 1;
 bool tc_f16_enabled() { return g_tc_f16 != 0; }
 void set_tc_f16(int on) { g_tc_f16 = on; }
@@ -911,6 +923,11 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
         if (a.Cout % 256 == 0 && !g_tc_two_wide) return launch_tc<256, true, true>(a, F, wpack, st);
         if (g_tc_two) return launch_tc<128, true, true, true>(a, F, wpack, st);
         return launch_tc<128, true, true>(a, F, wpack, st);
+    }
+    if (a.a_pack) {   // A pre-packed by the producing kernel: pure bulk-copy + MMA pipeline
+        MVX_REQUIRE(a.a_rowinv && a.Cout % 256 == 0 && a.Cin % 32 == 0 && a.rows_mode == 0 && F == 1 && !a.in_stats && !a.X2,
+                    MVX_EINVAL, "pre-packed A: unsupported layer configuration");
+        return launch_tc<256, true, false, false, true>(a, F, wpack, st);
     }
     if (a.f16_ok && tc_f16_enabled() && a.Cin % 32 == 0) {   // 3xFP16: half the tensor cycles and operand bytes of 3xTF32
         if (a.Cout % 256 == 0 && !g_tc_two_wide) return launch_tc<256, true>(a, F, wpack, st);
