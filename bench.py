@@ -371,7 +371,7 @@ def run_ours(args):
                 clocks=clocks,
                 e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=int(path.h2d_bytes),
                          d2h_bytes_per_step=int(path.d2h_bytes), ms_per_step=ms_e2e / args.steps,
-                         note=f'PointPath.forward_host: pinned-host points+calib+FPN maps -> H2D -> fused path -> D2H counts + feature head; sub-batches of {args.host_chunk} frame(s), H2D of sub-batch j+1 on a copy stream overlaps the kernels of sub-batch j'),
+                         note=f'PointPath.forward_host: pinned-host points+calib+FPN maps -> H2D -> fused path -> D2H counts + feature head; sub-batches of {args.host_chunk} frame(s) (the last one split in two), H2D of sub-batch j+1 on a copy stream overlaps the kernels of sub-batch j'),
                 gpu_launches=int(launches), roofline=roofline, stages_ms=stages, stage_rooflines=per_stage,
                 stages_note=f'per-stage CUDA events from a separate pass of {n_stage} steps with the map branch serialised (fusion mode 2, {ms_serial:.3f} ms/step); the timed region runs it on a side stream concurrently with the point branch')
     if world == 1 and not args.no_cpu_baseline and not dense:

@@ -40,6 +40,7 @@ class PointPath:
         self._sub_chunk = 0
         self.host_chunk = 1        # frames per sub-batch of forward_host: H2D of chunk j+1 overlaps compute of chunk j
         self.host_streams = 2      # sub-batches alternate between this many compute streams (their kernels may overlap)
+        self.host_taper = True     # split the last sub-batch in two: less compute left after the last copy has landed
 
     def load_state_dict(self, sd):
         self.wt, self.bias = [], []
@@ -258,7 +259,7 @@ class PointPath:
         c.device, c.grid_spec, c.grid, c.imsize_hw, c.eps = self.device, self.grid_spec, self.grid, self.imsize_hw, self.eps
         c.wt, c.bias = self.wt, self.bias          # shared weights
         c._ws = c._ws_key = c._args = c._subs = None
-        c._sub_chunk, c.host_chunk = 0, 0
+        c._sub_chunk, c.host_chunk, c.host_taper = 0, 0, False
         return c
 
     def forward_host(self, points_host: torch.Tensor, offsets: Sequence[int], calib32_host: torch.Tensor,
@@ -271,13 +272,24 @@ class PointPath:
         Returns (grid on device, counts on host, head block on host); synchronises the stream."""
         dev = self.device
         B = len(offsets) - 1
-        chunk = max(1, min(int(self.host_chunk) or B, B))
+        # sub-batch schedule: `host_chunk` frames per sub-batch, or an explicit list of sizes; the default tapers the tail
+        # (…, 1, 1): the step ends one sub-batch of compute after the LAST copy lands, so the last sub-batch should be small
+        if isinstance(self.host_chunk, (list, tuple)):
+            sizes = [int(c) for c in self.host_chunk]
+        else:
+            chunk = max(1, min(int(self.host_chunk) or B, B))
+            sizes = [chunk] * (B // chunk) + ([B % chunk] if B % chunk else [])
+            if self.host_taper and chunk > 1 and len(sizes) >= 2 and sizes[-1] == chunk:
+                sizes = sizes[:-1] + [chunk - chunk // 2, chunk // 2] if chunk > 2 else sizes[:-1] + [1, 1]
+        assert sum(sizes) == B and all(c > 0 for c in sizes), sizes
+        bounds = [0]
+        for c in sizes:
+            bounds.append(bounds[-1] + c)
         key = (tuple(points_host.shape), tuple(int(o) for o in offsets), tuple(calib32_host.shape),
-               tuple(tuple(m.shape) for m in maps_host), chunk, head_rows)
+               tuple(tuple(m.shape) for m in maps_host), tuple(sizes), head_rows)
         if getattr(self, '_in_key', None) != key:
             self._subs = []
-            for f0 in range(0, B, chunk):
-                f1 = min(B, f0 + chunk)
+            for f0, f1 in zip(bounds[:-1], bounds[1:]):
                 c = self._child()
                 c.f0, c.f1, c.p0, c.p1 = f0, f1, int(offsets[f0]), int(offsets[f1])
                 c.offsets = [int(o) - c.p0 for o in offsets[f0:f1 + 1]]
@@ -286,7 +298,7 @@ class PointPath:
                 c.in_maps = [torch.empty((f1 - f0,) + tuple(m.shape[1:]), dtype=torch.float32, device=dev) for m in maps_host]
                 c.ev = torch.cuda.Event()
                 self._subs.append(c)
-            self._sub_chunk = chunk
+            self._sub_chunk = None
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._out_counts = torch.empty((B, 4), dtype=torch.int32).pin_memory()
             self._out_head = torch.empty((head_rows, 128), dtype=torch.float32).pin_memory()
