@@ -34,7 +34,11 @@ struct LayerArgs {
     // (256-row tile, 32-k chunk) [hi 16 KB | lo 16 KB]; the layer kernel then has no register producers at all, the A tiles
     // arrive by bulk copy like the weights. a_rowinv[r] = 1 / (power-of-two scale the packer applied to row r).
     const void *a_pack;
-    const float *a_rowinv;
+    const float *a_rowinv;   // NULL: no per-row scale
+    int a_frame_tiles;       // 256-row tiles per frame inside a_pack (frame f, tile t, chunk kc at ((f * a_frame_tiles + t) * nk + kc) * 32 KB)
+    // per-frame pre-packed weights (BatchNorm of the producer folded into them by the caller): wpack holds F consecutive
+    // [blob | colinv] sets packed by the caller, `bias` is [F][Cout]; the kernel then does no weight packing itself
+    int w_per_frame;
     // fused concat (16-bit tensor-core producer only): input columns [Cin - x2_cols, Cin) of row r come from
     // X2[f][v(r)][0:x2_cols] (float bits, e.g. the per-voxel max of the producer layer) instead of X, with
     // v(r) = r >= K_f ? r - K_f : cat_row_vox[f][r]; both parts are normalised with the same in_stats (in_C channels)

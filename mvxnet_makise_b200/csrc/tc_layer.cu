@@ -174,13 +174,16 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
             s_rstd[c] = (float)(1.0 / sqrt(var + a.eps));
         }
     }
-    for (int c = tid; c < BN; c += NT) s_bias[c] = a.plain ? 0.f : a.bias[n0 + c];
+    for (int c = tid; c < BN; c += NT) s_bias[c] = a.plain ? 0.f : a.bias[(a.w_per_frame ? (size_t)f * a.Cout : 0) + n0 + c];
     if constexpr (F16) {
-        const float *colinv = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(wpack) + (size_t)a.Cin * a.Cout * 4);
+        // [blob: Cin*Cout*4 bytes | colinv: Cout floats], one such set per frame when the weights are per frame
+        const size_t wset = (size_t)a.Cin * a.Cout * 4 + (size_t)a.Cout * 4;
+        const uint8_t *wbase = reinterpret_cast<const uint8_t *>(wpack) + (a.w_per_frame ? (size_t)f * wset : 0);
+        const float *colinv = reinterpret_cast<const float *>(wbase + (size_t)a.Cin * a.Cout * 4);
         for (int c = tid; c < BN; c += NT) s_colinv[c] = colinv[n0 + c];
         for (int r = tid; r < kTM; r += NT) {
             const long long rr = row0 + r;
-            if constexpr (APK) s_rowinv[r] = rr < n_rows ? a.a_rowinv[rr] : 1.f;
+            if constexpr (APK) s_rowinv[r] = (a.a_rowinv && rr < n_rows) ? a.a_rowinv[(size_t)f * a.rowcap + rr] : 1.f;
             else s_rowinv[r] = (!BF1 && a.row_max && rr < n_rows) ? 1.f / pow2_scale(a.row_max[(size_t)f * a.rowcap + rr]) : 1.f;
         }
     }
@@ -371,13 +374,14 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
         // ================= B producer: one bulk copy per stage ===================================================
         if (lane == 0) {
             const float *src = wpack + (size_t)ctile * nk * (2 * BN * kBK);
+            if (F16 && a.w_per_frame) src += (size_t)f * (((size_t)a.Cin * a.Cout * 4 + (size_t)a.Cout * 4) / 4);
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % STAGES;
                 const uint32_t ph = (kc / STAGES) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
                 if constexpr (APK) {
                     mbar_arrive_expect_tx(full_bar(s), 2 * S::kAHalf + 2 * S::kBHalf);
-                    const uint8_t *asrc = static_cast<const uint8_t *>(a.a_pack) + ((size_t)blockIdx.y * nk + kc) * (2 * S::kAHalf);
+                    const uint8_t *asrc = static_cast<const uint8_t *>(a.a_pack) + (((size_t)f * a.a_frame_tiles + blockIdx.y) * nk + kc) * (2 * S::kAHalf);
                     bulk_g2s(sbase + s * S::kStage, asrc, 2 * S::kAHalf, full_bar(s));
                 } else {
                     mbar_arrive_expect_tx(full_bar(s), 2 * S::kBHalf);
@@ -544,7 +548,9 @@ int launch_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
         attr_set = true;
     }
     const int total = a.Cin * a.Cout;
-    if (F16) {   // [fp16 hi|lo images: Cin*Cout*4 bytes][inverse column scales: Cout floats]
+    if (a.w_per_frame) {
+        // the caller packed one [blob | colinv] set per frame (folded BatchNorm): nothing to do here
+    } else if (F16) {   // [fp16 hi|lo images: Cin*Cout*4 bytes][inverse column scales: Cout floats]
         uint8_t *blob = reinterpret_cast<uint8_t *>(wpack);
         pack_weights_f16_kernel<BN, BF1><<<a.Cout, 256, 0, st>>>(a.Wt, a.Cin, a.Cout, blob, reinterpret_cast<float *>(blob + (size_t)total * 4));
     } else {
@@ -925,8 +931,10 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
         return launch_tc<128, true, true>(a, F, wpack, st);
     }
     if (a.a_pack) {   // A pre-packed by the producing kernel: pure bulk-copy + MMA pipeline
-        MVX_REQUIRE(a.a_rowinv && a.Cout % 256 == 0 && a.Cin % 32 == 0 && a.rows_mode == 0 && F == 1 && !a.in_stats && !a.X2,
-                    MVX_EINVAL, "pre-packed A: unsupported layer configuration");
+        MVX_REQUIRE(a.Cin % 32 == 0 && !a.in_stats && !a.X2 && (a.Cout % 256 == 0 || a.Cout == 128), MVX_EINVAL,
+                    "pre-packed A: unsupported layer configuration");
+        MVX_REQUIRE((a.rows_mode == 0 && F == 1) || a.a_frame_tiles > 0, MVX_EINVAL, "pre-packed A: per-frame tile count missing");
+        if (a.Cout == 128) return launch_tc<128, true, false, false, true>(a, F, wpack, st);
         return launch_tc<256, true, false, false, true>(a, F, wpack, st);
     }
     if (a.f16_ok && tc_f16_enabled() && a.Cin % 32 == 0) {   // 3xFP16: half the tensor cycles and operand bytes of 3xTF32
