@@ -220,6 +220,30 @@ int mvx_cml_conv1_workspace_bytes(const mvx_pointpath_args_t *args, size_t *byte
 int mvx_cml_conv1_sparse(const mvx_pointpath_args_t *args, const float *conv_w, const float *conv_b, double eps, float *out,
                          void *ws, size_t ws_bytes);
 
+/* ------------------------------------------------------------------------------------------------
+ * Label side of the same native extension.
+ *
+ * mvx_bbox_pairwise replaces `bboxOverlap` (mode 0: IoU, cpp/voxelutil.cpp:96-116; caller modules/augment/Augment.py:54)
+ * and `bboxIntersection` (mode 1: intersection area, voxelutil.cpp:118-139) on top of the polygon clipper
+ * voxelutil.cpp:15-93: bboxes1 (n,4,2), bboxes2 (m,4,2) device fp32 corner quads (16-byte aligned) -> out (n,m) fp32.
+ * Bit-identical to the reference's scalar fp32 arithmetic; the second quad is read corner by corner (the reference
+ * indexes it by box number, voxelutil.cpp:108,129 — a slip that mixes stale corners and overruns its 5-element global).
+ *
+ * mvx_classify_anchors replaces `classifyAnchors` (voxelutil.cpp:141-316, bound as `_classifyAnchors`; python caller
+ * modules/Calc.py:88-96): gts (G,4,2) ground-truth BEV quads, anchors (L,W,A,4,2) anchor BEV quads, nls/nws int64[G] start
+ * cells. For every ground truth and anchor rotation the anchors reachable from the start cell through IoU >= 0.1
+ * (column walk up then down, row walk right then left) are classified: IoU >= pos_thr -> appended to pos (+ gi = ground
+ * truth index) AND neg, else IoU >= neg_thr -> appended to neg ("not negative"). pos/neg are (cap,3) int64 rows
+ * (l, w, z), gi (cap) int64, all in the reference's append order. counts (device int64[4]) = {npos, nneg, ground
+ * truths whose start cell is outside the anchor grid (undefined behaviour in the reference; skipped here), 0}; entries
+ * beyond cap are counted but not stored (re-run with a larger cap). No host synchronisation.
+ * ------------------------------------------------------------------------------------------------ */
+int mvx_bbox_pairwise(const float *bboxes1, int64_t n, const float *bboxes2, int64_t m, int32_t mode, float *out, void *stream);
+int mvx_classify_anchors_workspace_bytes(int64_t G, int32_t A, size_t *bytes);
+int mvx_classify_anchors(const float *gts, int64_t G, const float *anchors, int64_t L, int64_t W, int32_t A, const int64_t *nls,
+                         const int64_t *nws, float neg_thr, float pos_thr, int64_t *pos, int64_t *neg, int64_t *gi, int64_t cap,
+                         int64_t *counts, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Optional per-kernel timing of mvx_pointpath_forward with CUDA events recorded on the launching stream
  * (bench.py's roofline leg). mvx_timing_enable(n) arms n event sets (one per forward call, n = 0 disables);
  * mvx_timing_read(call, ms) waits for that call's last event and returns MVX_NUM_SEGMENTS durations in ms, in the

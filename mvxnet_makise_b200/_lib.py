@@ -31,6 +31,7 @@ EXPORTS = [
     'mvx_pointpath_workspace_bytes', 'mvx_pointpath_layout', 'mvx_pointpath_layout_name', 'mvx_pointpath_forward',
     'mvx_set_fusion_mode', 'mvx_pointpath_train_workspace_bytes', 'mvx_pointpath_forward_train', 'mvx_grad_floats',
     'mvx_pointpath_backward', 'mvx_cml_conv1_workspace_bytes', 'mvx_cml_conv1_sparse',
+    'mvx_bbox_pairwise', 'mvx_classify_anchors_workspace_bytes', 'mvx_classify_anchors',
     'mvx_timing_enable', 'mvx_timing_read', 'mvx_timing_segment_name',
 ]
 
@@ -102,6 +103,9 @@ def _load():
     lib.mvx_cml_conv1_workspace_bytes.argtypes = [POINTER(PointPathArgs), POINTER(c_size_t)]
     lib.mvx_cml_conv1_sparse.argtypes = [POINTER(PointPathArgs), vp, vp, c_double, vp, vp, c_size_t]
     lib.mvx_pointpath_backward.argtypes = [POINTER(PointPathArgs), vp, vp, vp, i32, vp, c_size_t]
+    lib.mvx_bbox_pairwise.argtypes = [vp, i64, vp, i64, i32, vp, vp]
+    lib.mvx_classify_anchors_workspace_bytes.argtypes = [i64, i32, POINTER(c_size_t)]
+    lib.mvx_classify_anchors.argtypes = [vp, i64, vp, i64, i64, i32, vp, vp, c_float, c_float, vp, vp, vp, i64, vp, vp, c_size_t, vp]
     lib.mvx_timing_enable.argtypes = [i32]
     lib.mvx_timing_read.argtypes = [i32, POINTER(c_float)]
     lib.mvx_timing_segment_name.argtypes = [i32]

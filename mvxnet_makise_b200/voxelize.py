@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import anchors as _anchors
 from ._lib import lib, check, ptr, stream_ptr
 
 
@@ -214,24 +215,13 @@ def cropFrame(pcd, range: Sequence[float], calib: dict, imsize: Sequence[int]):
 
 
 class VoxelUtil:
-    """The object ``modules/Extension.py`` exposes as ``cpp`` (voxelutil.cpp:362-368).
-
-    Only ``_group`` is on the hot path. The anchor/IoU functions are label-side code and out of
-    scope for this build; they raise instead of silently computing on the CPU."""
+    """The object ``modules/Extension.py`` exposes as ``cpp`` (voxelutil.cpp:362-368): all four bound functions, each
+    on the CUDA kernels (``_group``: csrc/voxelize.cu; the anchor / rotated-IoU functions: csrc/anchors.cu)."""
 
     _group = staticmethod(cpp_group)
-
-    @staticmethod
-    def _classifyAnchors(*args, **kwargs):
-        raise NotImplementedError('voxelutil._classifyAnchors is outside the B200 hot path (SURVEY.md §8f)')
-
-    @staticmethod
-    def bboxOverlap(*args, **kwargs):
-        raise NotImplementedError('voxelutil.bboxOverlap is outside the B200 hot path (SURVEY.md §8f)')
-
-    @staticmethod
-    def bboxIntersection(*args, **kwargs):
-        raise NotImplementedError('voxelutil.bboxIntersection is outside the B200 hot path (SURVEY.md §8f)')
+    _classifyAnchors = staticmethod(_anchors._classifyAnchors)
+    bboxOverlap = staticmethod(_anchors.bboxOverlap)
+    bboxIntersection = staticmethod(_anchors.bboxIntersection)
 
 
 cpp = VoxelUtil()

@@ -80,3 +80,19 @@ def load(device: str = 'cpu'):
     _mods = types.SimpleNamespace(cfg=cfg, pre=pre, calib=calib, layers=layers, imhead_pipe=imhead_pipe,
                                   vpipe=vpipe, VoxelNet=vnet.VoxelNet, cpp=ext.cpp)
     return _mods
+
+
+def load_calc():
+    """modules/Calc.py (bbox3d2bev, classifyAnchors). Its `from shapely.geometry import Polygon` serves only the shapely variants
+    (`iou2d`, `getPolygons`, `classifyAnchors_`), which are never called here; shapely is not installed, so an empty stand-in
+    module satisfies the import."""
+    load()
+    if 'shapely' not in sys.modules:
+        try:
+            importlib.import_module('shapely.geometry')
+        except ImportError:
+            sh, geo = types.ModuleType('shapely'), types.ModuleType('shapely.geometry')
+            geo.Polygon = object
+            sh.geometry = geo
+            sys.modules['shapely'], sys.modules['shapely.geometry'] = sh, geo
+    return importlib.import_module('modules.Calc')

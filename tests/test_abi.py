@@ -72,8 +72,11 @@ def test_no_cpu_fallback():
         pipeline.PointPath(synth.make_weights(0))
     with pytest.raises((RuntimeError, AssertionError)):
         voxelize.cpp._group(np.zeros((4, 4), np.float32), np.zeros((4, 3), np.int32), 35)
-    with pytest.raises(NotImplementedError):
-        voxelize.cpp.bboxOverlap()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        voxelize.cpp.bboxOverlap(np.zeros((1, 4, 2), np.float32), np.zeros((1, 4, 2), np.float32))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        voxelize.cpp._classifyAnchors(np.zeros((1, 4, 2), np.float32), np.zeros((2, 2, 2, 4, 2), np.float32), np.zeros(1, np.int64),
+                                      np.zeros(1, np.int64), 0.45, 0.6)
 
 
 def test_product_never_imports_the_oracle():
