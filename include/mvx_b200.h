@@ -239,7 +239,7 @@ int mvx_cml_conv1_sparse(const mvx_pointpath_args_t *args, const float *conv_w, 
  * beyond cap are counted but not stored (re-run with a larger cap). No host synchronisation.
  * ------------------------------------------------------------------------------------------------ */
 int mvx_bbox_pairwise(const float *bboxes1, int64_t n, const float *bboxes2, int64_t m, int32_t mode, float *out, void *stream);
-int mvx_classify_anchors_workspace_bytes(int64_t G, int32_t A, size_t *bytes);
+int mvx_classify_anchors_workspace_bytes(int64_t G, int64_t L, int64_t W, int32_t A, size_t *bytes);
 int mvx_classify_anchors(const float *gts, int64_t G, const float *anchors, int64_t L, int64_t W, int32_t A, const int64_t *nls,
                          const int64_t *nws, float neg_thr, float pos_thr, int64_t *pos, int64_t *neg, int64_t *gi, int64_t cap,
                          int64_t *counts, void *workspace, size_t workspace_bytes, void *stream);

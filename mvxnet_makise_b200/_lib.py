@@ -104,7 +104,7 @@ def _load():
     lib.mvx_cml_conv1_sparse.argtypes = [POINTER(PointPathArgs), vp, vp, c_double, vp, vp, c_size_t]
     lib.mvx_pointpath_backward.argtypes = [POINTER(PointPathArgs), vp, vp, vp, i32, vp, c_size_t]
     lib.mvx_bbox_pairwise.argtypes = [vp, i64, vp, i64, i32, vp, vp]
-    lib.mvx_classify_anchors_workspace_bytes.argtypes = [i64, i32, POINTER(c_size_t)]
+    lib.mvx_classify_anchors_workspace_bytes.argtypes = [i64, i64, i64, i32, POINTER(c_size_t)]
     lib.mvx_classify_anchors.argtypes = [vp, i64, vp, i64, i64, i32, vp, vp, c_float, c_float, vp, vp, vp, i64, vp, vp, c_size_t, vp]
     lib.mvx_timing_enable.argtypes = [i32]
     lib.mvx_timing_read.argtypes = [i32, POINTER(c_float)]

@@ -73,7 +73,7 @@ class AnchorClassifier:
         nl, nw = _dev_i64(nls), _dev_i64(nws)
         dev = self.anchors.device
         nbytes = ctypes.c_size_t()
-        check(lib.mvx_classify_anchors_workspace_bytes(G, self.A, ctypes.byref(nbytes)), 'classify_anchors_workspace_bytes')
+        check(lib.mvx_classify_anchors_workspace_bytes(G, self.L, self.W, self.A, ctypes.byref(nbytes)), 'classify_anchors_workspace_bytes')
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
         counts = torch.empty(4, dtype=torch.int64, device=dev)
         cap = max(1024, 128 * G * self.A)

@@ -9,11 +9,13 @@
 //
 // Parallel form of the sequential flood: the reference walks, per ground truth i and anchor rotation z, up (h = 0, 1, ..) and
 // then down (h = -1, -2, ..) the column of the start cell while IoU >= 0.1, and inside every such row right (v = 1, 2, ..) and
-// then left (v = -1, ..) while IoU >= 0.1, appending to three lists as it goes. Here one WARP owns one (i, z) task; the 32
-// lanes evaluate 32 consecutive cells of a row at once, a ballot finds the first cell below 0.1 (where the reference
-// breaks) and ballots of the two threshold tests give every surviving lane its list position, so the output order is the
-// reference's. A counting pass, an exclusive scan over the tasks and an emitting pass (same arithmetic, hence the same
-// decisions) replace the reference's growing vectors; nothing is synchronised with the host.
+// then left (v = -1, ..) while IoU >= 0.1, appending to three lists as it goes (a few hundred dependent IoU evaluations per
+// ground truth). Here one CTA owns one (i, z) task: two warps first walk the column in both directions 32 rows at a time (a
+// ballot finds the row where the reference breaks), then all live rows are walked at once, 8 lanes per (row, direction) and
+// 8 cells per step, each evaluated cell leaving its class in a per-task scratch map. The visiting order of the reference
+// is a fixed enumeration of (row, direction) units, so an exclusive scan over unit counts (and one over the tasks) gives
+// every entry its list position and a last kernel writes the lists without re-evaluating anything. The dependent chain
+// shrinks from hundreds of IoU evaluations to about four; nothing is synchronised with the host.
 //
 // Differences from the reference text (the test checker restates the same two): the second quad of bboxOverlap / bboxIntersection is
 // indexed by corner (the reference indexes it by box, voxelutil.cpp:108,129, which mixes stale corners and overruns the
@@ -129,84 +131,149 @@ __global__ void __launch_bounds__(128) pairwise_kernel(const float *__restrict__
 }
 
 // ---- classifyAnchors ---------------------------------------------------------------------------------------------------
+// One CTA per task = (ground truth i, anchor rotation z). Per-task scratch in the workspace:
+//   hdr[2] (+pad)     live rows of the upward walk (rows nl, nl+1, ..) and of the downward walk (rows nl-1, nl-2, ..)
+//   urec[2*L][4]      per unit u = 2*r + dir (r = row in the reference's visiting order: upward rows first; dir 0 = centre and the
+//                     cells to its right, dir 1 = the cells to its left): visited cells, positives, not-negatives, (after the scan
+//                     of the emit kernel) -
+//   cls[L*W] bytes    class of every visited cell: 0 = visited only, 1 = not negative, 2 = positive
+// u ascending IS the reference's append order, so an exclusive scan over u gives every unit its place in the lists.
 struct ClassifyParams {
     const float *gts;       // (G,4,2)
     const float *anchors;   // (L,W,A,4,2)
     const long long *nls, *nws;
     long long G, L, W, A;
     float neg_thr, pos_thr;
-    long long *task_cnt;    // [G*A][2] entries (pos, neg) of each task; after the scan: exclusive offsets, [G*A] = totals
+    long long *task_cnt;    // [G*A + 1][2]: entries (pos, neg) of each task; after the scan their exclusive offsets, last = totals
+    unsigned char *scratch; // [G*A] x task_stride bytes
+    size_t task_stride;
     long long *pos, *neg, *gi, cap;
     long long *counts;      // [4]: npos, nneg, ground truths outside the anchor grid, 0
 };
 
-template <bool EMIT>
-__global__ void __launch_bounds__(128) classify_kernel(ClassifyParams p) {
-    const int lane = threadIdx.x & 31;
-    const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (task >= p.G * p.A) return;
+__host__ __device__ inline size_t classify_task_stride(long long L, long long W) {
+    return (size_t)((16 + 16 * 2 * L + L * W + 15) / 16 * 16);
+}
+
+struct TaskScratch {
+    int *hdr, *urec;
+    unsigned char *cls;
+};
+__device__ __forceinline__ TaskScratch task_scratch(const ClassifyParams &p, long long task) {
+    unsigned char *b = p.scratch + (size_t)task * p.task_stride;
+    TaskScratch t;
+    t.hdr = reinterpret_cast<int *>(b);
+    t.urec = reinterpret_cast<int *>(b + 16);
+    t.cls = b + 16 + 16 * 2 * p.L;
+    return t;
+}
+
+struct IouEval {   // one ground truth against any anchor of the grid
+    Pt r1[5];
+    float area_sum;
+    const float *anchors;
+    long long W, A, z;
+    __device__ __forceinline__ float operator()(long long row, long long col) const {
+        Pt r2[5];
+        load_quad(r2, anchors + ((row * W + col) * A + z) * 8);
+        orient(r2);
+        const float inter = quad_intersect(r1, r2);
+        return __fdiv_rn(inter, __fsub_rn(area_sum, inter));
+    }
+};
+
+__device__ __forceinline__ int classify_code(float iou, float neg_thr, float pos_thr) {   // :173-186
+    return iou >= pos_thr ? 2 : (iou >= neg_thr ? 1 : 0);
+}
+
+constexpr int kClsThreads = 128;   // 4 warps = 16 groups of 8 lanes
+
+__global__ void __launch_bounds__(kClsThreads) classify_eval_kernel(ClassifyParams p) {
+    const long long task = blockIdx.x;
     const long long i = task / p.A, z = task - i * p.A;
     const long long nl = p.nls[i], nw = p.nws[i];
-    long long npos = 0, nneg = 0;   // warp-uniform
-    long long base_pos = 0, base_neg = 0;
-    if (EMIT) { base_pos = p.task_cnt[2 * task]; base_neg = p.task_cnt[2 * task + 1]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TaskScratch ts = task_scratch(p, task);
+    __shared__ int s_k[2], s_tot[2];
+    if (threadIdx.x < 2) { s_k[threadIdx.x] = 0; s_tot[threadIdx.x] = 0; }
     const bool inside = nl >= 0 && nl < p.L && nw >= 0 && nw < p.W;
-    if (inside) {
-        Pt r1[5], r2[5];
+    if (!inside) {   // an unchecked out-of-bounds read in the reference: no entries, counted once per ground truth
+        if (threadIdx.x == 0) {
+            ts.hdr[0] = ts.hdr[1] = 0;
+            p.task_cnt[2 * task] = p.task_cnt[2 * task + 1] = 0;
+            if (z == 0) atomicAdd(reinterpret_cast<unsigned long long *>(p.counts + 2), 1ull);
+        }
+        return;
+    }
+    IouEval ev;
+    {
+        Pt r2[5];
         load_quad(r2, p.anchors);
         const float anchor_area = area_n(r2, 4);   // :155: anchor (0,0,0) stands for every anchor
-        load_quad(r1, p.gts + i * 8);
-        const float gt_area = area_n(r1, 4);
-        orient(r1);
-        const float area_sum = __fadd_rn(gt_area, anchor_area);
-        for (int phase = 0; phase < 2; phase++) {
-            for (long long row = phase == 0 ? nl : nl - 1; phase == 0 ? row < p.L : row >= 0; row += phase == 0 ? 1 : -1) {
-                bool row_dead = false;
-                for (int dir = 0; dir < 2 && !row_dead; dir++) {   // centre and right, then left
-                    for (long long v0 = dir == 0 ? 0 : 1;; v0 += 32) {
-                        const long long col = dir == 0 ? nw + v0 + lane : nw - v0 - lane;
-                        const bool valid = col >= 0 && col < p.W;
-                        float iou = 0.f;
-                        if (valid) {
-                            load_quad(r2, p.anchors + ((row * p.W + col) * p.A + z) * 8);
-                            orient(r2);
-                            const float inter = quad_intersect(r1, r2);
-                            iou = __fdiv_rn(inter, __fsub_rn(area_sum, inter));
-                        }
-                        const bool stop = !valid || (double)iou < 0.1;   // NaN does not stop, as in the reference
-                        const unsigned stop_mask = __ballot_sync(0xffffffffu, stop);
-                        const int first = stop_mask ? __ffs(stop_mask) - 1 : 32;
-                        const bool live = lane < first;
-                        const bool is_pos = live && iou >= p.pos_thr;
-                        const bool is_neg = live && (iou >= p.pos_thr || iou >= p.neg_thr);
-                        const unsigned pm = __ballot_sync(0xffffffffu, is_pos), nm = __ballot_sync(0xffffffffu, is_neg);
-                        if (EMIT) {
-                            const unsigned lt = (1u << lane) - 1u;
-                            if (is_pos) {
-                                const long long k = base_pos + npos + __popc(pm & lt);
-                                if (k < p.cap) { p.pos[3 * k] = row; p.pos[3 * k + 1] = col; p.pos[3 * k + 2] = z; p.gi[k] = i; }
-                            }
-                            if (is_neg) {
-                                const long long k = base_neg + nneg + __popc(nm & lt);
-                                if (k < p.cap) { p.neg[3 * k] = row; p.neg[3 * k + 1] = col; p.neg[3 * k + 2] = z; }
-                            }
-                        }
-                        npos += __popc(pm);
-                        nneg += __popc(nm);
-                        if (first < 32) {
-                            // the centre cell (dir 0, first cell) below 0.1 ends the walk along the column (:170-172)
-                            if (dir == 0 && v0 == 0 && first == 0) row_dead = true;
-                            break;
-                        }
-                    }
-                }
-                if (row_dead) break;
+        load_quad(ev.r1, p.gts + i * 8);
+        const float gt_area = area_n(ev.r1, 4);    // signed, before the re-orientation
+        orient(ev.r1);
+        ev.area_sum = __fadd_rn(gt_area, anchor_area);
+        ev.anchors = p.anchors; ev.W = p.W; ev.A = p.A; ev.z = z;
+    }
+    __syncthreads();
+    // A. the two walks along the start column, 32 rows at a time: warp 0 upwards from nl, warp 1 downwards from nl - 1
+    if (warp < 2) {
+        for (long long k0 = 0;; k0 += 32) {
+            const long long row = warp == 0 ? nl + k0 + lane : nl - 1 - k0 - lane;
+            const bool valid = row >= 0 && row < p.L;
+            const float iou = valid ? ev(row, nw) : 0.f;
+            const bool stop = !valid || (double)iou < 0.1;   // NaN does not stop the walk, as in the reference
+            const unsigned sm = __ballot_sync(0xffffffffu, stop);
+            const int first = sm ? __ffs(sm) - 1 : 32;
+            if (lane < first) ts.cls[row * p.W + nw] = (unsigned char)classify_code(iou, p.neg_thr, p.pos_thr);
+            if (first < 32) {
+                if (lane == 0) s_k[warp] = (int)(k0 + first);
+                break;
             }
         }
-    } else if (!EMIT && lane == 0 && z == 0) {
-        atomicAdd(reinterpret_cast<unsigned long long *>(p.counts + 2), 1ull);
     }
-    if (!EMIT && lane == 0) { p.task_cnt[2 * task] = npos; p.task_cnt[2 * task + 1] = nneg; }
+    __syncthreads();
+    const int k_up = s_k[0], k_dn = s_k[1];
+    // B. the row walks of all live rows at once: a group of 8 lanes per (row, direction), 8 cells at a time
+    const int group = threadIdx.x >> 3, gl = threadIdx.x & 7;
+    const unsigned gmask = 0xffu << (lane & 24);
+    for (int u = group; u < 2 * (k_up + k_dn); u += kClsThreads / 8) {
+        const int r = u >> 1, dir = u & 1;
+        const long long row = r < k_up ? nl + r : nl - 1 - (r - k_up);
+        int len = 0, npos = 0, nneg = 0;
+        if (dir == 0) {   // the centre cell opens the row
+            const int c = ts.cls[row * p.W + nw];
+            len = 1; npos = c == 2; nneg = c >= 1;
+        }
+        for (long long v0 = 1;; v0 += 8) {
+            const long long col = dir == 0 ? nw + v0 + gl : nw - v0 - gl;
+            const bool valid = col >= 0 && col < p.W;
+            const float iou = valid ? ev(row, col) : 0.f;
+            const bool stop = !valid || (double)iou < 0.1;
+            const unsigned sm = (__ballot_sync(gmask, stop) & gmask) >> (lane & 24);
+            const int first = sm ? __ffs(sm) - 1 : 8;
+            const bool live = gl < first;
+            const int c = live ? classify_code(iou, p.neg_thr, p.pos_thr) : 0;
+            if (live) ts.cls[row * p.W + col] = (unsigned char)c;
+            npos += __popc(__ballot_sync(gmask, c == 2) & gmask);
+            nneg += __popc(__ballot_sync(gmask, c >= 1) & gmask);
+            len += first;
+            if (first < 8) break;
+        }
+        if (gl == 0) {
+            int4 rec = make_int4(len, npos, nneg, 0);
+            *reinterpret_cast<int4 *>(ts.urec + 4 * u) = rec;
+            atomicAdd(&s_tot[0], npos);
+            atomicAdd(&s_tot[1], nneg);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ts.hdr[0] = k_up; ts.hdr[1] = k_dn;
+        p.task_cnt[2 * task] = s_tot[0];
+        p.task_cnt[2 * task + 1] = s_tot[1];
+    }
 }
 
 // exclusive scan of the per-task (pos, neg) counts in place, totals to counts[0..1]; the task count is small (ground
@@ -235,6 +302,55 @@ __global__ void __launch_bounds__(1024) classify_scan_kernel(ClassifyParams p) {
     }
 }
 
+// C. lists in the reference's append order from the recorded classes: scan over the task's units, then one warp per unit
+__global__ void __launch_bounds__(kClsThreads) classify_emit_kernel(ClassifyParams p) {
+    const long long task = blockIdx.x;
+    const long long i = task / p.A, z = task - i * p.A;
+    const long long nl = p.nls[i], nw = p.nws[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TaskScratch ts = task_scratch(p, task);
+    const int k_up = ts.hdr[0], nunits = 2 * (ts.hdr[0] + ts.hdr[1]);
+    if (nunits == 0) return;
+    __shared__ int carry[2];
+    if (threadIdx.x < 2) carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (int u0 = 0; u0 < nunits; u0 += kClsThreads) {   // urec[u].y/.z: counts -> exclusive offsets inside the task
+        const int u = u0 + threadIdx.x;
+        const int a = u < nunits ? ts.urec[4 * u + 1] : 0, b = u < nunits ? ts.urec[4 * u + 2] : 0;
+        int ta, tb;
+        const int ea = block_exclusive_scan(a, &ta);
+        const int eb = block_exclusive_scan(b, &tb);
+        if (u < nunits) { ts.urec[4 * u + 1] = carry[0] + ea; ts.urec[4 * u + 2] = carry[1] + eb; }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry[0] += ta; carry[1] += tb; }
+        __syncthreads();
+    }
+    const long long base_pos = p.task_cnt[2 * task], base_neg = p.task_cnt[2 * task + 1];
+    for (int u = warp; u < nunits; u += kClsThreads / 32) {
+        const int r = u >> 1, dir = u & 1;
+        const long long row = r < k_up ? nl + r : nl - 1 - (r - k_up);
+        const int len = ts.urec[4 * u];
+        long long kp = base_pos + ts.urec[4 * u + 1], kn = base_neg + ts.urec[4 * u + 2];
+        for (int j0 = 0; j0 < len; j0 += 32) {
+            const int j = j0 + lane;   // dir 0: cell j is nw + j (j = 0 the centre); dir 1: cell j is nw - 1 - j
+            const long long col = dir == 0 ? nw + j : nw - 1 - j;
+            const int c = j < len ? ts.cls[row * p.W + col] : 0;
+            const unsigned pm = __ballot_sync(0xffffffffu, c == 2), nm = __ballot_sync(0xffffffffu, c >= 1);
+            const unsigned lt = (1u << lane) - 1u;
+            if (c == 2) {
+                const long long k = kp + __popc(pm & lt);
+                if (k < p.cap) { p.pos[3 * k] = row; p.pos[3 * k + 1] = col; p.pos[3 * k + 2] = z; p.gi[k] = i; }
+            }
+            if (c >= 1) {
+                const long long k = kn + __popc(nm & lt);
+                if (k < p.cap) { p.neg[3 * k] = row; p.neg[3 * k + 1] = col; p.neg[3 * k + 2] = z; }
+            }
+            kp += __popc(pm);
+            kn += __popc(nm);
+        }
+    }
+}
+
 }  // namespace
 
 }  // namespace mvx
@@ -257,9 +373,9 @@ extern "C" int mvx_bbox_pairwise(const float *bboxes1, int64_t n, const float *b
     return MVX_OK;
 }
 
-extern "C" int mvx_classify_anchors_workspace_bytes(int64_t G, int32_t A, size_t *bytes) {
-    MVX_REQUIRE(bytes && G >= 0 && A > 0, MVX_EINVAL, "classify_anchors_workspace_bytes: bad argument");
-    *bytes = (size_t)round_up((G * A + 1) * 2 * (int64_t)sizeof(long long), 256);
+extern "C" int mvx_classify_anchors_workspace_bytes(int64_t G, int64_t L, int64_t W, int32_t A, size_t *bytes) {
+    MVX_REQUIRE(bytes && G >= 0 && L > 0 && W > 0 && A > 0, MVX_EINVAL, "classify_anchors_workspace_bytes: bad argument");
+    *bytes = (size_t)round_up((G * A + 1) * 2 * (int64_t)sizeof(long long), 256) + (size_t)(G * A) * classify_task_stride(L, W);
     return MVX_OK;
 }
 
@@ -270,10 +386,10 @@ extern "C" int mvx_classify_anchors(const float *gts, int64_t G, const float *an
     MVX_REQUIRE(G >= 0 && L > 0 && W > 0 && A > 0 && cap >= 0, MVX_EINVAL, "classify_anchors: bad extent");
     MVX_REQUIRE(anchors && counts && workspace && (G == 0 || (gts && nls && nws)) && (cap == 0 || (pos && neg && gi)), MVX_EINVAL,
                 "classify_anchors: null pointer");
-    MVX_REQUIRE((reinterpret_cast<uintptr_t>(gts) | reinterpret_cast<uintptr_t>(anchors)) % 16 == 0, MVX_EINVAL,
-                "classify_anchors: quads must be 16-byte aligned");
+    MVX_REQUIRE((reinterpret_cast<uintptr_t>(gts) | reinterpret_cast<uintptr_t>(anchors) | reinterpret_cast<uintptr_t>(workspace)) % 16 == 0,
+                MVX_EINVAL, "classify_anchors: quads and workspace must be 16-byte aligned");
     size_t need = 0;
-    mvx_classify_anchors_workspace_bytes(G, A, &need);
+    mvx_classify_anchors_workspace_bytes(G, L, W, A, &need);
     MVX_REQUIRE(workspace_bytes >= need, MVX_ESPACE, "classify_anchors: workspace too small");
     int dev_count = 0;
     MVX_CUDA_CHECK(cudaGetDeviceCount(&dev_count));
@@ -284,18 +400,19 @@ extern "C" int mvx_classify_anchors(const float *gts, int64_t G, const float *an
     p.G = G; p.L = L; p.W = W; p.A = A;
     p.neg_thr = neg_thr; p.pos_thr = pos_thr;
     p.task_cnt = static_cast<long long *>(workspace);
+    p.scratch = static_cast<unsigned char *>(workspace) + round_up((G * A + 1) * 2 * (int64_t)sizeof(long long), 256);
+    p.task_stride = classify_task_stride(L, W);
     p.pos = reinterpret_cast<long long *>(pos); p.neg = reinterpret_cast<long long *>(neg); p.gi = reinterpret_cast<long long *>(gi);
     p.cap = cap;
     p.counts = reinterpret_cast<long long *>(counts);
     MVX_CUDA_CHECK(cudaMemsetAsync(counts, 0, 4 * sizeof(int64_t), st));
     const long long tasks = G * A;
     if (tasks > 0) {
-        const unsigned blocks = (unsigned)ceil_div(tasks, 4);
-        classify_kernel<false><<<blocks, 128, 0, st>>>(p);
+        classify_eval_kernel<<<(unsigned)tasks, kClsThreads, 0, st>>>(p);
         MVX_LAUNCH_CHECK();
         classify_scan_kernel<<<1, 1024, 0, st>>>(p);
         MVX_LAUNCH_CHECK();
-        classify_kernel<true><<<blocks, 128, 0, st>>>(p);
+        classify_emit_kernel<<<(unsigned)tasks, kClsThreads, 0, st>>>(p);
         MVX_LAUNCH_CHECK();
     }
     return MVX_OK;
