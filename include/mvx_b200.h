@@ -169,6 +169,10 @@ typedef struct {
     void *workspace;
     size_t workspace_bytes;
     void *stream;
+    /* Optional (GT-paste: train.py:29-42 projects every pasted object through ITS OWN calibration
+     * before the point sets are merged and voxelized together): device [sum P] calibration index of every point; calib32
+     * then holds max(index)+1 sets instead of one per frame. NULL: every point of frame f uses calib32[f]. */
+    const int32_t *point_calib;
 } mvx_pointpath_args_t;
 
 /* byte offsets of named workspace regions, for tests/diagnostics (names in mvx_pointpath_layout_name) */

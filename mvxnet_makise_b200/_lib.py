@@ -51,7 +51,8 @@ class PointPathArgs(ctypes.Structure):
                 ('map_h', c_int32 * NUM_LEVELS), ('map_w', c_int32 * NUM_LEVELS), ('map_c', c_int32),
                 ('imsize_h', c_float), ('imsize_w', c_float), ('gather_eps', c_float), ('bn_eps', c_double),
                 ('wt', c_void_p * NUM_LAYERS), ('bias', c_void_p * NUM_LAYERS), ('grid_out', c_void_p),
-                ('counts', c_void_p), ('workspace', c_void_p), ('workspace_bytes', c_size_t), ('stream', c_void_p)]
+                ('counts', c_void_p), ('workspace', c_void_p), ('workspace_bytes', c_size_t), ('stream', c_void_p),
+                ('point_calib', c_void_p)]
 
 
 def make_grid(velorange, voxelsize, voxelshape, T) -> Grid:

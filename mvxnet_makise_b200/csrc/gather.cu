@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) feature_mapping_kernel(float *__restrict_
 __global__ void __launch_bounds__(256) rows_build_kernel(RowsParams p) {
     __shared__ float c32[32];
     const int f = blockIdx.y;
-    if (threadIdx.x < 32) c32[threadIdx.x] = p.calib32[f * 32 + threadIdx.x];
+    if (!p.point_calib && threadIdx.x < 32) c32[threadIdx.x] = p.calib32[f * 32 + threadIdx.x];
     __syncthreads();
     const int N = p.counts[f * 4 + 0], K = p.counts[f * 4 + 1];
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -222,13 +222,15 @@ __global__ void __launch_bounds__(256) rows_build_kernel(RowsParams p) {
             const float *q = pts + (size_t)p.row_point[(size_t)f * p.cap + r0 + k] * p.point_stride;
             sx += (double)q[0], sy += (double)q[1], sz += (double)q[2];
         }
-        const float *q = pts + (size_t)p.row_point[(size_t)f * p.cap + r] * p.point_stride;
+        const int pi = p.row_point[(size_t)f * p.cap + r];
+        const float *q = pts + (size_t)pi * p.point_stride;
         const float x = q[0], y = q[1], z = q[2], refl = q[3];
         if (!(x == 0.f && y == 0.f && z == 0.f)) {  // a real point at the exact origin is treated as a pad slot (Pipe.py:53-59)
             lo = make_float4(x, y, z, (float)((double)x - sx / (double)n));
             hi = make_float4((float)((double)y - sy / (double)n), (float)((double)z - sz / (double)n), refl, 0.f);
             float u, vv;
-            project_point(c32, x, y, z, u, vv);
+            // merged point sets (GT-paste, train.py:36-41): every point is projected through the calibration it came with
+            project_point(p.point_calib ? p.calib32 + (size_t)p.point_calib[p.off[f] + pi] * 32 : c32, x, y, z, u, vv);
             pr = make_float2(vv, u);  // (row, col) = lidar2Img(...)[:, [1, 0]]  (train.py:33)
         }
     }

@@ -26,7 +26,8 @@ struct RowsParams {
     const float *points;
     int point_stride;
     int off[33];
-    const float *calib32;   // [B][32]
+    const float *calib32;   // [B][32], or the calibration table that point_calib indexes
+    const int *point_calib; // optional [sum P]: calibration set of every point (merged point sets with their own calibrations)
     const int *counts;      // [B][4]
     const int *vox_cnt, *vox_row0, *row_point, *row_vox;
     float *vox8;            // [B][capA][8]  x,y,z,dx,dy,dz,r,0   (pad row K_f = zeros)

@@ -285,7 +285,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     rp.B = B, rp.cap = cap, rp.capA = L.capA, rp.T = T;
     rp.points = a->points, rp.point_stride = a->point_stride;
     for (int f = 0; f <= B; ++f) rp.off[f] = a->pt_off_host[f];
-    rp.calib32 = a->calib32, rp.counts = a->counts;
+    rp.calib32 = a->calib32, rp.point_calib = a->point_calib, rp.counts = a->counts;
     rp.vox_cnt = vo.vox_cnt, rp.vox_row0 = vo.vox_row0, rp.row_point = vo.row_point, rp.row_vox = vo.row_vox;
     rp.vox8 = F32(R_VOX8), rp.proj = F32(R_PROJ), rp.rowA_w = F32(R_ROWA_W);
     rc = launch_rows_build(rp, st);

@@ -100,10 +100,13 @@ class PointPath:
     # ------------------------------------------------------------------------------------------------
     def forward_device(self, points: torch.Tensor, offsets: Sequence[int], calib32: torch.Tensor,
                        maps: List[torch.Tensor], want_grid: bool = True, cap: int | None = None,
-                       grid_out: torch.Tensor | None = None, counts: torch.Tensor | None = None, train: bool = False):
+                       grid_out: torch.Tensor | None = None, counts: torch.Tensor | None = None, train: bool = False,
+                       point_calib: torch.Tensor | None = None):
         """points (sum P, stride>=4) fp32 CUDA, offsets host [B+1], calib32 (B,32) CUDA, maps 3 x (B,256,Hf,Wf) CUDA.
         grid_out / counts: optional caller-owned outputs ((B,128,nz,nx,ny) fp32, (B,4) int32, contiguous).
-        train=True keeps every activation for `backward` (row-first fcn1; mvx_pointpath_forward_train)."""
+        train=True keeps every activation for `backward` (row-first fcn1; mvx_pointpath_forward_train).
+        point_calib: optional (sum P) int32 CUDA — merged point sets (GT-paste, train.py:29-42): calibration set of every
+        point; calib32 is then the (n_sets, 32) table it indexes."""
         B = len(offsets) - 1
         maxp = max(offsets[i + 1] - offsets[i] for i in range(B))
         cap = cap or max(128, (maxp + 127) // 128 * 128)
@@ -122,6 +125,10 @@ class PointPath:
         off = (ctypes.c_int32 * (B + 1))(*[int(o) for o in offsets])
         a.pt_off_host = off
         a.calib32 = calib32.data_ptr()
+        if point_calib is not None:
+            assert point_calib.is_cuda and point_calib.dtype == torch.int32 and point_calib.is_contiguous()
+            assert point_calib.numel() == offsets[-1] and calib32.dim() == 2 and calib32.shape[1] == 32
+            a.point_calib = point_calib.data_ptr()
         for l in range(3):
             assert maps[l].is_contiguous() and maps[l].shape[0] == B and maps[l].shape[1] == 256
             a.maps[l] = maps[l].data_ptr()
@@ -138,11 +145,11 @@ class PointPath:
         a.stream = torch.cuda.current_stream().cuda_stream
         if train:
             check(lib.mvx_pointpath_forward_train(ctypes.byref(a)), 'pointpath_forward_train')
-            self._train_args = (a, off, points, calib32, maps)      # kept alive for backward()
+            self._train_args = (a, off, points, calib32, maps, point_calib)      # kept alive for backward()
         else:
             check(lib.mvx_pointpath_forward(ctypes.byref(a)), 'pointpath_forward')
             self._train_args = None
-        self._last_args = (a, off, points, calib32, maps)           # kept alive for cml_conv1()
+        self._last_args = (a, off, points, calib32, maps, point_calib)           # kept alive for cml_conv1()
         return (self.grid_out if want_grid else None), self.counts
 
     # ---- after the path: sparse hand-off to CML.conv1 -------------------------------------
@@ -245,13 +252,31 @@ class PointPath:
 
     def __call__(self, points_list: List, calibs: List[dict], fpn_maps: List, want_grid: bool = True):
         """points_list: B arrays/tensors (P_f, >=4) [x,y,z,r]; calibs: B dicts of 4x4 matrices (Load.py:24-41);
-        fpn_maps: 3 tensors (B,256,Hf,Wf) (FPN levels '0','1','2')."""
-        pts = [torch.as_tensor(np.asarray(p, dtype=np.float32)) if not isinstance(p, torch.Tensor) else p for p in points_list]
+        fpn_maps: 3 tensors (B,256,Hf,Wf) (FPN levels '0','1','2').
+        A frame may also be a LIST of point sets with a LIST of calibration dicts, one per set — the scene followed by the
+        pasted ground-truth objects of the GT-paste augmentation, each projected through its own calibration and then
+        merged in that order (train.py:29-42)."""
+        def as_t(p):
+            return torch.as_tensor(np.asarray(p, dtype=np.float32)) if not isinstance(p, torch.Tensor) else p
+        merged = any(isinstance(c, (list, tuple)) for c in calibs)
+        pts, table, pc = [], [], []
+        for p, c in zip(points_list, calibs):
+            sets, cals = (list(p), list(c)) if isinstance(c, (list, tuple)) else ([p], [c])
+            assert len(sets) == len(cals), 'one calibration per point set'
+            sets = [as_t(q) for q in sets]
+            pts.append(torch.cat([q[:, :4].to(torch.float32) for q in sets], dim=0))
+            if merged:
+                for q, cal in zip(sets, cals):
+                    pc.append(np.full(q.shape[0], len(table), dtype=np.int32))
+                    table.append(pack_calib(cal))
+            else:
+                table.append(pack_calib(cals[0]))
         offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in pts])]).tolist()
-        points = torch.cat([p[:, :4].to(torch.float32) for p in pts], dim=0).contiguous().to(self.device, non_blocking=True)
-        calib32 = torch.stack([pack_calib(c) for c in calibs]).to(self.device, non_blocking=True)
+        points = torch.cat(pts, dim=0).contiguous().to(self.device, non_blocking=True)
+        calib32 = torch.stack(table).to(self.device, non_blocking=True)
+        point_calib = torch.from_numpy(np.concatenate(pc)).to(self.device, non_blocking=True) if merged else None
         maps = [torch.as_tensor(m).to(self.device, torch.float32).contiguous() for m in fpn_maps]
-        return self.forward_device(points, offsets, calib32, maps, want_grid)
+        return self.forward_device(points, offsets, calib32, maps, want_grid, point_calib=point_calib)
 
     # ---- host-buffer entry: H2D of this batch's inputs, the fused path, D2H of the counts ---------------
     def _child(self):

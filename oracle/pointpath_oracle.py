@@ -167,6 +167,14 @@ def points_with_proj(pcd4: np.ndarray, calib_np: Dict[str, np.ndarray]) -> np.nd
     return torch.concat([pcd, proj], dim=1).numpy()
 
 
+def merged_points_with_proj(point_sets, calibs_np) -> np.ndarray:
+    """train.py:29-42 (GT-paste): the scene (torch branch of lidar2Img, columns swapped by `[:, [1, 0]]`) followed by every pasted
+    object (numpy branch, `proj[:, ::-1]`), each projected through ITS OWN calibration, concatenated in that order -> (P,6).
+    Both branches evaluate the same fp32 4x4 products; tests/test_oracle.py checks on the live reference that they agree
+    bit for bit, so one restatement serves both."""
+    return np.concatenate([points_with_proj(p, c) for p, c in zip(point_sets, calibs_np)], axis=0)
+
+
 # --------------------------------------------------------------------------- stage 2b: gather
 def feature_mapping(voxels: torch.Tensor, features: List[torch.Tensor], imsize: torch.Tensor,
                     eps: float = 1e-6) -> torch.Tensor:
@@ -274,7 +282,8 @@ def forward_frame(pcd4: np.ndarray, calib_np, fpn_maps: List[np.ndarray], sd_np,
     t = {}
     sd = {k: torch.from_numpy(np.asarray(v)).to(dtype) for k, v in sd_np.items()}
     t0 = time.perf_counter()
-    pcd6 = points_with_proj(pcd4, calib_np)
+    # a list of calibrations: pcd4 is the matching list of point sets (scene + pasted objects, train.py:29-42)
+    pcd6 = merged_points_with_proj(pcd4, calib_np) if isinstance(calib_np, (list, tuple)) else points_with_proj(pcd4, calib_np)
     t['project'] = time.perf_counter() - t0
     t0 = time.perf_counter()
     voxel9, uidx = group(pcd6, grid.velorange, grid.voxelsize, grid.T)
