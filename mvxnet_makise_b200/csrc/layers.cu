@@ -31,7 +31,7 @@ __device__ __forceinline__ double stat_rows(const NormSrc &n, int f) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256) fcn_layer_kernel(LayerArgs a) {
+__global__ void __launch_bounds__(256, BN == 64 ? 3 : 0) fcn_layer_kernel(LayerArgs a) {
     constexpr int TN = BN / 16;
     __shared__ __align__(16) float smem[kBK * kAS + kBK * 128];
     __shared__ float s_mean[768], s_rstd[768];

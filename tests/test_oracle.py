@@ -90,6 +90,27 @@ def test_oracle_matches_live_reference():
         assert torch.allclose(fcn(x), O.crb(x, fcn.fc.weight, fcn.fc.bias), rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.skipif(not refshim.available(), reason='/root/reference absent (GPU box)')
+def test_merged_point_sets_follow_train_py():
+    """train.py:29-42: scene through the torch branch of lidar2Img (`[:, [1, 0]]`), pasted objects through the numpy branch
+    (`[:, ::-1]`), each with its own calibration; the two branches agree bit for bit, which is what lets the oracle (and the
+    CUDA path) use one projection routine for every set."""
+    m = refshim.load()
+    base = synth.kitti_calib()
+    other = {k: np.array(v, dtype=np.float32, copy=True) for k, v in base.items()}
+    other['P2'][0, 0] += np.float32(11.5); other['P2'][0, 2] -= np.float32(3.25); other['Tr_velo_to_cam'][0, 3] += np.float32(0.031)
+    scene, pasted = synth.make_points(31, 4000), synth.make_points(32, 700)
+    pcd = torch.Tensor(scene)                                                       # train.py:31-35
+    ct = {k: torch.Tensor(np.asarray(v)) for k, v in base.items()}
+    ref_scene = torch.concat([pcd, m.calib.lidar2Img(pcd, ct, True)[:, [1, 0]]], dim=1).numpy()
+    proj = m.calib.lidar2Img(pasted, other, True)[:, ::-1]                          # train.py:37-41 (numpy branch)
+    ref = np.concatenate([ref_scene, np.concatenate([pasted, proj], axis=1)], axis=0)
+    ours = O.merged_points_with_proj([scene, pasted], [base, other])
+    assert ours.dtype == ref.dtype == np.float32 and np.array_equal(ours.view(np.uint32), ref.view(np.uint32))
+    both = m.calib.lidar2Img(torch.Tensor(pasted), {k: torch.Tensor(v) for k, v in other.items()}, True).numpy()
+    assert np.array_equal(both[:, ::-1].view(np.uint32), np.ascontiguousarray(proj).view(np.uint32))
+
+
 def test_oracle_empty_and_single_point():
     idx = np.zeros((0, 3), dtype=np.int32)
     vox, (x, y, z), cnt = O.cpp_group(np.zeros((0, 4), np.float32), idx, 35)
