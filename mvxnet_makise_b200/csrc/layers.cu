@@ -16,6 +16,7 @@ namespace mvx {
 namespace {
 
 constexpr int kBM = 128, kBK = 16, kTM = 8;
+constexpr int kTilesPerCta = 4;   // row tiles per CTA of the SIMT layer kernel
 constexpr int kAS = kBM + 4;  // padded A^T tile row (floats), keeps 16-byte alignment
 
 __device__ __forceinline__ void norm_coef(const double *stats, double R, double eps, float &mean, float &rstd) {
@@ -31,10 +32,11 @@ __device__ __forceinline__ double stat_rows(const NormSrc &n, int f) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, BN == 64 ? 3 : 0) fcn_layer_kernel(LayerArgs a) {
+__global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_layer_kernel(LayerArgs a) {
     constexpr int TN = BN / 16;
     __shared__ __align__(16) float smem[kBK * kAS + kBK * 128];
     __shared__ float s_mean[768], s_rstd[768];
+    __shared__ double s_red[2 * 8 * BN];   // [sum | sum of squares][8 warps][BN], accumulated over the tiles of this CTA
     float *As = smem, *Bs = smem + kBK * kAS;
 
     const int f = blockIdx.z, n0 = blockIdx.y * BN, tid = threadIdx.x;
@@ -48,15 +50,21 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : 0) fcn_layer_kernel(LayerA
         n_rows = a.rows_mode == 1 ? K + 1 : (a.rows_mode == 2 ? K + N : (a.rows_mode == 3 ? N : a.rows_fixed));
         Rstat = (double)N * (double)a.T;
     }
-    const long long row0 = (long long)blockIdx.x * kBM;
-    if (row0 >= n_rows) return;
+    // A CTA walks kTilesPerCta consecutive 128-row tiles and keeps its BatchNorm partial sums in shared memory across
+    // them: the fp64 atomics of all CTAs of a frame land on 2 x Cout addresses (one or two 128-byte lines for the 16-channel
+    // layers), where they serialise at about 6 ns each - with one tile per CTA that chain, not the math, bounded fcn3 / vfe1
+    if ((long long)blockIdx.x * kTilesPerCta * kBM >= n_rows) return;
+    for (int i = tid; i < 2 * 8 * BN; i += 256) s_red[i] = 0.0;
 
     if (a.in_stats) {
         for (int c = tid; c < a.Cin; c += 256)
             norm_coef(a.in_stats + ((size_t)f * a.Cin + c) * 2, Rstat, a.eps, s_mean[c], s_rstd[c]);
-        __syncthreads();
     }
+    __syncthreads();
 
+    for (int tile = 0; tile < kTilesPerCta; ++tile) {
+    const long long row0 = ((long long)blockIdx.x * kTilesPerCta + tile) * kBM;
+    if (row0 >= n_rows) break;
     float acc[kTM][TN];
 #pragma unroll
     for (int i = 0; i < kTM; ++i)
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : 0) fcn_layer_kernel(LayerA
             else vox[i] = (int)(r / a.T);
         }
     }
-    double *red = reinterpret_cast<double *>(smem);  // [2][8 warps][BN], aliases the (now idle) tiles
+    double *red = s_red;
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
@@ -159,9 +167,9 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : 0) fcn_layer_kernel(LayerA
         if (a.vmax && cv >= 0) atomicMax(a.vmax + ((size_t)f * a.vcap + cv) * a.Cout + n0 + col, __float_as_int(cm));
         s += __shfl_xor_sync(0xffffffffu, s, 16);
         ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-        if (lane < 16) {
-            red[(0 * 8 + warp) * BN + col] = s;
-            red[(1 * 8 + warp) * BN + col] = ss;
+        if (lane < 16) {   // every (warp, column) entry has one owner thread
+            red[(0 * 8 + warp) * BN + col] += s;
+            red[(1 * 8 + warp) * BN + col] += ss;
         }
     }
     if (a.Y) {
@@ -180,13 +188,14 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : 0) fcn_layer_kernel(LayerA
             }
         }
     }
+    }   // tiles of this CTA
     __syncthreads();
     if (tid < BN && !a.plain) {
         double s = 0.0, ss = 0.0;
 #pragma unroll
         for (int wv = 0; wv < 8; ++wv) {
-            s += red[(0 * 8 + wv) * BN + tid];
-            ss += red[(1 * 8 + wv) * BN + tid];
+            s += s_red[(0 * 8 + wv) * BN + tid];
+            ss += s_red[(1 * 8 + wv) * BN + tid];
         }
         double *o = a.out_stats + ((size_t)f * a.Cout + n0 + tid) * 2;
         atomicAdd(o, s);
@@ -396,7 +405,7 @@ int launch_layer(const LayerArgs &a, int F, cudaStream_t st) {
     MVX_REQUIRE(a.Cout % 16 == 0 && (a.Y == nullptr || a.ldy % 4 == 0), MVX_EINVAL, "layer: Cout must be a multiple of 16");
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     if (max_rows <= 0) return MVX_OK;
-    const unsigned tiles = (unsigned)ceil_div(max_rows, kBM);
+    const unsigned tiles = (unsigned)ceil_div(ceil_div(max_rows, kBM), kTilesPerCta);
     if (a.Cout % 128 == 0) {
         fcn_layer_kernel<128><<<dim3(tiles, a.Cout / 128, F), 256, 0, st>>>(a);
     } else if (a.Cout % 64 == 0) {

@@ -482,53 +482,78 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
                         *reinterpret_cast<float4 *>(a.Y + ((size_t)f * a.rowcap + row0 + rbase + r) * a.ldy + n0 + pass * kEpiCols + lane * 4) = o;
                     }
                 }
-                // weighted column sums: thread = (column, row group). Ordinary rows (multiplicity 1) are summed in fp32
-                // over runs of 16 rows and the runs in fp64; the weighted pad row takes an exact fp64 side path.
+            }
+            // weighted column sums and per-voxel max: thread = (column, row group), ALL warps of the CTA take part (the
+            // producer / MMA warps are idle by now), so the one-CTA 16-bit variant walks 4 groups of 64 rows instead of 2 of
+            // 128. Each group of 16 rows is loaded once into registers (16 independent LDS in flight) and serves both the
+            // sums and the max. Ordinary rows (multiplicity 1) are summed in fp32 over the 16 rows and the runs in fp64; the
+            // weighted pad rows take an exact fp64 side path. Rows of a voxel are consecutive: running max in registers,
+            // one atomicMax per run.
+            constexpr int NG = (!TWO && NT >= 512) ? 4 : 2;   // row groups
+            constexpr int RG = TR / NG;                       // rows per group
+            double *s_part = reinterpret_cast<double *>(smem + S::kMean);
+            double stat_sy = 0.0, stat_syy = 0.0;
+            if (tid < NG * 128 && !a.plain) {
+                const int rbase = TWO ? hp * 128 : 0;
                 const int col = tid & 127, rg = tid >> 7;
-                constexpr int RG = TR / 2;               // rows per group
-                if (!a.plain) {
-                    double sy = 0.0, syy = 0.0;
-                    for (int r0 = rg * RG; r0 < rg * RG + RG; r0 += 16) {
-                        float ps = 0.f, pss = 0.f;
+                double sy = 0.0, syy = 0.0;
+                int *vm = a.vmax ? a.vmax + (size_t)f * a.vcap * a.Cout + n0 + pass * kEpiCols + col : nullptr;
+                int cv = -1;
+                float cm = 0.f;
+                for (int r0 = rg * RG; r0 < rg * RG + RG; r0 += 16) {
+                    float yv[16];
 #pragma unroll
-                        for (int r = r0; r < r0 + 16; ++r) {
-                            const float w = s_roww[rbase + r];
-                            const float y = ytile[(size_t)r * kEpiLd + col];
-                            const float my = w == 1.f ? y : 0.f;
-                            ps += my;
-                            pss = fmaf(my, y, pss);
-                            if (w != 1.f && w != 0.f) {
-                                const double wy = (double)w * (double)y;
-                                sy += wy;
-                                syy = fma(wy, (double)y, syy);
-                            }
+                    for (int j = 0; j < 16; ++j) yv[j] = ytile[(size_t)(r0 + j) * kEpiLd + col];
+                    float ps = 0.f, pss = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float w = s_roww[rbase + r0 + j];
+                        const float y = yv[j];
+                        const float my = w == 1.f ? y : 0.f;
+                        ps += my;
+                        pss = fmaf(my, y, pss);
+                        if (w != 1.f && w != 0.f) {
+                            const double wy = (double)w * (double)y;
+                            sy += wy;
+                            syy = fma(wy, (double)y, syy);
                         }
-                        sy += (double)ps;
-                        syy += (double)pss;
                     }
-                    double *o = a.out_stats + ((size_t)f * a.Cout + n0 + pass * kEpiCols + col) * 2;
-                    atomicAdd(o, sy);
-                    atomicAdd(o + 1, syy);
-                    if (a.vmax) {  // per-voxel max of the raw (>= 0) activations: rows of a voxel are consecutive
-                        int *vm = a.vmax + (size_t)f * a.vcap * a.Cout + n0 + pass * kEpiCols + col;
-                        int cv = -1;
-                        float cm = 0.f;
-                        for (int r = rg * RG; r < rg * RG + RG; ++r) {
-                            const int v = s_rowv[rbase + r];
-                            const float y = ytile[(size_t)r * kEpiLd + col];
+                    sy += (double)ps;
+                    syy += (double)pss;
+                    if (vm) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int v = s_rowv[rbase + r0 + j];
                             if (v != cv) {
                                 if (cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
                                 cv = v;
-                                cm = y;
+                                cm = yv[j];
                             } else {
-                                cm = fmaxf(cm, y);
+                                cm = fmaxf(cm, yv[j]);
                             }
                         }
-                        if (cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
                     }
                 }
+                if (vm && cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
+                // the fp64 atomics of all CTAs of a frame meet on 2 x Cout addresses: combine the row groups of this CTA first
+                // (partials of groups 1.. go through the idle mean/rstd area: 3 x 128 x 2 doubles = its 6 KB)
+                if (rg > 0) {
+                    s_part[((rg - 1) * 128 + col) * 2] = sy;
+                    s_part[((rg - 1) * 128 + col) * 2 + 1] = syy;
+                }
+                stat_sy = sy, stat_syy = syy;
             }
             __syncthreads();
+            if (tid < 128 && !a.plain) {
+#pragma unroll
+                for (int g = 1; g < NG; ++g) {
+                    stat_sy += s_part[((g - 1) * 128 + tid) * 2];
+                    stat_syy += s_part[((g - 1) * 128 + tid) * 2 + 1];
+                }
+                double *o = a.out_stats + ((size_t)f * a.Cout + n0 + pass * kEpiCols + tid) * 2;
+                atomicAdd(o, stat_sy);
+                atomicAdd(o + 1, stat_syy);
+            }
         }
     }
     tc_fence_before();
