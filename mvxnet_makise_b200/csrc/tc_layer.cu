@@ -124,7 +124,7 @@ __host__ __device__ constexpr int tc_producer_warps(bool f16, bool two) { return
 // APK: the A operand arrives pre-packed (LayerArgs::a_pack): no register producers, one bulk copy of 32 KB per stage.
 template <int BN, bool F16, bool BF1 = false, bool TWO = false, bool APK = false>
 __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2 : 1) tc_layer_kernel(LayerArgs a, const float *__restrict__ wpack) {
-    static_assert(!APK || (F16 && !BF1 && !TWO), "pre-packed A is the 3xFP16 one-CTA variant");
+    static_assert(!APK || (F16 && !BF1), "pre-packed A is a 3xFP16 variant");
     constexpr int PW = tc_producer_warps(F16, TWO), PT = PW * 32, NT = PT + 64;   // producer warps / threads, CTA threads
     static_assert(!BF1 || F16, "the bf16 variant shares the 16-bit operand path");
     static_assert(!TWO || (F16 && BN == 128), "the two-CTA variant is the 16-bit, 128-column kernel");
@@ -916,6 +916,7 @@ int launch_tc_persist(const LayerArgs &a, int F, float *wpack, cudaStream_t st) 
 
 static int g_tc_two = 0;        // MVX_TC_TWO=1: 128-column 16-bit layers run as two CTAs per SM (measured slower for conv1/fcn2: 0.99 vs 0.86 ms, 0.42 vs 0.35 ms;
                                 // 1-deep prefetch and a 2-stage ring cost more than the overlapped epilogue gains) - experimental
+static int g_apk_two = 1;       // pre-packed-A layers (the pixel GEMM) run as two CTAs per SM: 0.593 -> 0.552 ms (MVX_APK_TWO=0: one 256-column CTA)
 static int g_tc_two_wide = 0;   // 1: also split 256-column tiles (the pixel GEMM) into 128-column two-CTA tiles (MVX_TC_TWO=2)
 static int g_tc_bf16 = 0;
 void set_tc_bf16(int on) { g_tc_bf16 = on; }
@@ -940,6 +941,7 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
     if (const char *e = getenv("MVX_DBG")) a.dbg = atoi(e);
     static const bool env_read = [] {
         if (const char *e = getenv("MVX_TC_TWO")) g_tc_two = atoi(e) != 0, g_tc_two_wide = atoi(e) == 2;
+        if (const char *e = getenv("MVX_APK_TWO")) g_apk_two = atoi(e) != 0;
         return true;
     }();
     (void)env_read;
@@ -960,6 +962,9 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
                     "pre-packed A: unsupported layer configuration");
         MVX_REQUIRE((a.rows_mode == 0 && F == 1) || a.a_frame_tiles > 0, MVX_EINVAL, "pre-packed A: per-frame tile count missing");
         if (a.Cout == 128) return launch_tc<128, true, false, false, true>(a, F, wpack, st);
+        // no register producers here, so the two-CTAs-per-SM form (128-column tiles, 2 stages, half-at-a-time epilogue) costs
+        // no duplicated operand conversion: one CTA's epilogue overlaps the other's bulk copies and MMAs
+        if (g_apk_two) return launch_tc<128, true, false, true, true>(a, F, wpack, st);
         return launch_tc<256, true, false, false, true>(a, F, wpack, st);
     }
     if (a.f16_ok && tc_f16_enabled() && a.Cin % 32 == 0) {   // 3xFP16: half the tensor cycles and operand bytes of 3xTF32
