@@ -138,7 +138,7 @@ int mvx_fcn_max_forward(const float *x, int64_t R, int32_t T, int32_t Cin, const
  * (`reindex`): out (1,C,nz,nx,ny) fp32 fully written (zeros + features) in ONE streaming pass.
  * idx (N,4) int64 [batch, ix, iy, iz] (train.py:119,126).  map_ws: (G + G/32 + 1) int32 of scratch, G = nz*nx*ny.
  * ------------------------------------------------------------------------------------------------ */
-int mvx_set_grid_mode(int32_t mode); /* 2 = plane-sequential stores + occupancy bits (default), 0 = cell-major st.global.cs, 1 = cp.async.bulk stores */
+int mvx_set_grid_mode(int32_t mode); /* 2 = plane-sequential stores + occupancy bits (default), 0 = cell-major st.global.cs, 1 = cp.async.bulk stores, 3 = (fused path, experimental, measured slower) the zeros go out early on a side stream and only the sectors that hold a voxel are written at the end */
 int mvx_scatter_dense(const float *feat, const int64_t *idx, int64_t N, int32_t C, int32_t nx, int32_t ny,
                       int32_t nz, float *out, int32_t *map_ws, void *stream);
 

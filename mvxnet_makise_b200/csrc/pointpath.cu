@@ -28,6 +28,8 @@ const char *kRegionNames[R_COUNT] = {
 static int g_fusion_mode = 1;
 int fusion_mode() { return g_fusion_mode; }
 static int g_apack = 1;     // MVX_APACK=0: channels-last fp32 copy + register producers for the pixel GEMM (A/B comparison)
+static int g_split_fill = 1;   // where the zero pass of the split grid fill (mvx_set_grid_mode(3)) starts: 1 after voxelization, 2 after the combine kernel, 3 after conv1
+static int g_zero_ctas = 1;    // persistent CTAs per SM of the zero pass
 static int g_overlap = 1;   // 1: run the map branch of the pixel-first path on a side stream (mvx_set_fusion_mode(2) = pixel-first, serial)
 
 int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
@@ -147,6 +149,7 @@ struct Stamp {
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t occ = nullptr, zero = nullptr;   // split grid fill: occupancy bits ready (caller's stream) / zero pass done (side stream)
     int device = -1;
 };
 static int side_stream(SideStream **out) {
@@ -159,6 +162,8 @@ static int side_stream(SideStream **out) {
         MVX_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         MVX_CUDA_CHECK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
         MVX_CUDA_CHECK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+        MVX_CUDA_CHECK(cudaEventCreateWithFlags(&s.occ, cudaEventDisableTiming));
+        MVX_CUDA_CHECK(cudaEventCreateWithFlags(&s.zero, cudaEventDisableTiming));
         s.device = dev;
     }
     *out = &s;
@@ -198,6 +203,8 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
 
     static const bool env_read = [] {
         if (const char *e = getenv("MVX_APACK")) g_apack = atoi(e);
+        if (const char *e = getenv("MVX_SPLIT_FILL")) g_split_fill = atoi(e);
+        if (const char *e = getenv("MVX_ZERO_CTAS")) g_zero_ctas = atoi(e);
         return true;
     }();
     (void)env_read;
@@ -291,6 +298,23 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     rc = launch_rows_build(rp, st);
     if (rc) return rc;
 
+    // split grid fill: the zeros of the dense grid need only the occupancy bits. They go out on the side stream, behind the
+    // pixel GEMM, and stream to HBM under the combine / tensor-core layer kernels; the occupied sectors follow at the end
+    const bool split_fill = side && grid_split_fill() && a->grid_out && L.G % 32 == 0;
+    auto zero_pass = [&]() -> int {   // enqueued on the side stream once the caller's stream has reached this point
+        MVX_CUDA_CHECK(cudaEventRecord(side->occ, st));
+        MVX_CUDA_CHECK(cudaStreamWaitEvent(ms, side->occ, 0));
+        int r = launch_grid_zero_sectors(reinterpret_cast<unsigned *>(ws + L.off[R_OCC]), a->grid_out, B, L.G, 128, g_zero_ctas, ms);
+        if (r) return r;
+        MVX_CUDA_CHECK(cudaEventRecord(side->zero, ms));
+        return MVX_OK;
+    };
+    if (split_fill) {
+        MVX_REQUIRE((reinterpret_cast<uintptr_t>(a->grid_out) & 31) == 0, MVX_EINVAL, "grid_out must be 32-byte aligned");
+        rc = launch_occ_from_map(vo.cell2vid, reinterpret_cast<unsigned *>(ws + L.off[R_OCC]), B, L.G, st);
+        if (rc) return rc;
+        if (g_split_fill == 1) { rc = zero_pass(); if (rc) return rc; }
+    }
     stamp.mark(S_CLEAR);
     MVX_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)MVX_NUM_LAYERS * B * kStatStride * 8, st));
     zero_vmax_kernel<<<dim3(kSMs, B), 256, 0, st>>>(a->counts, cap, I32(R_VMAX6), I32(R_VMAX7), I32(R_VMAX8));
@@ -327,6 +351,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         if (l == 0 && pixel_first) {
             rc = launch_combine_rows(ca, B, st);
             if (rc) return rc;
+            if (split_fill && g_split_fill == 2) { rc = zero_pass(); if (rc) return rc; }
             continue;
         }
         LayerArgs la{};
@@ -340,6 +365,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         if (l == 0) la.row_max = F32(R_A1MAX);
         rc = launch_layer_auto(la, B, F32(R_WPACK), st);
         if (rc) return rc;
+        if (split_fill && g_split_fill == 3 && l == 1) { rc = zero_pass(); if (rc) return rc; }
     }
     VfePrepArgs vp{};
     vp.B = B, vp.cap = cap, vp.capA = L.capA, vp.capB = L.capB, vp.T = T;
@@ -348,7 +374,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     vp.Y6 = F32(R_Y6), vp.vmax6 = I32(R_VMAX6), vp.X7 = F32(R_X7), vp.rowB_w = F32(R_ROWB_W), vp.rowB_v = I32(R_ROWB_V);
     vp.Y7 = F32(R_Y7), vp.vmax7 = I32(R_VMAX7), vp.X8 = F32(R_X8);
     vp.vmax8 = I32(R_VMAX8), vp.vfeat = F32(R_VFEAT);
-    vp.vfeat_t = (grid_mode() == 2 && L.G % 32 == 0 && a->grid_out) ? F32(R_VFEAT_T) : nullptr;
+    vp.vfeat_t = (grid_mode() == 2 && L.G % 32 == 0 && a->grid_out && !split_fill) ? F32(R_VFEAT_T) : nullptr;
     vp.n5 = NormSrc{stat_of(4), a->counts, 0, T, a->bn_eps};
     vp.n6 = NormSrc{stat_of(5), a->counts, 0, T, a->bn_eps};
     vp.n7 = NormSrc{stat_of(6), a->counts, 0, T, a->bn_eps};
@@ -411,7 +437,10 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     // ---- stage 4 ----------------------------------------------------------------------------------------
     if (a->grid_out) {
         MVX_REQUIRE((reinterpret_cast<uintptr_t>(a->grid_out) & 15) == 0, MVX_EINVAL, "grid_out must be 16-byte aligned");
-        if (vp.vfeat_t) {
+        if (split_fill) {
+            MVX_CUDA_CHECK(cudaStreamWaitEvent(st, side->zero, 0));
+            rc = launch_grid_patch_sectors(a->counts, vo.vox_coord, vo.cell2vid, F32(R_VFEAT), cap, a->grid_out, B, L.G, 128, st);
+        } else if (vp.vfeat_t) {
             unsigned *occ = reinterpret_cast<unsigned *>(ws + L.off[R_OCC]);
             rc = launch_occ_from_map(vo.cell2vid, occ, B, L.G, st);
             if (rc) return rc;

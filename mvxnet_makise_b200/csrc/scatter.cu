@@ -83,6 +83,69 @@ __global__ void __launch_bounds__(256) grid_fill_planes_kernel(const unsigned *_
     }
 }
 
+// ---- split fill: zeros early, occupied sectors late ---------------------------------------------------------------------
+// 98.5 % of the grid is zeros whose positions are known right after voxelization, long before the features exist. The
+// zero pass writes every EMPTY 32-byte sector (8 cells of one channel plane) and can therefore run on a side stream under the
+// tensor-/latency-bound layer kernels; the patch pass at the end of the chain writes only the sectors that hold a voxel
+// (about 12 % of the bytes), whole sectors, so neither pass ever needs a read-modify-write.
+//
+// Zero pass: ONE persistent CTA per SM (256 threads, <= 32 registers: it fits next to a 576-thread tensor-core CTA in
+// the register file instead of displacing it), walking the (frame, plane, run) items plane-sequentially like the fused fill.
+__global__ void __launch_bounds__(256) grid_zero_sectors_kernel(const unsigned *__restrict__ occ, float *__restrict__ out, long long G,
+                                                                int C, int B) {
+    const int tid = threadIdx.x;
+    const int runs = (int)((G + kRunCells - 1) / kRunCells);
+    const long long items = (long long)runs * C * B;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+        const int run = (int)(it % runs);
+        const long long pc = it / runs;          // f * C + c
+        const int f = (int)(pc / C);
+        const long long cell0 = (long long)run * kRunCells;
+        const unsigned *bits = occ + (size_t)f * (G / 32) + cell0 / 32;
+        float *o = out + (size_t)pc * G + cell0;
+        const int nrun = (int)min((long long)kRunCells, G - cell0);
+#pragma unroll
+        for (int i = 0; i < kRunCells / 1024; ++i) {
+            const int cell = i * 1024 + tid * 4;
+            if (cell < nrun) {
+                const unsigned sector = (__ldg(bits + (cell >> 5)) >> (cell & 24)) & 0xFFu;   // the 8 cells of this 32-byte sector
+                if (sector == 0) st_cs_f4(reinterpret_cast<float4 *>(o + cell), z);
+            }
+        }
+    }
+}
+
+// Patch pass: one warp per voxel. The voxel whose cell is the first occupied one of its sector writes the sector for all C
+// channels (lane = channel: the feature rows are read coalesced, every store is one full 32-byte sector).
+__global__ void __launch_bounds__(256) grid_patch_sectors_kernel(const int *__restrict__ counts, const int *__restrict__ vox_coord,
+                                                                 const int *__restrict__ cell2vid, const float *__restrict__ feat,
+                                                                 int vcap, float *__restrict__ out, long long G, int C) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (v >= counts[f * 4 + 0]) return;
+    const int cell = vox_coord[((size_t)f * vcap + v) * 4 + 3];
+    if (cell < 0) return;
+    const int sb = cell & ~7;
+    const int4 m0 = __ldg(reinterpret_cast<const int4 *>(cell2vid + (size_t)f * G + sb));
+    const int4 m1 = __ldg(reinterpret_cast<const int4 *>(cell2vid + (size_t)f * G + sb + 4));
+    const int vid[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    int first = 0;
+#pragma unroll
+    for (int j = 7; j >= 0; --j)
+        if (vid[j] >= 0) first = j;
+    if (first != (cell & 7)) return;   // another voxel of this sector writes it
+    const float *ff = feat + (size_t)f * vcap * C;
+    for (int c = lane; c < C; c += 32) {
+        float q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = vid[j] >= 0 ? __ldg(ff + (size_t)vid[j] * C + c) : 0.f;
+        float *o = out + ((size_t)f * C + c) * G + sb;
+        st_cs_f4(reinterpret_cast<float4 *>(o), make_float4(q[0], q[1], q[2], q[3]));
+        st_cs_f4(reinterpret_cast<float4 *>(o + 4), make_float4(q[4], q[5], q[6], q[7]));
+    }
+}
+
 __global__ void __launch_bounds__(256) occ_from_map_kernel(const int *__restrict__ cell2vid, unsigned *__restrict__ occ, long long G) {
     const int f = blockIdx.y;
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 32 cells
@@ -189,7 +252,23 @@ int launch_grid_fill_planes(const unsigned *occ, const int *cell2vid, const floa
     return MVX_OK;
 }
 
-int grid_mode() { return g_grid_mode; }
+int launch_grid_zero_sectors(const unsigned *occ, float *out, int B, long long G, int C, int ctas_per_sm, cudaStream_t st) {
+    MVX_REQUIRE(G % 32 == 0 && ctas_per_sm >= 1, MVX_EINVAL, "split grid fill needs a cell count divisible by 32");
+    grid_zero_sectors_kernel<<<kSMs * ctas_per_sm, 256, 0, st>>>(occ, out, G, C, B);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+int launch_grid_patch_sectors(const int *counts, const int *vox_coord, const int *cell2vid, const float *feat, int vcap, float *out,
+                              int B, long long G, int C, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(vcap, 8), B);
+    grid_patch_sectors_kernel<<<grid, 256, 0, st>>>(counts, vox_coord, cell2vid, feat, vcap, out, G, C);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+int grid_mode() { return g_grid_mode == 3 ? 2 : g_grid_mode; }   // mode 3 = mode 2 kernels, split in time by the fused path
+bool grid_split_fill() { return g_grid_mode == 3; }
 
 int launch_grid_fill(const int *cell2vid, const float *feat, float *out, int B, long long G, int C, int vcap, cudaStream_t st) {
     const int cgroups = (C % 4 == 0) ? 4 : 1;
@@ -216,7 +295,7 @@ void set_grid_mode(int m) { g_grid_mode = m; }
 }  // namespace mvx
 
 extern "C" int mvx_set_grid_mode(int32_t mode) {
-    if (mode < 0 || mode > 2) return MVX_EINVAL;
+    if (mode < 0 || mode > 3) return MVX_EINVAL;
     mvx::set_grid_mode(mode);
     return MVX_OK;
 }
