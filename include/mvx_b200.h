@@ -191,6 +191,11 @@ int mvx_pointpath_forward(const mvx_pointpath_args_t *args);
  *   2           pixel-first like 1 but without running the map branch (channels-last copy + pixel GEMMs) on a side stream
  *               concurrently with the point branch (voxelization, row build, row sort) - for per-stage profiling. */
 int mvx_set_fusion_mode(int32_t mode);
+/* Pixel-first inference only. 1: the combine kernel writes fcn1's raw rows directly as conv1's pre-packed tensor-core operand
+ * (fp16 hi/lo images, per-row power-of-two scale from an a-priori bound) and conv1 (Pipe.py:96) runs with fcn1's BatchNorm
+ * folded into per-frame weights: W' = W diag(rstd), b' = b - W'' mean, W'' = W' as its fp16 hi + lo images represent it;
+ * 0: conv1 reads the fp32 rows and normalises them while loading. */
+int mvx_set_fold_mode(int32_t mode);
 
 /* ------------------------------------------------------------------------------------------------
  * Training mode (BASELINE.json configs[3]): forward that keeps every activation, then the backward of the 8 hot-path

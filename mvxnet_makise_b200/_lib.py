@@ -29,7 +29,7 @@ EXPORTS = [
     'mvx_lidar2img', 'mvx_maps_nhwc_bytes', 'mvx_feature_mapping',
     'mvx_set_gemm_mode', 'mvx_layer_workspace_bytes', 'mvx_fcn_forward', 'mvx_vfe_forward', 'mvx_fcn_max_forward', 'mvx_set_grid_mode', 'mvx_scatter_dense',
     'mvx_pointpath_workspace_bytes', 'mvx_pointpath_layout', 'mvx_pointpath_layout_name', 'mvx_pointpath_forward',
-    'mvx_set_fusion_mode', 'mvx_pointpath_train_workspace_bytes', 'mvx_pointpath_forward_train', 'mvx_grad_floats',
+    'mvx_set_fusion_mode', 'mvx_set_fold_mode', 'mvx_pointpath_train_workspace_bytes', 'mvx_pointpath_forward_train', 'mvx_grad_floats',
     'mvx_pointpath_backward', 'mvx_cml_conv1_workspace_bytes', 'mvx_cml_conv1_sparse',
     'mvx_bbox_pairwise', 'mvx_classify_anchors_workspace_bytes', 'mvx_classify_anchors',
     'mvx_timing_enable', 'mvx_timing_read', 'mvx_timing_segment_name',
@@ -98,6 +98,7 @@ def _load():
     lib.mvx_pointpath_layout_name.restype = c_char_p
     lib.mvx_pointpath_forward.argtypes = [POINTER(PointPathArgs)]
     lib.mvx_set_fusion_mode.argtypes = [i32]
+    lib.mvx_set_fold_mode.argtypes = [i32]
     lib.mvx_pointpath_train_workspace_bytes.argtypes = [POINTER(PointPathArgs), POINTER(c_size_t), POINTER(c_size_t)]
     lib.mvx_pointpath_forward_train.argtypes = [POINTER(PointPathArgs)]
     lib.mvx_grad_floats.restype = i64
@@ -154,6 +155,10 @@ def set_gemm_mode(mode: int):
     5 = like 1 and the dense layer API also uses fp16 operands (inputs must be O(1)), 6 = bf16 mode (single-pass bf16
     operands for the layers mode 1 runs in 3xFP16; reduced precision)."""
     check(lib.mvx_set_gemm_mode(int(mode)), 'set_gemm_mode')
+
+
+def set_fold_mode(mode: int):
+    check(lib.mvx_set_fold_mode(int(mode)), 'set_fold_mode')
 
 
 def set_fusion_mode(mode: int):

@@ -55,6 +55,13 @@ int launch_layer(const LayerArgs &a, int F, cudaStream_t st);            // exac
 bool tc_layer_eligible(const LayerArgs &a);
 size_t tc_wpack_bytes(int Cin, int Cout);
 int launch_layer_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
+// Per-frame weight sets for a layer whose A operand arrives pre-packed and UN-normalised (LayerArgs::w_per_frame): the
+// BatchNorm of the producer is folded in, W'[o][c] = W[o][c] * rstd_c, bias'[o] = b[o] - sum_c W''[o][c] * mean_c, where W'' is
+// W' exactly as its fp16 hi + lo images represent it (so the weight rounding multiplies (y - mean), not y). Output: B
+// consecutive [blob Cin*Cout*4 bytes | colinv Cout floats] sets for 128-column tiles, and bias_sets [B][Cout].
+size_t tc_fold_set_bytes(int Cin, int Cout);
+int launch_fold_pack_weights(const float *Wt, const float *bias, const double *in_stats, const int *counts, int T, double eps,
+                             int Cin, int Cout, int B, void *blob_sets, float *bias_sets, cudaStream_t st);
 // CTA-pair (cta_group::2) persistent kernel with double-buffered accumulators (layers without a per-voxel max)
 bool tc2_layer_eligible(const LayerArgs &a);
 int launch_layer_tc2(const LayerArgs &a, int F, float *wpack, cudaStream_t st);

@@ -20,7 +20,7 @@ namespace mvx {
 const char *kRegionNames[R_COUNT] = {
     "vox_ws", "vox_coord", "vox_cnt", "vox_row0", "row_point", "row_vox", "cell2vid", "nhwc0", "nhwc1", "nhwc2",
     "vox8", "proj", "rowA_w", "A1", "Y1", "Y2", "Y3", "Y4", "Y5", "X6", "Y6", "X7", "Y7", "rowB_w", "rowB_v", "X8",
-    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t", "Z", "bin_count", "bin_start", "perm", "rowmax", "chmax", "A1max", "Y8"};
+    "vfeat", "stats", "vmax6", "vmax7", "vmax8", "wpack", "occ", "vfeat_t", "Z", "bin_count", "bin_start", "perm", "rowmax", "chmax", "A1max", "wfold", "bfold", "wbound", "Y8"};
 
 // 1 (default): pixel-first fcn1 - one tensor-core GEMM per FPN level over the map pixels, then a 12-corner combine per
 // point row (gather.cuh CombineArgs); 0: materialise the gathered (K,768) matrix A1 and run fcn1 over the point rows
@@ -29,6 +29,7 @@ static int g_fusion_mode = 1;
 int fusion_mode() { return g_fusion_mode; }
 static int g_apack = 1;     // MVX_APACK=0: channels-last fp32 copy + register producers for the pixel GEMM (A/B comparison)
 static int g_split_fill = 1;   // where the zero pass of the split grid fill (mvx_set_grid_mode(3)) starts: 1 after voxelization, 2 after the combine kernel, 3 after conv1
+static int g_fold = 0;         // mvx_set_fold_mode(1): fcn1_combine writes the rows as conv1's pre-packed fp16 A operand, conv1 runs with fcn1's BatchNorm folded into per-frame weights
 static int g_zero_ctas = 1;    // persistent CTAs per SM of the zero pass
 static int g_overlap = 1;   // 1: run the map branch of the pixel-first path on a side stream (mvx_set_fusion_mode(2) = pixel-first, serial)
 
@@ -94,6 +95,9 @@ int make_layout(const mvx_pointpath_args_t *a, Layout &L) {
         take(R_ROWMAX, B * px * 4);
         take(R_CHMAX, B * 768 * 4);
         take(R_A1MAX, B * capA * 4);
+        take(R_WFOLD, B * tc_fold_set_bytes(768, 128));   // per-frame conv1 weights with fcn1's BatchNorm folded in (fold mode)
+        take(R_BFOLD, B * 128 * 4);
+        take(R_WBOUND, 4 * 4);
     }
     L.total = o;
     take(R_Y8, B * capB * 128 * 4);   // last region: only present in a training workspace
@@ -205,6 +209,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         if (const char *e = getenv("MVX_APACK")) g_apack = atoi(e);
         if (const char *e = getenv("MVX_SPLIT_FILL")) g_split_fill = atoi(e);
         if (const char *e = getenv("MVX_ZERO_CTAS")) g_zero_ctas = atoi(e);
+        if (const char *e = getenv("MVX_FOLD")) g_fold = atoi(e);
         return true;
     }();
     (void)env_read;
@@ -230,6 +235,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     }
     // pixel-first with 3xFP16: the maps are written directly as the pre-packed A operand of the pixel GEMM (no NHWC copy)
     const bool apack = pixel_first && tc_f16_enabled() && !tc_bf16_enabled() && g_apack;
+    const bool fold = apack && g_fold;
     auto map_branch = [&](MapSet &m) -> int {
         stamp.begin(S_NHWC, ms);
         size_t rowmax_off = 0;
@@ -332,6 +338,17 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         ca.eps = a->gather_eps, ca.bias = a->bias[0], ca.Y1 = F32(R_Y1), ca.out_stats = stat_of(0);
         ca.bin_count = I32(R_BINCNT), ca.bin_start = I32(R_BINSTART), ca.perm = I32(R_PERM);
         ca.nbins = combine_bins(a->map_h[0], a->map_w[0]);
+        if (fold) {   // rows leave the combine kernel as conv1's pre-packed A operand (the idle A1 / Y1 regions hold it)
+            ca.y1pack = reinterpret_cast<unsigned char *>(ws + L.off[R_A1]), ca.y1_rowinv = F32(R_A1MAX), ca.pack_tiles = (int)ceil_div(L.capA, 256);
+            ca.wbound = F32(R_WBOUND);
+            size_t boff = 0;
+            for (int lv = 0; lv < MVX_NUM_LEVELS; ++lv) {
+                ca.pix_bound[lv] = F32(R_ROWMAX) + boff;
+                boff += (size_t)B * a->map_h[lv] * a->map_w[lv];
+            }
+            rc = launch_fcn1_bounds(a->wt[0], a->bias[0], F32(R_WBOUND), st);
+            if (rc) return rc;
+        }
         rc = launch_combine_sort(ca, B, st);      // needs only the projections: still part of the point branch
         if (rc) return rc;
     }
@@ -363,6 +380,17 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         la.eps = a->bn_eps;
         la.f16_ok = 1;       // BatchNorm-ed inputs; fcn1 row-first reads raw gathered features: per-row power-of-two scaling
         if (l == 0) la.row_max = F32(R_A1MAX);
+        if (l == 1 && fold) {   // conv1 on the packed rows: fcn1's BatchNorm lives in per-frame weights and biases
+            rc = launch_fold_pack_weights(a->wt[1], a->bias[1], stat_of(0), a->counts, T, a->bn_eps, 768, 128, B, ws + L.off[R_WFOLD],
+                                          F32(R_BFOLD), st);
+            if (rc) return rc;
+            la.X = nullptr, la.in_stats = nullptr;
+            la.a_pack = ws + L.off[R_A1], la.a_rowinv = F32(R_A1MAX), la.a_frame_tiles = (int)ceil_div(L.capA, 256);
+            la.w_per_frame = 1, la.bias = F32(R_BFOLD);
+            rc = launch_layer_auto(la, B, reinterpret_cast<float *>(ws + L.off[R_WFOLD]), st);
+            if (rc) return rc;
+            continue;
+        }
         rc = launch_layer_auto(la, B, F32(R_WPACK), st);
         if (rc) return rc;
         if (split_fill && g_split_fill == 3 && l == 1) { rc = zero_pass(); if (rc) return rc; }
@@ -515,6 +543,12 @@ extern "C" const char *mvx_pointpath_layout_name(int32_t region) {
 }
 
 extern "C" int mvx_pointpath_forward(const mvx_pointpath_args_t *args) { return mvx::pointpath_forward(args, false); }
+
+extern "C" int mvx_set_fold_mode(int32_t mode) {
+    if (mode < 0 || mode > 1) return MVX_EINVAL;
+    mvx::g_fold = mode;
+    return MVX_OK;
+}
 
 extern "C" int mvx_set_fusion_mode(int32_t mode) {
     if (mode < 0 || mode > 2) return MVX_EINVAL;   // 2 = pixel-first without the side stream (serial, for per-stage profiling)

@@ -112,6 +112,63 @@ __global__ void __launch_bounds__(256) pack_weights_f16_kernel(const float *__re
     }
 }
 
+// Folded-BatchNorm weight sets (see layers.cuh): one CTA per (output column, frame), 128-column tile images.
+__global__ void __launch_bounds__(256) fold_pack_weights_kernel(const float *__restrict__ Wt, const float *__restrict__ bias,
+                                                                const double *__restrict__ in_stats, const int *__restrict__ counts,
+                                                                int T, double eps, int Cin, int Cout, uint8_t *__restrict__ sets,
+                                                                float *__restrict__ bias_sets) {
+    __shared__ float s_max[256];
+    __shared__ double s_sum[256];
+    const int n = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const double R = (double)counts[f * 4 + 0] * (double)T;
+    const size_t set_bytes = (size_t)Cin * Cout * 4 + (size_t)Cout * 4;
+    uint8_t *out = sets + (size_t)f * set_bytes;
+    float mx = 0.f;
+    for (int k = tid; k < Cin; k += 256) {
+        const double *st = in_stats + ((size_t)f * Cin + k) * 2;
+        const double m = st[0] / R;
+        double var = st[1] / R - m * m;
+        var = var < 0.0 ? 0.0 : var;
+        const float rstd = (float)(1.0 / sqrt(var + eps));
+        mx = fmaxf(mx, fabsf(Wt[(size_t)k * Cout + n] * rstd));
+    }
+    s_max[tid] = mx;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) s_max[tid] = fmaxf(s_max[tid], s_max[tid + s]);
+        __syncthreads();
+    }
+    const float sc = pow2_scale(s_max[0]);
+    const double inv = 1.0 / (double)sc;
+    double acc = 0.0;
+    for (int k = tid; k < Cin; k += 256) {
+        const double *st = in_stats + ((size_t)f * Cin + k) * 2;
+        const double m = st[0] / R;
+        double var = st[1] / R - m * m;
+        var = var < 0.0 ? 0.0 : var;
+        const float rstd = (float)(1.0 / sqrt(var + eps));
+        const float v = Wt[(size_t)k * Cout + n] * rstd * sc;
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn(v - __half2float(h));
+        acc += ((double)__half2float(h) + (double)__half2float(l)) * inv * m;
+        const int kc = k >> 5, kl = k & 31;
+        const size_t blob = (size_t)kc * (2 * 128 * 64);   // bytes; one 128-column tile (Cout == 128)
+        const uint32_t off = sw64_offset(n, kl >> 3) + (kl & 7) * 2;
+        *reinterpret_cast<__half *>(out + blob + off) = h;
+        *reinterpret_cast<__half *>(out + blob + 128 * 64 + off) = l;
+    }
+    s_sum[tid] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) s_sum[tid] += s_sum[tid + s];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        reinterpret_cast<float *>(out + (size_t)Cin * Cout * 4)[n] = 1.f / sc;
+        bias_sets[(size_t)f * Cout + n] = (float)((double)bias[n] - s_sum[0]);
+    }
+}
+
 // BF1: single-pass bf16 operands (no lo parts, one MMA per K-step, no scaling: bf16 has the fp32 exponent range) - the
 // reduced-precision mode whose tolerance is stated separately (tests/test_gpu_parity.py::test_bf16_mode_tolerance).
 // TWO: two CTAs per SM (BN = 128, 16-bit operands): 2 pipeline stages, the epilogue staged one 128-row half at a time (96 KB of
@@ -932,6 +989,18 @@ void set_tc_persistent(int on) { g_tc_persistent = on; }
 bool tc_layer_eligible(const LayerArgs &a) {
     return a.Cin % kBK == 0 && a.Cin <= 768 && a.Cout % 128 == 0 && a.ldx % 4 == 0 &&
            (a.Y == nullptr || a.ldy % 4 == 0);
+}
+
+size_t tc_fold_set_bytes(int Cin, int Cout) { return (size_t)Cin * Cout * 4 + (size_t)Cout * 4; }
+
+int launch_fold_pack_weights(const float *Wt, const float *bias, const double *in_stats, const int *counts, int T, double eps,
+                             int Cin, int Cout, int B, void *blob_sets, float *bias_sets, cudaStream_t st) {
+    MVX_REQUIRE(Cout == 128 && Cin % 32 == 0 && Wt && bias && in_stats && counts && blob_sets && bias_sets, MVX_EINVAL,
+                "folded weight sets: 128 output columns, Cin a multiple of 32");
+    fold_pack_weights_kernel<<<dim3(Cout, B), 256, 0, st>>>(Wt, bias, in_stats, counts, T, eps, Cin, Cout,
+                                                            static_cast<uint8_t *>(blob_sets), bias_sets);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
 }
 
 size_t tc_wpack_bytes(int Cin, int Cout) { return (size_t)2 * Cin * Cout * sizeof(float); }
