@@ -33,14 +33,19 @@ __device__ __forceinline__ double stat_rows(const NormSrc &n, int f) {
 
 template <int BN>
 __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_layer_kernel(LayerArgs a) {
-    constexpr int TN = BN / 16;
+    // thread tile: RT rows x TN columns. The 16-column layers use 4 x 2 (8 x 1 needs two broadcast LDS.128 of A per 8 FFMA and is
+    // bound by the shared-memory pipe: 928 wavefront cycles per tile and k chunk against 256 FFMA issue cycles)
+    constexpr int TN = BN == 16 ? 2 : BN / 16;
+    constexpr int RT = BN == 16 ? 4 : 8;        // rows per thread
+    constexpr int TX = BN / TN;                 // threads across the columns (8 or 16); 256 / TX row groups x RT rows = 128 rows
+    static_assert((256 / TX) * RT == kBM, "thread tile does not cover the CTA tile");
     __shared__ __align__(16) float smem[kBK * kAS + kBK * 128];
     __shared__ float s_mean[768], s_rstd[768];
     __shared__ double s_red[2 * 8 * BN];   // [sum | sum of squares][8 warps][BN], accumulated over the tiles of this CTA
     float *As = smem, *Bs = smem + kBK * kAS;
 
     const int f = blockIdx.z, n0 = blockIdx.y * BN, tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tx = tid % TX, ty = tid / TX;
     long long n_rows = a.rows_fixed;
     double Rstat = (double)a.rows_fixed;
     int K = 0;
@@ -65,9 +70,9 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
     for (int tile = 0; tile < kTilesPerCta; ++tile) {
     const long long row0 = ((long long)blockIdx.x * kTilesPerCta + tile) * kBM;
     if (row0 >= n_rows) break;
-    float acc[kTM][TN];
+    float acc[RT][TN];
 #pragma unroll
-    for (int i = 0; i < kTM; ++i)
+    for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
@@ -100,19 +105,19 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kBK; ++k) {
-            float av[kTM], bv[TN];
-            *reinterpret_cast<float4 *>(av) = *reinterpret_cast<const float4 *>(As + k * kAS + ty * 8);
-            *reinterpret_cast<float4 *>(av + 4) = *reinterpret_cast<const float4 *>(As + k * kAS + ty * 8 + 4);
+            float av[RT], bv[TN];
+            *reinterpret_cast<float4 *>(av) = *reinterpret_cast<const float4 *>(As + k * kAS + ty * RT);
+            if constexpr (RT == 8) *reinterpret_cast<float4 *>(av + 4) = *reinterpret_cast<const float4 *>(As + k * kAS + ty * RT + 4);
             if constexpr (TN == 8) {
                 *reinterpret_cast<float4 *>(bv) = *reinterpret_cast<const float4 *>(Bs + k * BN + tx * 4);
                 *reinterpret_cast<float4 *>(bv + 4) = *reinterpret_cast<const float4 *>(Bs + k * BN + 64 + tx * 4);
             } else if constexpr (TN == 4) {
                 *reinterpret_cast<float4 *>(bv) = *reinterpret_cast<const float4 *>(Bs + k * BN + tx * 4);
             } else {
-                bv[0] = Bs[k * BN + tx];
+                *reinterpret_cast<float2 *>(bv) = *reinterpret_cast<const float2 *>(Bs + k * BN + tx * 2);
             }
 #pragma unroll
-            for (int i = 0; i < kTM; ++i)
+            for (int i = 0; i < RT; ++i)
 #pragma unroll
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
@@ -120,11 +125,11 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
     }
 
     // ---- epilogue: bias, ReLU, raw store, weighted fp64 statistics, per-voxel max ------------------------
-    float w[kTM];
-    int vox[kTM];
+    float w[RT];
+    int vox[RT];
 #pragma unroll
-    for (int i = 0; i < kTM; ++i) {
-        const long long r = row0 + ty * 8 + i;
+    for (int i = 0; i < RT; ++i) {
+        const long long r = row0 + ty * RT + i;
         const bool valid = r < n_rows;
         const size_t ro = (size_t)f * a.rowcap + r;
         w[i] = valid ? (a.row_w ? a.row_w[ro] : 1.f) : 0.f;
@@ -138,14 +143,14 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
-        const int col = TN == 8 ? (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4)) : (TN == 4 ? tx * 4 + j : tx);
+        const int col = TN == 8 ? (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4)) : (TN == 4 ? tx * 4 + j : tx * 2 + j);
         const float b = a.plain ? 0.f : __ldg(a.bias + n0 + col);
         const float floor_v = a.plain ? -INFINITY : 0.f;
         double s = 0.0, ss = 0.0;
         int cv = -1;
         float cm = 0.f;
 #pragma unroll
-        for (int i = 0; i < kTM; ++i) {
+        for (int i = 0; i < RT; ++i) {
             const float y = fmaxf(acc[i][j] + b, floor_v);
             acc[i][j] = y;
             if (w[i] != 0.f) {
@@ -165,17 +170,21 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
             }
         }
         if (a.vmax && cv >= 0) atomicMax(a.vmax + ((size_t)f * a.vcap + cv) * a.Cout + n0 + col, __float_as_int(cm));
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);   // lanes that hold the same columns (lane % TX)
         ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-        if (lane < 16) {   // every (warp, column) entry has one owner thread
+        if constexpr (TX == 8) {
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+        }
+        if (lane < TX) {   // every (warp, column) entry has one owner thread
             red[(0 * 8 + warp) * BN + col] += s;
             red[(1 * 8 + warp) * BN + col] += ss;
         }
     }
     if (a.Y) {
 #pragma unroll
-        for (int i = 0; i < kTM; ++i) {
-            const long long r = row0 + ty * 8 + i;
+        for (int i = 0; i < RT; ++i) {
+            const long long r = row0 + ty * RT + i;
             if (r >= n_rows) continue;
             float *yr = a.Y + ((size_t)f * a.rowcap + r) * a.ldy + n0;
             if constexpr (TN == 8) {
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
             } else if constexpr (TN == 4) {
                 *reinterpret_cast<float4 *>(yr + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
             } else {
-                yr[tx] = acc[i][0];
+                *reinterpret_cast<float2 *>(yr + tx * 2) = make_float2(acc[i][0], acc[i][1]);
             }
         }
     }
