@@ -350,12 +350,18 @@ __global__ void __launch_bounds__(256) prep_vfe2_kernel(VfePrepArgs a) {
     const float *ypad = a.Y6 + ((size_t)f * a.capA + K) * 16;            // the frame's pad row after VFE1's FCN
     const float *ysrc = pad ? ypad : a.Y6 + ((size_t)f * a.capA + r) * 16;
     const int *vm = a.vmax6 + ((size_t)f * a.cap + v) * 16;
-    float o[32];
+    float o[32], ys[16], yp[16], mv[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {   // 16-byte loads: the rows are 64 bytes
+        *reinterpret_cast<float4 *>(ys + q * 4) = __ldg(reinterpret_cast<const float4 *>(ysrc) + q);
+        *reinterpret_cast<float4 *>(yp + q * 4) = __ldg(reinterpret_cast<const float4 *>(ypad) + q);
+        *reinterpret_cast<int4 *>(mv + q * 4) = __ldg(reinterpret_cast<const int4 *>(vm) + q);
+    }
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
-        float m = __int_as_float(vm[c]);
-        if (cnt < a.T) m = fmaxf(m, ypad[c]);  // pad slots take part in the max over T (SURVEY.md trap 6)
-        o[c] = (ysrc[c] - s_mean[c]) * s_rstd[c];
+        float m = mv[c];
+        if (cnt < a.T) m = fmaxf(m, yp[c]);  // pad slots take part in the max over T (SURVEY.md trap 6)
+        o[c] = (ys[c] - s_mean[c]) * s_rstd[c];
         o[16 + c] = (m - s_mean[c]) * s_rstd[c];
     }
     float4 *dst = reinterpret_cast<float4 *>(a.X7 + ((size_t)f * a.capB + r) * 32);
