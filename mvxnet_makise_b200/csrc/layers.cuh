@@ -70,6 +70,7 @@ bool tc_f16_enabled();
 bool tc_bf16_enabled();
 void set_tc_bf16(int on);  // 1: single-pass bf16 operands where LayerArgs::f16_ok (reduced precision, tolerance stated in the tests)
 void set_tc_f16(int on);   // 1 (default): 3xFP16 where LayerArgs::f16_ok, 0: 3xTF32 everywhere
+void set_tc_persist16(int on);   // 1: conv1 / fcn2 of the fused path through the persistent 3xFP16 kernel (TMEM double buffering; experimental)
 void set_tc_persistent(int on);  // 0 = one 256 x BN tile per CTA (default), 1 = persistent 256 x 128 kernel with overlapped epilogue
 // dispatch by mvx_set_gemm_mode(): 0 = SIMT everywhere, 1 = tensor cores where eligible (default)
 int gemm_mode();

@@ -969,11 +969,344 @@ int launch_tc_persist(const LayerArgs &a, int F, float *wpack, cudaStream_t st) 
     return MVX_OK;
 }
 
+
+// =====================================================================================================================
+// Persistent 3xFP16 variant (conv1, fcn2: BatchNorm-ed inputs, no per-voxel max, 128 output columns). Same roles and
+// barrier protocol as the TF32 persistent kernel above, with the operand format of the one-tile 16-bit kernel:
+//   warps 0-15  A producers (fp32 rows -> BatchNorm of the producer layer -> fp16 hi/lo, 32 k = one 64-byte swizzle row per stage)
+//   warp 16     B bulk-copy producer      warp 17  MMA issuer (kind::f16, 3 products per K-step) + TMEM alloc
+//   warps 18-21 epilogue from registers: tcgen05.ld -> column scale, bias, ReLU -> 16-byte row stores; butterfly column sums
+// The switch timings of the one-tile kernel show its producer, MMA and epilogue phases running one after the
+// other; here the accumulators ping-pong between two TMEM buffers, so tile i drains while tile i+1 is produced and multiplied.
+// =====================================================================================================================
+constexpr int kP16ProducerWarps = 16, kP16ProducerThreads = kP16ProducerWarps * 32;
+constexpr int kP16EpiWarps = 4;            // one per TMEM lane quarter (8: two per quarter, each pair splits the 128 columns)
+constexpr int kP16Threads = (kP16ProducerWarps + 2 + kP16EpiWarps) * 32;   // 704
+constexpr int kP16RS = kP16ProducerThreads / 4, kP16RPT = kTM / kP16RS;   // row stride between a producer thread's rows, rows per thread
+
+struct P16Smem {
+    static constexpr int BN = 128;
+    static constexpr int kAHalf = kTM * 64;        // 256 rows x 64 bytes (32 fp16)
+    static constexpr int kBHalf = BN * 64;
+    static constexpr int kStage = 2 * kAHalf + 2 * kBHalf;   // 48 KB
+    static constexpr int kTiles = kPStages * kStage;
+    static constexpr int kMean = kTiles;
+    static constexpr int kRstd = kMean + 768 * 4;
+    static constexpr int kPart = kRstd + 768 * 4;              // [epilogue warps][BN][2] fp64 column partials
+    static constexpr int kBars = kPart + kP16EpiWarps * BN * 2 * 8;       // full[4], empty[4], accum_full[2], tmem_empty[2]
+    static constexpr int kTmemPtr = kBars + 8 * (2 * kPStages + 2 * kAccBufs);
+    static constexpr int kTotal = kTmemPtr + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(LayerArgs a, const float *__restrict__ wpack, int F,
+                                                                            int row_tiles) {
+    using S = P16Smem;
+    constexpr int BN = 128, KB = 32;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    float *s_mean = reinterpret_cast<float *>(smem + S::kMean);
+    float *s_rstd = reinterpret_cast<float *>(smem + S::kRstd);
+    double *s_part = reinterpret_cast<double *>(smem + S::kPart);
+    const uint32_t bars = sbase + S::kBars;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kPStages + s); };
+    auto accum_bar = [&](int b) { return bars + 8u * (2 * kPStages + b); };
+    auto tmem_empty_bar = [&](int b) { return bars + 8u * (2 * kPStages + kAccBufs + b); };
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(smem + S::kTmemPtr);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nk = a.Cin / KB;
+    const int total = F * row_tiles;
+    constexpr int W_B = kP16ProducerWarps, W_MMA = kP16ProducerWarps + 1, W_EPI = kP16ProducerWarps + 2;
+
+    // tile decode shared by every role: identical decisions => identical pipeline phase bookkeeping
+    auto decode = [&](int t, int &f, long long &row0, long long &n_rows) -> bool {
+        const int rt = t % row_tiles;
+        f = t / row_tiles;
+        n_rows = a.rows_fixed;
+        if (a.counts) {
+            const int N = a.counts[f * 4 + 0], K = a.counts[f * 4 + 1];
+            n_rows = a.rows_mode == 1 ? K + 1 : (a.rows_mode == 2 ? K + N : a.rows_fixed);
+        }
+        row0 = (long long)rt * kTM;
+        return row0 < n_rows;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < kPStages; ++s) {
+            mbar_init(full_bar(s), kP16ProducerThreads + 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < kAccBufs; ++b) {
+            mbar_init(accum_bar(b), 1);
+            mbar_init(tmem_empty_bar(b), kP16EpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::kTmemPtr), "r"(kAccBufs * 2 * BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < kP16ProducerWarps) {
+        // ================= A producers: a thread owns 8 k (one 16-byte unit of fp16) of 2 rows per stage =============
+        constexpr int RS = kP16RS, RPT = kP16RPT;
+        const int c = tid & 3, rsub = tid >> 2;   // rows rsub + RS * i
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        int g = 0, cur_f = -1;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            int f;
+            long long row0, n_rows;
+            if (!decode(t, f, row0, n_rows)) continue;
+            if (f != cur_f) {  // BatchNorm coefficients of the producer layer for this frame
+                named_bar_sync(1, kP16ProducerThreads);
+                const double Rstat = a.counts ? (double)a.counts[f * 4 + 0] * (double)a.T : (double)a.rows_fixed;
+                for (int cc = tid; cc < a.Cin; cc += kP16ProducerThreads) {
+                    const double *st = a.in_stats + ((size_t)f * a.Cin + cc) * 2;
+                    const double m = st[0] / Rstat;
+                    double var = st[1] / Rstat - m * m;
+                    var = var < 0.0 ? 0.0 : var;
+                    s_mean[cc] = (float)m;
+                    s_rstd[cc] = (float)(1.0 / sqrt(var + a.eps));
+                }
+                named_bar_sync(1, kP16ProducerThreads);
+            }
+            cur_f = f;
+            const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx + c * 8;
+            bool valid[RPT];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) valid[i] = row0 + rsub + RS * i < n_rows;
+            auto load_chunk = [&](float4 (&buf)[2 * RPT], int kc) {
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    const float4 *p = reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + RS * i) * a.ldx + kc * KB);
+                    buf[2 * i] = valid[i] ? __ldg(p) : z4;
+                    buf[2 * i + 1] = valid[i] ? __ldg(p + 1) : z4;
+                }
+            };
+            auto produce = [&](float4 (&buf)[2 * RPT], int kc) {
+                float4 cur[2 * RPT];
+#pragma unroll
+                for (int i = 0; i < 2 * RPT; ++i) cur[i] = buf[i];
+                const int k = kc * KB + c * 8;
+                const float4 m0 = *reinterpret_cast<const float4 *>(s_mean + k), m1 = *reinterpret_cast<const float4 *>(s_mean + k + 4);
+                const float4 r0 = *reinterpret_cast<const float4 *>(s_rstd + k), r1 = *reinterpret_cast<const float4 *>(s_rstd + k + 4);
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    if (valid[i]) {
+                        cur[2 * i].x = (cur[2 * i].x - m0.x) * r0.x, cur[2 * i].y = (cur[2 * i].y - m0.y) * r0.y;
+                        cur[2 * i].z = (cur[2 * i].z - m0.z) * r0.z, cur[2 * i].w = (cur[2 * i].w - m0.w) * r0.w;
+                        cur[2 * i + 1].x = (cur[2 * i + 1].x - m1.x) * r1.x, cur[2 * i + 1].y = (cur[2 * i + 1].y - m1.y) * r1.y;
+                        cur[2 * i + 1].z = (cur[2 * i + 1].z - m1.z) * r1.z, cur[2 * i + 1].w = (cur[2 * i + 1].w - m1.w) * r1.w;
+                    }
+                }
+                if (kc + 2 < nk) load_chunk(buf, kc + 2);
+                const int s = g % kPStages;
+                const uint32_t ph = (g / kPStages) & 1;
+                ++g;
+                if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);
+                __syncwarp();
+                uint8_t *stage = smem + (size_t)s * S::kStage;
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    const uint32_t off = sw64_offset(rsub + RS * i, c);
+                    uint4 hi, lo;
+                    split_f16_pair(cur[2 * i].x, cur[2 * i].y, hi.x, lo.x);
+                    split_f16_pair(cur[2 * i].z, cur[2 * i].w, hi.y, lo.y);
+                    split_f16_pair(cur[2 * i + 1].x, cur[2 * i + 1].y, hi.z, lo.z);
+                    split_f16_pair(cur[2 * i + 1].z, cur[2 * i + 1].w, hi.w, lo.w);
+                    *reinterpret_cast<uint4 *>(stage + off) = hi;
+                    *reinterpret_cast<uint4 *>(stage + S::kAHalf + off) = lo;
+                }
+                fence_async_smem();
+                mbar_arrive(full_bar(s));
+            };
+            float4 buf0[2 * RPT], buf1[2 * RPT];
+            load_chunk(buf0, 0);
+            if (nk > 1) load_chunk(buf1, 1);
+            for (int kc = 0; kc < nk; kc += 2) {
+                produce(buf0, kc);
+                if (kc + 1 < nk) produce(buf1, kc + 1);
+            }
+        }
+    } else if (warp == W_B) {
+        // ================= B producer ============================================================================
+        if (lane == 0) {
+            int g = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                int f;
+                long long row0, n_rows;
+                if (!decode(t, f, row0, n_rows)) continue;
+                for (int kc = 0; kc < nk; ++kc, ++g) {
+                    const int s = g % kPStages;
+                    const uint32_t ph = (g / kPStages) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_arrive_expect_tx(full_bar(s), 2 * S::kBHalf);
+                    bulk_g2s(sbase + s * S::kStage + 2 * S::kAHalf, reinterpret_cast<const uint8_t *>(wpack) + (size_t)kc * (2 * S::kBHalf),
+                             2 * S::kBHalf, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ================= MMA issuer ============================================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);   // kind::f16, fp16 x fp16 -> fp32
+            int g = 0, it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                int f;
+                long long row0, n_rows;
+                if (!decode(t, f, row0, n_rows)) continue;
+                const int ab = it & 1;                              // accumulator buffer of this tile
+                mbar_wait(tmem_empty_bar(ab), ((it >> 1) & 1) ^ 1);  // the epilogue drained this buffer two tiles ago
+                tc_fence_after();
+                for (int kc = 0; kc < nk; ++kc, ++g) {
+                    const int s = g % kPStages;
+                    const uint32_t ph = (g / kPStages) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sA = sbase + s * S::kStage, sB = sA + 2 * S::kAHalf;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t d = tmem_base + ab * (2 * BN) + h * BN;
+                        const uint32_t aoff = h * (128 * 64);
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint64_t a_hi = make_desc(sA + aoff + ks * 32), a_lo = make_desc(sA + S::kAHalf + aoff + ks * 32);
+                            const uint64_t b_hi = make_desc(sB + ks * 32), b_lo = make_desc(sB + S::kBHalf + ks * 32);
+                            mma_f16(d, a_lo, b_hi, idesc, (kc | ks) != 0);
+                            mma_f16(d, a_hi, b_lo, idesc, 1);
+                            mma_f16(d, a_hi, b_hi, idesc, 1);
+                        }
+                    }
+                    mma_commit(empty_bar(s));
+                }
+                mma_commit(accum_bar(ab));
+                ++it;
+            }
+        }
+    } else {
+        // ================= epilogue warps: TMEM lane quarter q = warp % 4 =========================================
+        const int q = warp & 3, ew = warp - W_EPI, et = tid - W_EPI * 32;  // et: 0 .. 32 * kP16EpiWarps - 1
+        constexpr int NCB = (BN / 32) / (kP16EpiWarps / 4), ET = kP16EpiWarps * 32;   // 32-column blocks per warp
+        const int cb0 = (ew >> 2) * NCB;   // with 8 epilogue warps, warps ew and ew + 4 share a lane quarter and split the columns
+        const float *colinv = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(wpack) + (size_t)a.Cin * a.Cout * 4);
+        int it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            int f;
+            long long row0, n_rows;
+            if (!decode(t, f, row0, n_rows)) continue;
+            double acc_s[NCB], acc_ss[NCB];
+#pragma unroll
+            for (int cb = 0; cb < NCB; ++cb) acc_s[cb] = 0.0, acc_ss[cb] = 0.0;
+            named_bar_sync(2, ET);  // previous tile's partial reads are done
+            for (int i = et; i < kP16EpiWarps * BN * 2; i += ET) s_part[i] = 0.0;
+            named_bar_sync(2, ET);
+            const int ab = it & 1;
+            mbar_wait(accum_bar(ab), (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const long long r = row0 + h * 128 + q * 32 + lane;
+                const bool valid = r < n_rows;
+                const float w = valid ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + r] : 1.f) : 0.f;
+                const float m = w == 1.f ? 1.f : 0.f;         // ordinary rows go through the fp32 butterfly
+                const bool heavy = w != 0.f && w != 1.f;      // the weighted pad row: exact fp64 side path
+                float *yrow = a.Y ? a.Y + ((size_t)f * a.rowcap + r) * a.ldy : nullptr;
+#pragma unroll 1
+                for (int cbl = 0; cbl < NCB; ++cbl) {
+                    const int cb = cb0 + cbl;
+                    float v[32], p2[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * (2 * BN) + h * BN + cb * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + cb * 32 + j));
+                        const float4 c4 = __ldg(reinterpret_cast<const float4 *>(colinv + cb * 32 + j));   // undo the column scales (exact)
+                        v[j] = fmaxf(v[j] * c4.x + b4.x, 0.f);
+                        v[j + 1] = fmaxf(v[j + 1] * c4.y + b4.y, 0.f);
+                        v[j + 2] = fmaxf(v[j + 2] * c4.z + b4.z, 0.f);
+                        v[j + 3] = fmaxf(v[j + 3] * c4.w + b4.w, 0.f);
+                    }
+                    if (yrow && valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(yrow + cb * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                    if (heavy) {
+                        for (int j = 0; j < 32; ++j) {
+                            const double y = (double)v[j], wy = (double)w * y;
+                            atomicAdd(&s_part[((size_t)ew * BN + cb * 32 + j) * 2], wy);
+                            atomicAdd(&s_part[((size_t)ew * BN + cb * 32 + j) * 2 + 1], wy * y);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] *= m;
+                        p2[j] = v[j] * v[j];
+                    }
+                    acc_s[cbl] += (double)butterfly_colsum(v, lane);
+                    acc_ss[cbl] += (double)butterfly_colsum(p2, lane);
+                }
+            }
+            // accumulators are drained: the MMA warp may start the next tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(ab));
+#pragma unroll
+            for (int cbl = 0; cbl < NCB; ++cbl) {
+                atomicAdd(&s_part[((size_t)ew * BN + (cb0 + cbl) * 32 + lane) * 2], acc_s[cbl]);
+                atomicAdd(&s_part[((size_t)ew * BN + (cb0 + cbl) * 32 + lane) * 2 + 1], acc_ss[cbl]);
+            }
+            named_bar_sync(2, ET);
+            for (int i = et; i < BN * 2; i += ET) {
+                double s8 = 0.0;
+#pragma unroll
+                for (int w8 = 0; w8 < kP16EpiWarps; ++w8) s8 += s_part[w8 * BN * 2 + i];
+                atomicAdd(a.out_stats + (size_t)f * a.Cout * 2 + i, s8);
+            }
+            ++it;
+        }
+    }
+    __syncwarp();  // single-lane role warps: lanes 1-31 wait here for their looping lane 0
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAccBufs * 2 * BN) : "memory");
+    }
+}
+
+int launch_tc_persist16(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
+    using S = P16Smem;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc_layer_persist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        attr_set = true;
+    }
+    const int total = a.Cin * a.Cout;
+    uint8_t *blob = reinterpret_cast<uint8_t *>(wpack);
+    pack_weights_f16_kernel<128, false><<<a.Cout, 256, 0, st>>>(a.Wt, a.Cin, a.Cout, blob, reinterpret_cast<float *>(blob + (size_t)total * 4));
+    MVX_LAUNCH_CHECK();
+    const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
+    const int row_tiles = (int)ceil_div(max_rows, kTM);
+    const long long slots = (long long)F * row_tiles;
+    const int grid = (int)(slots < kSMs ? slots : kSMs);
+    tc_layer_persist16_kernel<<<grid, kP16Threads, S::kTotal, st>>>(a, wpack, F, row_tiles);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
 }  // namespace
 
 static int g_tc_two = 0;        // MVX_TC_TWO=1: 128-column 16-bit layers run as two CTAs per SM (measured slower for conv1/fcn2: 0.99 vs 0.86 ms, 0.42 vs 0.35 ms;
                                 // 1-deep prefetch and a 2-stage ring cost more than the overlapped epilogue gains) - experimental
 static int g_apk_two = 1;       // pre-packed-A layers (the pixel GEMM) run as two CTAs per SM: 0.593 -> 0.552 ms (MVX_APK_TWO=0: one 256-column CTA)
+static int g_persist16 = 0;     // MVX_PERSIST16=1: conv1 / fcn2 through the persistent 3xFP16 kernel. Correct (parity tests pass) but measured SLOWER: 16 producer + 4 epilogue
+                                // warps: conv1 1.00 ms, fcn2 0.52 (one-tile kernel: 0.77 / 0.32); 8 + 8 warps: 1.88 / 0.47 (producers spill). The register epilogue
+                                // (per-lane row stores, butterfly sums) costs ~20 us per tile; it needs the staged, coalesced epilogue of the one-tile kernel
 static int g_tc_two_wide = 0;   // 1: also split 256-column tiles (the pixel GEMM) into 128-column two-CTA tiles (MVX_TC_TWO=2)
 static int g_tc_bf16 = 0;
 void set_tc_bf16(int on) { g_tc_bf16 = on; }
@@ -982,6 +1315,7 @@ static int g_tc_f16 = 1;
 bool tc_f16_enabled() { return g_tc_f16 != 0; }
 void set_tc_f16(int on) { g_tc_f16 = on; }
 
+void set_tc_persist16(int on) { g_persist16 = on; }
 static int g_tc_persistent = 0;
 bool tc_persistent_enabled() { return g_tc_persistent != 0; }
 void set_tc_persistent(int on) { g_tc_persistent = on; }
@@ -1011,6 +1345,7 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
     static const bool env_read = [] {
         if (const char *e = getenv("MVX_TC_TWO")) g_tc_two = atoi(e) != 0, g_tc_two_wide = atoi(e) == 2;
         if (const char *e = getenv("MVX_APK_TWO")) g_apk_two = atoi(e) != 0;
+        if (const char *e = getenv("MVX_PERSIST16")) g_persist16 = atoi(e) != 0;
         return true;
     }();
     (void)env_read;
@@ -1036,6 +1371,9 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
         if (g_apk_two) return launch_tc<128, true, false, true, true>(a, F, wpack, st);
         return launch_tc<256, true, false, false, true>(a, F, wpack, st);
     }
+    if (g_persist16 && a.f16_ok && tc_f16_enabled() && a.Cin % 32 == 0 && a.Cout == 128 && !a.vmax && !a.X2 && !a.plain && a.in_stats &&
+        !a.row_max && a.rows_mode != 3 && !a.in_C)
+        return launch_tc_persist16(a, F, wpack, st);   // conv1, fcn2: persistent kernel, epilogue overlapped with the next tile
     if (a.f16_ok && tc_f16_enabled() && a.Cin % 32 == 0) {   // 3xFP16: half the tensor cycles and operand bytes of 3xTF32
         if (a.Cout % 256 == 0 && !g_tc_two_wide) return launch_tc<256, true>(a, F, wpack, st);
         if (g_tc_two) return launch_tc<128, true, false, true>(a, F, wpack, st);   // two CTAs per SM: epilogue of one overlaps the main loop of the other

@@ -473,6 +473,33 @@ def test_fold_mode_conv1_with_folded_batchnorm(mvx, golden_dir, case):
     assert e0 < (TOL if case != 'tiny' else TOL + 2 * noise), (e0, noise)   # the default (unfolded) path meets the bar on every case
 
 
+def test_persistent_fp16_layer_kernel(mvx, golden_dir):
+    """mvx_set_gemm_mode(7): conv1 and fcn2 through the persistent 3xFP16 kernel (two TMEM accumulator buffers, dedicated
+    epilogue warps). Experimental (slower than the one-tile kernel), but it must meet the same bar."""
+    from mvxnet_makise_b200 import _lib
+    g = np.load(os.path.join(golden_dir, 'path_b.npz'))
+    maps = small_maps(int(g['map_seed']))
+    sd = synth.make_weights(int(g['weight_seed']))
+    calib = synth.kitti_calib()
+    path = mvx.P.PointPath(sd, G)
+    try:
+        _lib.set_gemm_mode(7)
+        frames = [g['pcd4'], synth.make_points(77, 900), np.zeros((0, 4), np.float32)]   # several tiles per CTA, a small and an empty frame
+        fm = [torch.from_numpy(np.concatenate([m, small_maps(5)[l], small_maps(6)[l]], axis=0)) for l, m in enumerate(maps)]
+        grid, counts = path(frames, [calib] * 3, fm)
+        torch.cuda.synchronize()
+        vf, idx = path.voxel_features(0)
+        vf1, _ = path.voxel_features(1)
+    finally:
+        _lib.set_gemm_mode(1)
+    with torch.no_grad():
+        ref64 = O.forward_frame(g['pcd4'], calib, maps, sd, G, synth.KITTI_IMSIZE_HW, dtype=torch.float64, want_grid=False)
+        ref64b = O.forward_frame(frames[1], calib, [m[1:2].numpy() for m in fm], sd, G, synth.KITTI_IMSIZE_HW, dtype=torch.float64,
+                                 want_grid=False)
+    assert rel_err(vf, ref64['vfeat']) < TOL and rel_err(vf1, ref64b['vfeat']) < TOL
+    assert int(counts[2, 0]) == 0
+
+
 BF16_TOL = 8e-2
 
 
