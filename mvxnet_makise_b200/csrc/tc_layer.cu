@@ -995,8 +995,11 @@ struct P16Smem {
     static constexpr int kPart = kRstd + 768 * 4;              // [epilogue warps][BN][2] fp64 column partials
     static constexpr int kBars = kPart + kP16EpiWarps * BN * 2 * 8;       // full[4], empty[4], accum_full[2], tmem_empty[2]
     static constexpr int kTmemPtr = kBars + 8 * (2 * kPStages + 2 * kAccBufs);
-    static constexpr int kTotal = kTmemPtr + 16 + 1024;
+    static constexpr int kEpi = kTmemPtr + 16;                 // per epilogue warp: a 32 x 33 float transposition tile
+    static constexpr int kEpiWarpBytes = 32 * 33 * 4;
+    static constexpr int kTotal = kEpi + kP16EpiWarps * kEpiWarpBytes + 1024;
 };
+static_assert(P16Smem::kTotal <= 232448, "persistent 16-bit kernel: shared memory");
 
 __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(LayerArgs a, const float *__restrict__ wpack, int F,
                                                                             int row_tiles) {
@@ -1195,6 +1198,7 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
         constexpr int NCB = (BN / 32) / (kP16EpiWarps / 4), ET = kP16EpiWarps * 32;   // 32-column blocks per warp
         const int cb0 = (ew >> 2) * NCB;   // with 8 epilogue warps, warps ew and ew + 4 share a lane quarter and split the columns
         const float *colinv = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(wpack) + (size_t)a.Cin * a.Cout * 4);
+        float *etile = reinterpret_cast<float *>(smem + S::kEpi + (size_t)ew * S::kEpiWarpBytes);
         int it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             int f;
@@ -1210,17 +1214,16 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
             mbar_wait(accum_bar(ab), (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < ((a.dbg & 2) ? 0 : 2); ++h) {   // dbg 2: no epilogue work (timing experiments)
                 const long long r = row0 + h * 128 + q * 32 + lane;
                 const bool valid = r < n_rows;
                 const float w = valid ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + r] : 1.f) : 0.f;
                 const float m = w == 1.f ? 1.f : 0.f;         // ordinary rows go through the fp32 butterfly
                 const bool heavy = w != 0.f && w != 1.f;      // the weighted pad row: exact fp64 side path
-                float *yrow = a.Y ? a.Y + ((size_t)f * a.rowcap + r) * a.ldy : nullptr;
 #pragma unroll 1
                 for (int cbl = 0; cbl < NCB; ++cbl) {
                     const int cb = cb0 + cbl;
-                    float v[32], p2[32];
+                    float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * (2 * BN) + h * BN + cb * 32, v);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -1231,11 +1234,6 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
                         v[j + 2] = fmaxf(v[j + 2] * c4.z + b4.z, 0.f);
                         v[j + 3] = fmaxf(v[j + 3] * c4.w + b4.w, 0.f);
                     }
-                    if (yrow && valid) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4 *>(yrow + cb * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
                     if (heavy) {
                         for (int j = 0; j < 32; ++j) {
                             const double y = (double)v[j], wy = (double)w * y;
@@ -1243,13 +1241,37 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
                             atomicAdd(&s_part[((size_t)ew * BN + cb * 32 + j) * 2 + 1], wy * y);
                         }
                     }
+                    // transpose the 32 x 32 block through this warp's tile: lane = row before, lane = column after. Row stores
+                    // become full 128-byte lines (8 lanes per row, 4 rows per instruction) and the column sums a plain loop.
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] *= m;
-                        p2[j] = v[j] * v[j];
+                    for (int j = 0; j < 32; ++j) etile[lane * 33 + j] = v[j];
+                    __syncwarp();
+                    if (a.Y && !(a.dbg & 16)) {   // dbg 16: no row stores
+                        const int c4 = (lane & 7) * 4;
+#pragma unroll
+                        for (int it8 = 0; it8 < 8; ++it8) {
+                            const int rr = it8 * 4 + (lane >> 3);
+                            const long long rg = row0 + h * 128 + q * 32 + rr;
+                            if (rg < n_rows) {
+                                const float *src = etile + rr * 33 + c4;
+                                *reinterpret_cast<float4 *>(a.Y + ((size_t)f * a.rowcap + rg) * a.ldy + cb * 32 + c4) =
+                                    make_float4(src[0], src[1], src[2], src[3]);
+                            }
+                        }
                     }
-                    acc_s[cbl] += (double)butterfly_colsum(v, lane);
-                    acc_ss[cbl] += (double)butterfly_colsum(p2, lane);
+                    if (!(a.dbg & 32)) {   // dbg 32: no column sums
+                        float ps = 0.f, pss = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float y = etile[rr * 33 + lane];
+                            const float my = y * __shfl_sync(0xffffffffu, m, rr);   // ordinary rows only (multiplicity 1)
+                            ps += my;
+                            pss = fmaf(my, y, pss);
+                        }
+                        acc_s[cbl] += (double)ps;
+                        acc_ss[cbl] += (double)pss;
+                    }
+                    __syncwarp();
                 }
             }
             // accumulators are drained: the MMA warp may start the next tile
@@ -1304,9 +1326,9 @@ int launch_tc_persist16(const LayerArgs &a, int F, float *wpack, cudaStream_t st
 static int g_tc_two = 0;        // MVX_TC_TWO=1: 128-column 16-bit layers run as two CTAs per SM (measured slower for conv1/fcn2: 0.99 vs 0.86 ms, 0.42 vs 0.35 ms;
                                 // 1-deep prefetch and a 2-stage ring cost more than the overlapped epilogue gains) - experimental
 static int g_apk_two = 1;       // pre-packed-A layers (the pixel GEMM) run as two CTAs per SM: 0.593 -> 0.552 ms (MVX_APK_TWO=0: one 256-column CTA)
-static int g_persist16 = 0;     // MVX_PERSIST16=1: conv1 / fcn2 through the persistent 3xFP16 kernel. Correct (parity tests pass) but measured SLOWER: 16 producer + 4 epilogue
-                                // warps: conv1 1.00 ms, fcn2 0.52 (one-tile kernel: 0.77 / 0.32); 8 + 8 warps: 1.88 / 0.47 (producers spill). The register epilogue
-                                // (per-lane row stores, butterfly sums) costs ~20 us per tile; it needs the staged, coalesced epilogue of the one-tile kernel
+static int g_persist16 = 0;     // mvx_set_gemm_mode(7) / MVX_PERSIST16=1: conv1 / fcn2 through the persistent 3xFP16 kernel. Correct (parity tests pass) but
+                                // measured SLOWER: conv1 0.94 ms, fcn2 0.49 (one-tile kernel: 0.77 / 0.32). Without its epilogue work: 0.78 / 0.15 - conv1 is bound
+                                // by the 80-register producers, fcn2 by the 4 epilogue warps
 static int g_tc_two_wide = 0;   // 1: also split 256-column tiles (the pixel GEMM) into 128-column two-CTA tiles (MVX_TC_TWO=2)
 static int g_tc_bf16 = 0;
 void set_tc_bf16(int on) { g_tc_bf16 = on; }
