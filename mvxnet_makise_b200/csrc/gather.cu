@@ -378,7 +378,8 @@ __global__ void __launch_bounds__(kCombWarps * 32) combine_rows_kernel(CombineAr
     __shared__ int s_row[kCombRows];                     // compact row; ~row for rows without corners
     __shared__ float s_w[kCombRows];                     // BatchNorm multiplicity
     __shared__ float s_sc[PACK ? kCombRows : 1];         // PACK: power-of-two scale of the row
-    __shared__ CombRec s_rec[kCombRows][MVX_NUM_LEVELS];
+    __shared__ float4 s_recw[kCombRows][MVX_NUM_LEVELS];   // corner weights: one 16-byte broadcast load per row and level
+    __shared__ int s_cell[kCombRows][MVX_NUM_LEVELS];      // packed corner coordinates (the cache tag)
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = a.counts[f * 4 + 1];
     const int p0 = blockIdx.x * kCombRows;
@@ -408,7 +409,8 @@ __global__ void __launch_bounds__(kCombWarps * 32) combine_rows_kernel(CombineAr
             const int y0 = min(max(c.i0, 0), H - 1), y1 = min(max(c.i0 + 1, 0), H - 1);
             const int x0 = min(max(c.i1, 0), W - 1), x1 = min(max(c.i1 + 1, 0), W - 1);
             rec.cell = x0 | (y0 << 12) | ((x1 - x0) << 24) | ((y1 - y0) << 25);
-            s_rec[i][l] = rec;
+            s_recw[i][l] = make_float4(rec.w[0], rec.w[1], rec.w[2], rec.w[3]);
+            s_cell[i][l] = rec.cell;
             if constexpr (PACK) {   // |Z_l| at the four corners <= L1max_l * (bound of max |F| of that pixel); the weights sum to 1
                 const float *pb = a.pix_bound[l] + (size_t)f * H * W;
                 const float m = fmaxf(fmaxf(__ldg(pb + y0 * W + x0), __ldg(pb + y1 * W + x0)), fmaxf(__ldg(pb + y0 * W + x1), __ldg(pb + y1 * W + x1)));
@@ -444,18 +446,19 @@ __global__ void __launch_bounds__(kCombWarps * 32) combine_rows_kernel(CombineAr
         if (rr >= 0) {
 #pragma unroll
             for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
-                const CombRec rec = s_rec[i][l];
-                if (rec.cell != tag[l]) {  // warp-uniform: this level's cell changed, fetch its 4 corner vectors
-                    tag[l] = rec.cell;
+                const float4 rw = s_recw[i][l];
+                const int cell = s_cell[i][l];
+                if (cell != tag[l]) {  // warp-uniform: this level's cell changed, fetch its 4 corner vectors
+                    tag[l] = cell;
                     const int W = a.w[l];
-                    const int x0 = rec.cell & 0xFFF, y0 = (rec.cell >> 12) & 0xFFF, dx = (rec.cell >> 24) & 1, dy = (rec.cell >> 25) & 1;
+                    const int x0 = cell & 0xFFF, y0 = (cell >> 12) & 0xFFF, dx = (cell >> 24) & 1, dy = (cell >> 25) & 1;
                     const float *b00 = a.Z[l] + (size_t)f * a.frame_stride[l] + ((size_t)y0 * W + x0) * kCombCout + col0;
                     v00[l] = __ldg(reinterpret_cast<const float4 *>(b00));
                     v10[l] = __ldg(reinterpret_cast<const float4 *>(b00 + (size_t)dy * W * kCombCout));
                     v01[l] = __ldg(reinterpret_cast<const float4 *>(b00 + (size_t)dx * kCombCout));
                     v11[l] = __ldg(reinterpret_cast<const float4 *>(b00 + ((size_t)dy * W + dx) * kCombCout));
                 }
-#define MVX_COMB(e) acc.e = fmaf(v11[l].e, rec.w[3], fmaf(v01[l].e, rec.w[2], fmaf(v10[l].e, rec.w[1], fmaf(v00[l].e, rec.w[0], acc.e))));
+#define MVX_COMB(e) acc.e = fmaf(v11[l].e, rw.w, fmaf(v01[l].e, rw.z, fmaf(v10[l].e, rw.y, fmaf(v00[l].e, rw.x, acc.e))));
                 MVX_COMB(x) MVX_COMB(y) MVX_COMB(z) MVX_COMB(w)
 #undef MVX_COMB
             }
