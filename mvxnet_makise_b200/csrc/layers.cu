@@ -15,7 +15,7 @@ namespace mvx {
 
 namespace {
 
-constexpr int kBM = 128, kBK = 16, kTM = 8;
+constexpr int kBM = 128, kBK = 16;
 constexpr int kTilesPerCta = 4;   // row tiles per CTA of the SIMT layer kernel
 constexpr int kAS = kBM + 4;  // padded A^T tile row (floats), keeps 16-byte alignment
 
