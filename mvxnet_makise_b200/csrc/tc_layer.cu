@@ -30,7 +30,6 @@ namespace {
 constexpr int kTM = 256;        // rows per CTA
 constexpr int kStages = 3;
 constexpr int kProducerThreads = 256;
-constexpr int kThreads = kProducerThreads + 64;   // (tcgen05 TF32 kernels; the 16-bit one-CTA variant runs 16 producer warps)
 constexpr int kEpiCols = 128;   // columns per epilogue pass
 constexpr int kEpiLd = kEpiCols + 4;
 
