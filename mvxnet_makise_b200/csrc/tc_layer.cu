@@ -974,13 +974,14 @@ int launch_tc_persist(const LayerArgs &a, int F, float *wpack, cudaStream_t st) 
 // barrier protocol as the TF32 persistent kernel above, with the operand format of the one-tile 16-bit kernel:
 //   warps 0-15  A producers (fp32 rows -> BatchNorm of the producer layer -> fp16 hi/lo, 32 k = one 64-byte swizzle row per stage)
 //   warp 16     B bulk-copy producer      warp 17  MMA issuer (kind::f16, 3 products per K-step) + TMEM alloc
-//   warps 18-21 epilogue from registers: tcgen05.ld -> column scale, bias, ReLU -> 16-byte row stores; butterfly column sums
+//   warps 18-25 epilogue: tcgen05.ld -> scale, bias, ReLU -> 32 x 32 transposition tile -> full-line stores and column sums (two warps per TMEM lane quarter): tcgen05.ld -> column scale, bias, ReLU -> 16-byte row stores; butterfly column sums
 // The switch timings of the one-tile kernel show its producer, MMA and epilogue phases running one after the
 // other; here the accumulators ping-pong between two TMEM buffers, so tile i drains while tile i+1 is produced and multiplied.
 // =====================================================================================================================
 constexpr int kP16ProducerWarps = 16, kP16ProducerThreads = kP16ProducerWarps * 32;
-constexpr int kP16EpiWarps = 4;            // one per TMEM lane quarter (8: two per quarter, each pair splits the 128 columns)
-constexpr int kP16Threads = (kP16ProducerWarps + 2 + kP16EpiWarps) * 32;   // 704
+constexpr int kP16EpiWarps = 8;            // one per TMEM lane quarter (8: two per quarter, each pair splits the 128 columns)
+constexpr int kP16Threads = (kP16ProducerWarps + 2 + kP16EpiWarps) * 32;   // 832
+constexpr int kP16Stages = 3;   // 3 x 48 KB: leaves room for the 8 transposition tiles
 constexpr int kP16RS = kP16ProducerThreads / 4, kP16RPT = kTM / kP16RS;   // row stride between a producer thread's rows, rows per thread
 
 struct P16Smem {
@@ -988,12 +989,12 @@ struct P16Smem {
     static constexpr int kAHalf = kTM * 64;        // 256 rows x 64 bytes (32 fp16)
     static constexpr int kBHalf = BN * 64;
     static constexpr int kStage = 2 * kAHalf + 2 * kBHalf;   // 48 KB
-    static constexpr int kTiles = kPStages * kStage;
+    static constexpr int kTiles = kP16Stages * kStage;
     static constexpr int kMean = kTiles;
     static constexpr int kRstd = kMean + 768 * 4;
     static constexpr int kPart = kRstd + 768 * 4;              // [epilogue warps][BN][2] fp64 column partials
     static constexpr int kBars = kPart + kP16EpiWarps * BN * 2 * 8;       // full[4], empty[4], accum_full[2], tmem_empty[2]
-    static constexpr int kTmemPtr = kBars + 8 * (2 * kPStages + 2 * kAccBufs);
+    static constexpr int kTmemPtr = kBars + 8 * (2 * kP16Stages + 2 * kAccBufs);
     static constexpr int kEpi = kTmemPtr + 16;                 // per epilogue warp: a 32 x 33 float transposition tile
     static constexpr int kEpiWarpBytes = 32 * 33 * 4;
     static constexpr int kTotal = kEpi + kP16EpiWarps * kEpiWarpBytes + 1024;
@@ -1012,9 +1013,9 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
     double *s_part = reinterpret_cast<double *>(smem + S::kPart);
     const uint32_t bars = sbase + S::kBars;
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (kPStages + s); };
-    auto accum_bar = [&](int b) { return bars + 8u * (2 * kPStages + b); };
-    auto tmem_empty_bar = [&](int b) { return bars + 8u * (2 * kPStages + kAccBufs + b); };
+    auto empty_bar = [&](int s) { return bars + 8u * (kP16Stages + s); };
+    auto accum_bar = [&](int b) { return bars + 8u * (2 * kP16Stages + b); };
+    auto tmem_empty_bar = [&](int b) { return bars + 8u * (2 * kP16Stages + kAccBufs + b); };
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(smem + S::kTmemPtr);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nk = a.Cin / KB;
@@ -1035,7 +1036,7 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
     };
 
     if (tid == 0) {
-        for (int s = 0; s < kPStages; ++s) {
+        for (int s = 0; s < kP16Stages; ++s) {
             mbar_init(full_bar(s), kP16ProducerThreads + 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -1108,8 +1109,8 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
                     }
                 }
                 if (kc + 2 < nk) load_chunk(buf, kc + 2);
-                const int s = g % kPStages;
-                const uint32_t ph = (g / kPStages) & 1;
+                const int s = g % kP16Stages;
+                const uint32_t ph = (g / kP16Stages) & 1;
                 ++g;
                 if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);
                 __syncwarp();
@@ -1145,8 +1146,8 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
                 long long row0, n_rows;
                 if (!decode(t, f, row0, n_rows)) continue;
                 for (int kc = 0; kc < nk; ++kc, ++g) {
-                    const int s = g % kPStages;
-                    const uint32_t ph = (g / kPStages) & 1;
+                    const int s = g % kP16Stages;
+                    const uint32_t ph = (g / kP16Stages) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);
                     mbar_arrive_expect_tx(full_bar(s), 2 * S::kBHalf);
                     bulk_g2s(sbase + s * S::kStage + 2 * S::kAHalf, reinterpret_cast<const uint8_t *>(wpack) + (size_t)kc * (2 * S::kBHalf),
@@ -1167,8 +1168,8 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
                 mbar_wait(tmem_empty_bar(ab), ((it >> 1) & 1) ^ 1);  // the epilogue drained this buffer two tiles ago
                 tc_fence_after();
                 for (int kc = 0; kc < nk; ++kc, ++g) {
-                    const int s = g % kPStages;
-                    const uint32_t ph = (g / kPStages) & 1;
+                    const int s = g % kP16Stages;
+                    const uint32_t ph = (g / kP16Stages) & 1;
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t sA = sbase + s * S::kStage, sB = sA + 2 * S::kAHalf;
@@ -1326,8 +1327,8 @@ static int g_tc_two = 0;        // MVX_TC_TWO=1: 128-column 16-bit layers run as
                                 // 1-deep prefetch and a 2-stage ring cost more than the overlapped epilogue gains) - experimental
 static int g_apk_two = 1;       // pre-packed-A layers (the pixel GEMM) run as two CTAs per SM: 0.593 -> 0.552 ms (MVX_APK_TWO=0: one 256-column CTA)
 static int g_persist16 = 0;     // mvx_set_gemm_mode(7) / MVX_PERSIST16=1: conv1 / fcn2 through the persistent 3xFP16 kernel. Correct (parity tests pass) but
-                                // measured SLOWER: conv1 0.94 ms, fcn2 0.49 (one-tile kernel: 0.77 / 0.32). Without its epilogue work: 0.78 / 0.15 - conv1 is bound
-                                // by the 80-register producers, fcn2 by the 4 epilogue warps
+                                // measured SLOWER than the one-tile kernel (conv1 0.77 ms, fcn2 0.32): 16 producer + 4 epilogue warps, 4 stages: 0.94 / 0.49;
+                                // 16 + 8 warps, 3 stages (this configuration): 1.12 / 0.38; without the epilogue work: 0.78 / 0.15 and 1.02 / 0.18
 static int g_tc_two_wide = 0;   // 1: also split 256-column tiles (the pixel GEMM) into 128-column two-CTA tiles (MVX_TC_TWO=2)
 static int g_tc_bf16 = 0;
 void set_tc_bf16(int on) { g_tc_bf16 = on; }
