@@ -33,6 +33,28 @@ WORKLOAD = ('configs[1]: batch-8 synthetic KITTI-shaped frames per GPU (P=120000
             '8-layer fusion/VFE stack (fp32) + dense (128,10,352,400) grid')
 
 
+def static_config(world: int, dense: bool = False):
+    """The `config` object of the JSON line: identical for both arms (`--impl ours` / `--impl reference`) of one workload."""
+    B = FRAMES_PER_GPU
+    G = (512 * 512 * 10) if dense else (352 * 400 * 10)
+    return dict(workload=(WORKLOAD if not dense else
+                          'configs[4]: batch-8 dense 128-beam-like synthetic frames per GPU (P=250000 pts/frame, velorange [0,-51.2,-3,102.4,51.2,1], '
+                          'grid 512x512x10 = 1.34 GB dense output per frame, same FPN maps / layers): NOT the headline configuration'),
+                frames_per_gpu=B, points_per_frame=250_000 if dense else POINTS,
+                inputs='frame id g (global, rank r owns g = r, r + world, ...): synth.make_points(g, P), synth.make_fpn_maps(g), synth.make_weights(0), synth.kitti_calib()',
+                l2=f'no flush: per step the inputs (376 MB FPN maps) and outputs ({B * 128 * G * 4 / 1e9:.1f} GB grid) exceed the 126 MB L2',
+                parallelism=f'frame-sharded x{world}, no forward collective')
+
+
+def refuse_debug_env():
+    """The release library reads no environment switch (work-skipping MVX_DBG & co. exist only in -DMVX_DEVTOOLS builds);
+    a bench run with one of them set is refused so that no number can come from a kernel with work removed."""
+    bad = sorted(k for k in os.environ if k.startswith('MVX_'))
+    if bad:
+        print(f'bench.py: refusing to run with {bad} set (debug switches; unset them)', file=sys.stderr)
+        sys.exit(2)
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -98,9 +120,43 @@ class ClockSampler:
         return out
 
 
+def bind_near_gpu(local: int):
+    """Run this rank, and first-touch its pinned host buffers, on the NUMA node its GPU hangs off: eight ranks whose pinned
+    buffers all sit on one socket pull 3 GB of FPN maps per step through one memory controller and the socket interconnect
+    (round 1: 23 GB/s per GPU at 8 GPUs against 45 GB/s at 1). Best effort - every failure leaves the process as it was."""
+    info = dict(node=None, cpus=None, mempolicy=None)
+    try:
+        import ctypes
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+        base = f'/sys/bus/pci/devices/{bdf}'
+        node = int(open(f'{base}/numa_node').read().strip())
+        info['pci'] = bdf
+        if node < 0:
+            return info
+        info['node'] = node
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            info['cpus'] = len(use)
+        mask = ctypes.c_ulong(1 << node)
+        rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), 65)   # set_mempolicy(MPOL_PREFERRED, {node})
+        info['mempolicy'] = 'preferred' if rc == 0 else f'errno {ctypes.get_errno()}'
+    except Exception as exc:
+        info['error'] = f'{type(exc).__name__}: {exc}'[:120]
+    return info
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_frame(frame_id: int, threads: int):
-    """One full-size frame through the oracle port of the reference path on the host cores; returns seconds + stages."""
+def cpu_reference_frame(frame_id: int, threads: int, dtype=None, keep: bool = False):
+    """One full-size frame through the oracle port of the reference path on the host cores; returns seconds + stages
+    (+ the oracle's voxel features / idx when `keep`: the parity check of the bench line uses them, outside any timed region)."""
     import torch
     from mvxnet_makise_b200 import synth
     from oracle import pointpath_oracle as O
@@ -111,8 +167,12 @@ def cpu_reference_frame(frame_id: int, threads: int):
     stages = {}
     t0 = time.perf_counter()
     with torch.no_grad():
-        O.forward_frame(pts, synth.kitti_calib(), maps, sd, synth.KITTI_GRID, synth.KITTI_IMSIZE_HW, stages=stages)
-    return time.perf_counter() - t0, stages
+        out = O.forward_frame(pts, synth.kitti_calib(), maps, sd, synth.KITTI_GRID, synth.KITTI_IMSIZE_HW, stages=stages,
+                              **({'dtype': dtype} if dtype is not None else {}))
+    t = time.perf_counter() - t0
+    if keep:
+        return t, stages, dict(vfeat=out['vfeat'], idx=out['idx'])
+    return t, stages
 
 
 def gpu_eager_reference_frame(frame_id: int, device):
@@ -185,7 +245,7 @@ def run_reference(args):
               f'(time-bounded to ~{int(budget)} s)')
     line = dict(impl='reference', metric=METRIC, value=fps, unit='frames/s', n_gpus=args.gpus, steps=steps, warmup=warm + 1,
                 ms_per_step=1e3 * total / steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-                data='synthetic', config=dict(workload=WORKLOAD),
+                data='synthetic', config=static_config(int(os.environ.get('WORLD_SIZE', str(args.gpus)))),
                 cpu_baseline=dict(value=fps, unit='frames/s', cores=threads, kind='port', sample=sample,
                                   stages_s={k: round(v, 4) for k, v in stages_acc.items()}),
                 e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -223,33 +283,34 @@ def algorithmic_work(seg: str, N, K, B, G, npts=POINTS):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mvxnet_makise_b200 import synth, _lib
+    from mvxnet_makise_b200 import synth, _lib, dist as mdist
     from mvxnet_makise_b200.pipeline import PointPath
     from mvxnet_makise_b200.modules import pack_calib
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
+    rank, world, local = mdist.env_rank_world()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', os.devnull)   # keep stdout to the one JSON line
-        dist.init_process_group('nccl', device_id=dev)
+    numa = bind_near_gpu(local)            # before any pinned allocation: first touch decides where the host pages live
+    mdist.init('nccl')
     dense = args.workload == 'dense'       # BASELINE.json configs[4]: 128-beam-like frames on the larger 512x512x10 grid
     grid_spec = synth.DENSE_GRID if dense else synth.KITTI_GRID
     npts = 250_000 if dense else POINTS
     B, G = FRAMES_PER_GPU, grid_spec.cells
 
-    # ---- synthetic inputs for THIS rank's frames (frame ids are global: weak scaling, frames sharded by rank)
-    frames = [synth.make_points(rank * B + f, npts, grid=grid_spec, beams=128 if dense else 64) for f in range(B)]
+    # ---- synthetic inputs for THIS rank's frames: global frame ids, sharded round-robin (weak scaling: B frames per GPU)
+    frame_ids = mdist.shard_frames(world * B, rank, world)
+    frames = [synth.make_points(g_, npts, grid=grid_spec, beams=128 if dense else 64) for g_ in frame_ids]
     offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in frames])]).tolist()
     points_h = torch.from_numpy(np.concatenate(frames, 0)).pin_memory()
     calib_h = torch.stack([pack_calib(synth.kitti_calib()) for _ in range(B)]).pin_memory()
-    g = torch.Generator().manual_seed(1234 + rank)
-    maps_h = [torch.randn((B, 256, h, w), generator=g).pin_memory() for (h, w) in synth.fpn_shapes()]
+    per_frame_maps = [synth.make_fpn_maps(g_) for g_ in frame_ids]
+    maps_h = [torch.from_numpy(np.concatenate([m[l] for m in per_frame_maps], 0)).pin_memory() for l in range(3)]
+    del per_frame_maps
     points_d, calib_d = points_h.to(dev), calib_h.to(dev)
     maps_d = [m.to(dev) for m in maps_h]
     _lib.set_fusion_mode(args.fusion_mode)
+    if args.dtype == 'bf16':
+        _lib.set_gemm_mode(6)
     path = PointPath(synth.make_weights(0), grid_spec, device=dev)
     path.host_chunk, path.host_streams = args.host_chunk, args.host_streams
 
@@ -311,16 +372,24 @@ def run_ours(args):
         ms_total = float(t.item())
 
     # ---- host-buffer leg (`e2e`): pinned H2D of every input + path + D2H of the result, every step -------
-    for _ in range(2):
+    # Steps are pipelined across calls (two buffer sets): step s+1's copies run while step s computes. Every step still
+    # copies ITS inputs host->device and its result device->host inside the timed region; the host consumes the result of
+    # step s-1 (waits for it) before it submits step s+1, like a data loader running one batch ahead.
+    for _ in range(3):
         path.forward_host(points_h, offsets, calib_h, maps_h)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
+    prev, checksum = None, 0
     for _ in range(args.steps):
-        path.forward_host(points_h, offsets, calib_h, maps_h)
+        step_h = path.forward_host(points_h, offsets, calib_h, maps_h, sync=False)
+        if prev is not None:
+            checksum += int(prev.wait()[1][:, 0].sum())
+        prev = step_h
+    checksum += int(prev.wait()[1][:, 0].sum())
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    assert checksum == args.steps * int(counts[:, 0].sum()), 'e2e leg: host-visible voxel counts differ from the device leg'
     if world > 1:
         t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -344,8 +413,15 @@ def run_ours(args):
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath) and not dense:      # the ncu capture was taken on the headline (KITTI) configuration
         traffic = json.load(open(tpath)).get(dom)
+    # whole path against the HBM bound of SURVEY.md §8(d)'s MINIMAL bytes: points + FPN maps + grid + coords per frame, weights once
+    min_bytes = B * (npts * 16.0 + 4.0 * 256 * sum(h * w for h, w in synth.fpn_shapes()) + 128.0 * G * 4) + float(counts[:, 0].sum()) * 32 + 726_880 * 4
+    step_s = ms_total / args.steps * 1e-3
+    whole = dict(algorithmic_bytes_per_frame=round(min_bytes / B), achieved_gbs=round(min_bytes / step_s / 1e9, 1), peak_gbs=pk['hbm'],
+                 frac=round(min_bytes / step_s / 1e9 / pk['hbm'], 4),
+                 note='minimal HBM bytes of the fused path (SURVEY.md §8d: 93 % of them the dense grid write) / measured step time; the fp32 layer stack between the reads and the grid write is tensor-bound, see stage_rooflines')
     roofline = dict(kernel=dom, bound=bound, achieved=round(achieved, 3), peak=peak, unit=unit, frac=round(achieved / peak, 4),
-                    traffic=traffic, peak_source=pk['src'], ms_per_launch=stages[dom], share_of_step=round(stages[dom] / ms_serial, 4))
+                    traffic=traffic, peak_source=pk['src'], ms_per_launch=stages[dom], share_of_step=round(stages[dom] / ms_serial, 4),
+                    whole_path=whole)
     # every memory-bound stage against the HBM roofline (the north star's per-stage report)
     per_stage = {}
     for n in ('voxelize', 'maps_nhwc', 'gather', 'fcn1_combine', 'grid_fill'):
@@ -360,25 +436,34 @@ def run_ours(args):
 
     line = dict(metric=METRIC, value=world * B * args.steps / (ms_total * 1e-3), unit='frames/s', n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak',
-                vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload=(WORKLOAD if not dense else
-                                      'configs[4]: batch-8 dense 128-beam-like synthetic frames per GPU (P=250000 pts/frame, velorange [0,-51.2,-3,102.4,51.2,1], '
-                                      'grid 512x512x10 = 1.34 GB dense output per frame, same FPN maps / layers): NOT the headline configuration'),
-                            frames_per_gpu=B, points_per_frame=npts,
-                            voxels_per_frame=int(counts[:, 0].mean()), kept_points_per_frame=int(counts[:, 1].mean()),
-                            l2=f'no flush: per step the inputs (376 MB FPN maps) and outputs ({B * 128 * G * 4 / 1e9:.1f} GB grid) exceed the 126 MB L2',
-                            parallelism=f'frame-sharded x{world}, no forward collective'),
-                clocks=clocks,
+                vs_baseline=None, dtype='bf16' if args.dtype == 'bf16' else 'f32', data='synthetic',
+                config=static_config(world, dense),
+                workload_stats=dict(voxels_per_frame=int(counts[:, 0].mean()), kept_points_per_frame=int(counts[:, 1].mean()), frame_ids=frame_ids),
+                host_numa=numa, clocks=clocks,
                 e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=int(path.h2d_bytes),
                          d2h_bytes_per_step=int(path.d2h_bytes), ms_per_step=ms_e2e / args.steps,
-                         note=f'PointPath.forward_host: pinned-host points+calib+FPN maps -> H2D -> fused path -> D2H counts + feature head; sub-batches of {args.host_chunk} frame(s) (the last one split in two), H2D of sub-batch j+1 on a copy stream overlaps the kernels of sub-batch j'),
+                         note=f'PointPath.forward_host(sync=False): pinned-host points+calib+FPN maps -> H2D -> fused path -> D2H counts + feature head, every step; sub-batches of {args.host_chunk} frame(s) (H2D of sub-batch j+1 overlaps the kernels of sub-batch j) and two buffer sets (the copies of step s+1 overlap the kernels of step s); the host waits for the result of step s-1 before it submits step s+1. The FPN maps (376 of the 391 MB) are shipped from the host although the reference produces them on the GPU: the conservative reading of "host inputs"'),
                 gpu_launches=int(launches), roofline=roofline, stages_ms=stages, stage_rooflines=per_stage,
                 stages_note=f'per-stage CUDA events from a separate pass of {n_stage} steps with the map branch serialised (fusion mode 2, {ms_serial:.3f} ms/step); the timed region runs it on a side stream concurrently with the point branch')
     if world == 1 and not args.no_cpu_baseline and not dense:
-        t, st = cpu_reference_frame(0, os.cpu_count() or 1)
+        # the checker, outside every timed region: frame 0 of the timed batch through the oracle (fp32 = the reference's own
+        # arithmetic, timed as the CPU baseline; fp64 = its rounding-free value) against what the timed kernels produced
+        path.forward_device(points_d, offsets, calib_d, maps_d)
+        got_v, got_i = (t_.cpu() for t_ in path.voxel_features(0))
+        t, st, ref32 = cpu_reference_frame(frame_ids[0], os.cpu_count() or 1, keep=True)
         line['cpu_baseline'] = dict(value=1.0 / t, unit='frames/s', cores=os.cpu_count() or 1, kind='port',
                                     sample=f'1 full-size frame (P={POINTS}) of the batch through oracle/pointpath_oracle.py (numpy + torch CPU fp32)',
                                     stages_s={k: round(v, 3) for k, v in st.items()})
+        _, _, ref64 = cpu_reference_frame(frame_ids[0], os.cpu_count() or 1, dtype=torch.float64, keep=True)
+
+        def rel(a_, b_):
+            return float((a_.double() - b_.double()).abs().max() / b_.double().abs().max().clamp_min(1e-30))
+        line['parity'] = dict(checked_frames=1, frame_id=frame_ids[0], voxel_coords_bit_exact=bool(torch.equal(got_i[:, 1:], ref32['idx'][:, 1:])),
+                              rel_err_fp64=rel(got_v, ref64['vfeat']), rel_err_fp32=rel(got_v, ref32['vfeat']),
+                              fp32_reference_noise=rel(ref32['vfeat'], ref64['vfeat']),
+                              tolerance=5e-2 if args.dtype == 'bf16' else 1e-4,
+                              note='max|a-ref|/max|ref| over the (N,128) voxel features of frame 0 of the timed batch vs oracle.forward_frame evaluated in fp64 / fp32; all 8 frames: tests/test_gpu_fullsize.py')
+        del ref32, ref64
         if not args.no_gpu_eager_baseline:
             try:
                 del path
@@ -386,6 +471,11 @@ def run_ours(args):
                 line['gpu_eager_baseline'] = gpu_eager_reference_frame(0, dev)
             except Exception as exc:   # a context line only: never let it take the bench line down
                 line['gpu_eager_baseline'] = dict(error=f'{type(exc).__name__}: {exc}'[:200])
+        ge = line.get('gpu_eager_baseline', {}).get('value')
+        # two denominators, equal prominence: the whole path ported to the host cores (the contract's CPU baseline) and the
+        # reference AS DEPLOYED (CPU lidar2Img + group, then its GPU half as torch-eager ops on this same B200)
+        line['speedup_e2e'] = dict(vs_cpu_port=round(line['e2e']['value'] / line['cpu_baseline']['value'], 1),
+                                   vs_reference_as_deployed_gpu_eager=round(line['e2e']['value'] / ge, 1) if ge else None)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -398,20 +488,16 @@ def run_train(args):
     the forward path above); run with `--workload train`."""
     import torch
     import torch.distributed as dist
-    from mvxnet_makise_b200 import synth, _lib
+    from mvxnet_makise_b200 import synth, _lib, dist as mdist
     from mvxnet_makise_b200.training import HotPathTrainer
     from mvxnet_makise_b200.modules import pack_calib
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
+    rank, world, local = mdist.env_rank_world()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', os.devnull)
-        dist.init_process_group('nccl', device_id=dev)
+    mdist.init('nccl')
     B = args.train_frames
-    frames = [synth.make_points(rank * B + f, POINTS) for f in range(B)]
+    frames = [synth.make_points(g_, POINTS) for g_ in mdist.shard_frames(world * B, rank, world)]
     offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in frames])]).tolist()
     points = torch.from_numpy(np.concatenate(frames, 0)).to(dev)
     calib = torch.stack([pack_calib(synth.kitti_calib()) for _ in range(B)]).to(dev)
@@ -443,7 +529,7 @@ def run_train(args):
         ev[s_][1].record()
         tr.path.backward(d_vfeat=d_vfeat, grad_flat=tr.grad)
         ev[s_][2].record()
-        tr.opt.reduce_and_step(tr.grad, B)
+        tr.opt.reduce_and_step(tr.bucket, B)
         tr._push_weights()
         ev[s_][3].record()
     e1.record()
@@ -495,7 +581,10 @@ def main():
     ap.add_argument('--train-frames', type=int, default=16)
     ap.add_argument('--device-split', type=int, default=1, help='run the device-resident leg as this many concurrent sub-batches (streams)')
     ap.add_argument('--host-chunk', type=int, default=2, help='frames per sub-batch of the host-buffer (e2e) leg')
+    ap.add_argument('--dtype', default='f32', choices=['f32', 'bf16'],
+                    help="'bf16' = reduced-precision mode of the layer stack (tolerance stated separately: tests/test_gpu_parity.py); not the headline line")
     args = ap.parse_args()
+    refuse_debug_env()
     if args.impl == 'reference':
         run_reference(args)
     elif args.workload == 'train':

@@ -150,7 +150,7 @@ c_float = c_float  # re-export for callers building timing buffers
 
 def set_gemm_mode(mode: int):
     """0 = exact-fp32 SIMT layers everywhere, 1 = tcgen05 3xTF32 layers, one tile per CTA (default),
-    2 = tcgen05 3xTF32 layers, persistent variant with overlapped register epilogue (experimental), 3 = CTA-pair kernel
+    2 = tcgen05 3xTF32 layers, persistent variant with overlapped register epilogue (experimental), (3 = CTA-pair kernel: removed)
     (experimental), 4 = 3xTF32 operands everywhere (mode 1 uses fp16 hi/lo operands for BatchNorm-ed / row-scaled inputs),
     5 = like 1 and the dense layer API also uses fp16 operands (inputs must be O(1)), 6 = bf16 mode (single-pass bf16
     operands for the layers mode 1 runs in 3xFP16; reduced precision)."""

@@ -435,12 +435,10 @@ int launch_layer(const LayerArgs &a, int F, cudaStream_t st) {
 static int g_gemm_mode = 1;
 int gemm_mode() { return g_gemm_mode; }
 
-static int g_tc_pair = 0;
 static int g_dense_f16 = 0;
 
 int launch_layer_auto(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     if (g_gemm_mode == 1 && wpack) {
-        if (g_tc_pair && !a.plain && a.rows_mode != 3 && tc2_layer_eligible(a)) return launch_layer_tc2(a, F, wpack, st);
         if (tc_layer_eligible(a)) return launch_layer_tc(a, F, wpack, st);
     }
     return launch_layer(a, F, st);
@@ -488,13 +486,12 @@ static int dense_layer(const float *x, int64_t R, int32_t T, int32_t Cin, const 
 }  // namespace mvx
 
 extern "C" int mvx_set_gemm_mode(int32_t mode) {
-    if (mode < 0 || mode > 7) return MVX_EINVAL;   // 7 = like 1, conv1 / fcn2 through the persistent 3xFP16 kernel (experimental, measured slower)   // 6 = bf16 mode: single-pass bf16 operands for the same layers mode 1 runs in 3xFP16
+    if (mode < 0 || mode > 7 || mode == 3) return MVX_EINVAL;   // 3 (CTA-pair kernel) was removed: measured slower, never default   // 7 = like 1, conv1 / fcn2 through the persistent 3xFP16 kernel (experimental, measured slower)   // 6 = bf16 mode: single-pass bf16 operands for the same layers mode 1 runs in 3xFP16
     mvx::set_tc_bf16(mode == 6);   // 4 = tensor cores, 3xTF32 everywhere (no fp16 operands)
     mvx::set_tc_f16(mode != 4);                    // 5 = like 1, and the dense layer API (mvx_fcn_forward ...) also uses fp16
-    mvx::g_dense_f16 = mode == 5;                  //     operands: the caller promises inputs of O(1) magnitude (tests)   // 3 = tensor cores, CTA-pair (cta_group::2) persistent kernel   // 2 = tensor cores, persistent 256x128 variant (measured slower: SS-mode
+    mvx::g_dense_f16 = mode == 5;                  //     operands: the caller promises inputs of O(1) magnitude (tests)   // 2 = tensor cores, persistent 256x128 variant (measured slower: SS-mode
     mvx::g_gemm_mode = mode == 0 ? 0 : 1;          //     MMAs at N=128 saturate shared-memory bandwidth); kept for experiments
     mvx::set_tc_persistent(mode == 2);
-    mvx::g_tc_pair = mode == 3;
     mvx::set_tc_persist16(mode == 7);
     return MVX_OK;
 }

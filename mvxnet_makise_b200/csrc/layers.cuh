@@ -26,7 +26,7 @@ struct LayerArgs {
     long long rows_fixed;
     int rowcap, vcap, T;
     double eps;
-    int dbg;                 // experiments only (0 in production): bit 0 = skip the producer proxy fence
+    int dbg;                 // work-skipping timing switches; only read in -DMVX_DEVTOOLS builds (MVX_DBG() is the constant 0 otherwise)
     int f16_ok;              // 1: the tensor-core kernel may use fp16 operands (3xFP16): inputs are BatchNorm-ed (in_stats, or
                              // stored normalised) or row_max is given; 0 keeps 3xTF32 (arbitrary input range)
     const float *row_max;    // [F][rowcap] max|x| of each input row for the fp16 row scaling, or NULL (scale 1)
@@ -49,6 +49,13 @@ struct LayerArgs {
     int in_C;                // channels of in_stats (0: Cin)
     int plain;               // 1: Y = norm_in(X) W^T only (no bias, no ReLU, no statistics, no max) - the per-pixel half of fcn1
 };
+// Work-skipping switches (no epilogue, no producers ...) exist for timing experiments only: a release build compiles them
+// out (the expression is the literal 0), so no environment variable can remove work from a timed region.
+#ifdef MVX_DEVTOOLS
+#define MVX_DBG(a) ((a).dbg)
+#else
+#define MVX_DBG(a) 0
+#endif
 int launch_layer(const LayerArgs &a, int F, cudaStream_t st);            // exact-fp32 SIMT kernel
 
 // tensor-core (tcgen05, 3xTF32) implementation of the same layer; wpack = tc_wpack_bytes() of scratch
@@ -62,9 +69,6 @@ int launch_layer_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
 size_t tc_fold_set_bytes(int Cin, int Cout);
 int launch_fold_pack_weights(const float *Wt, const float *bias, const double *in_stats, const int *counts, int T, double eps,
                              int Cin, int Cout, int B, void *blob_sets, float *bias_sets, cudaStream_t st);
-// CTA-pair (cta_group::2) persistent kernel with double-buffered accumulators (layers without a per-voxel max)
-bool tc2_layer_eligible(const LayerArgs &a);
-int launch_layer_tc2(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
 bool tc_persistent_enabled();
 bool tc_f16_enabled();
 bool tc_bf16_enabled();

@@ -205,6 +205,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     auto F32 = [&](Region r) { return reinterpret_cast<float *>(ws + L.off[r]); };
     auto I32 = [&](Region r) { return reinterpret_cast<int *>(ws + L.off[r]); };
 
+#ifdef MVX_DEVTOOLS   // A/B switches for experiments; a release build reads no environment variable
     static const bool env_read = [] {
         if (const char *e = getenv("MVX_APACK")) g_apack = atoi(e);
         if (const char *e = getenv("MVX_SPLIT_FILL")) g_split_fill = atoi(e);
@@ -213,6 +214,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         return true;
     }();
     (void)env_read;
+#endif
     const Stamp stamp(st);
     if (train) MVX_CUDA_CHECK(cudaMemsetAsync(I32(R_CHMAX), 0, (size_t)B * 768 * 4, st));
     // training keeps the gathered matrix A1 (dW1 = dpre1^T A1), so it always runs row-first

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const bool mma_only = (a.dbg & 8) != 0;
+    const bool mma_only = (MVX_DBG(a) & 8) != 0;
     if (mma_only && warp != PW + 1) {
     } else if (warp < PW && APK) {
         // pre-packed A: nothing to produce (these warps run the epilogue)
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
         auto load_chunk = [&](float4 (&buf)[4], int kc) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                buf[i] = (valid[i] && !(a.dbg & 4)) ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + kc * kBK)) : z4;
+                buf[i] = (valid[i] && !(MVX_DBG(a) & 4)) ? __ldg(reinterpret_cast<const float4 *>(Xf + (size_t)(rsub + 64 * i) * a.ldx + kc * kBK)) : z4;
         };
         // two chunks of raw activations are always in flight in registers (DRAM/L2 latency >> one chunk of MMA time)
         auto produce = [&](float4 (&buf)[4], int kc) {
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
                 *reinterpret_cast<float4 *>(stage + off) = hi;
                 *reinterpret_cast<float4 *>(stage + S::kAHalf + off) = lo;
             }
-            if (!(a.dbg & 1)) fence_async_smem();  // make the generic-proxy writes visible to the tensor core (async proxy)
+            if (!(MVX_DBG(a) & 1)) fence_async_smem();  // make the generic-proxy writes visible to the tensor core (async proxy)
             mbar_arrive(full_bar(s));
         };
         float4 buf0[4], buf1[4];
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
     const float floor_v = a.plain ? -INFINITY : 0.f;  // plain mode: no ReLU (bias is zero)
     constexpr int HP = TWO ? 2 : 1;                  // half passes: TWO stages one 128-row accumulator at a time
     constexpr int TR = TWO ? 128 : kTM;              // rows in the staging tile
-    for (int pass = 0; pass < ((a.dbg & 2) ? 0 : BN / kEpiCols); ++pass) {
+    for (int pass = 0; pass < ((MVX_DBG(a) & 2) ? 0 : BN / kEpiCols); ++pass) {
 #pragma unroll 1
         for (int hp = 0; hp < HP; ++hp) {
             if (warp < 8) {
@@ -796,7 +796,7 @@ __global__ void __launch_bounds__(kPThreads, 1) tc_layer_persist_kernel(LayerArg
                     *reinterpret_cast<float4 *>(stage + off) = hi;
                     *reinterpret_cast<float4 *>(stage + S::kAHalf + off) = lo;
                 }
-                if (!(a.dbg & 1)) fence_async_smem();
+                if (!(MVX_DBG(a) & 1)) fence_async_smem();
                 mbar_arrive(full_bar(s));
             };
             float4 buf0[4], buf1[4];
@@ -1214,7 +1214,7 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
             mbar_wait(accum_bar(ab), (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int h = 0; h < ((a.dbg & 2) ? 0 : 2); ++h) {   // dbg 2: no epilogue work (timing experiments)
+            for (int h = 0; h < ((MVX_DBG(a) & 2) ? 0 : 2); ++h) {   // dbg 2: no epilogue work (timing experiments)
                 const long long r = row0 + h * 128 + q * 32 + lane;
                 const bool valid = r < n_rows;
                 const float w = valid ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + r] : 1.f) : 0.f;
@@ -1246,7 +1246,7 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
 #pragma unroll
                     for (int j = 0; j < 32; ++j) etile[lane * 33 + j] = v[j];
                     __syncwarp();
-                    if (a.Y && !(a.dbg & 16)) {   // dbg 16: no row stores
+                    if (a.Y && !(MVX_DBG(a) & 16)) {   // dbg 16: no row stores
                         const int c4 = (lane & 7) * 4;
 #pragma unroll
                         for (int it8 = 0; it8 < 8; ++it8) {
@@ -1259,7 +1259,7 @@ __global__ void __launch_bounds__(kP16Threads, 1) tc_layer_persist16_kernel(Laye
                             }
                         }
                     }
-                    if (!(a.dbg & 32)) {   // dbg 32: no column sums
+                    if (!(MVX_DBG(a) & 32)) {   // dbg 32: no column sums
                         float ps = 0.f, pss = 0.f;
 #pragma unroll
                         for (int rr = 0; rr < 32; ++rr) {
@@ -1363,6 +1363,7 @@ size_t tc_wpack_bytes(int Cin, int Cout) { return (size_t)2 * Cin * Cout * sizeo
 
 int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st) {
     LayerArgs a = a_in;
+#ifdef MVX_DEVTOOLS
     if (const char *e = getenv("MVX_DBG")) a.dbg = atoi(e);
     static const bool env_read = [] {
         if (const char *e = getenv("MVX_TC_TWO")) g_tc_two = atoi(e) != 0, g_tc_two_wide = atoi(e) == 2;
@@ -1371,6 +1372,7 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
         return true;
     }();
     (void)env_read;
+#endif
     MVX_REQUIRE(tc_layer_eligible(a) && wpack, MVX_EINVAL, "layer not eligible for the tensor-core kernel");
     const long long max_rows = a.counts ? a.rowcap : a.rows_fixed;
     if (max_rows <= 0) return MVX_OK;

@@ -4,12 +4,13 @@ Every frame is independent end to end (the reference is batch-1 with per-frame B
 config.yml:18, modules/voxelnet/VoxelNet.py:19), so the forward path is batch-partitioned: frame b runs on rank
 b % world. The only exchange step the path has is the training-mode sum of the hot-path layer
 gradients (726 880 parameters, 2.9 MB): one all-reduce over a single flat fp32 bucket (NCCL over NVLink on the
-GPUs, gloo in the CPU tests).
+GPUs, gloo in the CPU tests) - `training.FlatAdamW.reduce_and_step`, whose bucket the CUDA backward fills directly.
+Callers: bench.py (rank / world / frame ids of every workload), training.HotPathTrainer.
 """
 from __future__ import annotations
 
 import os
-from typing import Iterable, List, Sequence
+from typing import List, Sequence
 
 import torch
 import torch.distributed as dist
@@ -39,47 +40,6 @@ def shard_frames(n_frames: int, rank: int, world: int) -> List[int]:
 
 def owner_of(frame: int, world: int) -> int:
     return frame % world
-
-
-class GradBucket:
-    """One flat fp32 bucket for the gradients of the hot-path layers; a single all-reduce per step.
-
-    The message is latency-bound (2.9 MB at 900 GB/s per direction is ~3 us of wire time), so it is one
-    collective, not one per parameter. `average=True` divides by the global number of frames (the reference
-    optimises a per-frame loss, train.py:140-162)."""
-
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
-        self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
-        dev = self.params[0].device if self.params else torch.device('cpu')
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.views, o = [], 0
-        for p in self.params:
-            self.views.append(self.flat[o:o + p.numel()].view_as(p))
-            o += p.numel()
-
-    def pack(self):
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                v.zero_()
-            else:
-                v.copy_(p.grad)
-
-    def unpack(self):
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
-
-    def allreduce(self, global_frames: int | None = None, average: bool = True):
-        self.pack()
-        if dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        if average and global_frames:
-            self.flat.div_(float(global_frames))
-        self.unpack()
-        return self.flat
 
 
 def gather_frame_results(local: Sequence, n_frames: int, rank: int, world: int) -> List:

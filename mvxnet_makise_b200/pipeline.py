@@ -23,6 +23,27 @@ from .modules import _wt, pack_calib
 LAYER_NAMES = [name for name, *_ in synth.HOT_LAYERS]
 
 
+class _HostSlot:
+    """One complete set of host-entry buffers (sub-batch input buffers + workspaces, device outputs, pinned results)."""
+
+    def __init__(self):
+        self.subs, self.used = [], False
+        self.grid_out = self.counts = self.out_counts = self.out_head = self.done = None
+
+
+class HostStep:
+    """Handle of one asynchronous `PointPath.forward_host(..., sync=False)` call."""
+
+    def __init__(self, slot: _HostSlot):
+        self._slot = slot
+        self.event = slot.done
+
+    def wait(self):
+        """Blocks until this call's results are in host memory; returns (grid on device, counts on host, head block on host)."""
+        self.event.synchronize()
+        return self._slot.grid_out, self._slot.out_counts, self._slot.out_head
+
+
 class PointPath:
     def __init__(self, state_dict: Dict[str, torch.Tensor], grid: synth.GridSpec = synth.KITTI_GRID,
                  imsize_hw: Sequence[int] = synth.KITTI_IMSIZE_HW, eps: float = 1e-6, device='cuda'):
@@ -41,6 +62,7 @@ class PointPath:
         self.host_chunk = 1        # frames per sub-batch of forward_host: H2D of chunk j+1 overlaps compute of chunk j
         self.host_streams = 2      # sub-batches alternate between this many compute streams (their kernels may overlap)
         self.host_taper = True     # split the last sub-batch in two: less compute left after the last copy has landed
+        self.host_slots = 2        # complete buffer sets of forward_host, used alternately: call s+1's copies overlap call s's kernels
 
     def load_state_dict(self, sd):
         self.wt, self.bias = [], []
@@ -288,17 +310,23 @@ class PointPath:
         return c
 
     def forward_host(self, points_host: torch.Tensor, offsets: Sequence[int], calib32_host: torch.Tensor,
-                     maps_host: List[torch.Tensor], want_grid: bool = True, head_rows: int = 1024):
+                     maps_host: List[torch.Tensor], want_grid: bool = True, head_rows: int = 1024, sync: bool = True):
         """Inputs in (ideally pinned) HOST memory: points (sum P, 4) fp32, calib32 (B,32), maps 3 x (B,256,Hf,Wf).
         Frames are independent, so the batch is cut into sub-batches of `self.host_chunk` frames: the H2D copy of
-        sub-batch j+1 (copy stream) overlaps the kernels of sub-batch j (current stream); each sub-batch has its own
+        sub-batch j+1 (copy stream) overlaps the kernels of sub-batch j (compute streams); each sub-batch has its own
         input buffers and workspace and writes its slice of the batch outputs. Reads back the per-frame counts and
         the first `head_rows` voxel feature rows of frame 0 (the host-visible result).
-        Returns (grid on device, counts on host, head block on host); synchronises the stream."""
+
+        Steps are pipelined ACROSS calls as well: there are `self.host_slots` (2) complete sets of input buffers,
+        workspaces and outputs, used alternately, and the copies of call s+1 wait only for the kernels that last read
+        the same slot (call s-1), not for call s - so while call s computes, the copy engine already moves call s+1's
+        inputs. sync=True (default) waits for this call's results and returns (grid on device, counts on host, head block
+        on host); sync=False returns a `HostStep` handle at once: `.wait()` blocks until the results of THAT call are in
+        its pinned buffers and returns the same triple (valid until the slot is reused two calls later)."""
         dev = self.device
         B = len(offsets) - 1
         # sub-batch schedule: `host_chunk` frames per sub-batch, or an explicit list of sizes; the default tapers the tail
-        # (…, 1, 1): the step ends one sub-batch of compute after the LAST copy lands, so the last sub-batch should be small
+        # (..., 1, 1): the step ends one sub-batch of compute after the LAST copy lands, so the last sub-batch should be small
         if isinstance(self.host_chunk, (list, tuple)):
             sizes = [int(c) for c in self.host_chunk]
         else:
@@ -310,59 +338,83 @@ class PointPath:
         bounds = [0]
         for c in sizes:
             bounds.append(bounds[-1] + c)
-        key = (tuple(points_host.shape), tuple(int(o) for o in offsets), tuple(calib32_host.shape),
-               tuple(tuple(m.shape) for m in maps_host), tuple(sizes), head_rows)
+        # contexts are keyed on capacity BUCKETS, not on the exact per-frame point counts: real sweeps differ in size from
+        # call to call, and rebuilding the sub-batch contexts would re-allocate multi-GB workspaces and pinned buffers
+        maxp = max([int(offsets[i + 1]) - int(offsets[i]) for i in range(B)] + [1])
+        cap = (maxp + 4095) // 4096 * 4096
+        stride = int(points_host.shape[1])
+        n_slots = max(1, int(getattr(self, 'host_slots', 2)))
+        key = (B, cap, stride, tuple(tuple(m.shape[1:]) for m in maps_host), tuple(sizes), int(head_rows), n_slots)
         if getattr(self, '_in_key', None) != key:
-            self._subs = []
-            for f0, f1 in zip(bounds[:-1], bounds[1:]):
-                c = self._child()
-                c.f0, c.f1, c.p0, c.p1 = f0, f1, int(offsets[f0]), int(offsets[f1])
-                c.offsets = [int(o) - c.p0 for o in offsets[f0:f1 + 1]]
-                c.in_points = torch.empty((c.p1 - c.p0, points_host.shape[1]), dtype=torch.float32, device=dev)
-                c.in_calib = torch.empty((f1 - f0, 32), dtype=torch.float32, device=dev)
-                c.in_maps = [torch.empty((f1 - f0,) + tuple(m.shape[1:]), dtype=torch.float32, device=dev) for m in maps_host]
-                c.ev = torch.cuda.Event()
-                self._subs.append(c)
-            self._sub_chunk = None
+            self._slots = []
+            for _ in range(n_slots):
+                slot = _HostSlot()
+                for f0, f1 in zip(bounds[:-1], bounds[1:]):
+                    c = self._child()
+                    c.f0, c.f1 = f0, f1
+                    c.in_points = torch.empty(((f1 - f0) * cap, stride), dtype=torch.float32, device=dev)
+                    c.in_calib = torch.empty((f1 - f0, 32), dtype=torch.float32, device=dev)
+                    c.in_maps = [torch.empty((f1 - f0,) + tuple(m.shape[1:]), dtype=torch.float32, device=dev) for m in maps_host]
+                    c.ev = torch.cuda.Event()
+                    slot.subs.append(c)
+                nz, nx, ny = self.grid.shape[2], self.grid.shape[0], self.grid.shape[1]
+                slot.grid_out = torch.empty((B, 128, nz, nx, ny), dtype=torch.float32, device=dev) if want_grid else None
+                slot.counts = torch.empty((B, 4), dtype=torch.int32, device=dev)
+                slot.out_counts = torch.empty((B, 4), dtype=torch.int32).pin_memory()
+                slot.out_head = torch.empty((min(int(head_rows), cap), 128), dtype=torch.float32).pin_memory()
+                slot.done = torch.cuda.Event()
+                self._slots.append(slot)
             self._copy_stream = torch.cuda.Stream(device=dev)
-            self._out_counts = torch.empty((B, 4), dtype=torch.int32).pin_memory()
-            self._out_head = torch.empty((head_rows, 128), dtype=torch.float32).pin_memory()
-            self._h2d_bytes = (points_host.numel() + calib32_host.numel() + sum(m.numel() for m in maps_host)) * 4
+            ns = max(1, min(int(self.host_streams), len(sizes)))
+            self._compute_streams = [torch.cuda.Stream(device=dev) for _ in range(ns)]
+            self._host_calls = 0
             self._in_key = key
-        self._alloc_outputs(B)
-        self.B = B
+        slot = self._slots[self._host_calls % len(self._slots)]
+        self._host_calls += 1
+        if want_grid and slot.grid_out is None:
+            nz, nx, ny = self.grid.shape[2], self.grid.shape[0], self.grid.shape[1]
+            slot.grid_out = torch.empty((B, 128, nz, nx, ny), dtype=torch.float32, device=dev)
+        self._h2d_bytes = (points_host.numel() + calib32_host.numel() + sum(m.numel() for m in maps_host)) * 4
+        self.B, self.grid_out, self.counts = B, slot.grid_out, slot.counts
         cur = torch.cuda.current_stream()
         cs = self._copy_stream
-        ns = max(1, min(int(self.host_streams), len(self._subs)))
-        if len(getattr(self, '_compute_streams', [])) != ns:
-            self._compute_streams = [torch.cuda.Stream(device=dev) for _ in range(ns)] if ns > 1 else [None]
-        cs.wait_stream(cur)                      # earlier work on the input buffers has been ordered before the copies
-        for s_ in self._compute_streams:
-            if s_ is not None:
-                s_.wait_stream(cur)
+        ns = len(self._compute_streams)
+        if slot.used:
+            cs.wait_event(slot.done)             # the kernels of the call that last used this slot have read its inputs
         with torch.cuda.stream(cs):              # every copy is queued up front: the copy engine never waits for the CPU
-            for c in self._subs:
-                c.in_points.copy_(points_host[c.p0:c.p1], non_blocking=True)
+            for c in slot.subs:
+                p0, p1 = int(offsets[c.f0]), int(offsets[c.f1])
+                c.offsets = [int(o) - p0 for o in offsets[c.f0:c.f1 + 1]]
+                c.n_points = p1 - p0
+                if p1 > p0:
+                    c.in_points[:p1 - p0].copy_(points_host[p0:p1], non_blocking=True)
                 c.in_calib.copy_(calib32_host[c.f0:c.f1], non_blocking=True)
                 for d, h in zip(c.in_maps, maps_host):
                     d.copy_(h[c.f0:c.f1], non_blocking=True)
                 c.ev.record(cs)
-        for j, c in enumerate(self._subs):
-            ks = self._compute_streams[j % ns] or cur
+        for j, c in enumerate(slot.subs):
+            ks = self._compute_streams[j % ns]
+            if j < ns:
+                ks.wait_stream(cur)              # work the caller queued before this call (weight updates ...) is ordered first
             with torch.cuda.stream(ks):
                 ks.wait_event(c.ev)
-                c.forward_device(c.in_points, c.offsets, c.in_calib, c.in_maps, want_grid,
-                                 grid_out=self.grid_out[c.f0:c.f1] if want_grid else None, counts=self.counts[c.f0:c.f1])
-        for s_ in self._compute_streams:
-            if s_ is not None:
-                cur.wait_stream(s_)
-        self._subs_active = True
-        self._out_counts.copy_(self.counts, non_blocking=True)
-        c0 = self._subs[0]
-        head = c0.region('vfeat', torch.float32, (c0.B, c0.cap, 128))[0, :head_rows]
-        self._out_head.copy_(head, non_blocking=True)
-        cur.synchronize()
-        return (self.grid_out if want_grid else None), self._out_counts, self._out_head
+                c.forward_device(c.in_points[:c.n_points], c.offsets, c.in_calib, c.in_maps, want_grid, cap=cap,
+                                 grid_out=slot.grid_out[c.f0:c.f1] if want_grid else None, counts=slot.counts[c.f0:c.f1])
+        k0 = self._compute_streams[0]
+        for s_ in self._compute_streams[1:]:
+            k0.wait_stream(s_)
+        with torch.cuda.stream(k0):              # device -> host read of the step's result
+            slot.out_counts.copy_(slot.counts, non_blocking=True)
+            c0 = slot.subs[0]
+            n_head = slot.out_head.shape[0]
+            slot.out_head.copy_(c0.region('vfeat', torch.float32, (c0.B, c0.cap, 128))[0, :n_head], non_blocking=True)
+            slot.done.record(k0)
+        slot.used = True
+        cur.wait_event(slot.done)                # later work on the caller's stream sees this call's device outputs
+        self._subs, self._sub_chunk, self._subs_active = slot.subs, None, True
+        self._d2h_bytes = slot.out_counts.numel() * 4 + slot.out_head.numel() * 4
+        step = HostStep(slot)
+        return step.wait() if sync else step
 
     @property
     def h2d_bytes(self):
@@ -370,7 +422,7 @@ class PointPath:
 
     @property
     def d2h_bytes(self):
-        return self._out_counts.numel() * 4 + self._out_head.numel() * 4
+        return self._d2h_bytes
 
     # ---- compact outputs (reference voxel order), for callers that do not want the dense grid -----------
     def voxel_features(self, f: int):

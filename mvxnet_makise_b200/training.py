@@ -33,10 +33,27 @@ class FlatAdamW:
         self.t = 0
 
     def reduce_and_step(self, grad: torch.Tensor, local_frames: int, global_frames: int | None = None):
+        """`grad` is this rank's bucket with ONE spare element at the end (`numel() == params.numel() + 1`) or exactly the
+        parameter count. With the spare element the number of frames travels in the same message, so ragged shards (5 frames
+        on 2 ranks = 3 + 2) divide by the same global count on every rank; without it `global_frames` is mandatory when
+        world > 1 (a per-rank guess `local_frames * world` would make the replicas diverge silently)."""
         world = dist.get_world_size() if dist.is_initialized() else 1
+        n = self.params.numel()
+        carries_count = grad.numel() == n + 1
+        assert carries_count or grad.numel() == n
+        if world > 1 and not carries_count and global_frames is None:
+            raise ValueError('global_frames is required when the bucket has no frame-count slot (ragged shards would diverge)')
+        if carries_count:
+            grad[n] = float(local_frames)
         if world > 1:
             dist.all_reduce(grad, op=dist.ReduceOp.SUM)          # NCCL over NVLink: the path's only collective
-        grad.div_(float(global_frames or local_frames * world))  # the reference optimises a per-frame loss
+        if global_frames is None:
+            # the count rides in the bucket; the division stays on the device (no host read-back in the step)
+            denom = grad[n:n + 1] if carries_count else torch.full((1,), float(local_frames), device=grad.device)
+        else:
+            denom = torch.full((1,), float(global_frames), device=grad.device)
+        grad = grad[:n]
+        grad.div_(denom)                                         # the reference optimises a per-frame loss
         b1, b2 = self.betas
         self.t += 1
         self.params.mul_(1.0 - self.lr * self.weight_decay)
@@ -59,7 +76,8 @@ class HotPathTrainer:
         for name, o, shape in self.layout:
             t = torch.as_tensor(np.asarray(state_dict[name])) if not isinstance(state_dict[name], torch.Tensor) else state_dict[name]
             self.params[o:o + t.numel()] = t.detach().reshape(-1).to(dev, torch.float32)
-        self.grad = torch.zeros_like(self.params)
+        self.bucket = torch.zeros(n + 1, dtype=torch.float32, device=dev)   # gradients + one slot for the frame count
+        self.grad = self.bucket[:n]                                          # what the CUDA backward fills
         self.opt = FlatAdamW(self.params, lr, eps, betas, weight_decay)
         self._push_weights()
 
@@ -80,6 +98,6 @@ class HotPathTrainer:
         """One optimisation step on this rank's frames. Returns (grid, counts) of the forward."""
         grid, counts = self.path.forward_train(points, offsets, calib32, maps, want_grid)
         self.path.backward(d_vfeat=d_vfeat, d_grid=d_grid, grad_flat=self.grad, accumulate=False)
-        self.opt.reduce_and_step(self.grad, len(offsets) - 1, global_frames)
+        self.opt.reduce_and_step(self.bucket, len(offsets) - 1, global_frames)
         self._push_weights()
         return grid, counts

@@ -26,17 +26,17 @@ def _worker(rank, world, port, n_frames, q):
     # stand-in for the per-frame forward: a deterministic function of the global frame id
     local = [(b, b * b + 1) for b in mine]
     allres = mdist.gather_frame_results(local, n_frames, rank, world)
-    # gradients: each rank contributes the sum over its frames of a frame-dependent gradient
-    torch.manual_seed(0)
-    lin = torch.nn.Linear(5, 3)
-    lin.weight.grad = torch.zeros_like(lin.weight)
-    lin.bias.grad = torch.zeros_like(lin.bias)
+    # gradients: each rank contributes the sum over ITS frames of a frame-dependent gradient; the flat bucket carries
+    # the frame count in its last slot, so the ragged case (5 frames = 3 + 2) divides by 5 on both ranks
+    from mvxnet_makise_b200.training import FlatAdamW
+    params = torch.zeros(18)
+    opt = FlatAdamW(params, lr=1.0, eps=1e-12, betas=(0.0, 0.0), weight_decay=0.0)   # update = -sign-ish(g): g is what we check
+    bucket = torch.zeros(19)
     for b in mine:
-        lin.weight.grad += float(b + 1)
-        lin.bias.grad += float(2 * b)
-    bucket = mdist.GradBucket(lin.parameters())
-    flat = bucket.allreduce(global_frames=n_frames, average=True).clone()
-    q.put((rank, mine, allres, flat, lin.weight.grad.clone(), lin.bias.grad.clone()))
+        bucket[:15] += float(b + 1)
+        bucket[15:18] += float(2 * b)
+    opt.reduce_and_step(bucket, len(mine))
+    q.put((rank, mine, allres, bucket[:18].clone(), float(bucket[18])))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -55,13 +55,13 @@ def test_frame_sharding_and_grad_allreduce_gloo(n_frames):
         assert p.exitcode == 0
     owned = sorted(b for _, mine, *_ in res for b in mine)
     assert owned == list(range(n_frames))                                  # every frame exactly once
-    for rank, mine, allres, flat, wg, bg in res:
+    for rank, mine, allres, flat, nframes in res:
         assert all(mdist.owner_of(b, world) == rank for b in mine)
         assert allres == [(b, b * b + 1) for b in range(n_frames)]         # global order restored on every rank
         exp_w = sum(b + 1 for b in range(n_frames)) / n_frames
         exp_b = sum(2 * b for b in range(n_frames)) / n_frames
-        assert torch.allclose(wg, torch.full_like(wg, exp_w)) and torch.allclose(bg, torch.full_like(bg, exp_b))
-        assert flat.numel() == 5 * 3 + 3
+        assert nframes == n_frames                                         # the count travelled with the gradients
+        assert torch.allclose(flat[:15], torch.full((15,), exp_w)) and torch.allclose(flat[15:], torch.full((3,), exp_b))
     assert torch.equal(res[0][3], res[1][3])                               # identical on both ranks
 
 
@@ -69,11 +69,11 @@ def test_single_process_paths():
     assert mdist.shard_frames(8, 0, 1) == list(range(8))
     assert mdist.shard_frames(8, 3, 8) == [3] and mdist.shard_frames(16, 1, 8) == [1, 9]
     assert mdist.gather_frame_results([1, 2, 3], 3, 0, 1) == [1, 2, 3]
-    lin = torch.nn.Linear(2, 2)
-    lin.weight.grad = torch.ones_like(lin.weight)
-    b = mdist.GradBucket(lin.parameters())
-    b.allreduce(global_frames=2)
-    assert torch.allclose(lin.weight.grad, torch.full_like(lin.weight, 0.5)) and lin.bias.grad is not None
+    from mvxnet_makise_b200.training import FlatAdamW
+    opt = FlatAdamW(torch.zeros(4), lr=1.0, weight_decay=0.0)
+    g = torch.ones(5)
+    opt.reduce_and_step(g, 2)                         # single process: the count slot still normalises the gradient
+    assert torch.allclose(g[:4], torch.full((4,), 0.5)) and float(g[4]) == 2.0
 
 
 def _opt_worker(rank, world, port, q):
@@ -84,10 +84,15 @@ def _opt_worker(rank, world, port, q):
     params = torch.randn(1000)
     p0 = params.clone()
     opt = FlatAdamW(params)
-    frames_per_rank = 3
+    frames = 3 if rank == 0 else 2                          # ragged shards: 5 global frames
     for step in range(2):
-        g = torch.full((1000,), float(rank + 1 + step))      # this rank's bucket: sum over its 3 frames
-        opt.reduce_and_step(g, frames_per_rank)
+        g = torch.full((1001,), float(rank + 1 + step))     # this rank's bucket (+ the frame-count slot)
+        opt.reduce_and_step(g, frames)
+    try:                                                    # a bucket without the slot must not guess the global count
+        opt.reduce_and_step(torch.zeros(1000), frames)
+        raise AssertionError('expected ValueError')
+    except ValueError:
+        pass
     q.put((rank, p0, params.clone()))
     dist.barrier()
     dist.destroy_process_group()
@@ -111,6 +116,6 @@ def test_flat_adamw_allreduce_gloo():
     ref = torch.nn.Parameter(res[0][1].clone())
     opt = torch.optim.AdamW([ref], lr=1e-3, eps=1e-6)
     for step in range(2):
-        ref.grad = torch.full((1000,), ((1 + step) + (2 + step)) / 6.0)     # (rank0 + rank1 buckets) / 6 global frames
+        ref.grad = torch.full((1000,), ((1 + step) + (2 + step)) / 5.0)     # (rank0 + rank1 buckets) / 5 global frames (3 + 2)
         opt.step()
     assert torch.allclose(res[0][2], ref.detach(), rtol=1e-6, atol=1e-7)
