@@ -93,6 +93,12 @@ int mvx_crop_workspace_bytes(int32_t B, int64_t total_points, int64_t max_points
 int mvx_crop_points(const float *points, int32_t point_stride, int32_t B, const int32_t *pt_off_host, const double *range6,
                     const float *calib32, double imsize_w, double imsize_h, float *out_points, int32_t *out_counts,
                     void *workspace, size_t workspace_bytes, void *stream);
+/* The same with float64 calibrations (calib64 = device [B][32] doubles, (R0@Tr | P2) with the 4x4 product formed in fp64):
+ * what the reference's numpy branch evaluates when `calib` holds the float64 matrices `readCalib` returns
+ * (modules/data/Load.py:24-41, caller Load.py:73): projection, depth test and image-bound test all in fp64. */
+int mvx_crop_points_f64(const float *points, int32_t point_stride, int32_t B, const int32_t *pt_off_host, const double *range6,
+                        const double *calib64, double imsize_w, double imsize_h, float *out_points, int32_t *out_counts,
+                        void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 2a — projection.  Replaces modules/utils/Calib.py:47-70 (`lidar2Img(pcd, calib, True)`).
@@ -101,6 +107,10 @@ int mvx_crop_points(const float *points, int32_t point_stride, int32_t B, const 
  * ------------------------------------------------------------------------------------------------ */
 int mvx_lidar2img(const float *points, int32_t point_stride, int64_t P, const float *calib32, float *out_uv,
                   void *stream);
+/* numpy branch with float64 calibration matrices (train.py:36-39 projects the pasted ground-truth sets through the float64
+ * dicts of modules/augment/LoadGT.py:31): fp32 coordinates promoted, fp64 arithmetic, fp64 (P,2) result. */
+int mvx_lidar2img_f64(const float *points, int32_t point_stride, int64_t P, const double *calib64, double *out_uv,
+                      void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 2b — PointFusion gather.  Replaces modules/imhead/Pipe.py:23-82 (`featureMaping`) for one frame.
@@ -173,7 +183,28 @@ typedef struct {
      * before the point sets are merged and voxelized together): device [sum P] calibration index of every point; calib32
      * then holds max(index)+1 sets instead of one per frame. NULL: every point of frame f uses calib32[f]. */
     const int32_t *point_calib;
+    /* Optional float64 calibrations: calib64 = device doubles, indexed like calib32; calib_f64 = device int32 flag per
+     * calibration set (1: project this set in fp64 from calib64 and round the pixel coordinates to fp32 once - the reference's
+     * numpy lidar2Img with readCalib's float64 matrices followed by `torch.Tensor(voxel)`, train.py:36-39,125; 0: fp32
+     * arithmetic from calib32 - the torch branch, train.py:31-33). Both NULL: every set is fp32. */
+    const double *calib64;
+    const int32_t *calib_f64;
+    /* Optional dense-voxel input - the arguments of the reference's own `MVXNet.forward(voxels, imgs, idx, calibs, imsize)`
+     * (MVXNet.py:21-27; produced by pre.group + train.py:118-128): voxels_dense = device (sum N_f, T, 9) fp32
+     * [x,y,z,dx,dy,dz,r,row,col], voxel_idx = device (sum N_f, 4) int64 [batch, ix, iy, iz], vox_off_host = HOST [B+1] voxel
+     * offsets. When voxels_dense is set, stage 1 and the projection are skipped (points / pt_off_host / calib32 are not
+     * read): slots with x == y == z == 0 are pad slots exactly as featureMaping decides (Pipe.py:53-54) and, like there, are
+     * zeroed IN PLACE in the caller's tensor (Pipe.py:58-59); every other slot becomes one compact row.
+     * cap must be >= max_f max(N_f, K_f) with K_f = real slots of frame f (mvx_dense_voxel_counts reports them). */
+    float *voxels_dense;
+    const int64_t *voxel_idx;
+    const int32_t *vox_off_host;
 } mvx_pointpath_args_t;
+
+/* counts[f] = (N_f, K_f = slots of frame f with (x,y,z) != 0, 0, max real slots per voxel) for a dense voxel tensor: what a
+ * caller needs to size `cap` before mvx_pointpath_forward with voxels_dense. counts: device [B][4]. */
+int mvx_dense_voxel_counts(const float *voxels_dense, const int32_t *vox_off_host, int32_t B, int32_t T, int32_t *counts,
+                           void *stream);
 
 /* byte offsets of named workspace regions, for tests/diagnostics (names in mvx_pointpath_layout_name) */
 #define MVX_WS_REGIONS 64

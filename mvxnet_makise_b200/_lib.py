@@ -25,8 +25,8 @@ NUM_SEGMENTS = 20
 EXPORTS = [
     'mvx_last_error', 'mvx_version', 'mvx_launch_count',
     'mvx_voxelize_workspace_bytes', 'mvx_voxelize', 'mvx_group_emit7', 'mvx_group_emit9',
-    'mvx_crop_workspace_bytes', 'mvx_crop_points',
-    'mvx_lidar2img', 'mvx_maps_nhwc_bytes', 'mvx_feature_mapping',
+    'mvx_crop_workspace_bytes', 'mvx_crop_points', 'mvx_crop_points_f64',
+    'mvx_lidar2img', 'mvx_lidar2img_f64', 'mvx_dense_voxel_counts', 'mvx_maps_nhwc_bytes', 'mvx_feature_mapping',
     'mvx_set_gemm_mode', 'mvx_layer_workspace_bytes', 'mvx_fcn_forward', 'mvx_vfe_forward', 'mvx_fcn_max_forward', 'mvx_set_grid_mode', 'mvx_scatter_dense',
     'mvx_pointpath_workspace_bytes', 'mvx_pointpath_layout', 'mvx_pointpath_layout_name', 'mvx_pointpath_forward',
     'mvx_set_fusion_mode', 'mvx_set_fold_mode', 'mvx_pointpath_train_workspace_bytes', 'mvx_pointpath_forward_train', 'mvx_grad_floats',
@@ -52,7 +52,8 @@ class PointPathArgs(ctypes.Structure):
                 ('imsize_h', c_float), ('imsize_w', c_float), ('gather_eps', c_float), ('bn_eps', c_double),
                 ('wt', c_void_p * NUM_LAYERS), ('bias', c_void_p * NUM_LAYERS), ('grid_out', c_void_p),
                 ('counts', c_void_p), ('workspace', c_void_p), ('workspace_bytes', c_size_t), ('stream', c_void_p),
-                ('point_calib', c_void_p)]
+                ('point_calib', c_void_p), ('calib64', c_void_p), ('calib_f64', c_void_p),
+                ('voxels_dense', c_void_p), ('voxel_idx', c_void_p), ('vox_off_host', POINTER(c_int32))]
 
 
 def make_grid(velorange, voxelsize, voxelshape, T) -> Grid:
@@ -82,6 +83,9 @@ def _load():
     lib.mvx_crop_workspace_bytes.argtypes = [i32, i64, i64, POINTER(c_size_t)]
     lib.mvx_crop_points.argtypes = [vp, i32, i32, POINTER(i32), POINTER(c_double), vp, c_double, c_double, vp, vp, vp, c_size_t, vp]
     lib.mvx_lidar2img.argtypes = [vp, i32, i64, vp, vp, vp]
+    lib.mvx_lidar2img_f64.argtypes = [vp, i32, i64, vp, vp, vp]
+    lib.mvx_crop_points_f64.argtypes = [vp, i32, i32, POINTER(i32), POINTER(c_double), vp, c_double, c_double, vp, vp, vp, c_size_t, vp]
+    lib.mvx_dense_voxel_counts.argtypes = [vp, POINTER(i32), i32, i32, vp, vp]
     lib.mvx_maps_nhwc_bytes.argtypes = [POINTER(i32), POINTER(i32), i32, POINTER(c_size_t)]
     lib.mvx_feature_mapping.argtypes = [vp, i64, POINTER(vp), POINTER(i32), POINTER(i32), i32, c_float, c_float, c_float,
                                         vp, vp, c_size_t, vp]

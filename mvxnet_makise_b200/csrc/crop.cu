@@ -22,6 +22,7 @@ struct CropParams {
     int use_range, use_sight;
     double lo[3], hi[3];
     const float *calib32;      // [B][32]
+    const double *calib64;     // [B][32] fp64 calibrations (readCalib's float64 matrices): the reference's numpy branch, or NULL
     double lim_w, lim_h;       // imsize - 1e-3 (fp64)
     unsigned char *flag;       // [sum P]
     int *blocksum;             // [B][nblk] kept points per 1024-point block, then (in place) their exclusive scan
@@ -30,13 +31,18 @@ struct CropParams {
     int *out_counts;           // [B]
 };
 
-__device__ __forceinline__ bool keep_point(const CropParams &p, const float *c32, const float *q) {
+__device__ __forceinline__ bool keep_point(const CropParams &p, const float *c32, const double *c64, const float *q) {
     const float x = q[0], y = q[1], z = q[2];
     if (p.use_range) {
         const double xd = x, yd = y, zd = z;
         if (!(p.lo[0] <= xd && xd < p.hi[0] && p.lo[1] <= yd && yd < p.hi[1] && p.lo[2] <= zd && zd < p.hi[2])) return false;
     }
-    if (p.use_sight) {
+    if (p.use_sight && c64) {                               // float64 calibration: the whole test in fp64 (Load.py:73)
+        double u, v, cz;
+        project_point_z_f64(c64, x, y, z, u, v, cz);
+        if (!(cz > 0.0)) return false;
+        if (!(u >= 0.0 && v >= 0.0 && u < p.lim_w && v < p.lim_h)) return false;
+    } else if (p.use_sight) {
         float u, v, cz;
         project_point_z(c32, x, y, z, u, v, cz);
         if (!(cz > 0.f)) return false;                      // behind the camera (Preprocessing.py:46-48)
@@ -47,15 +53,19 @@ __device__ __forceinline__ bool keep_point(const CropParams &p, const float *c32
 
 __global__ void __launch_bounds__(kCropBlock) crop_flag_kernel(CropParams p) {
     __shared__ float c32[32];
+    __shared__ double c64[32];
     const int f = blockIdx.y;
-    if (p.use_sight && threadIdx.x < 32) c32[threadIdx.x] = p.calib32[f * 32 + threadIdx.x];
+    if (p.use_sight && threadIdx.x < 32) {
+        if (p.calib64) c64[threadIdx.x] = p.calib64[f * 32 + threadIdx.x];
+        else c32[threadIdx.x] = p.calib32[f * 32 + threadIdx.x];
+    }
     __syncthreads();
     const int n = p.fo.off[f + 1] - p.fo.off[f];
     const int i = blockIdx.x * kCropBlock + threadIdx.x;
     if (blockIdx.x * kCropBlock >= n) return;
     bool k = false;
     if (i < n) {
-        k = keep_point(p, c32, p.points + (size_t)(p.fo.off[f] + i) * p.stride);
+        k = keep_point(p, c32, p.calib64 ? c64 : nullptr, p.points + (size_t)(p.fo.off[f] + i) * p.stride);
         p.flag[p.fo.off[f] + i] = k ? 1 : 0;
     }
     const int cnt = __syncthreads_count(k ? 1 : 0);
@@ -108,11 +118,11 @@ extern "C" int mvx_crop_workspace_bytes(int32_t B, int64_t total_points, int64_t
     return MVX_OK;
 }
 
-extern "C" int mvx_crop_points(const float *points, int32_t point_stride, int32_t B, const int32_t *pt_off_host, const double *range6,
-                               const float *calib32, double imsize_w, double imsize_h, float *out_points, int32_t *out_counts,
-                               void *workspace, size_t workspace_bytes, void *stream) {
+static int crop_points_impl(const float *points, int32_t point_stride, int32_t B, const int32_t *pt_off_host, const double *range6,
+                            const float *calib32, const double *calib64, double imsize_w, double imsize_h, float *out_points,
+                            int32_t *out_counts, void *workspace, size_t workspace_bytes, void *stream) {
     MVX_REQUIRE(pt_off_host && out_counts && B >= 1 && B <= mvx::kMaxFrames && point_stride >= 3, MVX_EINVAL, "bad crop argument");
-    MVX_REQUIRE(range6 || calib32, MVX_EINVAL, "crop: give a range, a calibration, or both");
+    MVX_REQUIRE(range6 || calib32 || calib64, MVX_EINVAL, "crop: give a range, a calibration, or both");
     mvx::CropParams p{};
     long long maxp = 0;
     for (int f = 0; f <= B; ++f) p.fo.off[f] = pt_off_host[f];
@@ -131,10 +141,10 @@ extern "C" int mvx_crop_points(const float *points, int32_t point_stride, int32_
     mvx_crop_workspace_bytes(B, pt_off_host[B], maxp, &need);
     MVX_REQUIRE(workspace_bytes >= need, MVX_ESPACE, "crop workspace too small");
     p.B = B, p.points = points, p.stride = point_stride, p.out = out_points, p.out_counts = out_counts;
-    p.use_range = range6 != nullptr, p.use_sight = calib32 != nullptr;
+    p.use_range = range6 != nullptr, p.use_sight = calib32 != nullptr || calib64 != nullptr;
     if (range6)
         for (int d = 0; d < 3; ++d) p.lo[d] = range6[d], p.hi[d] = range6[3 + d];
-    p.calib32 = calib32;
+    p.calib32 = calib32, p.calib64 = calib64;
     p.lim_w = imsize_w - 1e-3, p.lim_h = imsize_h - 1e-3;   // Preprocessing.py:37
     p.nblk = (int)((maxp + mvx::kCropBlock - 1) / mvx::kCropBlock) + 1;
     p.flag = static_cast<unsigned char *>(workspace);
@@ -147,4 +157,18 @@ extern "C" int mvx_crop_points(const float *points, int32_t point_stride, int32_
     mvx::crop_emit_kernel<<<grid, mvx::kCropBlock, 0, st>>>(p);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
+}
+
+extern "C" int mvx_crop_points(const float *points, int32_t point_stride, int32_t B, const int32_t *pt_off_host, const double *range6,
+                               const float *calib32, double imsize_w, double imsize_h, float *out_points, int32_t *out_counts,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+    return crop_points_impl(points, point_stride, B, pt_off_host, range6, calib32, nullptr, imsize_w, imsize_h, out_points, out_counts,
+                            workspace, workspace_bytes, stream);
+}
+
+extern "C" int mvx_crop_points_f64(const float *points, int32_t point_stride, int32_t B, const int32_t *pt_off_host,
+                                   const double *range6, const double *calib64, double imsize_w, double imsize_h, float *out_points,
+                                   int32_t *out_counts, void *workspace, size_t workspace_bytes, void *stream) {
+    return crop_points_impl(points, point_stride, B, pt_off_host, range6, nullptr, calib64, imsize_w, imsize_h, out_points, out_counts,
+                            workspace, workspace_bytes, stream);
 }

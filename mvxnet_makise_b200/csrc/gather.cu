@@ -42,6 +42,19 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restri
     }
 }
 
+__global__ void __launch_bounds__(256) lidar2img_f64_kernel(const float *__restrict__ pts, int stride, long long P,
+                                                            const double *__restrict__ calib64, double *__restrict__ out_uv) {
+    __shared__ double c64[32];
+    if (threadIdx.x < 32) c64[threadIdx.x] = calib64[threadIdx.x];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float *q = pts + (size_t)i * stride;
+    double u, v, cz;
+    project_point_z_f64(c64, q[0], q[1], q[2], u, v, cz);
+    reinterpret_cast<double2 *>(out_uv)[i] = make_double2(u, v);
+}
+
 __global__ void __launch_bounds__(256) lidar2img_kernel(const float *__restrict__ pts, int stride, long long P,
                                                         const float *__restrict__ calib32, float *__restrict__ out_uv) {
     __shared__ float c32[32];
@@ -230,7 +243,14 @@ __global__ void __launch_bounds__(256) rows_build_kernel(RowsParams p) {
             hi = make_float4((float)((double)y - sy / (double)n), (float)((double)z - sz / (double)n), refl, 0.f);
             float u, vv;
             // merged point sets (GT-paste, train.py:36-41): every point is projected through the calibration it came with
-            project_point(p.point_calib ? p.calib32 + (size_t)p.point_calib[p.off[f] + pi] * 32 : c32, x, y, z, u, vv);
+            const int cs = p.point_calib ? p.point_calib[p.off[f] + pi] : f;
+            if (p.calib_f64 && p.calib_f64[cs]) {   // float64 calibration: fp64 projection, rounded once (torch.Tensor(voxel), train.py:125)
+                double ud, vd, czd;
+                project_point_z_f64(p.calib64 + (size_t)cs * 32, x, y, z, ud, vd, czd);
+                u = (float)ud, vv = (float)vd;
+            } else {
+                project_point(p.point_calib ? p.calib32 + (size_t)cs * 32 : c32, x, y, z, u, vv);
+            }
             pr = make_float2(vv, u);  // (row, col) = lidar2Img(...)[:, [1, 0]]  (train.py:33)
         }
     }
@@ -572,6 +592,16 @@ extern "C" int mvx_lidar2img(const float *points, int32_t point_stride, int64_t 
     MVX_REQUIRE(points && calib32 && out_uv && P > 0 && point_stride >= 3, MVX_EINVAL, "bad lidar2img argument");
     mvx::lidar2img_kernel<<<(unsigned)((P + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(points, point_stride, P,
                                                                                                      calib32, out_uv);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+extern "C" int mvx_lidar2img_f64(const float *points, int32_t point_stride, int64_t P, const double *calib64, double *out_uv,
+                                 void *stream) {
+    if (P == 0) return MVX_OK;
+    MVX_REQUIRE(points && calib64 && out_uv && P > 0 && point_stride >= 3, MVX_EINVAL, "bad lidar2img argument");
+    mvx::lidar2img_f64_kernel<<<(unsigned)((P + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(points, point_stride, P,
+                                                                                                         calib64, out_uv);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }

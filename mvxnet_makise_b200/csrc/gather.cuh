@@ -28,6 +28,9 @@ struct RowsParams {
     int off[33];
     const float *calib32;   // [B][32], or the calibration table that point_calib indexes
     const int *point_calib; // optional [sum P]: calibration set of every point (merged point sets with their own calibrations)
+    const double *calib64;  // optional fp64 copy of the calibration table (same indexing as calib32)
+    const int *calib_f64;   // optional flag per calibration set: 1 = project in fp64 from calib64, then round to fp32 (the
+                            // reference's numpy branch with readCalib's float64 matrices, train.py:36-39); NULL / 0 = fp32
     const int *counts;      // [B][4]
     const int *vox_cnt, *vox_row0, *row_point, *row_vox;
     float *vox8;            // [B][capA][8]  x,y,z,dx,dy,dz,r,0   (pad row K_f = zeros)
@@ -78,5 +81,9 @@ int launch_fcn1_bounds(const float *w1t, const float *bias, float *wbound, cudaS
 inline int combine_bins(int h0, int w0) { return ((h0 + 3) / 4) * ((w0 + 3) / 4) * 16; }
 int launch_combine_sort(const CombineArgs &a, int B, cudaStream_t st);   // counting sort of the rows (needs vox8 / proj only)
 int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st);   // the combine itself (needs Z and the sort)
+
+// dense-voxel entry (dense_entry.cu): compact rows from the reference's (N,T,9) voxel tensor + (N,4) index list
+int dense_rows_run(const mvx_pointpath_args_t *a, int capA, long long G, int *vox_coord, int *vox_cnt, int *vox_row0, int *row_point,
+                   int *row_vox, int *cell2vid, float *vox8, float *proj, float *rowA_w, cudaStream_t st);
 
 }  // namespace mvx

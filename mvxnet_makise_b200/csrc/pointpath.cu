@@ -194,9 +194,13 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     int rc = make_layout(a, L);
     if (rc) return rc;
     MVX_REQUIRE(a->workspace && a->workspace_bytes >= (train ? L.total_train : L.total), MVX_ESPACE, "pointpath workspace too small");
-    MVX_REQUIRE(a->pt_off_host && a->calib32 && a->counts, MVX_EINVAL, "null input pointer");
-    MVX_REQUIRE(a->points || a->pt_off_host[a->B] == a->pt_off_host[0], MVX_EINVAL, "null points pointer");   // an all-empty batch may pass NULL
-    MVX_REQUIRE(a->point_stride >= 4, MVX_EINVAL, "point_stride must be >= 4");
+    const bool dense_in = a->voxels_dense != nullptr || a->vox_off_host != nullptr;   // the reference's (voxels, idx) arguments instead of raw points
+    MVX_REQUIRE(a->counts, MVX_EINVAL, "null counts pointer");
+    if (!dense_in) {
+        MVX_REQUIRE(a->pt_off_host && a->calib32, MVX_EINVAL, "null input pointer");
+        MVX_REQUIRE(a->points || a->pt_off_host[a->B] == a->pt_off_host[0], MVX_EINVAL, "null points pointer");   // an all-empty batch may pass NULL
+        MVX_REQUIRE(a->point_stride >= 4, MVX_EINVAL, "point_stride must be >= 4");
+    }
     for (int l = 0; l < MVX_NUM_LEVELS; ++l) MVX_REQUIRE(a->maps[l], MVX_EINVAL, "null FPN map");
     for (int l = 0; l < MVX_NUM_LAYERS; ++l) MVX_REQUIRE(a->wt[l] && a->bias[l], MVX_EINVAL, "null layer weights");
     cudaStream_t st = static_cast<cudaStream_t>(a->stream);
@@ -292,6 +296,11 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     vo.counts = a->counts;
     vo.vox_coord = I32(R_VOX_COORD), vo.vox_cnt = I32(R_VOX_CNT), vo.vox_row0 = I32(R_VOX_ROW0);
     vo.row_point = I32(R_ROW_POINT), vo.row_vox = I32(R_ROW_VOX), vo.cell2vid = I32(R_CELL2VID);
+    if (dense_in) {   // stage 1 and the projection were done by the caller (pre.group on the host): compact the dense tensor
+        rc = dense_rows_run(a, L.capA, L.G, vo.vox_coord, vo.vox_cnt, vo.vox_row0, vo.row_point, vo.row_vox, vo.cell2vid, F32(R_VOX8),
+                            F32(R_PROJ), F32(R_ROWA_W), st);
+        if (rc) return rc;
+    } else {
     rc = vox_run(&a->grid, B, cap, a->points, a->point_stride, a->pt_off_host, nullptr, T, &vo, ws + L.off[R_VOXWS],
                  vox_workspace_bytes(B, cap), st);
     if (rc) return rc;
@@ -301,10 +310,12 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     rp.points = a->points, rp.point_stride = a->point_stride;
     for (int f = 0; f <= B; ++f) rp.off[f] = a->pt_off_host[f];
     rp.calib32 = a->calib32, rp.point_calib = a->point_calib, rp.counts = a->counts;
+    rp.calib64 = a->calib64, rp.calib_f64 = a->calib64 ? a->calib_f64 : nullptr;
     rp.vox_cnt = vo.vox_cnt, rp.vox_row0 = vo.vox_row0, rp.row_point = vo.row_point, rp.row_vox = vo.row_vox;
     rp.vox8 = F32(R_VOX8), rp.proj = F32(R_PROJ), rp.rowA_w = F32(R_ROWA_W);
     rc = launch_rows_build(rp, st);
     if (rc) return rc;
+    }
 
     // split grid fill: the zeros of the dense grid need only the occupancy bits. They go out on the side stream, behind the
     // pixel GEMM, and stream to HBM under the combine / tensor-core layer kernels; the occupied sectors follow at the end

@@ -37,14 +37,40 @@ def pack_calib(calib: Dict[str, torch.Tensor]) -> torch.Tensor:
     return torch.cat([(r0 @ tr).reshape(-1), p2.reshape(-1)]).contiguous()
 
 
+def calib_is_f64(calib: Dict) -> bool:
+    """True when the calibration holds float64 matrices - what `readCalib` returns (Load.py:24-41: `np.zeros((4, 4))` and
+    `np.concatenate([float32 block, [[0, 0, 0, 1]]])` are float64). The reference's numpy branches then evaluate the whole
+    projection in fp64 (cropToSight at Load.py:73; lidar2Img of the pasted ground-truth sets, train.py:36-39); its torch
+    branches see `torch.Tensor(calib[k])`, i.e. fp32 (Load.py:75-76, train.py:113-115)."""
+    return any((isinstance(v, np.ndarray) and v.dtype == np.float64) or (isinstance(v, torch.Tensor) and v.dtype == torch.float64)
+               for v in (calib['R0_rect'], calib['Tr_velo_to_cam'], calib['P2']))
+
+
+def pack_calib64(calib: Dict) -> torch.Tensor:
+    """[R0_rect @ Tr_velo_to_cam | P2] as 32 fp64 values, the 4x4 product formed by numpy in fp64 like Calib.py:65 does."""
+    r0, tr, p2 = (np.asarray(calib[k].cpu() if isinstance(calib[k], torch.Tensor) else calib[k], dtype=np.float64)
+                  for k in ('R0_rect', 'Tr_velo_to_cam', 'P2'))
+    return torch.from_numpy(np.concatenate([(r0 @ tr).reshape(-1), p2.reshape(-1)])).contiguous()
+
+
 def lidar2Img(pcd, calib: dict, uncheck: bool = False):
     """Project points to the image; returns (N,2) in (width, height) order like the reference.
-    Accepts numpy or torch input and returns the same kind (torch results stay on the GPU)."""
+    Accepts numpy or torch input and returns the same kind (torch results stay on the GPU). numpy points with a float64
+    calibration (readCalib's dicts) follow the reference's numpy branch: fp64 arithmetic, float64 result."""
     _lib.require_cuda()
     assert pcd.ndim == 2, 'Point cloud should be in (N, 3 + C)'
     as_numpy = isinstance(pcd, np.ndarray)
     pts = torch.from_numpy(np.ascontiguousarray(pcd, dtype=np.float32)).cuda() if as_numpy \
         else pcd.to(device='cuda', dtype=torch.float32).contiguous()
+    if as_numpy and calib_is_f64(calib):
+        c64 = pack_calib64(calib).cuda()
+        out = torch.empty((pts.shape[0], 2), dtype=torch.float64, device=pts.device)
+        check(lib.mvx_lidar2img_f64(ptr(pts), pts.shape[1], pts.shape[0], ptr(c64), ptr(out), stream_ptr()), 'lidar2img_f64')
+        if not uncheck:
+            m = c64[:16].reshape(4, 4)
+            depth = pts[:, :3].double() @ m[2, :3] + m[2, 3]
+            out = out[depth > 0]
+        return out.cpu().numpy()
     c32 = pack_calib(calib).cuda()
     out = torch.empty((pts.shape[0], 2), dtype=torch.float32, device=pts.device)
     check(lib.mvx_lidar2img(ptr(pts), pts.shape[1], pts.shape[0], ptr(c32), ptr(out), stream_ptr()), 'lidar2img')

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib, synth
 from ._lib import lib, check, ptr, stream_ptr
-from .modules import _wt, pack_calib
+from .modules import _wt, pack_calib, pack_calib64, calib_is_f64
 
 LAYER_NAMES = [name for name, *_ in synth.HOT_LAYERS]
 
@@ -63,6 +63,13 @@ class PointPath:
         self.host_streams = 2      # sub-batches alternate between this many compute streams (their kernels may overlap)
         self.host_taper = True     # split the last sub-batch in two: less compute left after the last copy has landed
         self.host_slots = 2        # complete buffer sets of forward_host, used alternately: call s+1's copies overlap call s's kernels
+        # The reference shuffles the points INSIDE group / group_ (Preprocessing.py:66,86), so "the first T points of a voxel"
+        # is a random T-subset, redrawn every epoch. None: shuffle in training mode (forward_train), keep the caller's order in
+        # inference; True / False force it. `shuffle_generator` seeds it (torch.Generator on the device); the permutation
+        # applied by the last call is kept in `last_perm` (global row indices into the call's point array).
+        self.shuffle = None
+        self.shuffle_generator = None
+        self.last_perm = None
 
     def load_state_dict(self, sd):
         self.wt, self.bias = [], []
@@ -123,13 +130,31 @@ class PointPath:
     def forward_device(self, points: torch.Tensor, offsets: Sequence[int], calib32: torch.Tensor,
                        maps: List[torch.Tensor], want_grid: bool = True, cap: int | None = None,
                        grid_out: torch.Tensor | None = None, counts: torch.Tensor | None = None, train: bool = False,
-                       point_calib: torch.Tensor | None = None):
+                       point_calib: torch.Tensor | None = None, shuffle: bool | None = None,
+                       calib64: torch.Tensor | None = None, calib_f64: torch.Tensor | None = None):
         """points (sum P, stride>=4) fp32 CUDA, offsets host [B+1], calib32 (B,32) CUDA, maps 3 x (B,256,Hf,Wf) CUDA.
         grid_out / counts: optional caller-owned outputs ((B,128,nz,nx,ny) fp32, (B,4) int32, contiguous).
         train=True keeps every activation for `backward` (row-first fcn1; mvx_pointpath_forward_train).
         point_calib: optional (sum P) int32 CUDA — merged point sets (GT-paste, train.py:29-42): calibration set of every
-        point; calib32 is then the (n_sets, 32) table it indexes."""
+        point; calib32 is then the (n_sets, 32) table it indexes.
+        calib64 (n_sets, 32) float64 CUDA + calib_f64 (n_sets) int32 CUDA: calibration sets flagged 1 are projected in fp64
+        (the reference's numpy lidar2Img with readCalib's float64 matrices, train.py:36-39) and rounded to fp32 once.
+        shuffle: permute every frame's points on the device first, like the in-function shuffle of the reference's `group`
+        (None: `self.shuffle`, which defaults to training mode only)."""
         B = len(offsets) - 1
+        if shuffle is None:
+            shuffle = getattr(self, 'shuffle', None)
+        if shuffle is None:
+            shuffle = train
+        self.last_perm = None
+        if shuffle and points.shape[0] > 0:
+            gen = getattr(self, 'shuffle_generator', None)
+            perm = torch.cat([torch.randperm(int(offsets[f + 1]) - int(offsets[f]), device=points.device, generator=gen) + int(offsets[f])
+                              for f in range(B)])
+            points = points.index_select(0, perm)
+            if point_calib is not None:
+                point_calib = point_calib.index_select(0, perm).contiguous()
+            self.last_perm = perm
         maxp = max(offsets[i + 1] - offsets[i] for i in range(B))
         cap = cap or max(128, (maxp + 127) // 128 * 128)
         map_hw = [(int(m.shape[-2]), int(m.shape[-1])) for m in maps]
@@ -151,6 +176,10 @@ class PointPath:
             assert point_calib.is_cuda and point_calib.dtype == torch.int32 and point_calib.is_contiguous()
             assert point_calib.numel() == offsets[-1] and calib32.dim() == 2 and calib32.shape[1] == 32
             a.point_calib = point_calib.data_ptr()
+        if calib64 is not None:
+            assert calib64.is_cuda and calib64.dtype == torch.float64 and calib64.is_contiguous() and calib64.shape == calib32.shape
+            assert calib_f64 is not None and calib_f64.is_cuda and calib_f64.dtype == torch.int32 and calib_f64.numel() == calib32.shape[0]
+            a.calib64, a.calib_f64 = calib64.data_ptr(), calib_f64.data_ptr()
         for l in range(3):
             assert maps[l].is_contiguous() and maps[l].shape[0] == B and maps[l].shape[1] == 256
             a.maps[l] = maps[l].data_ptr()
@@ -167,11 +196,78 @@ class PointPath:
         a.stream = torch.cuda.current_stream().cuda_stream
         if train:
             check(lib.mvx_pointpath_forward_train(ctypes.byref(a)), 'pointpath_forward_train')
-            self._train_args = (a, off, points, calib32, maps, point_calib)      # kept alive for backward()
+            self._train_args = (a, off, points, calib32, maps, point_calib, calib64, calib_f64)      # kept alive for backward()
         else:
             check(lib.mvx_pointpath_forward(ctypes.byref(a)), 'pointpath_forward')
             self._train_args = None
-        self._last_args = (a, off, points, calib32, maps, point_calib)           # kept alive for cml_conv1()
+        self._last_args = (a, off, points, calib32, maps, point_calib, calib64, calib_f64)           # kept alive for cml_conv1()
+        return (self.grid_out if want_grid else None), self.counts
+
+    # ---- the reference's own arguments: MVXNet.forward(voxels, imgs, idx, calibs, imsize) (MVXNet.py:21-27) ----------------
+    def forward_voxels(self, voxels, idx, maps: List[torch.Tensor], want_grid: bool = True, train: bool = False,
+                       grid_out: torch.Tensor | None = None):
+        """Dense-voxel entry: `voxels` = the (1, N, T, 9) / (N, T, 9) fp32 CUDA tensor [x,y,z,dx,dy,dz,r,row,col] that
+        `pre.group` + train.py:118-128 produce, `idx` = (N, 4) int64 [batch, ix, iy, iz]; or lists of B such pairs (one per
+        frame, per-frame BatchNorm statistics like the batch-1 reference). maps: 3 x (B,256,Hf,Wf) CUDA.
+        Stage 1 and the projection are the caller's (the reference runs them on the CPU); stages 2b-4 run here. Pad slots
+        (x == y == z == 0, Pipe.py:53-54) are zeroed IN PLACE in `voxels` like featureMaping does (Pipe.py:58-59).
+        Costs one device->host read of the per-frame real-slot counts (the reference's featureMaping synchronises three
+        times, Pipe.py:71). Returns (grid (B,128,nz,nx,ny), counts (B,4))."""
+        orig = list(voxels) if isinstance(voxels, (list, tuple)) else [voxels]
+        il = list(idx) if isinstance(idx, (list, tuple)) else [idx]
+        assert len(orig) == len(il)
+        T = int(self.grid.T)
+        vl = [v.reshape(-1, T, 9) for v in orig]              # a view when the caller's tensor is contiguous
+        for v, i in zip(vl, il):
+            assert v.is_cuda and v.dtype == torch.float32 and i.is_cuda and i.dtype == torch.int64 and i.shape == (v.shape[0], 4)
+        B = len(vl)
+        single_inplace = B == 1 and vl[0].is_contiguous() and vl[0].data_ptr() == orig[0].data_ptr()
+        vcat = vl[0] if single_inplace else torch.cat(vl, dim=0).contiguous()
+        icat = il[0].contiguous() if B == 1 else torch.cat(il, dim=0).contiguous()
+        voff = np.concatenate([[0], np.cumsum([v.shape[0] for v in vl])]).astype(np.int64).tolist()
+        voff_c = (ctypes.c_int32 * (B + 1))(*[int(o) for o in voff])
+        cnt = torch.empty((B, 4), dtype=torch.int32, device=self.device)
+        check(lib.mvx_dense_voxel_counts(ptr(vcat), voff_c, B, T, ptr(cnt), stream_ptr()), 'dense_voxel_counts')
+        c = cnt.cpu()
+        need = max(int(c[:, 1].max()), int(c[:, 0].max()), 1)
+        cap = (need + 4095) // 4096 * 4096                     # capacity bucket: no re-allocation for every new frame size
+        map_hw = [(int(m.shape[-2]), int(m.shape[-1])) for m in maps]
+        self._prepare(B, cap, map_hw, own_outputs=grid_out is None, train=train)
+        if grid_out is not None:
+            assert grid_out.is_contiguous() and grid_out.dtype == torch.float32
+            self.grid_out = grid_out
+            if getattr(self, 'counts', None) is None or self.counts.shape[0] != B:
+                self.counts = torch.empty((B, 4), dtype=torch.int32, device=self.device)
+        self._subs_active = False
+        a = _lib.PointPathArgs()
+        a.grid = self.grid
+        a.B, a.cap = B, cap
+        a.voxels_dense, a.voxel_idx, a.vox_off_host = vcat.data_ptr(), icat.data_ptr(), voff_c
+        for l in range(3):
+            assert maps[l].is_cuda and maps[l].is_contiguous() and maps[l].shape[0] == B and maps[l].shape[1] == 256
+            a.maps[l] = maps[l].data_ptr()
+            a.map_h[l], a.map_w[l] = map_hw[l]
+        a.map_c = 256
+        a.imsize_h, a.imsize_w = self.imsize_hw
+        a.gather_eps, a.bn_eps = self.eps, self.eps
+        for l in range(8):
+            a.wt[l] = self.wt[l].data_ptr()
+            a.bias[l] = self.bias[l].data_ptr()
+        a.grid_out = self.grid_out.data_ptr() if want_grid else None
+        a.counts = self.counts.data_ptr()
+        a.workspace, a.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        a.stream = torch.cuda.current_stream().cuda_stream
+        keep = (a, voff_c, vcat, icat, maps)
+        if train:
+            check(lib.mvx_pointpath_forward_train(ctypes.byref(a)), 'pointpath_forward_train')
+            self._train_args = keep
+        else:
+            check(lib.mvx_pointpath_forward(ctypes.byref(a)), 'pointpath_forward')
+            self._train_args = None
+        self._last_args = keep
+        if not single_inplace:                                 # the in-place side effect, for callers that handed in views / lists
+            for f, v in enumerate(orig):
+                v.copy_(vcat[voff[f]:voff[f + 1]].reshape(v.shape))
         return (self.grid_out if want_grid else None), self.counts
 
     # ---- after the path: sparse hand-off to CML.conv1 (SURVEY.md §8f rank 2) -------------------------------------
@@ -198,9 +294,11 @@ class PointPath:
         return out
 
     # ---- training mode -------------------------------------------------------------------------------------
-    def forward_train(self, points, offsets, calib32, maps, want_grid: bool = True, cap: int | None = None):
-        """Forward that keeps the activations the backward needs (BASELINE.json configs[3])."""
-        return self.forward_device(points, offsets, calib32, maps, want_grid, cap, train=True)
+    def forward_train(self, points, offsets, calib32, maps, want_grid: bool = True, cap: int | None = None,
+                      shuffle: bool | None = None):
+        """Forward that keeps the activations the backward needs (BASELINE.json configs[3]). Shuffles every frame's points
+        first unless `shuffle=False` / `self.shuffle = False` (the reference's `group` does, Preprocessing.py:86)."""
+        return self.forward_device(points, offsets, calib32, maps, want_grid, cap, train=True, shuffle=shuffle)
 
     @staticmethod
     def grad_layout():
@@ -272,7 +370,8 @@ class PointPath:
         self._subs, self._sub_chunk, self._subs_active = self._split, None, True
         return (self.grid_out if want_grid else None), self.counts
 
-    def __call__(self, points_list: List, calibs: List[dict], fpn_maps: List, want_grid: bool = True):
+    def __call__(self, points_list: List, calibs: List[dict], fpn_maps: List, want_grid: bool = True,
+                 shuffle: bool | None = None):
         """points_list: B arrays/tensors (P_f, >=4) [x,y,z,r]; calibs: B dicts of 4x4 matrices (Load.py:24-41);
         fpn_maps: 3 tensors (B,256,Hf,Wf) (FPN levels '0','1','2').
         A frame may also be a LIST of point sets with a LIST of calibration dicts, one per set — the scene followed by the
@@ -281,24 +380,33 @@ class PointPath:
         def as_t(p):
             return torch.as_tensor(np.asarray(p, dtype=np.float32)) if not isinstance(p, torch.Tensor) else p
         merged = any(isinstance(c, (list, tuple)) for c in calibs)
-        pts, table, pc = [], [], []
+        pts, table, pc, table64, is64 = [], [], [], [], []
         for p, c in zip(points_list, calibs):
             sets, cals = (list(p), list(c)) if isinstance(c, (list, tuple)) else ([p], [c])
             assert len(sets) == len(cals), 'one calibration per point set'
             sets = [as_t(q) for q in sets]
             pts.append(torch.cat([q[:, :4].to(torch.float32) for q in sets], dim=0))
             if merged:
-                for q, cal in zip(sets, cals):
+                for k, (q, cal) in enumerate(zip(sets, cals)):
                     pc.append(np.full(q.shape[0], len(table), dtype=np.int32))
                     table.append(pack_calib(cal))
+                    table64.append(pack_calib64(cal))
+                    # train.py:31-33 projects the scene (set 0) with torch in fp32 whatever the dict holds; the pasted sets go
+                    # through the numpy branch (train.py:36-39), which is fp64 when their dicts are readCalib's float64 ones
+                    is64.append(1 if (k > 0 and calib_is_f64(cal)) else 0)
             else:
                 table.append(pack_calib(cals[0]))
         offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in pts])]).tolist()
         points = torch.cat(pts, dim=0).contiguous().to(self.device, non_blocking=True)
         calib32 = torch.stack(table).to(self.device, non_blocking=True)
         point_calib = torch.from_numpy(np.concatenate(pc)).to(self.device, non_blocking=True) if merged else None
+        c64 = f64 = None
+        if merged and any(is64):
+            c64 = torch.stack(table64).to(self.device)
+            f64 = torch.tensor(is64, dtype=torch.int32, device=self.device)
         maps = [torch.as_tensor(m).to(self.device, torch.float32).contiguous() for m in fpn_maps]
-        return self.forward_device(points, offsets, calib32, maps, want_grid, point_calib=point_calib)
+        return self.forward_device(points, offsets, calib32, maps, want_grid, point_calib=point_calib, shuffle=shuffle,
+                                   calib64=c64, calib_f64=f64)
 
     # ---- host-buffer entry: H2D of this batch's inputs, the fused path, D2H of the counts ---------------
     def _child(self):
@@ -307,6 +415,7 @@ class PointPath:
         c.wt, c.bias = self.wt, self.bias          # shared weights
         c._ws = c._ws_key = c._args = c._subs = None
         c._sub_chunk, c.host_chunk, c.host_taper = 0, 0, False
+        c.shuffle, c.shuffle_generator, c.last_perm = self.shuffle, self.shuffle_generator, None
         return c
 
     def forward_host(self, points_host: torch.Tensor, offsets: Sequence[int], calib32_host: torch.Tensor,

@@ -61,6 +61,20 @@ def kitti_calib() -> Dict[str, np.ndarray]:
     return {'P2': p2, 'R0_rect': r0, 'Tr_velo_to_cam': tr}
 
 
+def kitti_calib_f64() -> Dict[str, np.ndarray]:
+    """The same calibration as `readCalib` leaves it in memory (modules/data/Load.py:24-41): the fp32 file values inside
+    FLOAT64 matrices (`np.concatenate([fp32 (3,4), [[0, 0, 0, 1]]])` and `np.zeros((4, 4))` are float64). The reference's numpy
+    branches (cropToSight at Load.py:73, lidar2Img of the pasted sets at train.py:36-39) then compute in fp64."""
+    c = kitti_calib()
+    v2c = np.concatenate([c['Tr_velo_to_cam'][:3], [[0, 0, 0, 1]]], axis=0)
+    p2 = np.concatenate([c['P2'][:3], [[0, 0, 0, 1]]], axis=0)
+    r0 = np.zeros((4, 4))
+    r0[:3, :3] = c['R0_rect'][:3, :3]
+    r0[3, 3] = 1
+    assert v2c.dtype == np.float64 and p2.dtype == np.float64 and r0.dtype == np.float64
+    return {'P2': p2, 'R0_rect': r0, 'Tr_velo_to_cam': v2c}
+
+
 def fpn_shapes(imsize_hw: Sequence[int] = KITTI_IMSIZE_HW):
     """Shapes of FPN levels '0','1','2' for a KITTI image (probed):
     the torchvision transform resizes to min side 800 and pads to /32 -> 416x1344."""

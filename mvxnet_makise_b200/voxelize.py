@@ -156,11 +156,13 @@ def group(pcd: np.ndarray, range: Sequence[float], size: Sequence[float], sample
 # ---------------------------------------------------------------------------------------------------------------------
 # Before the path: range crop and field-of-view crop with order-preserving compaction (Preprocessing.py:12-55)
 def crop_frames(points: torch.Tensor, offsets: Sequence[int], range6: Sequence[float] | None = None,
-                calib32: torch.Tensor | None = None, imsize_wh: Sequence[float] | None = None):
+                calib32: torch.Tensor | None = None, imsize_wh: Sequence[float] | None = None,
+                calib64: torch.Tensor | None = None):
     """Batched device entry. points (sum P, C>=3) fp32 CUDA, offsets host [B+1]; range6 = velorange or None;
     calib32 (B,32) CUDA ([R0@Tr | P2], `modules.pack_calib`) + imsize (w, h) or None. Returns (out, counts): `out` has
     the layout of `points` with the kept points of frame f compacted, in input order, at rows offsets[f] ..
-    offsets[f] + counts[f]; counts (B,) int32 CUDA."""
+    offsets[f] + counts[f]; counts (B,) int32 CUDA. calib64 (B,32) float64 CUDA (`modules.pack_calib64`) instead of calib32
+    runs the sight test in fp64 - the reference's numpy branch with readCalib's float64 matrices (Load.py:73)."""
     _lib.require_cuda()
     assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous() and points.dim() == 2
     B = len(offsets) - 1
@@ -176,18 +178,27 @@ def crop_frames(points: torch.Tensor, offsets: Sequence[int], range6: Sequence[f
     if calib32 is not None:
         assert calib32.is_cuda and calib32.dtype == torch.float32 and calib32.is_contiguous() and tuple(calib32.shape) == (B, 32)
         assert imsize_wh is not None
+    if calib64 is not None:
+        assert calib32 is None and imsize_wh is not None
+        assert calib64.is_cuda and calib64.dtype == torch.float64 and calib64.is_contiguous() and tuple(calib64.shape) == (B, 32)
+        check(lib.mvx_crop_points_f64(ptr(points), points.shape[1], B, off, rng, ptr(calib64), w, h, ptr(out), ptr(counts), ptr(ws),
+                                      ws.numel(), stream_ptr()), 'crop_points_f64')
+        return out, counts
     check(lib.mvx_crop_points(ptr(points), points.shape[1], B, off, rng, ptr(calib32), w, h, ptr(out), ptr(counts), ptr(ws),
                               ws.numel(), stream_ptr()), 'crop_points')
     return out, counts
 
 
 def _crop_one(pcd, range6, calib, imsize):
-    from .modules import pack_calib
+    from .modules import pack_calib, pack_calib64, calib_is_f64
     as_numpy = isinstance(pcd, np.ndarray)
     assert pcd.ndim == 2
     x = _to_cuda_f32(np.ascontiguousarray(pcd, dtype=np.float32) if as_numpy else pcd)
-    c32 = pack_calib(calib)[None].to(x.device) if calib is not None else None
-    out, counts = crop_frames(x, [0, x.shape[0]], range6, c32, imsize)
+    # numpy points + float64 calibration (readCalib's dict, Load.py:73): the reference's numpy branch runs in fp64
+    f64 = calib is not None and as_numpy and calib_is_f64(calib)
+    c32 = pack_calib(calib)[None].to(x.device) if calib is not None and not f64 else None
+    c64 = pack_calib64(calib)[None].to(x.device) if f64 else None
+    out, counts = crop_frames(x, [0, x.shape[0]], range6, c32, imsize, calib64=c64)
     kept = out[:int(counts[0].item())]
     if as_numpy:
         return kept.cpu().numpy().astype(pcd.dtype, copy=False)

@@ -167,12 +167,30 @@ def points_with_proj(pcd4: np.ndarray, calib_np: Dict[str, np.ndarray]) -> np.nd
     return torch.concat([pcd, proj], dim=1).numpy()
 
 
+def lidar2img_numpy(pcd: np.ndarray, calib: Dict[str, np.ndarray]) -> np.ndarray:
+    """numpy branch of `lidar2Img(pcd, calib, uncheck=True)` - modules/utils/Calib.py:56-70, literally. The result dtype is
+    numpy's promotion of the calibration dtype with the fp32 point buffer: float64 for the float64 dicts `readCalib` returns
+    (Load.py:24-41), float32 for fp32 dicts."""
+    points = np.empty((4, pcd.shape[0]), dtype='float32')
+    points[:3] = pcd[:, :3].T
+    points[3] = 1
+    points = calib['R0_rect'] @ calib['Tr_velo_to_cam'] @ points
+    points = calib['P2'] @ points
+    points[:2] = points[:2] / points[2]
+    return points[:2].T
+
+
 def merged_points_with_proj(point_sets, calibs_np) -> np.ndarray:
-    """train.py:29-42 (GT-paste): the scene (torch branch of lidar2Img, columns swapped by `[:, [1, 0]]`) followed by every pasted
-    object (numpy branch, `proj[:, ::-1]`), each projected through ITS OWN calibration, concatenated in that order -> (P,6).
-    Both branches evaluate the same fp32 4x4 products; tests/test_oracle.py checks on the live reference that they agree
-    bit for bit, so one restatement serves both."""
-    return np.concatenate([points_with_proj(p, c) for p, c in zip(point_sets, calibs_np)], axis=0)
+    """train.py:29-42 (GT-paste): the scene through the TORCH branch of lidar2Img (`torch.Tensor` points and calibration, so
+    fp32 whatever the dict held; columns swapped by `[:, [1, 0]]`), then every pasted object through the NUMPY branch
+    (`proj[:, ::-1]`) with ITS OWN calibration dict as `readCalib` left it - float64 matrices give a float64 projection -
+    concatenated in that order -> (P,6), float64 as soon as one pasted set is. `group` copies the projection into the
+    voxel tensor and `torch.Tensor(voxel)` (train.py:125) rounds it to fp32 once."""
+    out = [points_with_proj(point_sets[0], calibs_np[0])]
+    for p, c in zip(point_sets[1:], calibs_np[1:]):
+        p = np.asarray(p, dtype=np.float32)
+        out.append(np.concatenate([p, lidar2img_numpy(p, c)[:, ::-1]], axis=1))                       # train.py:37-40
+    return np.concatenate(out, axis=0)                                                               # train.py:42
 
 
 # --------------------------------------------------------------------------- stage 2b: gather
@@ -269,7 +287,7 @@ def cml_conv1(grid: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float =
 # --------------------------------------------------------------------------- whole path, one frame
 def forward_frame(pcd4: np.ndarray, calib_np, fpn_maps: List[np.ndarray], sd_np, grid, imsize_hw,
                   eps: float = 1e-6, want_grid: bool = True, stages: dict | None = None,
-                  dtype: torch.dtype = torch.float32):
+                  dtype: torch.dtype = torch.float32, device: str = 'cpu'):
     """The reference's chain for ONE frame, shuffle disabled (trap 3):
     lidar2Img -> group -> [host glue train.py:118-128] -> featureMaping -> fusion -> concat
     (MVXNet.py:25-26) -> SVFE/FCN/max -> reindex. Returns dict of intermediate results.
@@ -277,10 +295,15 @@ def forward_frame(pcd4: np.ndarray, calib_np, fpn_maps: List[np.ndarray], sd_np,
     dtype=torch.float64 evaluates the SAME layer stack (stage 3) in double precision on the fp32 gather
     output: the rounding-free value of the reference algorithm, used by the tests to separate the fp32
     reference's own rounding noise (BatchNorm with 86 % identical pad rows normalises real rows to tens of
-    sigma, so fp32 statistics noise is amplified) from errors of the implementation under test."""
+    sigma, so fp32 statistics noise is amplified) from errors of the implementation under test.
+
+    device='cuda' evaluates the SAME torch expressions (stages 2b-4) with torch's CUDA kernels instead of its CPU
+    kernels - still the checker, never the product: the full-size parity tests use it to get the fp64 value of all 8
+    frames of the benchmarked batch in seconds, after pinning it on one frame against the CPU evaluation (fp64 GEMMs and
+    reductions agree to ~1e-12). Projection and voxelization (stages 1-2a) always run on the CPU."""
     import time
     t = {}
-    sd = {k: torch.from_numpy(np.asarray(v)).to(dtype) for k, v in sd_np.items()}
+    sd = {k: torch.from_numpy(np.asarray(v)).to(device=device, dtype=dtype) for k, v in sd_np.items()}
     t0 = time.perf_counter()
     # a list of calibrations: pcd4 is the matching list of point sets (scene + pasted objects, train.py:29-42)
     pcd6 = merged_points_with_proj(pcd4, calib_np) if isinstance(calib_np, (list, tuple)) else points_with_proj(pcd4, calib_np)
@@ -288,10 +311,10 @@ def forward_frame(pcd4: np.ndarray, calib_np, fpn_maps: List[np.ndarray], sd_np,
     t0 = time.perf_counter()
     voxel9, uidx = group(pcd6, grid.velorange, grid.voxelsize, grid.T)
     t['voxelize'] = time.perf_counter() - t0
-    voxels = torch.Tensor(voxel9)                                         # fp64 -> fp32 (train.py:125)
-    idx = torch.LongTensor(np.concatenate([np.zeros((uidx.shape[0], 1)), uidx], axis=1))   # train.py:119,126
-    imsize = torch.Tensor(list(imsize_hw))
-    feats = [torch.from_numpy(m) for m in fpn_maps]
+    voxels = torch.Tensor(voxel9).to(device)                              # fp64 -> fp32 (train.py:125)
+    idx = torch.LongTensor(np.concatenate([np.zeros((uidx.shape[0], 1)), uidx], axis=1)).to(device)   # train.py:119,126
+    imsize = torch.Tensor(list(imsize_hw)).to(device)
+    feats = [torch.from_numpy(np.asarray(m)).to(device) for m in fpn_maps]
     t0 = time.perf_counter()
     im768 = feature_mapping(voxels, feats, imsize, eps)
     t['gather'] = time.perf_counter() - t0

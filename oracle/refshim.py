@@ -22,9 +22,31 @@ import subprocess
 import sys
 import types
 
-REF = os.environ.get('MVX_REFERENCE_ROOT', '/root/reference')
 _HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+SOURCE = '/root/reference'                                   # read-only, build container only
+STAGED = os.path.join(_ROOT, 'baseline', '_ref')             # git-ignored copy that travels to the GPU box
+REF = os.environ.get('MVX_REFERENCE_ROOT') or (SOURCE if os.path.isfile(os.path.join(SOURCE, 'MVXNet.py')) else STAGED)
 _mods = None
+
+
+def stage() -> bool:
+    """Copy the reference's Python tree (+ config.yml, cpp/) into the git-ignored baseline/_ref/ so that the GPU box - which
+    has no /root/reference - can run the UNMODIFIED reference modules next to the drop-in (tests/test_gpu_dropin.py).
+    Never part of the product or of the git history; called by __graft_entry__.build() where /root/reference exists."""
+    import shutil
+    if not os.path.isfile(os.path.join(SOURCE, 'MVXNet.py')):
+        return False
+    keep = ('.py', '.yml', '.cpp', '.md', '.txt')
+    for dirpath, dirnames, files in os.walk(SOURCE):
+        dirnames[:] = [d for d in dirnames if not d.startswith('.') and d != '__pycache__']
+        rel = os.path.relpath(dirpath, SOURCE)
+        for f in files:
+            if f.endswith(keep):
+                dst = os.path.join(STAGED, rel, f)
+                os.makedirs(os.path.dirname(dst), exist_ok=True)
+                shutil.copyfile(os.path.join(dirpath, f), dst)
+    return True
 
 
 def available() -> bool:
@@ -33,7 +55,7 @@ def available() -> bool:
 
 def load_voxelutil():
     """The reference's native module, compiled from /root/reference/cpp/voxelutil.cpp (oracle/_ref)."""
-    if available():
+    if os.path.isfile(os.path.join(SOURCE, 'cpp', 'voxelutil.cpp')):      # the Makefile compiles it where it lies
         subprocess.run(['make', '-s', '-C', _HERE, 'ref'], check=True)
     so = glob.glob(os.path.join(_HERE, '_ref', 'voxelutil*.so'))
     if not so:
@@ -72,13 +94,14 @@ def load(device: str = 'cpu'):
             imhead_pipe = importlib.import_module('modules.imhead.Pipe')
             vpipe = importlib.import_module('modules.voxelnet.Pipe')
             vnet = importlib.import_module('modules.voxelnet.VoxelNet')
+            mvxnet = importlib.import_module('MVXNet')       # the model assembly (MVXNet.py:13-27); needs the patched Pipe import above
         finally:
             frcnn.fasterrcnn_resnet50_fpn_v2 = orig
     finally:
         os.chdir(cwd)
         sys.argv = argv
     _mods = types.SimpleNamespace(cfg=cfg, pre=pre, calib=calib, layers=layers, imhead_pipe=imhead_pipe,
-                                  vpipe=vpipe, VoxelNet=vnet.VoxelNet, cpp=ext.cpp)
+                                  vpipe=vpipe, VoxelNet=vnet.VoxelNet, cpp=ext.cpp, MVXNet=mvxnet.MVXNet)
     return _mods
 
 

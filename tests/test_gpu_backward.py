@@ -73,7 +73,7 @@ def test_backward_matches_autograd(seed, P):
     maps = small_maps(seed)
     path = PointPath(sd, G)
     points, offsets, calib32, dmaps = _device_inputs([pts], maps, calib)
-    grid, counts = path.forward_train(points, offsets, calib32, dmaps)
+    grid, counts = path.forward_train(points, offsets, calib32, dmaps, shuffle=False)
     N = int(counts[0, 0].item())
     rng = np.random.default_rng(seed + 100)
     d_vfeat = rng.standard_normal((N, 128)).astype(np.float32)
@@ -127,7 +127,7 @@ def test_backward_batch_is_sum_of_frames():
     maps = small_maps(21, B=3)
     path = PointPath(sd, G)
     points, offsets, calib32, dmaps = _device_inputs(frames, maps, calib)
-    _, counts = path.forward_train(points, offsets, calib32, dmaps, want_grid=False)
+    _, counts = path.forward_train(points, offsets, calib32, dmaps, want_grid=False, shuffle=False)
     rng = torch.Generator(device='cuda').manual_seed(5)
     dv = torch.randn((3, path.cap, 128), device='cuda', generator=rng)
     flat = path.backward(d_vfeat=dv).clone()
@@ -135,7 +135,7 @@ def test_backward_batch_is_sum_of_frames():
     for f in range(3):
         single = PointPath(sd, G)
         p1, o1, c1, m1 = _device_inputs([frames[f]], [m[f:f + 1] for m in maps], calib)
-        single.forward_train(p1, o1, c1, m1, want_grid=False, cap=path.cap)
+        single.forward_train(p1, o1, c1, m1, want_grid=False, cap=path.cap, shuffle=False)
         total += single.backward(d_vfeat=dv[f:f + 1].contiguous())
     assert rel_err(flat, total) < 1e-5
     assert torch.isfinite(flat).all() and float(flat.abs().max()) > 0

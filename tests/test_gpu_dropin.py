@@ -1,0 +1,210 @@
+"""The drop-in boundary exercised through the reference's OWN callers (SURVEY.md §8b seams 1-3), on the GPU.
+
+The unmodified reference Python (staged by `oracle/refshim.stage()` into the git-ignored baseline/_ref/, or /root/reference in
+the build container) is imported twice over: STOCK - its modules with its own compiled cpp/voxelutil.cpp (oracle/_ref) - and
+SWAPPED - the same modules with `modules/Extension.py`'s `cpp` object replaced by ours (`dropin.install_extension`) and the hot
+path of its `MVXNet` instance replaced by the fused CUDA path (`dropin.accelerate`). Compared:
+  * `pre.group_` (Preprocessing.py:57-73 -> cpp._group): bit-exact,
+  * `Calc.classifyAnchors` (Calc.py:88-96 -> cpp._classifyAnchors): identical index lists,
+  * `MVXNet.forward(voxels, imgs, idx, calibs, imsize)` (MVXNet.py:21-27): the CML input grid within 1e-4 of the stock model
+    evaluated in fp64,
+  * `loss.backward(); opt.step()` (train.py:64,161-162) through the swapped model: parameter gradients of the eight hot-path
+    layers against the stock model's autograd (bounded like tests/test_gpu_backward.py: by the fp32 stock model's own distance
+    to its fp64 evaluation), and an AdamW step that moves exactly those parameters."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from mvxnet_makise_b200 import synth
+from oracle import refshim
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refshim.available(), reason='no staged reference tree (run __graft_entry__.build() where /root/reference exists)')]
+G = synth.KITTI_GRID
+TOL = 1e-4
+
+
+def rel_err(a, ref):
+    a, ref = torch.as_tensor(a).double().cpu(), torch.as_tensor(ref).double().cpu()
+    return float((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope='module')
+def ref():
+    m = refshim.load(device='cuda')
+    m.cfg.config['device'] = 'cuda'
+    return m
+
+
+def _frame(ref, seed, P):
+    """what cputask + the host glue of train.py:26-49,113-128 hand to the model, from the STOCK reference functions"""
+    pts = synth.make_points(seed, P)
+    calib = {k: torch.Tensor(v) for k, v in synth.kitti_calib().items()}                  # Load.py:75-76
+    pcd = torch.Tensor(pts)
+    proj = ref.calib.lidar2Img(pcd, calib, True)[:, [1, 0]]                               # train.py:32-33
+    pcd6 = torch.concat([pcd, proj], dim=1).numpy()
+    # `group_` (the cpp-backed variant) does not carry the projection columns and the numba `group` costs a ~30 s JIT compile:
+    # the (N,T,9) tensor comes from the oracle's restatement of `group` (pinned bit-exact on the numba original, tests/test_oracle.py)
+    from oracle import pointpath_oracle as O
+    voxel, idx = O.group(pcd6, ref.cfg.velorange, ref.cfg.voxelsize, ref.cfg.samplenum)
+    return pts, calib, voxel, idx
+
+
+def test_extension_seam_group_and_classify_anchors(ref):
+    """Seam 1: the reference's callers of `cpp` run unchanged on the swapped object and return what the stock extension returns."""
+    import importlib
+    from mvxnet_makise_b200.dropin import install_extension
+    from mvxnet_makise_b200.voxelize import cpp as ours
+    calc = refshim.load_calc()
+    stock = ref.cpp
+    pts = synth.make_points(5, 20_000)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(pts.shape[0])
+    np.random.seed(123)
+    v_stock, u_stock = ref.pre.group_(pts.copy(), ref.cfg.velorange, ref.cfg.voxelsize, ref.cfg.samplenum)   # shuffles with numpy's RNG
+    # label side: anchors + ground truths through Calc.classifyAnchors (train.py:46,59-61)
+    from oracle import iou_oracle as IO
+    anchors = IO.create_anchors(176, 200, ref.cfg.velorange, ref.cfg.carsize)
+    abev = IO.anchor_bevs(anchors)
+    b3 = torch.tensor([[12.0, 3.0, -1, 3.9, 1.6, 1.56, 0.3], [31.0, -8.0, -1, 4.1, 1.7, 1.5, 1.2], [55.5, 20.0, -1, 3.6, 1.5, 1.4, -0.7]])
+    bev = calc.bbox3d2bev(b3)
+    got_stock = calc.classifyAnchors(bev, b3[:, [0, 1]], abev, ref.cfg.velorange, 0.45, 0.6)
+    try:
+        patched = install_extension()
+        assert {'modules.Extension', 'modules.data.Preprocessing', 'modules.Calc'} <= set(patched)
+        assert ref.pre.cpp is ours and calc.cpp is ours
+        np.random.seed(123)
+        v_ours, u_ours = ref.pre.group_(pts.copy(), ref.cfg.velorange, ref.cfg.voxelsize, ref.cfg.samplenum)
+        got_ours = calc.classifyAnchors(bev, b3[:, [0, 1]], abev, ref.cfg.velorange, 0.45, 0.6)
+    finally:
+        for name in ('modules.Extension', 'modules.data.Preprocessing', 'modules.Calc'):
+            importlib.import_module(name).cpp = stock
+    assert v_ours.dtype == v_stock.dtype and np.array_equal(v_ours, v_stock) and np.array_equal(u_ours, u_stock)
+    flat = lambda r: list(r[0]) + list(r[1]) + [r[2]]
+    assert all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(flat(got_ours), flat(got_stock)))
+    assert sum(len(np.asarray(a)) for a in got_stock[0]) > 0
+
+
+class _Probe(torch.nn.Module):
+    """stands in for the RPN in the tight comparison: a fixed linear functional of the CML input, so both models receive the
+    SAME upstream gradient (through the real CML/RPN 29 further batch-statistic BatchNorm layers amplify 1e-5 to 1e-2)"""
+
+    def __init__(self, weight):
+        super().__init__()
+        self.register_buffer('w', weight)
+
+    def forward(self, x):
+        return (x * self.w.to(x.dtype)).sum(), x.new_zeros(())
+
+
+def _small_model(ref, seed):
+    """the reference's MVXNet with a small stand-in for the frozen image backbone (random-init ResNet50-FPN costs 10 s and its
+    outputs are inputs of the path, not part of it; tests/test_gpu_full_model.py covers the real backbone)"""
+    torch.manual_seed(seed)
+    model = ref.MVXNet()
+
+    class TinyExtractor(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(seed)
+            self.maps = torch.nn.ParameterList([torch.nn.Parameter(torch.randn((1, 256, h, w), generator=g), requires_grad=False)
+                                                for h, w in ((13, 42), (7, 21), (4, 11))])
+
+        def forward(self, x):
+            return [m + 0 * x.sum() for m in self.maps]
+    model.head.extractor = TinyExtractor()
+    return model.cuda()
+
+
+def test_mvxnet_forward_and_train_step_through_the_swapped_model(ref):
+    from mvxnet_makise_b200.dropin import accelerate, hot_parameters
+    torch.backends.cudnn.allow_tf32 = False         # the stock 1x1 Conv2d layers would otherwise run in TF32 (SURVEY.md trap 11)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pts, calib, voxel9, uidx = _frame(ref, 21, 2500)
+    dev = torch.device('cuda')
+    calib_d = {k: v.to(dev) for k, v in calib.items()}                                   # train.py:113-115
+    voxel = torch.Tensor(voxel9[None, :]).to(dev)                                        # train.py:118,125
+    idx = torch.LongTensor(np.concatenate([np.zeros((uidx.shape[0], 1)), uidx], axis=1)).to(dev)   # train.py:119,126
+    img = torch.rand((1, 3, 370, 1224), device=dev)                                      # train.py:120-128
+    imsize = torch.Tensor(ref.cfg.imsize).to(dev)
+    stock = _small_model(ref, 3)
+    fast = accelerate(copy.deepcopy(stock))
+    names = [n for n, _ in stock.named_parameters()]
+    assert [n for n, _ in fast.named_parameters()] == names and set(fast.state_dict()) == set(stock.state_dict())
+
+    # ---- forward: the CML input of both models -------------------------------------------------------------------------
+    seen = {}
+    hooks = [m.backbone.cml.register_forward_pre_hook(lambda mod, inp, k=k: seen.__setitem__(k, inp[0].detach().clone()))
+             for k, m in (('stock', stock), ('fast', fast))]
+    with torch.no_grad():
+        s_stock = stock(voxel.clone(), img, idx, [calib_d], imsize)
+        v_fast = voxel.clone()
+        s_fast = fast(v_fast, img, idx, [calib_d], imsize)
+    for h in hooks:
+        h.remove()
+    assert s_fast[0].shape == s_stock[0].shape == (1, 2, 176, 200) and s_fast[1].shape == s_stock[1].shape == (1, 14, 176, 200)
+    # stock model in fp64 = the rounding-free value of the reference algorithm
+    stock64 = copy.deepcopy(stock).double()
+    ref.cfg.config['dtype'] = torch.float64
+    try:
+        seen64 = {}
+        h = stock64.backbone.cml.register_forward_pre_hook(lambda mod, inp: seen64.__setitem__('g', inp[0].detach().clone()))
+        with torch.no_grad():
+            stock64(voxel.double(), img.double(), idx, [{k: v.double() for k, v in calib_d.items()}], imsize.double())
+        h.remove()
+    finally:
+        ref.cfg.config['dtype'] = torch.float32
+    assert torch.equal(seen['fast'] != 0, seen64['g'] != 0)
+    e64, noise = rel_err(seen['fast'], seen64['g']), rel_err(seen['stock'], seen64['g'])
+    print(f'CML input: swapped model vs stock fp64 {e64:.3e}; stock fp32 vs stock fp64 {noise:.3e}')
+    assert e64 < TOL
+    # the in-place side effect of featureMaping on the caller's voxel tensor (Pipe.py:58-59) is kept
+    v_stock = voxel.clone()
+    with torch.no_grad():
+        stock(v_stock, img, idx, [calib_d], imsize)
+    assert torch.equal(v_fast, v_stock)
+
+    # ---- training step with the SAME upstream gradient: probe instead of CML/RPN ------------------------------------------
+    w = torch.randn((1, 1280, 352, 400), generator=torch.Generator().manual_seed(1)).to(dev) * 1e-3
+    grads = {}
+    for tag, model in (('stock64', stock64), ('stock', stock), ('fast', fast)):
+        model.backbone.cml, model.backbone.rpn = torch.nn.Identity(), _Probe(w)
+        model.zero_grad(set_to_none=True)
+        if tag == 'stock64':
+            ref.cfg.config['dtype'] = torch.float64
+            args = (voxel.double(), img.double(), idx, [{k: v.double() for k, v in calib_d.items()}], imsize.double())
+        else:
+            ref.cfg.config['dtype'] = torch.float32
+            args = (voxel.clone(), img, idx, [calib_d], imsize)
+        try:
+            score, reg = model(*args)                                                    # train.py:131
+            score.backward()                                                             # train.py:161
+        finally:
+            ref.cfg.config['dtype'] = torch.float32
+        grads[tag] = [p.grad.detach().double().cpu().clone() for p in hot_parameters(model)]
+    assert all(g.shape == p.shape for g, p in zip(grads['fast'], hot_parameters(fast)))
+    ours = max(rel_err(a, b) for a, b in zip(grads['fast'], grads['stock64']))
+    noise = max(rel_err(a, b) for a, b in zip(grads['stock'], grads['stock64']))
+    l2 = lambda x, y: (sum(float(((a - b) ** 2).sum()) for a, b in zip(x, y)) / sum(float((b ** 2).sum()) for b in y)) ** 0.5
+    print(f'hot-path gradients vs stock fp64 autograd: swapped max {ours:.3e} / L2 {l2(grads["fast"], grads["stock64"]):.3e}; '
+          f'stock fp32 max {noise:.3e} / L2 {l2(grads["stock"], grads["stock64"]):.3e}')
+    assert ours <= 2 * noise + TOL and l2(grads['fast'], grads['stock64']) <= 2 * l2(grads['stock'], grads['stock64']) + TOL
+
+    # ---- opt.step() (train.py:64,162): AdamW over model.parameters() moves the hot-path parameters, and the next forward sees them
+    opt = torch.optim.AdamW(fast.parameters(), lr=1e-3, eps=ref.cfg.eps)
+    before = [p.detach().clone() for p in hot_parameters(fast)]
+    with torch.no_grad():
+        g0 = fast(voxel.clone(), img, idx, [calib_d], imsize)[0].clone()
+    opt.step()
+    assert all(not torch.equal(a, p) for a, p in zip(before, hot_parameters(fast)))
+    with torch.no_grad():
+        g1 = fast(voxel.clone(), img, idx, [calib_d], imsize)[0]
+    assert not torch.equal(g0, g1), 'the optimiser step did not reach the kernels'
+    # state_dict round trip into a fresh stock model: same names, same shapes
+    fresh = _small_model(ref, 9)
+    fresh.backbone.cml, fresh.backbone.rpn = torch.nn.Identity(), _Probe(w)
+    fresh.load_state_dict(fast.state_dict())
+    with torch.no_grad():
+        g2 = fresh(voxel.clone(), img, idx, [calib_d], imsize)[0]
+    assert rel_err(g1, g2) < 5e-4

@@ -88,3 +88,35 @@ def test_merged_point_sets_with_their_own_calibrations():
     p_one = path2.region('proj', torch.float32, (1, path2.cap + 128, 2))[0, :counts[1, 1]].cpu()
     p_own = path.region('proj', torch.float32, (3, cap + 128, 2))[1, :counts[1, 1]].cpu()
     assert not torch.equal(p_one, p_own)
+
+
+def test_merged_sets_with_float64_calibrations(golden_dir):
+    """GT-paste with the calibration dicts as `readCalib` leaves them (float64 matrices, Load.py:24-41; LoadGT.py:31): the
+    reference projects the scene with torch in fp32 (train.py:31-33) and every pasted set with numpy in fp64 (train.py:36-39),
+    rounds once to fp32 (train.py:125). Golden: the UNMODIFIED lidar2Img (tests/golden/make_golden_crop.py)."""
+    import os
+    from mvxnet_makise_b200.pipeline import PointPath
+    from mvxnet_makise_b200 import modules as M
+    g = np.load(os.path.join(golden_dir, 'crop_a.npz'))
+    c64 = synth.kitti_calib_f64()
+    other = {'P2': g['m_other_P2'], 'R0_rect': g['m_other_R0'], 'Tr_velo_to_cam': g['m_other_Tr']}
+    sets, cals = [g['m_scene'], g['m_p1'], g['m_p2']], [c64, c64, other]
+    # numpy lidar2Img with a float64 dict: float64 result, equal to the reference's
+    uv = M.lidar2Img(g['m_p2'], other, True)
+    assert uv.dtype == np.float64 and np.array_equal(uv, g['m_uv64_p2'])
+    rng = np.random.default_rng(3)
+    maps = [rng.standard_normal((1, 256, h, w), dtype=np.float32) for h, w in [(13, 42), (7, 21), (4, 11)]]
+    sd = synth.make_weights(6)
+    path = PointPath(sd, G)
+    _, counts = path([sets], [cals], [torch.from_numpy(m) for m in maps], want_grid=False)
+    torch.cuda.synchronize()
+    K = int(counts[0, 1])
+    merged = g['m_merged32']                                               # (P,6) fp32 [x y z r row col] as the model sees it
+    rp = path.region('row_point', torch.int32, (1, path.cap))[0, :K].cpu().numpy()
+    proj = path.region('proj', torch.float32, (1, path.cap + 128, 2))[0, :K].cpu().numpy()
+    assert np.array_equal(proj.view(np.uint32), np.ascontiguousarray(merged[rp][:, 4:6]).view(np.uint32)), 'projections differ'
+    with torch.no_grad():
+        ref64 = O.forward_frame(sets, cals, maps, sd, G, synth.KITTI_IMSIZE_HW, dtype=torch.float64, want_grid=False)
+    vfeat, idx = path.voxel_features(0)
+    assert np.array_equal(idx.cpu().numpy()[:, 1:], ref64['idx'].numpy()[:, 1:])
+    assert rel(vfeat.cpu(), ref64['vfeat']) < 1e-4

@@ -67,6 +67,13 @@ def test_crop_matches_reference_golden(mvx, golden_dir, tag):
     assert np.array_equal(both[:, 3].astype(np.int32), g[f'both_{tag}'])
     t = mvx.V.cropTensor(torch.from_numpy(tagged).cuda(), synth.KITTI_VELORANGE)  # torch in -> CUDA tensor out
     assert t.is_cuda and np.array_equal(t.cpu().numpy(), c)
+    # float64 calibration dict (what readCalib returns, Load.py:24-41,73): the reference's numpy branch decides in fp64; the
+    # fixture holds border points where the fp32 and fp64 evaluations disagree
+    c64 = synth.kitti_calib_f64()
+    s64 = mvx.V.cropToSight(tagged, c64, wh)
+    assert np.array_equal(s64[:, 3].astype(np.int32), g[f'sight64_{tag}'])
+    assert np.array_equal(mvx.V.cropFrame(tagged, synth.KITTI_VELORANGE, c64, wh)[:, 3].astype(np.int32), g[f'both64_{tag}'])
+    assert not np.array_equal(g[f'sight64_{tag}'], g[f'sight_{tag}'])
 
 
 def test_crop_batched_ragged_and_feeds_the_path(mvx):
@@ -411,7 +418,7 @@ def test_fp16_operands_survive_extreme_feature_ranges(mvx, scale, fusion_mode):
         from mvxnet_makise_b200.modules import pack_calib
         pd = torch.from_numpy(pts).cuda()
         path.forward_train(pd, [0, pts.shape[0]], pack_calib(calib)[None].cuda(), [torch.from_numpy(m).cuda() for m in maps],
-                           want_grid=False)                      # row-first fcn1 in 3xFP16 (per-row scale from the gather)
+                           want_grid=False, shuffle=False)       # row-first fcn1 in 3xFP16 (per-row scale from the gather)
     else:
         path([pts], [calib], [torch.from_numpy(m) for m in maps], want_grid=False)
     torch.cuda.synchronize()
@@ -589,6 +596,88 @@ def test_host_entry_pipelined_equals_device_entry(mvx, chunk):
     assert torch.equal(grid != 0, grid_ref != 0) and rel_err(grid, grid_ref) < 1e-5
     assert rel_err(head, feats_ref[0][0][:64]) < 1e-5
     assert path.h2d_bytes == (points_h.numel() + calib_h.numel() + sum(m.numel() for m in maps_h)) * 4
+
+
+def test_host_entry_async_steps_and_capacity_buckets(mvx):
+    """forward_host(sync=False): calls are pipelined across steps on two buffer sets; frames whose point counts differ from
+    call to call reuse the same contexts (capacity buckets, no re-allocation); a first sub-batch smaller than `head_rows`
+    is clamped. Every call's host-visible results equal the synchronous device entry on the same inputs."""
+    from mvxnet_makise_b200.modules import pack_calib
+    sd = synth.make_weights(3)
+    calib = synth.kitti_calib()
+    B = 4
+    maps = [torch.from_numpy(m) for m in small_maps(6, B=B)]
+    maps_h = [m.pin_memory() for m in maps]
+    calib_h = torch.stack([pack_calib(calib) for _ in range(B)]).pin_memory()
+    path = mvx.P.PointPath(sd, G)
+    path.host_chunk = 2
+    ref_path = mvx.P.PointPath(sd, G)
+    calls, handles = [], []
+    for s_ in range(5):                                   # 5 calls on 2 slots: every slot is reused at least once
+        frames = [synth.make_points(60 + 7 * s_ + f, 300 + 97 * ((s_ + f) % 4)) for f in range(B)]   # ragged, different every call
+        offsets = np.concatenate([[0], np.cumsum([p.shape[0] for p in frames])]).tolist()
+        pts_h = torch.from_numpy(np.concatenate(frames, 0)).pin_memory()
+        calls.append((frames, offsets, pts_h))
+        handles.append(path.forward_host(pts_h, offsets, calib_h, maps_h, head_rows=1024, sync=False))
+        if s_ == 0:
+            slots = [id(sl) for sl in path._slots]
+        if s_ >= 1:                                       # consume the previous step while this one is in flight
+            frames_p, _, _ = calls[s_ - 1]
+            grid, counts_h, head = handles[s_ - 1].wait()
+            g_ref, c_ref = ref_path(frames_p, [calib] * B, maps)
+            assert torch.equal(counts_h, c_ref.cpu())
+            n0 = int(c_ref[0, 0])
+            vf0, _ = ref_path.voxel_features(0)
+            assert head.shape[0] <= 1024 and rel_err(head[:min(n0, head.shape[0])], vf0[:head.shape[0]]) < 1e-5
+            assert torch.equal(grid != 0, g_ref != 0) and rel_err(grid, g_ref) < 1e-5
+    assert [id(sl) for sl in path._slots] == slots, 'contexts were rebuilt although the capacity bucket did not change'
+    handles[-1].wait()
+
+
+def test_shuffle_option_matches_reference_group_semantics(mvx):
+    """The reference shuffles inside `group` (Preprocessing.py:86): above the T cap the kept points are a random T-subset.
+    shuffle=True permutes every frame on the device first; the result is bit-identical to the path run on the same
+    permutation applied by the caller, the permutation is a per-frame permutation, and voxels above the cap keep a
+    different point subset than the caller-order run (it is on by default in training mode, off in inference)."""
+    from mvxnet_makise_b200.modules import pack_calib
+    sd = synth.make_weights(2)
+    calib = synth.kitti_calib()
+    frames = [synth.make_points(70, 9000), synth.make_points(71, 5000)]
+    frames[0][:600, :3] = frames[0][0, :3]              # one voxel far above the cap of 35
+    offsets = [0, 9000, 14000]
+    pts = torch.from_numpy(np.concatenate(frames, 0)).cuda()
+    c32 = torch.stack([pack_calib(calib)] * 2).cuda()
+    maps = [torch.from_numpy(m).cuda() for m in small_maps(4, B=2)]
+    path = mvx.P.PointPath(sd, G)
+    path.shuffle_generator = torch.Generator(device='cuda').manual_seed(5)
+    _, c_sh = path.forward_device(pts, offsets, c32, maps, want_grid=False, shuffle=True)
+    perm = path.last_perm.clone()
+    assert sorted(perm[:9000].tolist()) == list(range(9000)) and sorted(perm[9000:].tolist()) == list(range(9000, 14000))
+    assert not torch.equal(perm, torch.arange(14000, device='cuda'))
+    feats_sh = [tuple(t.clone() for t in path.voxel_features(f)) for f in range(2)]
+    rp_sh = path.region('row_point', torch.int32, (2, path.cap))[0, :int(c_sh[0, 1])].clone()
+    other = mvx.P.PointPath(sd, G)
+    _, c_pre = other.forward_device(pts[perm].contiguous(), offsets, c32, maps, want_grid=False, shuffle=False)
+    assert other.last_perm is None and torch.equal(c_sh, c_pre)
+    for f in range(2):
+        vf, idx = other.voxel_features(f)
+        assert torch.equal(idx, feats_sh[f][1]) and torch.equal(vf, feats_sh[f][0])
+    # the oracle on the same permutation: same voxel list, same kept points
+    p0 = frames[0][perm[:9000].cpu().numpy()]
+    vid, slot, coords, cnt = O.group_assign(O.cell_index(p0, G.velorange, G.voxelsize), G.T)
+    assert np.array_equal(feats_sh[0][1][:, 1:].cpu().numpy(), coords) and int(c_sh[0, 1]) == int(cnt.sum())
+    # caller order keeps points 0..34 of the crowded voxel; the shuffled run keeps another subset
+    _, c_plain = other.forward_device(pts, offsets, c32, maps, want_grid=False)          # inference default: no shuffle
+    rp_plain = other.region('row_point', torch.int32, (2, other.cap))[0, :int(c_plain[0, 1])]
+    kept_plain = set(rp_plain[rp_plain < 600].tolist())
+    kept_sh = set(perm[:9000][rp_sh.long()][perm[:9000][rp_sh.long()] < 600].tolist())
+    assert kept_plain == set(range(35)) and len(kept_sh) == 35 and kept_sh != kept_plain
+    # training mode shuffles by default
+    tr = mvx.P.PointPath(sd, G)
+    tr.forward_train(pts, offsets, c32, maps, want_grid=False)
+    assert tr.last_perm is not None
+    tr.forward_train(pts, offsets, c32, maps, want_grid=False, shuffle=False)
+    assert tr.last_perm is None
 
 
 def test_fused_path_empty_and_tiny_frames(mvx):

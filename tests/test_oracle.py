@@ -165,3 +165,31 @@ def test_crop_oracle_matches_reference_golden(golden_dir, tag):
     assert np.array_equal(c[:, 3].astype(np.int32), g[f'crop_{tag}'])
     assert np.array_equal(O.crop_to_sight(tagged, calib, wh)[:, 3].astype(np.int32), g[f'sight_{tag}'])
     assert np.array_equal(O.crop_to_sight(c, calib, wh)[:, 3].astype(np.int32), g[f'both_{tag}'])
+    # the dict as readCalib builds it (float64 matrices, Load.py:24-41): the numpy branch decides in fp64, and the fixture holds
+    # border points on which the fp32 and fp64 evaluations disagree
+    c64 = synth.kitti_calib_f64()
+    assert np.array_equal(O.crop_to_sight(tagged, c64, wh)[:, 3].astype(np.int32), g[f'sight64_{tag}'])
+    assert np.array_equal(O.crop_to_sight(c, c64, wh)[:, 3].astype(np.int32), g[f'both64_{tag}'])
+    assert not np.array_equal(g[f'sight64_{tag}'], g[f'sight_{tag}'])
+
+
+def _golden_other_calib(g):
+    return {'P2': g['m_other_P2'], 'R0_rect': g['m_other_R0'], 'Tr_velo_to_cam': g['m_other_Tr']}
+
+
+def test_merged_sets_with_float64_calibrations_match_reference_golden(golden_dir):
+    """train.py:29-42 with readCalib-style float64 dicts: scene through the torch branch (fp32), pasted sets through the numpy
+    branch (fp64), merged, rounded to fp32 by `torch.Tensor(voxel)`. Golden written by the UNMODIFIED lidar2Img."""
+    from mvxnet_makise_b200 import synth
+    g = np.load(os.path.join(golden_dir, 'crop_a.npz'))
+    c64, other = synth.kitti_calib_f64(), _golden_other_calib(g)
+    assert other['P2'].dtype == np.float64
+    ours = O.merged_points_with_proj([g['m_scene'], g['m_p1'], g['m_p2']], [c64, c64, other])
+    assert ours.dtype == np.float64
+    assert np.array_equal(ours.astype(np.float32).view(np.uint32), g['m_merged32'].view(np.uint32))
+    uv = O.lidar2img_numpy(g['m_p2'], other)
+    assert uv.dtype == np.float64 and np.array_equal(uv, g['m_uv64_p2'])
+    # and it matters: the fp32 evaluation of the same sets differs in the last bit for a good part of the points
+    as32 = lambda c: {k: np.asarray(v, dtype=np.float32) for k, v in c.items()}
+    o32 = O.merged_points_with_proj([g['m_scene'], g['m_p1'], g['m_p2']], [as32(c64), as32(c64), as32(other)])
+    assert not np.array_equal(o32.astype(np.float32), g['m_merged32'])

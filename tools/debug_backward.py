@@ -12,7 +12,7 @@ rng = np.random.default_rng(seed)
 maps = [torch.from_numpy(rng.standard_normal((1, 256, h, w), dtype=np.float32)).cuda() for (h, w) in ((13, 42), (7, 21), (4, 11))]
 path = PointPath(sd, G)
 points = torch.from_numpy(pts).cuda(); calib32 = pack_calib(calib)[None].cuda()
-_, counts = path.forward_train(points, [0, P], calib32, maps, want_grid=False)
+_, counts = path.forward_train(points, [0, P], calib32, maps, want_grid=False, shuffle=False)
 N, K = int(counts[0, 0]), int(counts[0, 1]); cap = path.cap; capA, capB = cap + 128, 2 * cap; T = G.T
 dv = torch.zeros((1, cap, 128), device='cuda'); dv[0, :N] = torch.randn(N, 128, device='cuda')
 flat = path.backward(d_vfeat=dv); torch.cuda.synchronize()
