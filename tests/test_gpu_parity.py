@@ -661,7 +661,7 @@ def test_shuffle_option_matches_reference_group_semantics(mvx):
     assert other.last_perm is None and torch.equal(c_sh, c_pre)
     for f in range(2):
         vf, idx = other.voxel_features(f)
-        assert torch.equal(idx, feats_sh[f][1]) and torch.equal(vf, feats_sh[f][0])
+        assert torch.equal(idx, feats_sh[f][1]) and rel_err(vf, feats_sh[f][0]) < 1e-5   # accumulation order (atomics) is the only difference
     # the oracle on the same permutation: same voxel list, same kept points
     p0 = frames[0][perm[:9000].cpu().numpy()]
     vid, slot, coords, cnt = O.group_assign(O.cell_index(p0, G.velorange, G.voxelsize), G.T)
