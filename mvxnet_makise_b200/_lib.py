@@ -157,7 +157,9 @@ def set_gemm_mode(mode: int):
     2 = tcgen05 3xTF32 layers, persistent variant with overlapped register epilogue (experimental), (3 = CTA-pair kernel: removed)
     (experimental), 4 = 3xTF32 operands everywhere (mode 1 uses fp16 hi/lo operands for BatchNorm-ed / row-scaled inputs),
     5 = like 1 and the dense layer API also uses fp16 operands (inputs must be O(1)), 6 = bf16 mode (single-pass bf16
-    operands for the layers mode 1 runs in 3xFP16; reduced precision)."""
+    operands for the layers mode 1 runs in 3xFP16; reduced precision), 7 = persistent 3xFP16 register-producer kernel (experimental),
+    8 = 1 (conv1 / fcn2 / last FCN in the TMA-fed A-from-TMEM persistent kernel, tc3_layer.cu: the default), 9 = like 1 with the
+    one-tile kernel of round 1 for those layers (A/B timing)."""
     check(lib.mvx_set_gemm_mode(int(mode)), 'set_gemm_mode')
 
 

@@ -69,6 +69,10 @@ int launch_layer_tc(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
 size_t tc_fold_set_bytes(int Cin, int Cout);
 int launch_fold_pack_weights(const float *Wt, const float *bias, const double *in_stats, const int *counts, int T, double eps,
                              int Cin, int Cout, int B, void *blob_sets, float *bias_sets, cudaStream_t st);
+// TMA-fed persistent kernel with the A operand in tensor memory (tc3_layer.cu): BatchNorm-ed 128-column layers of the fused path
+bool tc3_layer_eligible(const LayerArgs &a);
+int launch_layer_tc3(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
+void set_tc3(int on);
 bool tc_persistent_enabled();
 bool tc_f16_enabled();
 bool tc_bf16_enabled();

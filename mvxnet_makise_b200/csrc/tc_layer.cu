@@ -1323,6 +1323,16 @@ int launch_tc_persist16(const LayerArgs &a, int F, float *wpack, cudaStream_t st
 
 }  // namespace
 
+int pack_weights_f16_128(const float *Wt, int Cin, int Cout, void *wpack, cudaStream_t st) {
+    uint8_t *blob = static_cast<uint8_t *>(wpack);
+    pack_weights_f16_kernel<128, false><<<Cout, 256, 0, st>>>(Wt, Cin, Cout, blob, reinterpret_cast<float *>(blob + (size_t)Cin * Cout * 4));
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+static int g_tc3 = 1;           // conv1 / fcn2 / last FCN through the TMA-fed, A-from-TMEM persistent kernel (tc3_layer.cu): default since r4
+                                // (conv1 0.79 -> 0.68 ms, fcn2 0.32 -> 0.21, FCN 0.47 -> 0.39); mvx_set_gemm_mode(9) = mode 1 with the one-tile kernel
+void set_tc3(int on) { g_tc3 = on; }
 static int g_tc_two = 0;        // MVX_TC_TWO=1: 128-column 16-bit layers run as two CTAs per SM (measured slower for conv1/fcn2: 0.99 vs 0.86 ms, 0.42 vs 0.35 ms;
                                 // 1-deep prefetch and a 2-stage ring cost more than the overlapped epilogue gains) - experimental
 static int g_apk_two = 1;       // pre-packed-A layers (the pixel GEMM) run as two CTAs per SM: 0.593 -> 0.552 ms (MVX_APK_TWO=0: one 256-column CTA)
@@ -1395,6 +1405,7 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
         if (g_apk_two) return launch_tc<128, true, false, true, true>(a, F, wpack, st);
         return launch_tc<256, true, false, false, true>(a, F, wpack, st);
     }
+    if (g_tc3 && tc_f16_enabled() && tc3_layer_eligible(a)) return launch_layer_tc3(a, F, wpack, st);
     if (g_persist16 && a.f16_ok && tc_f16_enabled() && a.Cin % 32 == 0 && a.Cout == 128 && !a.vmax && !a.X2 && !a.plain && a.in_stats &&
         !a.row_max && a.rows_mode != 3 && !a.in_C)
         return launch_tc_persist16(a, F, wpack, st);   // conv1, fcn2: persistent kernel, epilogue overlapped with the next tile

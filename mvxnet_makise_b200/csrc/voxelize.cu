@@ -197,6 +197,12 @@ __global__ void __launch_bounds__(256) vox_fill_segments_kernel(VoxParams p) {
     p.seg_vid[(size_t)f * p.cap + q] = v;
 }
 
+// A voxel with more points than this is ranked by vox_rank_big_kernel (selection of the T smallest point indices by a CTA)
+// instead of the per-point counting loop below, whose cost is quadratic in the points of a voxel: a parked sensor facing a
+// wall (or an adversarial input) can put a whole sweep into one voxel - 120 000^2 compares would stall the frame for seconds.
+constexpr int kRankDirect = 256;
+constexpr int kBigCtas = 32;    // CTAs per frame that look for crowded voxels
+
 // ---- K3c: canonical slot = rank of the point index inside its voxel; keep the first T ---------------
 __global__ void __launch_bounds__(256) vox_rank_emit_kernel(VoxParams p) {
     const int f = blockIdx.y;
@@ -209,12 +215,87 @@ __global__ void __launch_bounds__(256) vox_rank_emit_kernel(VoxParams p) {
     const int v = p.seg_vid[(size_t)f * p.cap + q];
     const int start = p.seg_off[(size_t)f * (p.cap + 1) + v];
     const int n = p.vox_total[(size_t)f * p.cap + v];
+    if (n > kRankDirect) return;   // crowded voxel: vox_rank_big_kernel
     int rank = 0;
     for (int j = 0; j < n; ++j) rank += seg[start + j] < i ? 1 : 0;
     if (rank < p.T) {
         const int row = p.out.vox_row0[(size_t)f * (p.cap + 1) + v] + rank;
         p.out.row_point[(size_t)f * p.cap + row] = i;
         p.out.row_vox[(size_t)f * p.cap + row] = v;
+    }
+}
+
+// ---- K3d: crowded voxels (more than kRankDirect points): the T smallest point indices by bisection on the index value.
+// CTA c of a frame takes the crowded voxels v with v % kBigCtas == c; per voxel ~17 counting passes over its segment
+// (n loads each, 1024 threads) find the T-th smallest index, one more pass collects the T kept points, ranked among
+// themselves. Linear in the points of the voxel; ordinary frames have no such voxel and the CTAs exit after one scan of
+// the per-voxel totals.
+__global__ void __launch_bounds__(1024) vox_rank_big_kernel(VoxParams p) {
+    __shared__ int s_cnt, s_nbig;
+    __shared__ int s_keep[1024];
+    __shared__ int s_big[64];        // crowded voxels found in the current scan window
+    const int f = blockIdx.y, tid = threadIdx.x;
+    if (p.counts[f * 4 + 3] <= kRankDirect) return;   // no crowded voxel in this frame (max points per voxel, from K3a)
+    const int N = p.counts[f * 4 + 0];
+    const int P = p.fo.off[f + 1] - p.fo.off[f];
+    const int *seg_all = p.seg_pts + (size_t)f * p.cap;
+    const int T = p.T;   // <= 1024 (checked by vox_run)
+    // CTA c scans the voxel windows c, c + kBigCtas, ... of 1024 voxels each, one voxel per thread
+    for (int base = blockIdx.x * 1024; base < N; base += kBigCtas * 1024) {
+        if (tid == 0) s_nbig = 0;
+        __syncthreads();
+        const int vv = base + tid;
+        bool mine = vv < N && p.vox_total[(size_t)f * p.cap + vv] > kRankDirect;
+        while (true) {   // at most 64 crowded voxels per round (a window holds at most cap / 256 = a few hundred)
+            if (mine) {
+                const int k = atomicAdd(&s_nbig, 1);
+                if (k < 64) s_big[k] = vv, mine = false;
+            }
+            __syncthreads();
+            const int nbig = min(s_nbig, 64);
+            for (int b = 0; b < nbig; ++b) {
+                const int v = s_big[b];
+                const int n = p.vox_total[(size_t)f * p.cap + v];
+                const int *seg = seg_all + p.seg_off[(size_t)f * (p.cap + 1) + v];
+                // smallest x with #{idx <= x} >= T  (indices are distinct, so exactly min(n, T) of them are <= x)
+                int lo = 0, hi = P - 1;
+                while (lo < hi) {
+                    const int mid = lo + ((hi - lo) >> 1);
+                    if (tid == 0) s_cnt = 0;
+                    __syncthreads();
+                    int c = 0;
+                    for (int j = tid; j < n; j += 1024) c += seg[j] <= mid ? 1 : 0;
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if ((tid & 31) == 0 && c) atomicAdd(&s_cnt, c);
+                    __syncthreads();
+                    const int total = s_cnt;
+                    __syncthreads();
+                    if (total >= T) hi = mid; else lo = mid + 1;
+                }
+                if (tid == 0) s_cnt = 0;
+                __syncthreads();
+                for (int j = tid; j < n; j += 1024) {
+                    const int i = seg[j];
+                    if (i <= lo) s_keep[atomicAdd(&s_cnt, 1)] = i;
+                }
+                __syncthreads();
+                const int kept = s_cnt;   // min(n, T)
+                if (tid < kept) {
+                    const int i = s_keep[tid];
+                    int rank = 0;
+                    for (int j = 0; j < kept; ++j) rank += s_keep[j] < i ? 1 : 0;
+                    const int row = p.out.vox_row0[(size_t)f * (p.cap + 1) + v] + rank;
+                    p.out.row_point[(size_t)f * p.cap + row] = i;
+                    p.out.row_vox[(size_t)f * p.cap + row] = v;
+                }
+                __syncthreads();
+            }
+            const int found = s_nbig;
+            __syncthreads();
+            if (found <= 64) break;
+            if (tid == 0) s_nbig = 0;   // more than 64 in this window: another round for the ones that did not get a slot
+            __syncthreads();
+        }
     }
 }
 
@@ -328,7 +409,7 @@ int vox_run(const mvx_grid_t *grid, int B, int cap, const float *points, int poi
     MVX_REQUIRE(out && out->counts && out->vox_coord && out->vox_cnt && out->vox_row0 && out->row_point && out->row_vox,
                 MVX_EINVAL, "null output pointer");
     MVX_REQUIRE(!out->cell2vid || grid, MVX_EINVAL, "cell2vid needs a grid");
-    MVX_REQUIRE(T >= 1, MVX_EINVAL, "T must be >= 1");
+    MVX_REQUIRE(T >= 1 && T <= 1024, MVX_EINVAL, "T must be in [1, 1024]");
     VoxLayout L = vox_layout(B, cap);
     MVX_REQUIRE(workspace && workspace_bytes >= L.total, MVX_ESPACE, "voxelize workspace too small");
 
@@ -388,6 +469,10 @@ int vox_run(const mvx_grid_t *grid, int B, int cap, const float *points, int poi
     MVX_LAUNCH_CHECK();
     vox_rank_emit_kernel<<<g256, 256, 0, st>>>(p);
     MVX_LAUNCH_CHECK();
+    if (maxP > kRankDirect) {   // a voxel can only be crowded if the frame has that many points
+        vox_rank_big_kernel<<<dim3(kBigCtas, B), 1024, 0, st>>>(p);
+        MVX_LAUNCH_CHECK();
+    }
     return MVX_OK;
 }
 

@@ -276,6 +276,21 @@ def reindex(x: torch.Tensor, idx: torch.Tensor, voxelshape) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- after the path: CML.conv1
+def crb3d(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, stride, padding, eps: float = 1e-6) -> torch.Tensor:
+    """`CRB3d(cin, cout, k, s, p).forward` - modules/layers/Blocks.py:20-29: bn(relu(Conv3d(x))), BatchNorm3d(affine=False,
+    track_running_stats=False) i.e. batch statistics, biased variance. Pinned on the reference's own CML by tests/golden/cml_a.npz."""
+    y = F.relu(F.conv3d(x, w, b, stride=stride, padding=padding))
+    return F.batch_norm(y, None, None, None, None, True, 0.0, eps)
+
+
+def cml(grid: torch.Tensor, ws, bs, eps: float = 1e-6):
+    """`CML.forward` - modules/voxelnet/Pipe.py:31-43: conv1 (2,1,1)/(1,1,1), conv2 1/(0,1,1), conv3 (2,1,1)/1. Returns all three outputs."""
+    y1 = crb3d(grid, ws[0], bs[0], (2, 1, 1), (1, 1, 1), eps)
+    y2 = crb3d(y1, ws[1], bs[1], 1, (0, 1, 1), eps)
+    y3 = crb3d(y2, ws[2], bs[2], (2, 1, 1), 1, eps)
+    return y1, y2, y3
+
+
 def cml_conv1(grid: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     """`CML.conv1` = CRB3d(128, 64, 3, (2,1,1), (1,1,1)) — modules/voxelnet/Pipe.py:31-43; CRB3d (modules/layers/Blocks.py):
     bn(relu(Conv3d(x))) with BatchNorm3d(affine=False, track_running_stats=False) i.e. batch statistics, biased variance.

@@ -149,6 +149,41 @@ def test_group_edge_cases(mvx):
         mvx.V.cpp._group(np.zeros((4,), np.float32), np.zeros((4, 3), np.int32), T)
 
 
+def test_voxelize_whole_sweep_in_one_voxel(mvx):
+    """Adversarial density: 120 000 points in ONE voxel (plus a few crowded and ordinary ones). The per-point rank loop would
+    need 1.4e10 compares; crowded voxels are ranked by a CTA-wide selection of the T smallest point indices instead.
+    Bit-exact against the C oracle, and fast (bounded below)."""
+    import time
+    T = 35
+    rng = np.random.default_rng(3)
+    P = 120_000
+    pts = np.empty((P, 4), np.float32)
+    pts[:, 0] = rng.uniform(10.0, 10.19, P)          # all inside cell (50, 200, 5) of the 0.2 x 0.2 x 0.4 grid
+    pts[:, 1] = rng.uniform(0.0, 0.19, P)
+    pts[:, 2] = rng.uniform(-1.0, -0.61, P)
+    pts[:, 3] = rng.uniform(0, 1, P)
+    idx_mid = rng.choice(P, 3000, replace=False)     # three voxels with ~300 / ~700 / ~2000 points, and 200 ordinary points
+    pts[idx_mid[:300], 0] += 1.0
+    pts[idx_mid[300:1000], 1] += 2.0
+    pts[idx_mid[1000:], 2] += 0.8
+    pts[rng.choice(P, 200, replace=False), :3] = synth.make_points(8, 200)[:, :3]
+    idx = O.cell_index(pts, G.velorange, G.voxelsize)
+    v_ref, (x_ref, y_ref, z_ref), cnt_ref = O.cpp_group(pts, idx, T)
+    mvx.V.cpp._group(pts[:1000], idx[:1000], T)      # warm-up (context, allocations)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    vox7, (x, y, z), cnt = mvx.V.cpp._group(pts, idx, T)
+    dt = time.perf_counter() - t0
+    assert np.array_equal(vox7, v_ref) and np.array_equal(cnt, cnt_ref)
+    assert np.array_equal(np.stack([x, y, z], 1), np.stack([x_ref, y_ref, z_ref], 1))
+    assert int(cnt.max()) == T and dt < 0.5, f'crowded-voxel frame took {dt:.3f} s'
+    # and through the fused path's voxelizer (raw points, fp64 index math on the GPU)
+    from mvxnet_makise_b200 import _lib
+    vb = mvx.V.voxelize(torch.from_numpy(pts).cuda(), [0, P], T, grid=_lib.make_grid(G.velorange, G.voxelsize, G.voxelshape, T))
+    c = vb.counts[0].cpu().numpy()
+    assert c[0] == cnt_ref.shape[0] and c[1] == cnt_ref.sum() and c[3] >= 100_000
+
+
 def test_cell_index_boundary_floats(mvx):
     """fp64 subtract + TRUE division + truncation on fp32 neighbours of every cell boundary (trap 1)."""
     r, s = G.velorange, G.voxelsize
@@ -505,6 +540,53 @@ def test_persistent_fp16_layer_kernel(mvx, golden_dir):
                                  want_grid=False)
     assert rel_err(vf, ref64['vfeat']) < TOL and rel_err(vf1, ref64b['vfeat']) < TOL
     assert int(counts[2, 0]) == 0
+
+
+def test_tma_fed_tmem_operand_layer_kernel(mvx, golden_dir):
+    """Default mode (1 = 8): conv1, fcn2 and the last FCN through the persistent TMA-fed kernel (tc3_layer.cu): raw fp32 tiles
+    by tensor copy, converter warps, A operand in tensor memory, double-buffered accumulators, tensor-store epilogue. Same
+    3xFP16 arithmetic as the one-tile kernel: raw activations and BatchNorm sums agree with it to fp32 accumulation-order
+    level, the voxel features meet the fp32 bar against the fp64 oracle; ragged batch with an empty frame, multi-tile frames."""
+    from mvxnet_makise_b200 import _lib
+    g = np.load(os.path.join(golden_dir, 'path_a.npz'))
+    maps = small_maps(int(g['map_seed']))
+    sd = synth.make_weights(int(g['weight_seed']))
+    calib = synth.kitti_calib()
+    frames = [g['pcd4'], synth.make_points(93, 5000), np.zeros((0, 4), np.float32), synth.make_points(94, 777)]
+    fm = [torch.from_numpy(np.concatenate([m, small_maps(31)[l], small_maps(32)[l], small_maps(33)[l]], 0)) for l, m in enumerate(maps)]
+    _lib.set_gemm_mode(9)                 # the one-tile kernel of tc_layer.cu as the comparison
+    base = mvx.P.PointPath(sd, G)
+    _, c0 = base(frames, [calib] * 4, fm, want_grid=False)
+    _lib.set_gemm_mode(1)
+    cap = base.cap
+    keep = {n: base.region(n, torch.float32, (4, cap + 128, 128)).clone() for n in ('Y2', 'Y3')}
+    st0 = base.region('stats', torch.float64, (8, 4 * 768 * 2)).clone()     # [layer][frame stride = 2 * Cout of the layer]
+    vf0 = [base.voxel_features(f)[0].clone() for f in range(4)]
+    try:
+        _lib.set_gemm_mode(8)
+        path = mvx.P.PointPath(sd, G)
+        _, counts = path(frames, [calib] * 4, fm, want_grid=False)
+        torch.cuda.synchronize()
+        assert torch.equal(counts, c0)
+        for f in (0, 1, 3):
+            K = int(counts[f, 1])
+            for n in ('Y2', 'Y3'):       # raw outputs of conv1 / fcn2 (rows 0..K: the kept points + the weighted pad row)
+                got = path.region(n, torch.float32, (4, cap + 128, 128))[f, :K + 1]
+                assert rel_err(got, keep[n][f, :K + 1]) < 2e-5, (f, n)
+            assert rel_err(path.voxel_features(f)[0], vf0[f]) < 2e-5
+        st = path.region('stats', torch.float64, (8, 4 * 768 * 2))
+        for layer, cout in ((1, 128), (2, 128), (7, 128)):
+            for f in (0, 1, 3):
+                assert rel_err(st[layer, 2 * cout * f:2 * cout * (f + 1)], st0[layer, 2 * cout * f:2 * cout * (f + 1)]) < 1e-5, (layer, f)
+        vf, _ = path.voxel_features(0)
+        vf1, _ = path.voxel_features(1)
+    finally:
+        _lib.set_gemm_mode(1)
+    with torch.no_grad():
+        ref64 = O.forward_frame(g['pcd4'], calib, maps, sd, G, synth.KITTI_IMSIZE_HW, dtype=torch.float64, want_grid=False)
+        ref64b = O.forward_frame(frames[1], calib, [m[1:2].numpy() for m in fm], sd, G, synth.KITTI_IMSIZE_HW, dtype=torch.float64,
+                                 want_grid=False)
+    assert rel_err(vf, ref64['vfeat']) < TOL and rel_err(vf1, ref64b['vfeat']) < TOL
 
 
 BF16_TOL = 8e-2

@@ -193,3 +193,27 @@ def test_merged_sets_with_float64_calibrations_match_reference_golden(golden_dir
     as32 = lambda c: {k: np.asarray(v, dtype=np.float32) for k, v in c.items()}
     o32 = O.merged_points_with_proj([g['m_scene'], g['m_p1'], g['m_p2']], [as32(c64), as32(c64), as32(other)])
     assert not np.array_equal(o32.astype(np.float32), g['m_merged32'])
+
+
+def test_cml_oracle_matches_reference_golden(golden_dir):
+    """The checker of the sparse hand-off (csrc/sparse_conv.cu) - `O.cml_conv1` / `O.crb3d` - against the UNMODIFIED reference's
+    `CML` (voxelnet/Pipe.py:31-43, CRB3d of layers/Blocks.py:20-29) run on a small sparse grid (tests/golden/make_golden_cml.py)."""
+    g = np.load(os.path.join(golden_dir, 'cml_a.npz'))
+    nz, nx, ny = (int(v) for v in g['shape'])
+    grid = torch.zeros((1, 128, nz, nx, ny))
+    iz, rem = np.divmod(g['cells'], nx * ny)
+    ix, iy = np.divmod(rem, ny)
+    grid[0, :, iz, ix, iy] = torch.from_numpy(g['feats']).T
+    ws = [torch.from_numpy(g[f'w{i}']) for i in (1, 2, 3)]
+    bs = [torch.from_numpy(g[f'b{i}']) for i in (1, 2, 3)]
+    with torch.no_grad():
+        y1 = O.cml_conv1(grid, ws[0], bs[0])
+        ys = O.cml(grid, ws, bs)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert tuple(y1.shape) == tuple(g['y1'].shape) and rel(y1, torch.from_numpy(g['y1'])) < 1e-6
+    for y, k in zip(ys, ('y1', 'y2', 'y3')):
+        assert tuple(y.shape) == tuple(g[k].shape) and rel(y, torch.from_numpy(g[k])) < 1e-5, k
+    # the fp64 evaluation the GPU test compares against stays within fp32 rounding of the reference's own fp32 run
+    with torch.no_grad():
+        y1_64 = O.cml_conv1(grid.double(), ws[0].double(), bs[0].double())
+    assert rel(y1_64, torch.from_numpy(g['y1']).double()) < 1e-4

@@ -27,4 +27,4 @@ seg = np.zeros(_lib.NUM_SEGMENTS); buf = (_lib.c_float * _lib.NUM_SEGMENTS)()
 for c in range(steps):
     _lib.check(_lib.lib.mvx_timing_read(c, buf), 'tr'); seg += np.array(buf[:]) / steps
 names = [(_lib.lib.mvx_timing_segment_name(i) or b'').decode() for i in range(_lib.NUM_SEGMENTS)]
-print(f'mode={mode} dbg={os.environ.get("MVX_DBG","0")} total={seg.sum():.3f} ms', {n: round(float(v), 3) for n, v in zip(names, seg) if n and v > 0.2})
+print(f'mode={mode} total={seg.sum():.3f} ms', {n: round(float(v), 3) for n, v in zip(names, seg) if n and v > 0.04})
