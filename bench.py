@@ -390,6 +390,28 @@ def run_ours(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     assert checksum == args.steps * int(counts[:, 0].sum()), 'e2e leg: host-visible voxel counts differ from the device leg'
+    # context leg: the reference's own data flow - the FPN maps are produced ON the GPU by the frozen backbone (Head.py:14-22) and
+    # never cross PCIe; only the raw points and the calibration do (train.py:125-128 ships the voxel tensor instead)
+    for _ in range(3):
+        path.forward_host(points_h, offsets, calib_h, maps_d)
+    barrier()
+    e0.record()
+    prev = None
+    for _ in range(args.steps):
+        step_h = path.forward_host(points_h, offsets, calib_h, maps_d, sync=False)
+        if prev is not None:
+            prev.wait()
+        prev = step_h
+    prev.wait()
+    e1.record()
+    barrier()
+    ms_e2e_res = e0.elapsed_time(e1)
+    h2d_res = int(path.h2d_bytes)
+    if world > 1:
+        t = torch.tensor([ms_e2e_res], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e_res = float(t.item())
+    path.forward_host(points_h, offsets, calib_h, maps_h)      # back to the host-maps contexts (h2d_bytes of the headline leg)
     if world > 1:
         t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -443,6 +465,8 @@ def run_ours(args):
                 e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=int(path.h2d_bytes),
                          d2h_bytes_per_step=int(path.d2h_bytes), ms_per_step=ms_e2e / args.steps,
                          note=f'PointPath.forward_host(sync=False): pinned-host points+calib+FPN maps -> H2D -> fused path -> D2H counts + feature head, every step; sub-batches of {args.host_chunk} frame(s) (H2D of sub-batch j+1 overlaps the kernels of sub-batch j) and two buffer sets (the copies of step s+1 overlap the kernels of step s); the host waits for the result of step s-1 before it submits step s+1. The FPN maps (376 of the 391 MB) are shipped from the host although the reference produces them on the GPU: the conservative reading of "host inputs"'),
+                e2e_maps_resident=dict(value=world * B * args.steps / (ms_e2e_res * 1e-3), unit='frames/s', h2d_bytes_per_step=h2d_res, ms_per_step=ms_e2e_res / args.steps,
+                                       note='context, not the headline: the same host entry with the FPN maps already on the GPU, where the reference produces them (Head.py:14-22); only points + calibration cross PCIe'),
                 gpu_launches=int(launches), roofline=roofline, stages_ms=stages, stage_rooflines=per_stage,
                 stages_note=f'per-stage CUDA events from a separate pass of {n_stage} steps with the map branch serialised (fusion mode 2, {ms_serial:.3f} ms/step); the timed region runs it on a side stream concurrently with the point branch')
     if world == 1 and not args.no_cpu_baseline and not dense:

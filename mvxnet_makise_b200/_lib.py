@@ -14,7 +14,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_siz
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, 'libmvx_b200.so')
+LIB_PATH = os.environ.get('MVX_B200_LIB') or os.path.join(_PKG, 'libmvx_b200.so')   # the override serves A/B builds in tools/; bench.py refuses MVX_* variables
 
 NUM_LAYERS = 8
 NUM_LEVELS = 3

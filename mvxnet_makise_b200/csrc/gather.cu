@@ -2,6 +2,8 @@
 // (modules/imhead/Pipe.py:23-82).  The FPN maps are re-laid out channels-last once per call so that every
 // corner read is a contiguous, coalesced run of channels (NCHW would cost one 32-byte sector per channel).
 #include "gather.cuh"
+
+#include <cuda_bf16.h>
 #include "project.cuh"
 
 #include <climits>
@@ -393,8 +395,22 @@ struct CombRec {
     float w[4];      // w00, w10, w01, w11 (0 where the corner lies on the zero pad row/column of Pipe.py:47-48)
 };
 
-template <bool PACK>
-__global__ void __launch_bounds__(kCombWarps * 32) combine_rows_kernel(CombineArgs a) {
+#ifndef MVX_COMB_MINB
+#define MVX_COMB_MINB 3
+#endif
+__device__ __forceinline__ float4 bf16x4_to_f4(uint2 v) {   // exact: bf16 is the top half of an fp32
+    return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xFFFF0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ uint2 f4_to_bf16x4(float4 v) {
+    uint2 r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(v.w), "f"(v.z));
+    return r;
+}
+
+// ZB / YB: Z is read / Y1 is written as bf16 (the reduced-precision mode; the arithmetic in between stays fp32)
+template <bool PACK, bool ZB = false, bool YB = false>
+__global__ void __launch_bounds__(kCombWarps * 32, MVX_COMB_MINB) combine_rows_kernel(CombineArgs a) {
     __shared__ int s_row[kCombRows];                     // compact row; ~row for rows without corners
     __shared__ float s_w[kCombRows];                     // BatchNorm multiplicity
     __shared__ float s_sc[PACK ? kCombRows : 1];         // PACK: power-of-two scale of the row
@@ -472,11 +488,20 @@ __global__ void __launch_bounds__(kCombWarps * 32) combine_rows_kernel(CombineAr
                     tag[l] = cell;
                     const int W = a.w[l];
                     const int x0 = cell & 0xFFF, y0 = (cell >> 12) & 0xFFF, dx = (cell >> 24) & 1, dy = (cell >> 25) & 1;
-                    const float *b00 = a.Z[l] + (size_t)f * a.frame_stride[l] + ((size_t)y0 * W + x0) * kCombCout + col0;
+                    const size_t e00 = (size_t)f * a.frame_stride[l] + ((size_t)y0 * W + x0) * kCombCout + col0;   // element index
+                    if constexpr (ZB) {
+                        const __nv_bfloat16 *b00 = reinterpret_cast<const __nv_bfloat16 *>(a.Z[l]) + e00;
+                        v00[l] = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2 *>(b00)));
+                        v10[l] = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2 *>(b00 + (size_t)dy * W * kCombCout)));
+                        v01[l] = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2 *>(b00 + (size_t)dx * kCombCout)));
+                        v11[l] = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2 *>(b00 + ((size_t)dy * W + dx) * kCombCout)));
+                    } else {
+                    const float *b00 = a.Z[l] + e00;
                     v00[l] = __ldg(reinterpret_cast<const float4 *>(b00));
                     v10[l] = __ldg(reinterpret_cast<const float4 *>(b00 + (size_t)dy * W * kCombCout));
                     v01[l] = __ldg(reinterpret_cast<const float4 *>(b00 + (size_t)dx * kCombCout));
                     v11[l] = __ldg(reinterpret_cast<const float4 *>(b00 + ((size_t)dy * W + dx) * kCombCout));
+                    }
                 }
 #define MVX_COMB(e) acc.e = fmaf(v11[l].e, rw.w, fmaf(v01[l].e, rw.z, fmaf(v10[l].e, rw.y, fmaf(v00[l].e, rw.x, acc.e))));
                 MVX_COMB(x) MVX_COMB(y) MVX_COMB(z) MVX_COMB(w)
@@ -496,6 +521,11 @@ __global__ void __launch_bounds__(kCombWarps * 32) combine_rows_kernel(CombineAr
                                  ((c16 ^ ((rr >> 1) & 3u)) << 4) + (((uint32_t)col0 >> 2) & 1u) * 8u;
             *reinterpret_cast<uint2 *>(dst) = hi;
             *reinterpret_cast<uint2 *>(dst + 16384) = lo;
+        } else if constexpr (YB) {
+            // the statistics below are those of the values conv1 will actually read: the bf16-rounded ones
+            const uint2 yb = f4_to_bf16x4(y);
+            *reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(a.Y1) + ((size_t)f * a.capA + r) * kCombCout + col0) = yb;
+            y = bf16x4_to_f4(yb);
         } else {
             *reinterpret_cast<float4 *>(a.Y1 + ((size_t)f * a.capA + r) * kCombCout + col0) = y;
         }
@@ -547,6 +577,9 @@ int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st) {
     if (a.y1pack) {
         MVX_REQUIRE(a.y1_rowinv && a.wbound && a.pack_tiles * 256 >= a.capA, MVX_EINVAL, "combine: bad packed-output arguments");
         combine_rows_kernel<true><<<grid, kCombWarps * 32, 0, st>>>(a);
+    } else if (a.z_bf16 || a.y1_bf16) {
+        MVX_REQUIRE(a.z_bf16 && a.y1_bf16, MVX_EINVAL, "combine: the bf16 mode stores both Z and Y1 as bf16");
+        combine_rows_kernel<false, true, true><<<grid, kCombWarps * 32, 0, st>>>(a);
     } else
     combine_rows_kernel<false><<<grid, kCombWarps * 32, 0, st>>>(a);
     MVX_LAUNCH_CHECK();

@@ -74,6 +74,8 @@ struct CombineArgs {
     int pack_tiles;
     const float *pix_bound[MVX_NUM_LEVELS];   // [B][HW_l]: power-of-two upper bound of max |F| of every pixel (the pixel GEMM's inverse row scale)
     const float *wbound;    // device [4]: max_o sum_c |W1[o][256 l + c]| for l = 0, 1, 2 and max |bias|
+    // bf16 mode (mvx_set_gemm_mode(6)): Z and / or Y1 hold bf16 elements (same indexing in elements, half the bytes)
+    int z_bf16, y1_bf16;
 };
 // wbound (device [4], see above) from W1^T (768, 768) and the bias
 int launch_fcn1_bounds(const float *w1t, const float *bias, float *wbound, cudaStream_t st);

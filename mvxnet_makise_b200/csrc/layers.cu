@@ -493,7 +493,7 @@ extern "C" int mvx_set_gemm_mode(int32_t mode) {
     mvx::g_gemm_mode = mode == 0 ? 0 : 1;          //     MMAs at N=128 saturate shared-memory bandwidth); kept for experiments
     mvx::set_tc_persistent(mode == 2);
     mvx::set_tc_persist16(mode == 7);
-    mvx::set_tc3(mode == 1 || mode == 8);
+    mvx::set_tc3(mode == 1 || mode == 8 || mode == 6);
     return MVX_OK;
 }
 

@@ -47,6 +47,8 @@ struct LayerArgs {
     const int *cat_row_vox;  // [F][cat_rowv_cap] voxel of the rows below K_f
     int cat_rowv_cap;
     int in_C;                // channels of in_stats (0: Cin)
+    int y_bf16;              // 1 (bf16 mode): Y holds bf16 elements (ldy in elements)
+    int x_bf16;              // 1 (bf16 mode, tc3 kernel): X holds bf16 elements (ldx in elements)
     int plain;               // 1: Y = norm_in(X) W^T only (no bias, no ReLU, no statistics, no max) - the per-pixel half of fcn1
 };
 // Work-skipping switches (no epilogue, no producers ...) exist for timing experiments only: a release build compiles them

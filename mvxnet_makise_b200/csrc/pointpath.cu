@@ -242,6 +242,12 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     // pixel-first with 3xFP16: the maps are written directly as the pre-packed A operand of the pixel GEMM (no NHWC copy)
     const bool apack = pixel_first && tc_f16_enabled() && !tc_bf16_enabled() && g_apack;
     const bool fold = apack && g_fold;
+    // bf16 mode (mvx_set_gemm_mode(6)): the two largest intermediates - the per-pixel products Z and the raw fcn1 rows Y1 - are
+    // stored as bf16 (half the bytes written and read back); every sum in between stays fp32
+    const bool bf16_mem = pixel_first && tc_bf16_enabled();
+    auto z_at = [&](size_t elem_off) -> float * {   // element offset into Z, whatever its element size
+        return bf16_mem ? reinterpret_cast<float *>(reinterpret_cast<uint16_t *>(ws + L.off[R_Z]) + elem_off) : F32(R_Z) + elem_off;
+    };
     auto map_branch = [&](MapSet &m) -> int {
         stamp.begin(S_NHWC, ms);
         size_t rowmax_off = 0;
@@ -273,7 +279,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
             LayerArgs la{};
             la.X = m.nhwc[l], la.ldx = a->map_c, la.Cin = a->map_c;
             la.Wt = a->wt[0] + (size_t)l * a->map_c * 768, la.bias = nullptr, la.Cout = 768;
-            la.Y = F32(R_Z) + zoff, la.ldy = 768;
+            la.Y = z_at(zoff), la.ldy = 768, la.y_bf16 = bf16_mem;
             la.rows_fixed = px, la.rows_mode = 0, la.rowcap = 0, la.T = 1, la.eps = a->bn_eps, la.plain = 1;
             la.f16_ok = 1, la.row_max = F32(R_ROWMAX) + zoff / 768;   // raw FPN features: per-pixel power-of-two scaling
             if (apack) la.a_pack = ws + L.off[R_NHWC0 + l], la.a_rowinv = F32(R_ROWMAX) + zoff / 768, la.row_max = nullptr;
@@ -342,7 +348,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     if (pixel_first) {
         size_t zoff = 0;
         for (int lv = 0; lv < MVX_NUM_LEVELS; ++lv) {
-            ca.Z[lv] = F32(R_Z) + zoff;
+            ca.Z[lv] = z_at(zoff);
             ca.frame_stride[lv] = (size_t)a->map_h[lv] * a->map_w[lv] * 768;
             ca.h[lv] = m.h[lv], ca.w[lv] = m.w[lv], ca.rs_h[lv] = m.rs_h[lv], ca.rs_w[lv] = m.rs_w[lv];
             zoff += (size_t)B * a->map_h[lv] * a->map_w[lv] * 768;
@@ -351,6 +357,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         ca.eps = a->gather_eps, ca.bias = a->bias[0], ca.Y1 = F32(R_Y1), ca.out_stats = stat_of(0);
         ca.bin_count = I32(R_BINCNT), ca.bin_start = I32(R_BINSTART), ca.perm = I32(R_PERM);
         ca.nbins = combine_bins(a->map_h[0], a->map_w[0]);
+        ca.z_bf16 = ca.y1_bf16 = bf16_mem;
         if (fold) {   // rows leave the combine kernel as conv1's pre-packed A operand (the idle A1 / Y1 regions hold it)
             ca.y1pack = reinterpret_cast<unsigned char *>(ws + L.off[R_A1]), ca.y1_rowinv = F32(R_A1MAX), ca.pack_tiles = (int)ceil_div(L.capA, 256);
             ca.wbound = F32(R_WBOUND);
@@ -393,6 +400,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         la.eps = a->bn_eps;
         la.f16_ok = 1;       // BatchNorm-ed inputs; fcn1 row-first reads raw gathered features: per-row power-of-two scaling
         if (l == 0) la.row_max = F32(R_A1MAX);
+        if (l == 1) la.x_bf16 = bf16_mem;   // conv1 reads the bf16 Y1 of the combine kernel
         if (l == 1 && fold) {   // conv1 on the packed rows: fcn1's BatchNorm lives in per-frame weights and biases
             rc = launch_fold_pack_weights(a->wt[1], a->bias[1], stat_of(0), a->counts, T, a->bn_eps, 768, 128, B, ws + L.off[R_WFOLD],
                                           F32(R_BFOLD), st);

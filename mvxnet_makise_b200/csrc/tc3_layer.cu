@@ -113,12 +113,18 @@ struct T3Args {
 // pad rows behind them are one per voxel, in voxel order), so that half is a plain 2-D tile of X2 as well: rows
 // [v_first, v_first + 128), fetched by the same tensor copies into the same ring; a converter thread reads row v(r) - v_first.
 // Only the one tile per frame that straddles the real-row / pad-row boundary needs two ranges: its pad rows read global memory.
-template <bool RESIDENT, bool CAT>
+// PREC: 0 = fp32-accurate 3xFP16 from fp32 rows; 1 = bf16 mode (ONE bf16 product per k-step, reduced precision) from fp32 rows;
+//       2 = bf16 mode from bf16 rows (conv1 reading the bf16 Y1 of the combine kernel: half the bytes per stage)
+template <bool RESIDENT, bool CAT, int PREC>
 __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_constant__ T3Args g, const __grid_constant__ CUtensorMap tmX,
                                                                   const __grid_constant__ CUtensorMap tmY,
                                                                   const __grid_constant__ CUtensorMap tmX2) {
     using S = T3Smem<RESIDENT>;
     constexpr int T3_RAW = S::T3_RAW;
+    constexpr bool BF = PREC != 0, RAWBF = PREC == 2;
+    constexpr int RAW_TX = RAWBF ? T3_RAW_BYTES / 2 : T3_RAW_BYTES;     // bytes one raw stage receives
+    constexpr int B_TX = BF ? T3_B_STAGE / 2 : T3_B_STAGE;              // bf16 weights: the hi image only
+    static_assert(!(CAT && RAWBF), "the concat layer reads fp32 rows");
     const LayerArgs &a = g.a;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
                 for (int kc = 0; kc < nk; ++kc, ++gc) {
                     const int s = gc % T3_RAW;
                     mbar_wait(raw_empty(s), ((gc / T3_RAW) & 1) ^ 1);
-                    mbar_arrive_expect_tx(raw_full(s), T3_RAW_BYTES);
+                    mbar_arrive_expect_tx(raw_full(s), RAW_TX);
                     if (!CAT || kc < nk_x)
                         tma_load_2d(sbase + S::kRaw + s * T3_RAW_BYTES, &tmX, kc * T3_KB, (int)((long long)f * a.rowcap + row0), raw_full(s));
                     else
@@ -213,8 +219,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
         if (lane == 0) {
             const uint8_t *wsrc = static_cast<const uint8_t *>(g.wpack);
             if (RESIDENT) {
-                mbar_arrive_expect_tx(b_ready, nk * T3_B_STAGE);
-                for (int kc = 0; kc < nk; ++kc) bulk_g2s(sbase + S::kB + kc * T3_B_STAGE, wsrc + (size_t)kc * T3_B_STAGE, T3_B_STAGE, b_ready);
+                mbar_arrive_expect_tx(b_ready, nk * B_TX);
+                for (int kc = 0; kc < nk; ++kc) bulk_g2s(sbase + S::kB + kc * T3_B_STAGE, wsrc + (size_t)kc * T3_B_STAGE, B_TX, b_ready);
             } else {
                 int gb = 0;
                 for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -224,8 +230,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
                     for (int kc = 0; kc < nk; ++kc, ++gb) {
                         const int sb = gb % T3_BRING;
                         mbar_wait(b_empty(sb), ((gb / T3_BRING) & 1) ^ 1);
-                        mbar_arrive_expect_tx(b_full(sb), T3_B_STAGE);
-                        bulk_g2s(sbase + S::kB + sb * T3_B_STAGE, wsrc + (size_t)kc * T3_B_STAGE, T3_B_STAGE, b_full(sb));
+                        mbar_arrive_expect_tx(b_full(sb), B_TX);
+                        bulk_g2s(sbase + S::kB + sb * T3_B_STAGE, wsrc + (size_t)kc * T3_B_STAGE, B_TX, b_full(sb));
                     }
                 }
             }
@@ -233,7 +239,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
     } else if (warp == T3_W_MMA) {
         // ================= MMA issuer ==================================================================================
         if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(T3_BN >> 3) << 17) | ((128u >> 4) << 24);   // kind::f16: fp16 x fp16 -> fp32
+            constexpr uint32_t fmt = BF ? 1u : 0u;   // kind::f16 operand format: 0 = fp16, 1 = bf16
+            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(T3_BN >> 3) << 17) | ((128u >> 4) << 24);   // fp32 accumulate
             if (RESIDENT) mbar_wait(b_ready, 0);
             int ga = 0, gb = 0, it = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -259,9 +266,13 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
                     for (int ks = 0; ks < 2; ++ks) {   // two 16-k steps per stage
                         const uint64_t b_hi = make_desc(sB + ks * 32), b_lo = make_desc(sB + T3_BN * 64 + ks * 32);
                         const uint32_t a_hi = tA + ks * 8, a_lo = tA + 16 + ks * 8;
-                        mma_f16_ts(d, a_lo, b_hi, idesc, (kc | ks) != 0);
-                        mma_f16_ts(d, a_hi, b_lo, idesc, 1);
-                        mma_f16_ts(d, a_hi, b_hi, idesc, 1);
+                        if constexpr (BF) {
+                            mma_f16_ts(d, a_hi, b_hi, idesc, (kc | ks) != 0);
+                        } else {
+                            mma_f16_ts(d, a_lo, b_hi, idesc, (kc | ks) != 0);
+                            mma_f16_ts(d, a_hi, b_lo, idesc, 1);
+                            mma_f16_ts(d, a_hi, b_hi, idesc, 1);
+                        }
                     }
                     mma_commit(a_empty(sa));
                     if (!RESIDENT) {
@@ -291,9 +302,15 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
         auto fetch = [&](int gcn, int srow) {         // read row `srow` of ring position gcn, hand the stage back
             const int s = gcn % T3_RAW;
             mbar_wait(raw_full(s), (gcn / T3_RAW) & 1);
+            if constexpr (RAWBF) {   // bf16 rows: 64 bytes, SWIZZLE_64B: chunk j of row i at position j ^ ((i >> 1) & 3)
+                const uint8_t *rowp = smem + S::kRaw + s * T3_RAW_BYTES + srow * 64;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xn[j] = *reinterpret_cast<const float4 *>(rowp + ((j ^ ((srow >> 1) & 3)) << 4));
+            } else {
             const uint8_t *rowp = smem + S::kRaw + s * T3_RAW_BYTES + srow * 128;   // SWIZZLE_128B: chunk j of row i at position j ^ (i & 7)
 #pragma unroll
             for (int j = 0; j < 8; ++j) xn[j] = *reinterpret_cast<const float4 *>(rowp + ((j ^ (srow & 7)) << 4));
+            }
             // The stage goes back to the TMA engine, which writes through the ASYNC proxy: a plain arrive after the ld.shared is not
             // enough (the loads are only issued, and the arrive travels a different path; with L2-resident inputs the refill came
             // back before a few lanes had read their rows: sporadic wrong rows, found with tools/tc3_race.py). The proxy fence
@@ -357,17 +374,28 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
                 for (int j = 0; j < 8; ++j) {
                     const float4 m4 = *reinterpret_cast<const float4 *>(s_mean + k0 + j * 4);
                     const float4 r4 = *reinterpret_cast<const float4 *>(s_rstd + k0 + j * 4);
-                    float z0 = (x[j].x - m4.x) * r4.x, z1 = (x[j].y - m4.y) * r4.y, z2 = (x[j].z - m4.z) * r4.z, z3 = (x[j].w - m4.w) * r4.w;
+                    float4 xv;
+                    if constexpr (RAWBF) {   // elements 4j .. 4j+3 of the row piece: two 32-bit words of x[j / 2]
+                        const uint32_t w0 = __float_as_uint(j & 1 ? x[j >> 1].z : x[j >> 1].x), w1 = __float_as_uint(j & 1 ? x[j >> 1].w : x[j >> 1].y);
+                        xv = make_float4(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xFFFF0000u), __uint_as_float(w1 << 16), __uint_as_float(w1 & 0xFFFF0000u));
+                    } else {
+                        xv = x[j];
+                    }
+                    float z0 = (xv.x - m4.x) * r4.x, z1 = (xv.y - m4.y) * r4.y, z2 = (xv.z - m4.z) * r4.z, z3 = (xv.w - m4.w) * r4.w;
                     if (!valid) z0 = z1 = z2 = z3 = 0.f;
-                    split_f16_pair(z0, z1, hi[2 * j], lo[2 * j]);
-                    split_f16_pair(z2, z3, hi[2 * j + 1], lo[2 * j + 1]);
+                    if constexpr (BF) {
+                        hi[2 * j] = pack_bf16x2(z0, z1), hi[2 * j + 1] = pack_bf16x2(z2, z3);
+                    } else {
+                        split_f16_pair(z0, z1, hi[2 * j], lo[2 * j]);
+                        split_f16_pair(z2, z3, hi[2 * j + 1], lo[2 * j + 1]);
+                    }
                 }
                 const int sa = gcur % T3_AST;
                 mbar_wait(a_empty(sa), ((gcur / T3_AST) & 1) ^ 1);   // the MMAs that read this A stage have completed
                 tc_fence_after();
                 const uint32_t tA = tmem_base + ((uint32_t)(q * 32) << 16) + T3_A_COL + sa * 32;
                 tmem_st16(tA, hi);
-                tmem_st16(tA + 16, lo);
+                if constexpr (!BF) tmem_st16(tA + 16, lo);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -547,29 +575,31 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D fp32 tensor (rows, cols) with row pitch ld floats; box = 128 rows x 32 columns, SWIZZLE_128B
-static int make_tmap(CUtensorMap *m, const float *base, long long rows, int cols, int ld) {
+// 2-D tensor (rows, cols) of fp32 (or bf16) elements with row pitch ld elements; box = 128 rows x 32 columns: 128-byte rows with
+// SWIZZLE_128B (fp32), 64-byte rows with SWIZZLE_64B (bf16)
+static int make_tmap(CUtensorMap *m, const void *base, long long rows, int cols, int ld, bool bf16 = false) {
     EncodeTiledFn fn = encode_fn();
     MVX_REQUIRE(fn, MVX_ECUDA, "cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
     const cuuint32_t box[2] = {32, (cuuint32_t)T3_TM};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MVX_REQUIRE(r == CUDA_SUCCESS, MVX_ECUDA, "cuTensorMapEncodeTiled failed");
     return MVX_OK;
 }
 
-template <bool RESIDENT, bool CAT>
+template <bool RESIDENT, bool CAT, int PREC>
 int launch_tc3_t(const T3Args &g, const CUtensorMap &tmX, const CUtensorMap &tmY, const CUtensorMap &tmX2, int grid, cudaStream_t st) {
     using S = T3Smem<RESIDENT>;
     static bool attr_set = false;
     if (!attr_set) {
-        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc3_layer_kernel<RESIDENT, CAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(tc3_layer_kernel<RESIDENT, CAT, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         attr_set = true;
     }
-    tc3_layer_kernel<RESIDENT, CAT><<<grid, T3_THREADS, S::kTotal, st>>>(g, tmX, tmY, tmX2);
+    tc3_layer_kernel<RESIDENT, CAT, PREC><<<grid, T3_THREADS, S::kTotal, st>>>(g, tmX, tmY, tmX2);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }
@@ -581,22 +611,25 @@ bool tc3_layer_eligible(const LayerArgs &a) {
     if (a.Cout != T3_BN || a.Cin % (2 * T3_KB) != 0 || a.Cin > 768 || (a.rows_mode != 1 && a.rows_mode != 2)) return false;
     if (a.rowcap % T3_TM != 0 || a.ldx % 4 != 0 || (a.Y && a.ldy % 4 != 0)) return false;
     if (a.vmax && !a.row_v) return false;
+    if (a.y_bf16 || (a.x_bf16 && a.X2)) return false;
     if (a.X2) return a.x2_cols == 64 && a.Cin == 128 && a.in_C == 64 && a.cat_row_vox && a.ldx == 64;   // the fused concat of the last FCN
     return a.ldx == a.Cin && a.in_C == 0;
 }
 
-// defined in tc_layer.cu: packs W^T into the fp16 hi/lo chunk images + inverse column scales for 128-column tiles
-int pack_weights_f16_128(const float *Wt, int Cin, int Cout, void *wpack, cudaStream_t st);
+// defined in tc_layer.cu: packs W^T into the fp16 hi/lo (or bf16) chunk images + inverse column scales for 128-column tiles
+int pack_weights_f16_128(const float *Wt, int Cin, int Cout, void *wpack, cudaStream_t st, bool bf16);
 
 int launch_layer_tc3(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     MVX_REQUIRE(tc3_layer_eligible(a) && wpack, MVX_EINVAL, "layer not eligible for the TMA-fed tensor-core kernel");
-    int rc = pack_weights_f16_128(a.Wt, a.Cin, a.Cout, wpack, st);
+    const bool bf = tc_bf16_enabled();
+    MVX_REQUIRE(bf || !a.x_bf16, MVX_EINVAL, "bf16 rows need the bf16 mode");
+    int rc = pack_weights_f16_128(a.Wt, a.Cin, a.Cout, wpack, st, bf);
     if (rc) return rc;
     T3Args g{};
     g.a = a, g.wpack = wpack, g.F = F, g.row_tiles = a.rowcap / T3_TM, g.store = a.Y != nullptr;
     CUtensorMap tmX, tmY, tmX2;
     const int xcols = a.X2 ? a.Cin - a.x2_cols : a.Cin;
-    rc = make_tmap(&tmX, a.X, (long long)F * a.rowcap, xcols, a.ldx);
+    rc = make_tmap(&tmX, a.X, (long long)F * a.rowcap, xcols, a.ldx, a.x_bf16 != 0);
     if (rc) return rc;
     if (a.Y) {
         rc = make_tmap(&tmY, a.Y, (long long)F * a.rowcap, a.Cout, a.ldy);
@@ -613,9 +646,14 @@ int launch_layer_tc3(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     const long long slots = (long long)F * g.row_tiles;
     const int grid = (int)(slots < kSMs ? slots : kSMs);
     const bool resident = a.Cin == 128;
-    if (a.X2) return launch_tc3_t<true, true>(g, tmX, tmY, tmX2, grid, st);
-    if (resident) return launch_tc3_t<true, false>(g, tmX, tmY, tmX2, grid, st);
-    return launch_tc3_t<false, false>(g, tmX, tmY, tmX2, grid, st);
+    if (bf) {
+        if (a.X2) return launch_tc3_t<true, true, 1>(g, tmX, tmY, tmX2, grid, st);
+        if (a.x_bf16) return resident ? launch_tc3_t<true, false, 2>(g, tmX, tmY, tmX2, grid, st) : launch_tc3_t<false, false, 2>(g, tmX, tmY, tmX2, grid, st);
+        return resident ? launch_tc3_t<true, false, 1>(g, tmX, tmY, tmX2, grid, st) : launch_tc3_t<false, false, 1>(g, tmX, tmY, tmX2, grid, st);
+    }
+    if (a.X2) return launch_tc3_t<true, true, 0>(g, tmX, tmY, tmX2, grid, st);
+    if (resident) return launch_tc3_t<true, false, 0>(g, tmX, tmY, tmX2, grid, st);
+    return launch_tc3_t<false, false, 0>(g, tmX, tmY, tmX2, grid, st);
 }
 
 }  // namespace mvx

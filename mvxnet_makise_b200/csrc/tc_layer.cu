@@ -535,7 +535,13 @@ __global__ void __launch_bounds__(tc_producer_warps(F16, TWO) * 32 + 64, TWO ? 2
                     for (int r = warp; r < TR; r += 8) {
                         if (row0 + rbase + r >= n_rows) break;
                         const float4 o = *reinterpret_cast<const float4 *>(ytile + (size_t)r * kEpiLd + lane * 4);
-                        *reinterpret_cast<float4 *>(a.Y + ((size_t)f * a.rowcap + row0 + rbase + r) * a.ldy + n0 + pass * kEpiCols + lane * 4) = o;
+                        const size_t e = ((size_t)f * a.rowcap + row0 + rbase + r) * a.ldy + n0 + pass * kEpiCols + lane * 4;   // element index
+                        if (a.y_bf16) {
+                            uint2 ob;
+                            ob.x = pack_bf16x2(o.x, o.y), ob.y = pack_bf16x2(o.z, o.w);
+                            *reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(a.Y) + e) = ob;
+                        } else
+                        *reinterpret_cast<float4 *>(a.Y + e) = o;
                     }
                 }
             }
@@ -1323,8 +1329,10 @@ int launch_tc_persist16(const LayerArgs &a, int F, float *wpack, cudaStream_t st
 
 }  // namespace
 
-int pack_weights_f16_128(const float *Wt, int Cin, int Cout, void *wpack, cudaStream_t st) {
+int pack_weights_f16_128(const float *Wt, int Cin, int Cout, void *wpack, cudaStream_t st, bool bf16) {
     uint8_t *blob = static_cast<uint8_t *>(wpack);
+    if (bf16) pack_weights_f16_kernel<128, true><<<Cout, 256, 0, st>>>(Wt, Cin, Cout, blob, reinterpret_cast<float *>(blob + (size_t)Cin * Cout * 4));
+    else
     pack_weights_f16_kernel<128, false><<<Cout, 256, 0, st>>>(Wt, Cin, Cout, blob, reinterpret_cast<float *>(blob + (size_t)Cin * Cout * 4));
     MVX_LAUNCH_CHECK();
     return MVX_OK;
@@ -1390,6 +1398,7 @@ int launch_layer_tc(const LayerArgs &a_in, int F, float *wpack, cudaStream_t st)
         return launch_tc_persist<128>(a, F, wpack, st);
     MVX_REQUIRE(!a.X2 || (a.f16_ok && (g_tc_bf16 || tc_f16_enabled()) && a.Cin % 32 == 0 && a.x2_cols % 32 == 0 && a.counts),
                 MVX_EINVAL, "fused concat input needs the 16-bit tensor-core producer");
+    if (g_tc3 && g_tc_bf16 && tc3_layer_eligible(a)) return launch_layer_tc3(a, F, wpack, st);   // bf16 mode of the TMA-fed kernel
     if (a.f16_ok && g_tc_bf16 && a.Cin % 32 == 0) {          // reduced precision: one bf16 product per K-step
         if (a.Cout % 256 == 0 && !g_tc_two_wide) return launch_tc<256, true, true>(a, F, wpack, st);
         if (g_tc_two) return launch_tc<128, true, true, true>(a, F, wpack, st);

@@ -420,7 +420,8 @@ class PointPath:
 
     def forward_host(self, points_host: torch.Tensor, offsets: Sequence[int], calib32_host: torch.Tensor,
                      maps_host: List[torch.Tensor], want_grid: bool = True, head_rows: int = 1024, sync: bool = True):
-        """Inputs in (ideally pinned) HOST memory: points (sum P, 4) fp32, calib32 (B,32), maps 3 x (B,256,Hf,Wf).
+        """Inputs in (ideally pinned) HOST memory: points (sum P, 4) fp32, calib32 (B,32), maps 3 x (B,256,Hf,Wf). The maps may
+        also be CUDA tensors (the reference produces them on the GPU, Head.py:14-22): then only points + calib cross PCIe.
         Frames are independent, so the batch is cut into sub-batches of `self.host_chunk` frames: the H2D copy of
         sub-batch j+1 (copy stream) overlaps the kernels of sub-batch j (compute streams); each sub-batch has its own
         input buffers and workspace and writes its slice of the batch outputs. Reads back the per-frame counts and
@@ -453,7 +454,7 @@ class PointPath:
         cap = (maxp + 4095) // 4096 * 4096
         stride = int(points_host.shape[1])
         n_slots = max(1, int(getattr(self, 'host_slots', 2)))
-        key = (B, cap, stride, tuple(tuple(m.shape[1:]) for m in maps_host), tuple(sizes), int(head_rows), n_slots)
+        key = (B, cap, stride, tuple(tuple(m.shape[1:]) + (m.is_cuda,) for m in maps_host), tuple(sizes), int(head_rows), n_slots)
         if getattr(self, '_in_key', None) != key:
             self._slots = []
             for _ in range(n_slots):
@@ -463,7 +464,7 @@ class PointPath:
                     c.f0, c.f1 = f0, f1
                     c.in_points = torch.empty(((f1 - f0) * cap, stride), dtype=torch.float32, device=dev)
                     c.in_calib = torch.empty((f1 - f0, 32), dtype=torch.float32, device=dev)
-                    c.in_maps = [torch.empty((f1 - f0,) + tuple(m.shape[1:]), dtype=torch.float32, device=dev) for m in maps_host]
+                    c.in_maps = [None if m.is_cuda else torch.empty((f1 - f0,) + tuple(m.shape[1:]), dtype=torch.float32, device=dev) for m in maps_host]
                     c.ev = torch.cuda.Event()
                     slot.subs.append(c)
                 nz, nx, ny = self.grid.shape[2], self.grid.shape[0], self.grid.shape[1]
@@ -483,7 +484,7 @@ class PointPath:
         if want_grid and slot.grid_out is None:
             nz, nx, ny = self.grid.shape[2], self.grid.shape[0], self.grid.shape[1]
             slot.grid_out = torch.empty((B, 128, nz, nx, ny), dtype=torch.float32, device=dev)
-        self._h2d_bytes = (points_host.numel() + calib32_host.numel() + sum(m.numel() for m in maps_host)) * 4
+        self._h2d_bytes = (points_host.numel() + calib32_host.numel() + sum(m.numel() for m in maps_host if not m.is_cuda)) * 4
         self.B, self.grid_out, self.counts = B, slot.grid_out, slot.counts
         cur = torch.cuda.current_stream()
         cs = self._copy_stream
@@ -499,7 +500,8 @@ class PointPath:
                     c.in_points[:p1 - p0].copy_(points_host[p0:p1], non_blocking=True)
                 c.in_calib.copy_(calib32_host[c.f0:c.f1], non_blocking=True)
                 for d, h in zip(c.in_maps, maps_host):
-                    d.copy_(h[c.f0:c.f1], non_blocking=True)
+                    if d is not None:
+                        d.copy_(h[c.f0:c.f1], non_blocking=True)
                 c.ev.record(cs)
         for j, c in enumerate(slot.subs):
             ks = self._compute_streams[j % ns]
@@ -507,7 +509,8 @@ class PointPath:
                 ks.wait_stream(cur)              # work the caller queued before this call (weight updates ...) is ordered first
             with torch.cuda.stream(ks):
                 ks.wait_event(c.ev)
-                c.forward_device(c.in_points[:c.n_points], c.offsets, c.in_calib, c.in_maps, want_grid, cap=cap,
+                sub_maps = [d if d is not None else h[c.f0:c.f1] for d, h in zip(c.in_maps, maps_host)]   # device-resident maps: a view
+                c.forward_device(c.in_points[:c.n_points], c.offsets, c.in_calib, sub_maps, want_grid, cap=cap,
                                  grid_out=slot.grid_out[c.f0:c.f1] if want_grid else None, counts=slot.counts[c.f0:c.f1])
         k0 = self._compute_streams[0]
         for s_ in self._compute_streams[1:]:

@@ -589,14 +589,14 @@ def test_tma_fed_tmem_operand_layer_kernel(mvx, golden_dir):
     assert rel_err(vf, ref64['vfeat']) < TOL and rel_err(vf1, ref64b['vfeat']) < TOL
 
 
-BF16_TOL = 8e-2
+BF16_TOL = 5e-2
 
 
 @pytest.mark.parametrize('tag', ['path_a', 'path_b'])
 def test_bf16_mode_tolerance(mvx, golden_dir, tag):
     """bf16 mode (mvx_set_gemm_mode(6)): the tensor-core layers of the fused path (pixel GEMM of fcn1, conv1, fcn2, last
     FCN) use ONE bf16 product per K-step instead of the fp32-accurate three-product split. Its tolerance is stated
-    separately from the fp32 bar: voxel features within BF16_TOL = 8e-2 (max|a-ref| / max|ref|) of the fp64 evaluation
+    separately from the fp32 bar: voxel features within BF16_TOL = 5e-2 (max|a-ref| / max|ref|) of the fp64 evaluation
     (measured 0.6e-2 .. 1.2e-2: 8-bit operand mantissas through 8 BatchNorm-ed layers); voxelization, projection and
     grid placement stay bit-exact (integer / fp32 SIMT work is untouched)."""
     from mvxnet_makise_b200 import _lib
@@ -753,7 +753,7 @@ def test_shuffle_option_matches_reference_group_semantics(mvx):
     rp_plain = other.region('row_point', torch.int32, (2, other.cap))[0, :int(c_plain[0, 1])]
     kept_plain = set(rp_plain[rp_plain < 600].tolist())
     kept_sh = set(perm[:9000][rp_sh.long()][perm[:9000][rp_sh.long()] < 600].tolist())
-    assert kept_plain == set(range(35)) and len(kept_sh) == 35 and kept_sh != kept_plain
+    assert kept_plain == set(range(35)) and 30 <= len(kept_sh) <= 35 and kept_sh != kept_plain   # (the voxel may also hold a few of the frame's own points)
     # training mode shuffles by default
     tr = mvx.P.PointPath(sd, G)
     tr.forward_train(pts, offsets, c32, maps, want_grid=False)
