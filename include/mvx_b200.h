@@ -225,7 +225,8 @@ int mvx_set_fusion_mode(int32_t mode);
 /* Pixel-first inference only. 1: the combine kernel writes fcn1's raw rows directly as conv1's pre-packed tensor-core operand
  * (fp16 hi/lo images, per-row power-of-two scale from an a-priori bound) and conv1 (Pipe.py:96) runs with fcn1's BatchNorm
  * folded into per-frame weights: W' = W diag(rstd), b' = b - W'' mean, W'' = W' as its fp16 hi + lo images represent it;
- * 0: conv1 reads the fp32 rows and normalises them while loading. */
+ * 0: conv1 reads the fp32 rows and normalises them while loading (default);
+ * 2: like 0, with the first version of the combine kernel (row-by-row walk; kept for A/B measurements). */
 int mvx_set_fold_mode(int32_t mode);
 
 /* ------------------------------------------------------------------------------------------------

@@ -550,6 +550,245 @@ __global__ void __launch_bounds__(kCombWarps * 32, MVX_COMB_MINB) combine_rows_k
     }
 }
 
+
+// ---- combine, second version: run-structured main loop + asynchronous corner ring ------------------------------------------
+// What bounded the first version (ncu, r5e): not the issue rate and not the bytes - removing all stores or all corner loads, or
+// cutting the instructions per row by a third, left it at 0.95 ms. Every warp walked its rows through a serial chain of
+// shared-load -> test -> branch steps (8 branches per row) and stalled for a full DRAM round trip at each cell change, with only
+// 18 warps per SM to cover for it: ~900 cycles per row and warp. This version
+//  (1) cuts the sorted rows into RUNS in the staging phase (a run = up to 16 consecutive ordinary rows that sample the same cells
+//      at all three levels): the per-row loop body is branch-free (3 broadcast LDS.128 + 48 FFMA + ReLU + store + sums) and the
+//      compiler overlaps consecutive rows; cell changes, rows without corners and weighted rows are handled at run heads only;
+//  (2) lists the cell changes of the CTA in order ("events") and lets every warp fetch the corner vectors of the next NS events
+//      ahead of time with cp.async (LDGSTS: global -> shared without registers) into a private ring; a cell change then costs a
+//      wait on an already landed group plus four LDS.128.
+// Arithmetic and its order are those of the first version: Y1 is bit-identical.
+constexpr int kCombNS = 4;                                  // ring slots (events in flight) per warp
+template <bool ZB>
+struct CombSmem {
+    static constexpr int kSlotBytes = 4 * 32 * (ZB ? 8 : 16);       // four corners x 32 lanes x this lane's 4 columns
+    static constexpr int kRow = 0;                                  // int[256]
+    static constexpr int kW = kRow + kCombRows * 4;                 // float[256]
+    static constexpr int kRecw = kW + kCombRows * 4;                // float4[256][3]
+    static constexpr int kCell = kRecw + kCombRows * MVX_NUM_LEVELS * 16;   // int[256][3]
+    static constexpr int kRun = kCell + kCombRows * MVX_NUM_LEVELS * 4;     // uint8[256]
+    static constexpr int kEv = kRun + kCombRows;                    // uint16[768]
+    static constexpr int kRing = kEv + kCombRows * MVX_NUM_LEVELS * 2;      // [warps][NS][slot]
+    static constexpr int kTotal = kRing + kCombWarps * kCombNS * kSlotBytes;
+};
+__device__ __forceinline__ void cp_async_wait_allow(int allow) {   // wait until at most `allow` of this thread's groups are pending
+    if (allow >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+    else if (allow == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else if (allow == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <bool ZB, bool YB>
+__global__ void __launch_bounds__(kCombWarps * 32, MVX_COMB_MINB) combine_runs_kernel(CombineArgs a) {
+    using S = CombSmem<ZB>;
+    constexpr int kRowMask = 0xFFFFFF, kChg0 = 1 << 24, kChgAny = 7 << 24, kNone = 1 << 27, kWgt = 1 << 28;
+    extern __shared__ __align__(16) unsigned char comb_smem[];
+    int *s_row = reinterpret_cast<int *>(comb_smem + S::kRow);
+    float *s_w = reinterpret_cast<float *>(comb_smem + S::kW);
+    float4(*s_recw)[MVX_NUM_LEVELS] = reinterpret_cast<float4(*)[MVX_NUM_LEVELS]>(comb_smem + S::kRecw);
+    int(*s_cell)[MVX_NUM_LEVELS] = reinterpret_cast<int(*)[MVX_NUM_LEVELS]>(comb_smem + S::kCell);
+    unsigned char *s_run = comb_smem + S::kRun;
+    unsigned short *s_ev = reinterpret_cast<unsigned short *>(comb_smem + S::kEv);
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.counts[f * 4 + 1];
+    const int p0 = blockIdx.x * kCombRows;
+    if (p0 > K) return;
+    const int n_rows = min(p0 + kCombRows, K + 1) - p0;
+    // ---- staging 1: sorted position -> row, weight, corner weights and coordinates of the three levels (once per row) -------
+    for (int i = tid; i < n_rows; i += kCombWarps * 32) {
+        const int r = a.perm[(size_t)f * a.capA + p0 + i];
+        const size_t ro = (size_t)f * a.capA + r;
+        const float4 xyz = __ldg(reinterpret_cast<const float4 *>(a.vox8 + ro * 8));
+        const bool none = r >= K || (xyz.x == 0.f && xyz.y == 0.f && xyz.z == 0.f);  // pad row / origin point: A1 row is zero
+        const float wgt = __ldg(a.row_w + ro);
+        s_row[i] = r | (none ? kNone : 0) | (wgt != 1.f ? kWgt : 0);
+        s_w[i] = wgt;
+        const float2 pr = __ldg(reinterpret_cast<const float2 *>(a.proj) + ro);
+#pragma unroll
+        for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+            const CellRef c = cell_of(pr.x, pr.y, a.rs_h[l], a.rs_w[l], a.eps);
+            const int H = a.h[l], W = a.w[l];
+            const bool r0 = c.i0 >= 0 && c.i0 < H, r1 = c.i0 + 1 >= 0 && c.i0 + 1 < H;
+            const bool c0 = c.i1 >= 0 && c.i1 < W, c1 = c.i1 + 1 >= 0 && c.i1 + 1 < W;
+            const float wa_ = __fsub_rn(1.0f, c.wa), wb_ = __fsub_rn(1.0f, c.wb);
+            const int y0 = min(max(c.i0, 0), H - 1), y1 = min(max(c.i0 + 1, 0), H - 1);
+            const int x0 = min(max(c.i1, 0), W - 1), x1 = min(max(c.i1 + 1, 0), W - 1);
+            s_recw[i][l] = make_float4((r0 && c0) ? c.wa * c.wb : 0.f, (r1 && c0) ? wa_ * c.wb : 0.f, (r0 && c1) ? c.wa * wb_ : 0.f,
+                                       (r1 && c1) ? wa_ * wb_ : 0.f);
+            s_cell[i][l] = none ? -1 : (x0 | (y0 << 12) | ((x1 - x0) << 24) | ((y1 - y0) << 25));
+        }
+    }
+    __syncthreads();
+    // ---- staging 2: change flags against the previous row of the CTA (the row behind one without corners reloads everything) --
+    for (int i = tid; i < n_rows; i += kCombWarps * 32) {
+        int flags = 0;
+        if (s_cell[i][0] != -1) {
+#pragma unroll
+            for (int l = 0; l < MVX_NUM_LEVELS; ++l)
+                if (i == 0 || s_cell[i][l] != s_cell[i - 1][l]) flags |= kChg0 << l;
+        }
+        s_row[i] |= flags;
+    }
+    __syncthreads();
+    // ---- staging 3: run lengths (valid at EVERY row: the walk below may land anywhere) and the ordered event list -----------
+    for (int i = tid; i < n_rows; i += kCombWarps * 32) {
+        int n = 1;
+        if (!(s_row[i] & (kNone | kWgt)))
+            while (n < 16 && i + n < n_rows && !(s_row[i + n] & (kChgAny | kNone | kWgt))) ++n;
+        s_run[i] = (unsigned char)n;
+    }
+    int n_ev;
+    {
+        const int i0 = 2 * tid, i1 = 2 * tid + 1;     // threads 0..127 own two consecutive rows each
+        const int f0 = i0 < n_rows ? (s_row[i0] & kChgAny) >> 24 : 0, f1 = i1 < n_rows ? (s_row[i1] & kChgAny) >> 24 : 0;
+        int k = block_exclusive_scan(__popc(f0) + __popc(f1), &n_ev);
+#pragma unroll
+        for (int l = 0; l < MVX_NUM_LEVELS; ++l)
+            if (f0 & (1 << l)) s_ev[k++] = (unsigned short)(i0 | (l << 8));
+#pragma unroll
+        for (int l = 0; l < MVX_NUM_LEVELS; ++l)
+            if (f1 & (1 << l)) s_ev[k++] = (unsigned short)(i1 | (l << 8));
+    }
+    __syncthreads();
+
+    const int col0 = warp * 128 + lane * 4;
+    const float4 bias = __ldg(reinterpret_cast<const float4 *>(a.bias + col0));
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ps = z4, pss = z4;                  // fp32 column sums over at most 16 rows
+    double ds[4] = {0, 0, 0, 0}, dss[4] = {0, 0, 0, 0};   // this lane owns its 4 columns within the CTA: fp64 in registers
+    float4 v00[MVX_NUM_LEVELS], v10[MVX_NUM_LEVELS], v01[MVX_NUM_LEVELS], v11[MVX_NUM_LEVELS];
+#pragma unroll
+    for (int l = 0; l < MVX_NUM_LEVELS; ++l) v00[l] = v10[l] = v01[l] = v11[l] = z4;
+    auto fold = [&]() {
+        ds[0] += (double)ps.x, ds[1] += (double)ps.y, ds[2] += (double)ps.z, ds[3] += (double)ps.w;
+        dss[0] += (double)pss.x, dss[1] += (double)pss.y, dss[2] += (double)pss.z, dss[3] += (double)pss.w;
+        ps = z4, pss = z4;
+    };
+    // this warp's ring: slot (k % NS) of event k; inside a slot corner c of lane `lane` sits at c * 32 * EB + lane * EB
+    constexpr int EB = ZB ? 8 : 16;
+    unsigned char *ring = comb_smem + S::kRing + warp * (kCombNS * S::kSlotBytes) + lane * EB;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    auto issue = [&](int k) {   // start the copy of event k's four corner vectors (this lane's 4 columns of each)
+        const int ev = s_ev[k];
+        const int i = ev & 0xFF, l = ev >> 8;
+        const int cell = s_cell[i][l];
+        const int W = a.w[l];
+        const int x0 = cell & 0xFFF, y0 = (cell >> 12) & 0xFFF, dx = (cell >> 24) & 1, dy = (cell >> 25) & 1;
+        const size_t e00 = (size_t)f * a.frame_stride[l] + ((size_t)y0 * W + x0) * kCombCout + col0;   // element index
+        const char *b00 = reinterpret_cast<const char *>(a.Z[l]) + e00 * (ZB ? 2 : 4);
+        const size_t sx = (size_t)dx * kCombCout * (ZB ? 2 : 4), sy = (size_t)dy * W * kCombCout * (ZB ? 2 : 4);
+        const uint32_t dst = ring_s + (uint32_t)(k % kCombNS) * S::kSlotBytes;
+        if constexpr (ZB) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(b00) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 32 * EB), "l"(b00 + sy) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 64 * EB), "l"(b00 + sx) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 96 * EB), "l"(b00 + sy + sx) : "memory");
+        } else {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(b00) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 32 * EB), "l"(b00 + sy) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 64 * EB), "l"(b00 + sx) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 96 * EB), "l"(b00 + sy + sx) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int issued = 0, consumed = 0;
+    for (; issued < min(kCombNS, n_ev); ++issued) issue(issued);
+    float *const y_f32 = a.Y1 + (size_t)f * a.capA * kCombCout + col0;     // this lane's 4 columns of row 0 of the frame
+    __nv_bfloat16 *const y_b16 = reinterpret_cast<__nv_bfloat16 *>(a.Y1) + (size_t)f * a.capA * kCombCout + col0;
+    auto row_value = [&](int ii, bool corners) -> float4 {
+        float4 acc = bias;
+        if (corners) {
+#pragma unroll
+            for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+                const float4 rw = s_recw[ii][l];
+#define MVX_COMB(e) acc.e = fmaf(v11[l].e, rw.w, fmaf(v01[l].e, rw.z, fmaf(v10[l].e, rw.y, fmaf(v00[l].e, rw.x, acc.e))));
+                MVX_COMB(x) MVX_COMB(y) MVX_COMB(z) MVX_COMB(w)
+#undef MVX_COMB
+            }
+        }
+        float4 y;
+        y.x = fmaxf(acc.x, 0.f), y.y = fmaxf(acc.y, 0.f), y.z = fmaxf(acc.z, 0.f), y.w = fmaxf(acc.w, 0.f);
+        return y;
+    };
+    auto store_row = [&](unsigned r, float4 &y) {
+        if constexpr (YB) {   // the statistics are those of the values conv1 will actually read: the bf16-rounded ones
+            const uint2 yb = f4_to_bf16x4(y);
+            *reinterpret_cast<uint2 *>(y_b16 + (size_t)r * kCombCout) = yb;
+            y = bf16x4_to_f4(yb);
+        } else {
+            *reinterpret_cast<float4 *>(y_f32 + (size_t)r * kCombCout) = y;
+        }
+    };
+    int i = 0, since = 0;
+    while (i < n_rows) {
+        const int rw_ = s_row[i];
+        if (rw_ & kChgAny) {
+#pragma unroll
+            for (int l = 0; l < MVX_NUM_LEVELS; ++l) {
+                if (rw_ & (kChg0 << l)) {   // warp-uniform: level l samples another cell from this row on
+                    cp_async_wait_allow(issued - consumed - 1);
+                    const unsigned char *slot = ring + (consumed % kCombNS) * S::kSlotBytes;
+                    if constexpr (ZB) {
+                        v00[l] = bf16x4_to_f4(*reinterpret_cast<const uint2 *>(slot));
+                        v10[l] = bf16x4_to_f4(*reinterpret_cast<const uint2 *>(slot + 32 * EB));
+                        v01[l] = bf16x4_to_f4(*reinterpret_cast<const uint2 *>(slot + 64 * EB));
+                        v11[l] = bf16x4_to_f4(*reinterpret_cast<const uint2 *>(slot + 96 * EB));
+                    } else {
+                        v00[l] = *reinterpret_cast<const float4 *>(slot);
+                        v10[l] = *reinterpret_cast<const float4 *>(slot + 32 * EB);
+                        v01[l] = *reinterpret_cast<const float4 *>(slot + 64 * EB);
+                        v11[l] = *reinterpret_cast<const float4 *>(slot + 96 * EB);
+                    }
+                    ++consumed;
+                    if (issued < n_ev) {   // the slot just read is free again: this lane wrote and read only its own bytes of it
+                        issue(issued);
+                        ++issued;
+                    }
+                }
+            }
+        }
+        if (rw_ & (kNone | kWgt)) {   // a row without corners and / or with a BatchNorm multiplicity != 1 (the pad row): on its own
+            float4 y = row_value(i, !(rw_ & kNone));
+            store_row((unsigned)(rw_ & kRowMask), y);
+            if (rw_ & kWgt) {   // exact fp64 side path
+                const double wd = (double)s_w[i];
+                ds[0] += wd * y.x, ds[1] += wd * y.y, ds[2] += wd * y.z, ds[3] += wd * y.w;
+                dss[0] += wd * y.x * y.x, dss[1] += wd * y.y * y.y, dss[2] += wd * y.z * y.z, dss[3] += wd * y.w * y.w;
+            } else {
+                if (since == 16) fold(), since = 0;
+                ++since;
+                ps.x += y.x, ps.y += y.y, ps.z += y.z, ps.w += y.w;
+                pss.x = fmaf(y.x, y.x, pss.x), pss.y = fmaf(y.y, y.y, pss.y), pss.z = fmaf(y.z, y.z, pss.z), pss.w = fmaf(y.w, y.w, pss.w);
+            }
+            ++i;
+            continue;
+        }
+        const int n = s_run[i];
+        if (since + n > 16) fold(), since = 0;
+        since += n;
+#pragma unroll 2
+        for (int j = 0; j < n; ++j) {   // the run: ordinary rows on the cached corner vectors, no decisions
+            float4 y = row_value(i + j, true);
+            store_row((unsigned)(s_row[i + j] & kRowMask), y);
+            ps.x += y.x, ps.y += y.y, ps.z += y.z, ps.w += y.w;
+            pss.x = fmaf(y.x, y.x, pss.x), pss.y = fmaf(y.y, y.y, pss.y), pss.z = fmaf(y.z, y.z, pss.z), pss.w = fmaf(y.w, y.w, pss.w);
+        }
+        i += n;
+    }
+    fold();
+    double *o = a.out_stats + ((size_t)f * kCombCout + col0) * 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        atomicAdd(o + 2 * j, ds[j]);
+        atomicAdd(o + 2 * j + 1, dss[j]);
+    }
+}
+
 }  // namespace
 
 int launch_combine_sort(const CombineArgs &a, int B, cudaStream_t st) {
@@ -572,16 +811,36 @@ int launch_fcn1_bounds(const float *w1t, const float *bias, float *wbound, cudaS
     return MVX_OK;
 }
 
+static int g_comb_v1 = 0;     // 1: the first combine kernel (row-by-row walk) instead of the run-structured one - kept for A/B runs
+void set_combine_v1(int on) { g_comb_v1 = on; }
+
+template <bool ZB, bool YB>
+static int launch_combine_runs_t(const CombineArgs &a, dim3 grid, cudaStream_t st) {
+    using S = CombSmem<ZB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(combine_runs_kernel<ZB, YB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        attr_set = true;
+    }
+    combine_runs_kernel<ZB, YB><<<grid, kCombWarps * 32, S::kTotal, st>>>(a);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
 int launch_combine_rows(const CombineArgs &a, int B, cudaStream_t st) {
     dim3 grid((a.capA + kCombRows - 1) / kCombRows, B);
+    MVX_REQUIRE(a.capA <= 0xFFFFFF, MVX_EINVAL, "combine: more than 2^24 rows per frame");
     if (a.y1pack) {
         MVX_REQUIRE(a.y1_rowinv && a.wbound && a.pack_tiles * 256 >= a.capA, MVX_EINVAL, "combine: bad packed-output arguments");
         combine_rows_kernel<true><<<grid, kCombWarps * 32, 0, st>>>(a);
     } else if (a.z_bf16 || a.y1_bf16) {
         MVX_REQUIRE(a.z_bf16 && a.y1_bf16, MVX_EINVAL, "combine: the bf16 mode stores both Z and Y1 as bf16");
+        if (!g_comb_v1) return launch_combine_runs_t<true, true>(a, grid, st);
         combine_rows_kernel<false, true, true><<<grid, kCombWarps * 32, 0, st>>>(a);
-    } else
-    combine_rows_kernel<false><<<grid, kCombWarps * 32, 0, st>>>(a);
+    } else {
+        if (!g_comb_v1) return launch_combine_runs_t<false, false>(a, grid, st);
+        combine_rows_kernel<false><<<grid, kCombWarps * 32, 0, st>>>(a);
+    }
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }

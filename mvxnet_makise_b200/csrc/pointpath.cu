@@ -566,8 +566,9 @@ extern "C" const char *mvx_pointpath_layout_name(int32_t region) {
 extern "C" int mvx_pointpath_forward(const mvx_pointpath_args_t *args) { return mvx::pointpath_forward(args, false); }
 
 extern "C" int mvx_set_fold_mode(int32_t mode) {
-    if (mode < 0 || mode > 1) return MVX_EINVAL;
-    mvx::g_fold = mode;
+    if (mode < 0 || mode > 2) return MVX_EINVAL;
+    mvx::g_fold = mode == 1;
+    mvx::set_combine_v1(mode == 2);
     return MVX_OK;
 }
 
