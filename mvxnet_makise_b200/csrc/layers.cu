@@ -31,8 +31,10 @@ __device__ __forceinline__ double stat_rows(const NormSrc &n, int f) {
     return n.counts ? (double)n.counts[f * 4 + 0] * (double)n.T : (double)n.rows_fixed;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_layer_kernel(LayerArgs a) {
+// LD: 0 = the A tile comes from a.X (normalised with a.in_stats when given); 1 / 2 = VFE1 / VFE2 with the input rows built on the
+// fly from z (what prep_vfe1_kernel / prep_vfe2_kernel below materialise as X6 / X7): Cin = 32
+template <int BN, int LD = 0>
+__global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_layer_kernel(LayerArgs a, RowFuseArgs z) {
     // thread tile: RT rows x TN columns. The 16-column layers use 4 x 2 (8 x 1 needs two broadcast LDS.128 of A per 8 FFMA and is
     // bound by the shared-memory pipe: 928 wavefront cycles per tile and k chunk against 256 FFMA issue cycles)
     constexpr int TN = BN == 16 ? 2 : BN / 16;
@@ -61,7 +63,9 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
     if ((long long)blockIdx.x * kTilesPerCta * kBM >= n_rows) return;
     for (int i = tid; i < 2 * 8 * BN; i += 256) s_red[i] = 0.0;
 
-    if (a.in_stats) {
+    if (LD != 0) {
+        if (tid < 16) norm_coef(z.in_stats + ((size_t)f * 16 + tid) * 2, Rstat, a.eps, s_mean[tid], s_rstd[tid]);
+    } else if (a.in_stats) {
         for (int c = tid; c < a.Cin; c += 256)
             norm_coef(a.in_stats + ((size_t)f * a.Cin + c) * 2, Rstat, a.eps, s_mean[c], s_rstd[c]);
     }
@@ -82,7 +86,46 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
         for (int j = 0; j < 2; ++j) {  // A tile: 128 rows x 16 k, stored transposed
             const int idx = tid + j * 256, r = idx >> 2, c4 = idx & 3;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + r < n_rows) {
+            if (LD == 1) {
+                // [x y z dx dy dz r | norm5(Y5) | 0 x 9]: the concat of MVXNet.py:26 (columns 23..31 are zero padding)
+                if (row0 + r < n_rows) {
+                    const size_t ro = (size_t)f * z.capA + row0 + r;
+                    float e[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = k0 + c4 * 4 + q;
+                        e[q] = k < 7 ? __ldg(z.vox8 + ro * 8 + k) : (k < 23 ? (__ldg(z.Y + ro * 16 + (k - 7)) - s_mean[k - 7]) * s_rstd[k - 7] : 0.f);
+                    }
+                    v = make_float4(e[0], e[1], e[2], e[3]);
+                }
+            } else if (LD == 2) {
+                // rows [0, K): the kept points, voxel-major; rows [K, K + N): one pad row per voxel standing for its T - cnt empty slots
+                // (value = the frame's pad row after VFE1's FCN, multiplicity T - cnt): [norm6(y) | norm6(max over the voxel)]
+                const long long rr = row0 + r;
+                if (rr < n_rows) {
+                    const bool pad = rr >= K;
+                    const int vv = pad ? (int)(rr - K) : __ldg(z.row_vox + (size_t)f * z.cap + rr);
+                    const int cnt = __ldg(z.vox_cnt + (size_t)f * z.cap + vv);
+                    const int c = (k0 + c4 * 4) & 15;
+                    const float4 yp = __ldg(reinterpret_cast<const float4 *>(z.Y + ((size_t)f * z.capA + K) * 16 + c));
+                    if (k0 + c4 * 4 < 16) {
+                        v = pad ? yp : __ldg(reinterpret_cast<const float4 *>(z.Y + ((size_t)f * z.capA + rr) * 16 + c));
+                    } else {
+                        const int4 mi = __ldg(reinterpret_cast<const int4 *>(z.vmax + ((size_t)f * z.cap + vv) * 16 + c));
+                        v = make_float4(__int_as_float(mi.x), __int_as_float(mi.y), __int_as_float(mi.z), __int_as_float(mi.w));
+                        if (cnt < a.T) v = make_float4(fmaxf(v.x, yp.x), fmaxf(v.y, yp.y), fmaxf(v.z, yp.z), fmaxf(v.w, yp.w));   // pad slots join the max over T
+                    }
+                    v.x = (v.x - s_mean[c + 0]) * s_rstd[c + 0];
+                    v.y = (v.y - s_mean[c + 1]) * s_rstd[c + 1];
+                    v.z = (v.z - s_mean[c + 2]) * s_rstd[c + 2];
+                    v.w = (v.w - s_mean[c + 3]) * s_rstd[c + 3];
+                    if (k0 == 0 && c4 == 0 && blockIdx.y == 0) {   // once per row: what the epilogue below and the last FCN read
+                        const int wpad = a.T - cnt;
+                        z.rowB_w[(size_t)f * a.rowcap + rr] = pad ? (float)wpad : 1.f;
+                        z.rowB_v[(size_t)f * a.rowcap + rr] = (pad && wpad == 0) ? -1 : vv;
+                    }
+                }
+            } else if (row0 + r < n_rows) {
                 v = *reinterpret_cast<const float4 *>(Xf + (size_t)r * a.ldx + k0 + c4 * 4);
                 if (a.in_stats) {
                     const int k = k0 + c4 * 4;
@@ -422,12 +465,32 @@ int launch_layer(const LayerArgs &a, int F, cudaStream_t st) {
     if (max_rows <= 0) return MVX_OK;
     const unsigned tiles = (unsigned)ceil_div(ceil_div(max_rows, kBM), kTilesPerCta);
     if (a.Cout % 128 == 0) {
-        fcn_layer_kernel<128><<<dim3(tiles, a.Cout / 128, F), 256, 0, st>>>(a);
+        fcn_layer_kernel<128><<<dim3(tiles, a.Cout / 128, F), 256, 0, st>>>(a, RowFuseArgs{});
     } else if (a.Cout % 64 == 0) {
-        fcn_layer_kernel<64><<<dim3(tiles, a.Cout / 64, F), 256, 0, st>>>(a);
+        fcn_layer_kernel<64><<<dim3(tiles, a.Cout / 64, F), 256, 0, st>>>(a, RowFuseArgs{});
     } else {
-        fcn_layer_kernel<16><<<dim3(tiles, a.Cout / 16, F), 256, 0, st>>>(a);
+        fcn_layer_kernel<16><<<dim3(tiles, a.Cout / 16, F), 256, 0, st>>>(a, RowFuseArgs{});
     }
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+
+static int g_vfe_fused = 1;   // 0: prep_vfe1 / prep_vfe2 + plain layers also in inference (mvx_set_gemm_mode(10), A/B timing)
+bool vfe_fused_enabled() { return g_vfe_fused != 0; }
+void set_vfe_fused(int on) { g_vfe_fused = on; }
+
+int launch_vfe1_fused(const LayerArgs &a, const RowFuseArgs &z, int F, cudaStream_t st) {
+    MVX_REQUIRE(a.Cin == 32 && a.Cout == 16 && a.rows_mode == 1 && a.counts && z.vox8 && z.Y && z.in_stats, MVX_EINVAL, "vfe1 fused: bad arguments");
+    const unsigned tiles = (unsigned)ceil_div(ceil_div((long long)a.rowcap, kBM), kTilesPerCta);
+    fcn_layer_kernel<16, 1><<<dim3(tiles, 1, F), 256, 0, st>>>(a, z);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
+}
+int launch_vfe2_fused(const LayerArgs &a, const RowFuseArgs &z, int F, cudaStream_t st) {
+    MVX_REQUIRE(a.Cin == 32 && a.Cout == 64 && a.rows_mode == 2 && a.counts && z.Y && z.vmax && z.vox_cnt && z.row_vox && z.rowB_w && z.rowB_v && z.in_stats,
+                MVX_EINVAL, "vfe2 fused: bad arguments");
+    const unsigned tiles = (unsigned)ceil_div(ceil_div((long long)a.rowcap, kBM), kTilesPerCta);
+    fcn_layer_kernel<64, 2><<<dim3(tiles, 1, F), 256, 0, st>>>(a, z);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }
@@ -486,14 +549,15 @@ static int dense_layer(const float *x, int64_t R, int32_t T, int32_t Cin, const 
 }  // namespace mvx
 
 extern "C" int mvx_set_gemm_mode(int32_t mode) {
-    if (mode < 0 || mode > 9 || mode == 3) return MVX_EINVAL;   // 1 and 8: conv1 / fcn2 / last FCN through the TMA-fed A-from-TMEM persistent kernel (tc3_layer.cu); 9 = like 1 with the one-tile kernel of tc_layer.cu for those layers   // 3 (CTA-pair kernel) was removed: measured slower, never default   // 7 = like 1, conv1 / fcn2 through the persistent 3xFP16 kernel (experimental, measured slower)   // 6 = bf16 mode: single-pass bf16 operands for the same layers mode 1 runs in 3xFP16
+    if (mode < 0 || mode > 10 || mode == 3) return MVX_EINVAL;   // 10 = like 1 with prep_vfe1 / prep_vfe2 materialising the VFE inputs also in inference (the earlier default, kept for A/B timing and for inspecting X6 / X7)   // 1 and 8: conv1 / fcn2 / last FCN through the TMA-fed A-from-TMEM persistent kernel (tc3_layer.cu); 9 = like 1 with the one-tile kernel of tc_layer.cu for those layers   // 3 (CTA-pair kernel) was removed: measured slower, never default   // 7 = like 1, conv1 / fcn2 through the persistent 3xFP16 kernel (experimental, measured slower)   // 6 = bf16 mode: single-pass bf16 operands for the same layers mode 1 runs in 3xFP16
     mvx::set_tc_bf16(mode == 6);   // 4 = tensor cores, 3xTF32 everywhere (no fp16 operands)
     mvx::set_tc_f16(mode != 4);                    // 5 = like 1, and the dense layer API (mvx_fcn_forward ...) also uses fp16
     mvx::g_dense_f16 = mode == 5;                  //     operands: the caller promises inputs of O(1) magnitude (tests)   // 2 = tensor cores, persistent 256x128 variant (measured slower: SS-mode
     mvx::g_gemm_mode = mode == 0 ? 0 : 1;          //     MMAs at N=128 saturate shared-memory bandwidth); kept for experiments
     mvx::set_tc_persistent(mode == 2);
     mvx::set_tc_persist16(mode == 7);
-    mvx::set_tc3(mode == 1 || mode == 8 || mode == 6);
+    mvx::set_tc3(mode == 1 || mode == 8 || mode == 6 || mode == 10);
+    mvx::set_vfe_fused(mode != 10);
     return MVX_OK;
 }
 

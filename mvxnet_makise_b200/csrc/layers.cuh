@@ -60,6 +60,23 @@ struct LayerArgs {
 #endif
 int launch_layer(const LayerArgs &a, int F, cudaStream_t st);            // exact-fp32 SIMT kernel
 
+// Fused VFE loaders (inference): the SIMT kernel builds VFE1's / VFE2's input tile on the fly instead of reading the X6 / X7
+// matrices that prep_vfe1 / prep_vfe2 materialise (one launch and one round trip through HBM less per VFE).
+struct RowFuseArgs {
+    const float *vox8;       // VFE1: [F][capA][8] x,y,z,dx,dy,dz,r,0
+    const float *Y;          // VFE1: Y5 [F][capA][16] raw fcn3 rows; VFE2: Y6 [F][capA][16] raw VFE1 rows (row K_f = the frame's pad row)
+    const double *in_stats;  // [F][16][2] sums of that producer layer
+    const int *vmax;         // VFE2: [F][cap][16] per-voxel max of Y6 (float bits)
+    const int *vox_cnt, *row_vox;   // VFE2: [F][cap] points kept per voxel, voxel of each kept row
+    float *rowB_w;           // VFE2 out: [F][capB] BatchNorm multiplicity of the K_f + N_f rows (1 / T - cnt)
+    int *rowB_v;             // VFE2 out: [F][capB] voxel of each row (-1: a pad row of a full voxel)
+    int cap, capA;
+};
+int launch_vfe1_fused(const LayerArgs &a, const RowFuseArgs &z, int F, cudaStream_t st);   // a.X unused: input = [vox7 | norm5(Y5) | 0]
+int launch_vfe2_fused(const LayerArgs &a, const RowFuseArgs &z, int F, cudaStream_t st);   // a.X unused: input = [norm6(Y6) | norm6(max6[v])]; writes rowB_w / rowB_v
+bool vfe_fused_enabled();
+void set_vfe_fused(int on);
+
 // tensor-core (tcgen05, 3xTF32) implementation of the same layer; wpack = tc_wpack_bytes() of scratch
 bool tc_layer_eligible(const LayerArgs &a);
 size_t tc_wpack_bytes(int Cin, int Cout);

@@ -429,9 +429,14 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
     vp.n7 = NormSrc{stat_of(6), a->counts, 0, T, a->bn_eps};
     vp.n8 = NormSrc{stat_of(7), a->counts, 0, T, a->bn_eps};
 
+    // inference: VFE1 / VFE2 build their input rows on the fly (fused loaders of the SIMT kernel) instead of reading the X6 / X7 matrices that
+    // prep_vfe1 / prep_vfe2 materialise; training keeps X6 / X7 (dW = dpre^T X)
+    const bool fuse_vfe = !train && vfe_fused_enabled();
     stamp.mark(S_PREP1);
-    rc = launch_prep_vfe1(vp, st);
-    if (rc) return rc;
+    if (!fuse_vfe) {
+        rc = launch_prep_vfe1(vp, st);
+        if (rc) return rc;
+    }
     {  // VFE1's FCN (23 -> 16) + per-voxel max (voxelnet/Pipe.py:12-18)
         stamp.mark(S_VFE1);
         LayerArgs la{};
@@ -439,12 +444,20 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         la.Y = F32(R_Y6), la.ldy = 16, la.out_stats = stat_of(5), la.vmax = I32(R_VMAX6);
         la.row_w = F32(R_ROWA_W), la.row_v = vo.row_vox, la.rowv_cap = cap, la.counts = a->counts, la.rows_mode = 1;
         la.rowcap = L.capA, la.vcap = cap, la.T = T, la.eps = a->bn_eps;
-        rc = launch_layer_auto(la, B, F32(R_WPACK), st);
+        if (fuse_vfe) {
+            RowFuseArgs z{};
+            z.vox8 = F32(R_VOX8), z.Y = F32(R_Y5), z.in_stats = stat_of(4), z.cap = cap, z.capA = L.capA;
+            rc = launch_vfe1_fused(la, z, B, st);
+        } else {
+            rc = launch_layer_auto(la, B, F32(R_WPACK), st);
+        }
         if (rc) return rc;
     }
     stamp.mark(S_PREP2);
-    rc = launch_prep_vfe2(vp, st);
-    if (rc) return rc;
+    if (!fuse_vfe) {
+        rc = launch_prep_vfe2(vp, st);
+        if (rc) return rc;
+    }
     {  // VFE2's FCN (32 -> 64) + per-voxel max; rows = K_f kept points + one weighted pad row per voxel
         stamp.mark(S_VFE2);
         LayerArgs la{};
@@ -452,7 +465,14 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         la.Y = F32(R_Y7), la.ldy = 64, la.out_stats = stat_of(6), la.vmax = I32(R_VMAX7);
         la.row_w = F32(R_ROWB_W), la.row_v = I32(R_ROWB_V), la.rowv_cap = L.capB, la.counts = a->counts, la.rows_mode = 2;
         la.rowcap = L.capB, la.vcap = cap, la.T = T, la.eps = a->bn_eps;
-        rc = launch_layer_auto(la, B, F32(R_WPACK), st);
+        if (fuse_vfe) {
+            RowFuseArgs z{};
+            z.Y = F32(R_Y6), z.in_stats = stat_of(5), z.vmax = I32(R_VMAX6), z.vox_cnt = vo.vox_cnt, z.row_vox = vo.row_vox;
+            z.rowB_w = F32(R_ROWB_W), z.rowB_v = I32(R_ROWB_V), z.cap = cap, z.capA = L.capA;
+            rc = launch_vfe2_fused(la, z, B, st);
+        } else {
+            rc = launch_layer_auto(la, B, F32(R_WPACK), st);
+        }
         if (rc) return rc;
     }
     stamp.mark(S_PREP3);

@@ -361,7 +361,18 @@ def test_fused_path_matches_reference_golden(mvx, golden_dir, tag, fusion_mode):
     row0 = path.region('vox_row0', torch.int32, (1, cap + 1))[0, :N + 1].cpu().numpy()
     cnt = path.region('vox_cnt', torch.int32, (1, cap))[0, :N].cpu().numpy()
     assert row0[N] == K and np.array_equal(cnt, (ref['voxels9'][..., :3] != 0).any(-1).sum(1).numpy())
+    # the concat [voxel columns | image features] of MVXNet.py:26: the default inference path builds it inside VFE1's loader
+    # (csrc/row_layer.cu); gemm mode 10 materialises it as X6 (prep_vfe1_kernel, what training uses), which is what is read here
+    from mvxnet_makise_b200 import _lib
+    try:
+        _lib.set_gemm_mode(10)
+        path([g['pcd4']], [calib], [torch.from_numpy(m) for m in maps])
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_gemm_mode(1)
     x6 = path.region('X6', torch.float32, (1, cap + 128, 32))[0, :K].cpu()
+    vox8 = path.region('vox8', torch.float32, (1, cap + 128, 8))[0, :K].cpu()
+    assert torch.equal(vox8[:, :7], x6[:, :7])      # the rows VFE1's fused loader reads
     dense_rows = np.concatenate([v * G.T + np.arange(c) for v, c in enumerate(cnt)])
     v9 = ref['voxels9'].reshape(-1, 9)[dense_rows]
     assert torch.equal(x6[:, :7], v9[:, :7]), 'voxel feature columns (x,y,z,dx,dy,dz,r) not bit-exact'
