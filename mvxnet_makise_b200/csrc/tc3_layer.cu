@@ -426,10 +426,26 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
             }
             named_bar_sync(bar_id, 128);
         };
-        for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            int f, Kf;
-            long long row0, n_rows;
-            if (!decode(t, f, row0, n_rows, Kf)) continue;
+        // The walk over the tiles carries the row metadata of the NEXT tile in registers: the two global loads per row (multiplicity,
+        // voxel id) used to sit at the head of every tile, a full memory round trip that nothing covered (14 % of the epilogue's
+        // stall samples; with K = 128 the epilogue, not the four-stage main loop, bounds the kernel).
+        auto next_valid = [&](int tn, int &f, long long &row0, long long &n_rows, int &Kf) -> int {
+            while (tn < total && !decode(tn, f, row0, n_rows, Kf)) tn += gridDim.x;
+            return tn;
+        };
+        auto load_meta = [&](int f, long long row0, long long n_rows, int Kf, float &w, int &v) {
+            const long long rr = row0 + et;
+            w = rr < n_rows ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + rr] : 1.f) : 0.f;
+            v = -1;
+            if (a.vmax && w != 0.f) v = (a.rows_mode == 1 && rr >= Kf) ? -1 : a.row_v[(size_t)f * a.rowv_cap + rr];
+        };
+        int f = 0, Kf = 0;
+        long long row0 = 0, n_rows = 0;
+        int t = next_valid(blockIdx.x, f, row0, n_rows, Kf);
+        float pw = 0.f;
+        int pv = -1;
+        if (t < total) load_meta(f, row0, n_rows, Kf, pw, pv);
+        while (t < total) {
             if (f != cur_f) {
                 if (cur_f >= 0) flush_stats(cur_f);
                 cur_f = f;
@@ -438,22 +454,24 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
             // row metadata of this tile: every group keeps its own copy (no cross-group synchronisation)
             float *roww = s_roww + (eg * 2 + ab) * T3_TM;
             int *rowv = s_rowv + (eg * 2 + ab) * T3_TM;
-            {
-                const long long rr = row0 + et;
-                const float w = rr < n_rows ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + rr] : 1.f) : 0.f;
-                int v = -1;
-                if (a.vmax && w != 0.f) v = (a.rows_mode == 1 && rr >= Kf) ? -1 : a.row_v[(size_t)f * a.rowv_cap + rr];
-                roww[et] = w;
-                rowv[et] = v;
-            }
-            // does this thread's 32-row group hold a row whose multiplicity is neither 0 nor 1 (the weighted pad rows)? Uniform
-            // per warp, so the fp64 side path below is skipped by whole warps on ordinary tiles
+            const float w_own = pw;
+            const int v_own = pv;
+            int fn = 0, Kfn = 0;
+            long long row0n = 0, n_rowsn = 0;
+            const int tn = next_valid(t + gridDim.x, fn, row0n, n_rowsn, Kfn);
+            if (tn < total) load_meta(fn, row0n, n_rowsn, Kfn, pw, pv);     // in flight during this tile
+            roww[et] = w_own;
+            rowv[et] = v_own;
+            // This warp's lanes hold the rows egrp * 32 + lane - exactly the rows its threads walk below. Run structure of the voxel
+            // ids as bit masks (a row starts / ends a run of equal ids), rows of multiplicity 1, and whether any row is weighted
+            // (neither 0 nor 1: the pad rows; the fp64 side path is skipped by whole warps on ordinary tiles): the walk tests
+            // register bits instead of chasing shared-memory loads with compares and branches row by row.
+            const int v_prev = __shfl_up_sync(0xffffffffu, v_own, 1), v_next = __shfl_down_sync(0xffffffffu, v_own, 1);
+            const unsigned startmask = __ballot_sync(0xffffffffu, lane == 0 || v_own != v_prev);
+            const unsigned endmask = __ballot_sync(0xffffffffu, v_own >= 0 && (lane == 31 || v_own != v_next));
+            const unsigned onesmask = __ballot_sync(0xffffffffu, w_own == 1.f);
+            const bool heavy = __any_sync(0xffffffffu, w_own != 1.f && w_own != 0.f);
             named_bar_sync(bar_id, 128);
-            bool heavy = false;
-            {
-                const float w = roww[egrp * 32 + lane];
-                heavy = __any_sync(0xffffffffu, w != 1.f && w != 0.f);
-            }
             mbar_wait(acc_full(ab), (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -492,8 +510,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
                 {
                     double sy = 0.0, syy = 0.0;
                     int *vm = a.vmax ? a.vmax + (size_t)f * a.vcap * a.Cout + cb * 32 + ecol : nullptr;
-                    int cv = -1;
-                    float cm = 0.f;
+                    float cm = 0.f;                       // running maximum of the current run (y >= 0 after the ReLU: 0 is neutral)
                     const float *rw_ = roww + egrp * 32;
                     const int *rv_ = rowv + egrp * 32;
 #pragma unroll
@@ -507,7 +524,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
                         float ps = 0.f, pss = 0.f;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float my = rw_[h * 16 + j] == 1.f ? yv[j] : 0.f;
+                            const float my = (onesmask >> (h * 16 + j)) & 1u ? yv[j] : 0.f;
                             ps += my;
                             pss = fmaf(my, yv[j], pss);
                         }
@@ -526,18 +543,12 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
                         if (vm) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                const int vv = rv_[h * 16 + j];
-                                if (vv != cv) {
-                                    if (cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
-                                    cv = vv;
-                                    cm = yv[j];
-                                } else {
-                                    cm = fmaxf(cm, yv[j]);
-                                }
+                                const int b = h * 16 + j;
+                                cm = fmaxf((startmask >> b) & 1u ? 0.f : cm, yv[j]);
+                                if ((endmask >> b) & 1u) atomicMax(vm + (size_t)rv_[b] * a.Cout, __float_as_int(cm));   // one atomic per run
                             }
                         }
                     }
-                    if (vm && cv >= 0) atomicMax(vm + (size_t)cv * a.Cout, __float_as_int(cm));
                     s_part[(egrp * 32 + ecol) * 2] = sy;
                     s_part[(egrp * 32 + ecol) * 2 + 1] = syy;
                 }
@@ -549,6 +560,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
                 }
             }
             ++it;
+            t = tn, f = fn, row0 = row0n, n_rows = n_rowsn, Kf = Kfn;
         }
         if (cur_f >= 0) flush_stats(cur_f);
         if (g.store && et == 0) tma_store_wait_all();
