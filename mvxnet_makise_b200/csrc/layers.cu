@@ -41,10 +41,14 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
     constexpr int RT = BN == 16 ? 4 : 8;        // rows per thread
     constexpr int TX = BN / TN;                 // threads across the columns (8 or 16); 256 / TX row groups x RT rows = 128 rows
     static_assert((256 / TX) * RT == kBM, "thread tile does not cover the CTA tile");
-    __shared__ __align__(16) float smem[kBK * kAS + kBK * 128];
+    // BN <= 64 (the narrow layers this kernel serves by default): the A / B tiles are double-buffered and the next k chunk travels
+    // in registers while the current one is multiplied - one block barrier per chunk and no exposed global-load latency (the
+    // single-buffered loop paid two barriers and one round trip per 16-k chunk). BN = 128 keeps one buffer (48 KB static limit).
+    constexpr int NBUF = BN <= 64 ? 2 : 1;
+    constexpr int kTileFloats = kBK * kAS + kBK * BN;
+    __shared__ __align__(16) float smem[NBUF * kTileFloats];
     __shared__ float s_mean[768], s_rstd[768];
     __shared__ double s_red[2 * 8 * BN];   // [sum | sum of squares][8 warps][BN], accumulated over the tiles of this CTA
-    float *As = smem, *Bs = smem + kBK * kAS;
 
     const int f = blockIdx.z, n0 = blockIdx.y * BN, tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
@@ -81,72 +85,100 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
     const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx;
-    for (int k0 = 0; k0 < a.Cin; k0 += kBK) {
+    // one 16-byte piece of the A tile (row r = idx / 4, columns k0 + 4 (idx % 4) ..) as the layer reads it: normalised / built on the fly
+    auto load_a = [&](int k0, int j) -> float4 {
+        const int idx = tid + j * 256, r = idx >> 2, c4 = idx & 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (LD == 1) {
+            // [x y z dx dy dz r | norm5(Y5) | 0 x 9]: the concat of MVXNet.py:26 (columns 23..31 are zero padding)
+            if (row0 + r < n_rows) {
+                const size_t ro = (size_t)f * z.capA + row0 + r;
+                float e[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = k0 + c4 * 4 + q;
+                    e[q] = k < 7 ? __ldg(z.vox8 + ro * 8 + k) : (k < 23 ? (__ldg(z.Y + ro * 16 + (k - 7)) - s_mean[k - 7]) * s_rstd[k - 7] : 0.f);
+                }
+                v = make_float4(e[0], e[1], e[2], e[3]);
+            }
+        } else if (LD == 2) {
+            // rows [0, K): the kept points, voxel-major; rows [K, K + N): one pad row per voxel standing for its T - cnt empty slots
+            // (value = the frame's pad row after VFE1's FCN, multiplicity T - cnt): [norm6(y) | norm6(max over the voxel)]
+            const long long rr = row0 + r;
+            if (rr < n_rows) {
+                const bool pad = rr >= K;
+                const int vv = pad ? (int)(rr - K) : __ldg(z.row_vox + (size_t)f * z.cap + rr);
+                const int cnt = __ldg(z.vox_cnt + (size_t)f * z.cap + vv);
+                const int c = (k0 + c4 * 4) & 15;
+                const float4 yp = __ldg(reinterpret_cast<const float4 *>(z.Y + ((size_t)f * z.capA + K) * 16 + c));
+                if (k0 + c4 * 4 < 16) {
+                    v = pad ? yp : __ldg(reinterpret_cast<const float4 *>(z.Y + ((size_t)f * z.capA + rr) * 16 + c));
+                } else {
+                    const int4 mi = __ldg(reinterpret_cast<const int4 *>(z.vmax + ((size_t)f * z.cap + vv) * 16 + c));
+                    v = make_float4(__int_as_float(mi.x), __int_as_float(mi.y), __int_as_float(mi.z), __int_as_float(mi.w));
+                    if (cnt < a.T) v = make_float4(fmaxf(v.x, yp.x), fmaxf(v.y, yp.y), fmaxf(v.z, yp.z), fmaxf(v.w, yp.w));   // pad slots join the max over T
+                }
+                v.x = (v.x - s_mean[c + 0]) * s_rstd[c + 0];
+                v.y = (v.y - s_mean[c + 1]) * s_rstd[c + 1];
+                v.z = (v.z - s_mean[c + 2]) * s_rstd[c + 2];
+                v.w = (v.w - s_mean[c + 3]) * s_rstd[c + 3];
+                if (k0 == 0 && c4 == 0 && blockIdx.y == 0) {   // once per row: what the epilogue below and the last FCN read
+                    const int wpad = a.T - cnt;
+                    z.rowB_w[(size_t)f * a.rowcap + rr] = pad ? (float)wpad : 1.f;
+                    z.rowB_v[(size_t)f * a.rowcap + rr] = (pad && wpad == 0) ? -1 : vv;
+                }
+            }
+        } else if (row0 + r < n_rows) {
+            v = *reinterpret_cast<const float4 *>(Xf + (size_t)r * a.ldx + k0 + c4 * 4);
+            if (a.in_stats) {
+                const int k = k0 + c4 * 4;
+                v.x = (v.x - s_mean[k + 0]) * s_rstd[k + 0];
+                v.y = (v.y - s_mean[k + 1]) * s_rstd[k + 1];
+                v.z = (v.z - s_mean[k + 2]) * s_rstd[k + 2];
+                v.w = (v.w - s_mean[k + 3]) * s_rstd[k + 3];
+            }
+        }
+        return v;
+    };
+    constexpr int NBP = (BN * 4 + 255) / 256;       // 16-byte pieces of the B tile (16 k x BN) per thread
+    auto load_b = [&](int k0, int q) -> float4 {
+        const int idx = tid + q * 256;
+        if (idx >= BN * 4) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const int k = idx / (BN / 4), n4 = idx % (BN / 4);
+        return __ldg(reinterpret_cast<const float4 *>(a.Wt + (size_t)(k0 + k) * a.Cout + n0 + n4 * 4));
+    };
+    auto store_tiles = [&](float *As, float *Bs, const float4 (&va)[2], const float4 (&vb)[NBP]) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {  // A tile: 128 rows x 16 k, stored transposed
             const int idx = tid + j * 256, r = idx >> 2, c4 = idx & 3;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (LD == 1) {
-                // [x y z dx dy dz r | norm5(Y5) | 0 x 9]: the concat of MVXNet.py:26 (columns 23..31 are zero padding)
-                if (row0 + r < n_rows) {
-                    const size_t ro = (size_t)f * z.capA + row0 + r;
-                    float e[4];
+            As[(c4 * 4 + 0) * kAS + r] = va[j].x;
+            As[(c4 * 4 + 1) * kAS + r] = va[j].y;
+            As[(c4 * 4 + 2) * kAS + r] = va[j].z;
+            As[(c4 * 4 + 3) * kAS + r] = va[j].w;
+        }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int k = k0 + c4 * 4 + q;
-                        e[q] = k < 7 ? __ldg(z.vox8 + ro * 8 + k) : (k < 23 ? (__ldg(z.Y + ro * 16 + (k - 7)) - s_mean[k - 7]) * s_rstd[k - 7] : 0.f);
-                    }
-                    v = make_float4(e[0], e[1], e[2], e[3]);
-                }
-            } else if (LD == 2) {
-                // rows [0, K): the kept points, voxel-major; rows [K, K + N): one pad row per voxel standing for its T - cnt empty slots
-                // (value = the frame's pad row after VFE1's FCN, multiplicity T - cnt): [norm6(y) | norm6(max over the voxel)]
-                const long long rr = row0 + r;
-                if (rr < n_rows) {
-                    const bool pad = rr >= K;
-                    const int vv = pad ? (int)(rr - K) : __ldg(z.row_vox + (size_t)f * z.cap + rr);
-                    const int cnt = __ldg(z.vox_cnt + (size_t)f * z.cap + vv);
-                    const int c = (k0 + c4 * 4) & 15;
-                    const float4 yp = __ldg(reinterpret_cast<const float4 *>(z.Y + ((size_t)f * z.capA + K) * 16 + c));
-                    if (k0 + c4 * 4 < 16) {
-                        v = pad ? yp : __ldg(reinterpret_cast<const float4 *>(z.Y + ((size_t)f * z.capA + rr) * 16 + c));
-                    } else {
-                        const int4 mi = __ldg(reinterpret_cast<const int4 *>(z.vmax + ((size_t)f * z.cap + vv) * 16 + c));
-                        v = make_float4(__int_as_float(mi.x), __int_as_float(mi.y), __int_as_float(mi.z), __int_as_float(mi.w));
-                        if (cnt < a.T) v = make_float4(fmaxf(v.x, yp.x), fmaxf(v.y, yp.y), fmaxf(v.z, yp.z), fmaxf(v.w, yp.w));   // pad slots join the max over T
-                    }
-                    v.x = (v.x - s_mean[c + 0]) * s_rstd[c + 0];
-                    v.y = (v.y - s_mean[c + 1]) * s_rstd[c + 1];
-                    v.z = (v.z - s_mean[c + 2]) * s_rstd[c + 2];
-                    v.w = (v.w - s_mean[c + 3]) * s_rstd[c + 3];
-                    if (k0 == 0 && c4 == 0 && blockIdx.y == 0) {   // once per row: what the epilogue below and the last FCN read
-                        const int wpad = a.T - cnt;
-                        z.rowB_w[(size_t)f * a.rowcap + rr] = pad ? (float)wpad : 1.f;
-                        z.rowB_v[(size_t)f * a.rowcap + rr] = (pad && wpad == 0) ? -1 : vv;
-                    }
-                }
-            } else if (row0 + r < n_rows) {
-                v = *reinterpret_cast<const float4 *>(Xf + (size_t)r * a.ldx + k0 + c4 * 4);
-                if (a.in_stats) {
-                    const int k = k0 + c4 * 4;
-                    v.x = (v.x - s_mean[k + 0]) * s_rstd[k + 0];
-                    v.y = (v.y - s_mean[k + 1]) * s_rstd[k + 1];
-                    v.z = (v.z - s_mean[k + 2]) * s_rstd[k + 2];
-                    v.w = (v.w - s_mean[k + 3]) * s_rstd[k + 3];
-                }
-            }
-            As[(c4 * 4 + 0) * kAS + r] = v.x;
-            As[(c4 * 4 + 1) * kAS + r] = v.y;
-            As[(c4 * 4 + 2) * kAS + r] = v.z;
-            As[(c4 * 4 + 3) * kAS + r] = v.w;
+        for (int q = 0; q < NBP; ++q) {
+            const int idx = tid + q * 256;
+            if (idx < BN * 4) *reinterpret_cast<float4 *>(Bs + (idx / (BN / 4)) * BN + (idx % (BN / 4)) * 4) = vb[q];
         }
-        for (int idx = tid; idx < BN * 4; idx += 256) {  // B tile: 16 k x BN
-            const int k = idx / (BN / 4), n4 = idx % (BN / 4);
-            *reinterpret_cast<float4 *>(Bs + k * BN + n4 * 4) =
-                __ldg(reinterpret_cast<const float4 *>(a.Wt + (size_t)(k0 + k) * a.Cout + n0 + n4 * 4));
-        }
+    };
+    float4 va[2], vb[NBP];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) va[j] = load_a(0, j);
+#pragma unroll
+    for (int q = 0; q < NBP; ++q) vb[q] = load_b(0, q);
+    int buf = 0;
+    for (int k0 = 0; k0 < a.Cin; k0 += kBK) {
+        float *As = smem + buf * kTileFloats, *Bs = As + kBK * kAS;
+        store_tiles(As, Bs, va, vb);
         __syncthreads();
+        if (k0 + kBK < a.Cin) {   // the next chunk: in flight while this one is multiplied
 #pragma unroll
+            for (int j = 0; j < 2; ++j) va[j] = load_a(k0 + kBK, j);
+#pragma unroll
+            for (int q = 0; q < NBP; ++q) vb[q] = load_b(k0 + kBK, q);
+        }
+        #pragma unroll
         for (int k = 0; k < kBK; ++k) {
             float av[RT], bv[TN];
             *reinterpret_cast<float4 *>(av) = *reinterpret_cast<const float4 *>(As + k * kAS + ty * RT);
@@ -164,8 +196,10 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
 #pragma unroll
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
-        __syncthreads();
+        if (NBUF == 1) __syncthreads();   // single buffer: everybody is done reading before the next chunk is stored
+        else buf ^= 1;                     // double buffer: the barrier of the next chunk orders its stores behind these reads (two chunks back)
     }
+    if (NBUF == 2) __syncthreads();        // the next tile of this CTA stores into a buffer that may still be read
 
     // ---- epilogue: bias, ReLU, raw store, weighted fp64 statistics, per-voxel max ------------------------
     float w[RT];

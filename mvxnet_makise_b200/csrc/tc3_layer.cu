@@ -435,9 +435,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
         };
         auto load_meta = [&](int f, long long row0, long long n_rows, int Kf, float &w, int &v) {
             const long long rr = row0 + et;
+            const bool has_v = a.vmax && rr < n_rows && !(a.rows_mode == 1 && rr >= Kf);
+            // both loads are issued back to back (the voxel id does not wait for the multiplicity to arrive)
+            const int vl = has_v ? a.row_v[(size_t)f * a.rowv_cap + rr] : -1;
             w = rr < n_rows ? (a.row_w ? a.row_w[(size_t)f * a.rowcap + rr] : 1.f) : 0.f;
-            v = -1;
-            if (a.vmax && w != 0.f) v = (a.rows_mode == 1 && rr >= Kf) ? -1 : a.row_v[(size_t)f * a.rowv_cap + rr];
+            v = w != 0.f ? vl : -1;
         };
         int f = 0, Kf = 0;
         long long row0 = 0, n_rows = 0;

@@ -18,6 +18,8 @@ import numpy as np
 import pytest
 import torch
 
+from _util import same_occupancy
+
 from mvxnet_makise_b200 import synth
 from oracle import pointpath_oracle as O
 
@@ -383,7 +385,7 @@ def test_fused_path_matches_reference_golden(mvx, golden_dir, tag, fusion_mode):
     # stage 4: exact placement (a copy) and exact zero elsewhere
     gcpu = grid[0].cpu()
     assert tuple(gcpu.shape) == tuple(g['grid_shape'][1:])
-    assert int((gcpu != 0).sum()) == int((ref['grid'] != 0).sum())
+    assert same_occupancy(gcpu, ref['grid'][0])
     vfeat, idx = path.voxel_features(0)
     i = idx.cpu()
     assert torch.equal(gcpu[:, i[:, 3], i[:, 1], i[:, 2]].T, vfeat.cpu())
@@ -415,7 +417,7 @@ def test_split_grid_fill_equals_single_fill(mvx):
     assert int(occ.sum()) == int(counts[0, 0])
     # bit-identical where both runs are deterministic (placement, zeros); features may differ in the last bits between two runs
     # (fp64 atomics of the statistics are unordered), so compare values with the run-to-run tolerance
-    assert torch.equal(out != 0, ref != 0)
+    assert same_occupancy(out, ref)
     assert rel_err(out.cpu(), ref.cpu()) < 1e-5
 
 
@@ -517,7 +519,7 @@ def test_fold_mode_conv1_with_folded_batchnorm(mvx, golden_dir, case):
     e0, e1 = rel_err(res[0][0], ref64['vfeat']), rel_err(res[1][0], ref64['vfeat'])
     print(f'{case}: voxel features vs fp64: unfolded {e0:.2e}, folded {e1:.2e} (fp32 reference {noise:.2e})')
     assert torch.equal(res[0][1], res[1][1]) and torch.isfinite(res[1][0]).all()
-    assert torch.equal(res[1][2] != 0, ref64['grid'][0].to(res[1][2].device) != 0)
+    assert same_occupancy(res[1][2], ref64['grid'][0])
     # Measured on B200: path_a 4.7e-5 (unfolded 1.8e-5), path_b 2.2e-5 (1.2e-5), shifted 1.9e-4 (2.0e-5). The folded mean cancels
     # against W'y whose fp16 hi/lo representation error scales with |y|, not |y - mean|: with a common feature offset the
     # 1e-4 bar is missed, which (with a slower packed store in the combine kernel) is why this mode is NOT the default.
@@ -686,7 +688,7 @@ def test_host_entry_pipelined_equals_device_entry(mvx, chunk):
         vf, idx = path.voxel_features(f)
         assert torch.equal(idx, feats_ref[f][1])
         assert rel_err(vf, feats_ref[f][0]) < 1e-5       # accumulation order is the only difference
-    assert torch.equal(grid != 0, grid_ref != 0) and rel_err(grid, grid_ref) < 1e-5
+    assert same_occupancy(grid, grid_ref) and rel_err(grid, grid_ref) < 1e-5
     assert rel_err(head, feats_ref[0][0][:64]) < 1e-5
     assert path.h2d_bytes == (points_h.numel() + calib_h.numel() + sum(m.numel() for m in maps_h)) * 4
 
@@ -722,7 +724,7 @@ def test_host_entry_async_steps_and_capacity_buckets(mvx):
             n0 = int(c_ref[0, 0])
             vf0, _ = ref_path.voxel_features(0)
             assert head.shape[0] <= 1024 and rel_err(head[:min(n0, head.shape[0])], vf0[:head.shape[0]]) < 1e-5
-            assert torch.equal(grid != 0, g_ref != 0) and rel_err(grid, g_ref) < 1e-5
+            assert same_occupancy(grid, g_ref) and rel_err(grid, g_ref) < 1e-5
     assert [id(sl) for sl in path._slots] == slots, 'contexts were rebuilt although the capacity bucket did not change'
     handles[-1].wait()
 
@@ -845,10 +847,18 @@ def test_device_split_equals_single_call(mvx, n_split):
     path = mvx.P.PointPath(sd, G)
     g, c = path.forward_device_split(pts, offsets, c32, maps, True, n_split)
     torch.cuda.synchronize()
-    assert torch.equal(c, c_ref) and torch.equal(g != 0, g_ref != 0) and rel_err(g, g_ref) < 1e-5
+    # values to rounding (the BatchNorm sums are fp64 atomics in launch-dependent order), occupancy through the voxel lists: a
+    # feature that is EXACTLY 0.0 in one run (max == mean) may be 1e-7 in the other, so `g != 0` is not a stable occupancy test
+    # (tools/split_stress.py: one such cell on this seed)
+    assert torch.equal(c, c_ref) and rel_err(g, g_ref) < 1e-5
     for f in range(B):
         vf, idx = path.voxel_features(f)
         assert torch.equal(idx, feats[f][1]) and rel_err(vf, feats[f][0]) < 1e-5
+        i = idx.long()
+        occ = torch.zeros(g.shape[2:], dtype=torch.bool, device=g.device)
+        occ[i[:, 3], i[:, 1], i[:, 2]] = True
+        assert not (g[f][:, ~occ] != 0).any() and not (g_ref[f][:, ~occ] != 0).any()      # exact zero outside the occupied cells
+        assert torch.equal(g[f][:, i[:, 3], i[:, 1], i[:, 2]].T, vf)                          # placement: a copy of the features
 
 
 def test_fused_path_full_size_properties(mvx):
