@@ -906,3 +906,60 @@ def test_dense_config5_frame(mvx):
     assert tuple(g0.shape) == (128, 10, 512, 512)
     assert int((g0 != 0).sum()) == int((vfeat != 0).sum())
     assert torch.equal(g0[:, vidx[:, 3], vidx[:, 1], vidx[:, 2]].T, vfeat)
+
+
+def _features_in_mode(mvx, frames, maps, sd, calib, gemm_mode=1, fold_mode=0):
+    """Voxel features + raw fcn1 rows of a small batch under one kernel selection (restores the defaults afterwards)."""
+    from mvxnet_makise_b200 import _lib
+    try:
+        _lib.set_gemm_mode(gemm_mode)
+        _lib.set_fold_mode(fold_mode)
+        path = mvx.P.PointPath(sd, G)
+        path(frames, [calib] * len(frames), [torch.from_numpy(m) for m in maps], want_grid=False)
+        torch.cuda.synchronize()
+        counts = path.counts.cpu().numpy()
+        feats = [path.voxel_features(f)[0].clone() for f in range(len(frames))]
+        capA = path.cap + 128
+        y1 = path.region('Y1', torch.float32, (len(frames), capA, 768)).clone()
+        return feats, y1, counts
+    finally:
+        _lib.set_gemm_mode(1)
+        _lib.set_fold_mode(0)
+
+
+def test_run_structured_combine_equals_row_by_row_kernel(mvx):
+    """The run-structured combine kernel (default: per-warp cp.async corner ring, branch-free runs) against the first-generation
+    kernel (mvx_set_fold_mode(2)): the raw fcn1 rows Y1 are BIT-IDENTICAL (same arithmetic in the same order), the voxel features
+    agree to rounding (the BatchNorm sums group their fp32 partial sums differently). Frames include an empty one, a tiny one
+    (a single CTA with one run) and duplicates of one point (long runs in one cell)."""
+    sd = synth.make_weights(12)
+    calib = synth.kitti_calib()
+    dup = np.repeat(synth.make_points(151, 40)[:3], 300, axis=0)      # 900 points in three cells: runs longer than 16 rows
+    frames = [synth.make_points(150, 2600), np.zeros((0, 4), np.float32), synth.make_points(152, 37), dup]
+    maps = small_maps(21, B=len(frames))
+    new, y1_new, c_new = _features_in_mode(mvx, frames, maps, sd, calib, fold_mode=0)
+    old, y1_old, c_old = _features_in_mode(mvx, frames, maps, sd, calib, fold_mode=2)
+    assert np.array_equal(c_new, c_old)
+    for f in range(len(frames)):
+        K = int(c_new[f, 1])
+        assert torch.equal(y1_new[f, :K + 1], y1_old[f, :K + 1]), f'frame {f}: raw fcn1 rows differ'
+        if old[f].numel():
+            # frames of a few dozen rows: batch statistics over so few rows amplify the regrouped fp32 partial sums (measured 9.5e-5)
+            assert rel_err(new[f], old[f]) < (1e-5 if K > 2000 else 1e-3), f
+
+
+def test_vfe_inputs_built_in_the_loader_equal_materialised_inputs(mvx):
+    """Inference builds VFE1's [vox7 | norm5(Y5)] and VFE2's [norm6(Y6) | norm6(max6[v])] rows inside the layer kernel's tile
+    loader; mvx_set_gemm_mode(10) materialises them with prep_vfe1 / prep_vfe2 as training does. Same arithmetic: the voxel
+    features agree to rounding; voxels at the T cap (no pad row weight) and single-point voxels are in the mix."""
+    sd = synth.make_weights(13)
+    calib = synth.kitti_calib()
+    crowd = synth.make_points(161, 30)
+    crowd = np.concatenate([np.repeat(crowd[:1], 60, axis=0), crowd])     # one voxel beyond the cap of 35
+    frames = [synth.make_points(160, 3100), crowd]
+    maps = small_maps(22, B=len(frames))
+    fused, _, c1 = _features_in_mode(mvx, frames, maps, sd, calib, gemm_mode=1)
+    mat, _, c2 = _features_in_mode(mvx, frames, maps, sd, calib, gemm_mode=10)
+    assert np.array_equal(c1, c2)
+    for f in range(len(frames)):
+        assert rel_err(fused[f], mat[f]) < 1e-5, f
