@@ -49,6 +49,11 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
     __shared__ __align__(16) float smem[NBUF * kTileFloats];
     __shared__ float s_mean[768], s_rstd[768];
     __shared__ double s_red[2 * 8 * BN];   // [sum | sum of squares][8 warps][BN], accumulated over the tiles of this CTA
+    // BatchNorm multiplicity and voxel id of the tile's rows: fetched (LD 0 / 1) or built (LD 2) at the head of the tile, so that the
+    // epilogue does not start with a round trip to global memory. Two copies by tile parity: the head of tile t + 1 may run while a
+    // slow warp still reads tile t's copy; tile t + 2 writes it again only behind the barriers of tile t + 1's k loop.
+    __shared__ float s_roww2[2][kBM];
+    __shared__ int s_rowv2[2][kBM];
 
     const int f = blockIdx.z, n0 = blockIdx.y * BN, tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
@@ -76,6 +81,8 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
     __syncthreads();
 
     for (int tile = 0; tile < kTilesPerCta; ++tile) {
+    float *s_roww = s_roww2[tile & 1];
+    int *s_rowv = s_rowv2[tile & 1];
     const long long row0 = ((long long)blockIdx.x * kTilesPerCta + tile) * kBM;
     if (row0 >= n_rows) break;
     float acc[RT][TN];
@@ -85,6 +92,20 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
     const float *Xf = a.X + ((size_t)f * a.rowcap + row0) * a.ldx;
+    if (tid < kBM) {   // visible to the epilogue through the barriers of the k loop (LD 2 fills the valid rows in its loader)
+        const long long r = row0 + tid;
+        const bool valid = r < n_rows;
+        float wq = 0.f;
+        int vq = -1;
+        if (LD != 2 && valid) {
+            wq = a.row_w ? a.row_w[(size_t)f * a.rowcap + r] : 1.f;
+            if (a.vmax && wq != 0.f) {
+                if (a.row_v) vq = (a.rows_mode == 1 && r >= K) ? -1 : a.row_v[(size_t)f * a.rowv_cap + r];
+                else vq = (int)(r / a.T);
+            }
+        }
+        if (LD != 2 || !valid) s_roww[tid] = wq, s_rowv[tid] = vq;
+    }
     // one 16-byte piece of the A tile (row r = idx / 4, columns k0 + 4 (idx % 4) ..) as the layer reads it: normalised / built on the fly
     auto load_a = [&](int k0, int j) -> float4 {
         const int idx = tid + j * 256, r = idx >> 2, c4 = idx & 3;
@@ -124,8 +145,12 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
                 v.w = (v.w - s_mean[c + 3]) * s_rstd[c + 3];
                 if (k0 == 0 && c4 == 0 && blockIdx.y == 0) {   // once per row: what the epilogue below and the last FCN read
                     const int wpad = a.T - cnt;
-                    z.rowB_w[(size_t)f * a.rowcap + rr] = pad ? (float)wpad : 1.f;
-                    z.rowB_v[(size_t)f * a.rowcap + rr] = (pad && wpad == 0) ? -1 : vv;
+                    const float wq = pad ? (float)wpad : 1.f;
+                    const int vq = (pad && wpad == 0) ? -1 : vv;
+                    z.rowB_w[(size_t)f * a.rowcap + rr] = wq;
+                    z.rowB_v[(size_t)f * a.rowcap + rr] = vq;
+                    s_roww[r] = wq;
+                    s_rowv[r] = wq != 0.f ? vq : -1;
                 }
             }
         } else if (row0 + r < n_rows) {
@@ -206,15 +231,8 @@ __global__ void __launch_bounds__(256, BN == 64 ? 3 : (BN == 16 ? 4 : 0)) fcn_la
     int vox[RT];
 #pragma unroll
     for (int i = 0; i < RT; ++i) {
-        const long long r = row0 + ty * RT + i;
-        const bool valid = r < n_rows;
-        const size_t ro = (size_t)f * a.rowcap + r;
-        w[i] = valid ? (a.row_w ? a.row_w[ro] : 1.f) : 0.f;
-        vox[i] = -1;
-        if (valid && a.vmax && w[i] != 0.f) {
-            if (a.row_v) vox[i] = (a.rows_mode == 1 && r >= K) ? -1 : a.row_v[(size_t)f * a.rowv_cap + r];
-            else vox[i] = (int)(r / a.T);
-        }
+        w[i] = s_roww[ty * RT + i];
+        vox[i] = a.vmax ? s_rowv[ty * RT + i] : -1;
     }
     double *red = s_red;
     const int lane = tid & 31, warp = tid >> 5;
