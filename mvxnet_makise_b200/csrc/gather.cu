@@ -563,7 +563,10 @@ __global__ void __launch_bounds__(kCombWarps * 32, MVX_COMB_MINB) combine_rows_k
 //      ahead of time with cp.async (LDGSTS: global -> shared without registers) into a private ring; a cell change then costs a
 //      wait on an already landed group plus four LDS.128.
 // Arithmetic and its order are those of the first version: Y1 is bit-identical.
-constexpr int kCombNS = 4;                                  // ring slots (events in flight) per warp
+#ifndef MVX_COMB_NS
+#define MVX_COMB_NS 4
+#endif
+constexpr int kCombNS = MVX_COMB_NS;                                  // ring slots (events in flight) per warp
 template <bool ZB>
 struct CombSmem {
     static constexpr int kSlotBytes = 4 * 32 * (ZB ? 8 : 16);       // four corners x 32 lanes x this lane's 4 columns
