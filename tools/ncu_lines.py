@@ -34,7 +34,7 @@ with tempfile.TemporaryDirectory() as td:
                 lines = dis.splitlines()
                 break
 start = next(i for i, l in enumerate(lines) if l.strip().startswith('.section') and ksub in l)
-off2line, cur = {}, None
+off2line, off2op, cur = {}, {}, None
 for l in lines[start + 1:]:
     if l.strip().startswith('.section') and '.text.' in l:
         break
@@ -42,9 +42,18 @@ for l in lines[start + 1:]:
     if m:
         cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
-    m = re.match(r'\s+/\*([0-9a-f]{4,})\*/', l)
+    m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)', l)
     if m:
         off2line[int(m.group(1), 16)] = cur
+        off2op[int(m.group(1), 16)] = m.group(2).split('.')[0]
+# the line table comes from the library on disk: make sure it is the binary that was profiled (same opcode at every address)
+same = tot_ops = 0
+for a, r in seen.items():
+    src = r[ix['Source']].strip().split()
+    op = (src[1] if src and src[0].startswith('@') and len(src) > 1 else (src[0] if src else '')).split('.')[0]
+    tot_ops += 1
+    same += off2op.get(a - base) == op
+print(f'# binary check: {same} of {tot_ops} instructions of the report match the library on disk' + ('' if same >= 0.98 * tot_ops else '  ** MISMATCH: rebuild the profiled source first, the lines below are not trustworthy **'))
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
 by, ins, why = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter)
 for a, r in seen.items():
