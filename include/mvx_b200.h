@@ -134,7 +134,7 @@ int mvx_feature_mapping(float *voxels, int64_t R, const float *const *maps, cons
  * group of T rows: y (R, 2*Cout) = [pointwise | max] (modules/voxelnet/Pipe.py:12-18).
  * mvx_fcn_max_forward returns only the per-voxel max (R/T, Cout) (VoxelNet.py:28-32).
  * ------------------------------------------------------------------------------------------------ */
-int mvx_set_gemm_mode(int32_t mode); /* 0 = SIMT fp32 everywhere, 1 = tensor cores, one 256xBN tile per CTA (default), 2 = tensor cores, persistent 256x128 variant, (3 was the CTA-pair kernel: removed, rejected with MVX_EINVAL), 4 = tensor cores with 3xTF32 operands everywhere (mode 1 uses fp16 hi/lo operands, "3xFP16", for the layers of the fused path whose inputs are BatchNorm-ed or row-scaled), 5 = like 1 and the dense layer entry points below also use fp16 operands (caller promises inputs of O(1) magnitude), 6 = bf16 mode: one bf16 product per K-step instead of the three-product split for those layers (reduced precision; tolerance in tests/test_gpu_parity.py::test_bf16_mode_tolerance), 7 = like 1 with conv1 / fcn2 of the fused path in the persistent 3xFP16 kernel (TMEM accumulator ping-pong, epilogue overlapped with the next tile; experimental, measured slower), 8 = 1 (default since round 2: conv1 / fcn2 / the last FCN of the fused path run in the persistent TMA-fed kernel with the A operand in tensor memory, csrc/tc3_layer.cu), 9 = like 1 but those layers in the one-tile kernel of csrc/tc_layer.cu (the round-1 default, kept for A/B timing) */
+int mvx_set_gemm_mode(int32_t mode); /* 0 = SIMT fp32 everywhere, 1 = tensor cores, one 256xBN tile per CTA (default), 2 = tensor cores, persistent 256x128 variant, (3 was the CTA-pair kernel: removed, rejected with MVX_EINVAL), 4 = tensor cores with 3xTF32 operands everywhere (mode 1 uses fp16 hi/lo operands, "3xFP16", for the layers of the fused path whose inputs are BatchNorm-ed or row-scaled), 5 = like 1 and the dense layer entry points below also use fp16 operands (caller promises inputs of O(1) magnitude), 6 = bf16 mode: one bf16 product per K-step instead of the three-product split for those layers (reduced precision; tolerance in tests/test_gpu_parity.py::test_bf16_mode_tolerance), 7 = like 1 with conv1 / fcn2 of the fused path in the persistent 3xFP16 kernel (TMEM accumulator ping-pong, epilogue overlapped with the next tile; experimental, measured slower), 8 = 1 (default since round 2: conv1 / fcn2 / the last FCN of the fused path run in the persistent TMA-fed kernel with the A operand in tensor memory, csrc/tc3_layer.cu), 9 = like 1 but those layers in the one-tile kernel of csrc/tc_layer.cu (the round-1 default, kept for A/B timing), 10 = like 1 with the VFE inputs materialised by prep kernels as in training (inspection of X6 / X7, A/B timing), 12 = like 1 with the one-tile two-CTAs-per-SM kernel for the per-pixel GEMM of fcn1 instead of the persistent one (A/B timing) */
 int mvx_layer_workspace_bytes(int32_t Cin, int32_t Cout, size_t *bytes);
 int mvx_fcn_forward(const float *x, int64_t R, int32_t Cin, const float *wt, const float *bias, int32_t Cout,
                     double eps, float *y, void *stats_ws, void *stream);

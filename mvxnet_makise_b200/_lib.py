@@ -159,7 +159,8 @@ def set_gemm_mode(mode: int):
     5 = like 1 and the dense layer API also uses fp16 operands (inputs must be O(1)), 6 = bf16 mode (single-pass bf16
     operands for the layers mode 1 runs in 3xFP16; reduced precision), 7 = persistent 3xFP16 register-producer kernel (experimental),
     8 = 1 (conv1 / fcn2 / last FCN in the TMA-fed A-from-TMEM persistent kernel, tc3_layer.cu: the default), 9 = like 1 with the
-    one-tile kernel of round 1 for those layers (A/B timing)."""
+    one-tile kernel of round 1 for those layers (A/B timing), 10 = like 1 with the VFE inputs materialised by prep_vfe1 / prep_vfe2
+    as in training, 12 = like 1 with the one-tile kernel for the per-pixel GEMM of fcn1 instead of the persistent one (A/B timing)."""
     check(lib.mvx_set_gemm_mode(int(mode)), 'set_gemm_mode')
 
 

@@ -91,6 +91,10 @@ int launch_fold_pack_weights(const float *Wt, const float *bias, const double *i
 // TMA-fed persistent kernel with the A operand in tensor memory (tc3_layer.cu): BatchNorm-ed 128-column layers of the fused path
 bool tc3_layer_eligible(const LayerArgs &a);
 int launch_layer_tc3(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
+// persistent pre-packed-operand GEMM for the per-pixel half of fcn1 (tc3_layer.cu)
+bool pixel_gemm_persistent_eligible(const LayerArgs &a);
+int launch_pixel_gemm_persistent(const LayerArgs &a, float *wpack, cudaStream_t st);
+void set_pixel_persistent(int on);
 void set_tc3(int on);
 bool tc_persistent_enabled();
 bool tc_f16_enabled();

@@ -283,7 +283,7 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
             la.rows_fixed = px, la.rows_mode = 0, la.rowcap = 0, la.T = 1, la.eps = a->bn_eps, la.plain = 1;
             la.f16_ok = 1, la.row_max = F32(R_ROWMAX) + zoff / 768;   // raw FPN features: per-pixel power-of-two scaling
             if (apack) la.a_pack = ws + L.off[R_NHWC0 + l], la.a_rowinv = F32(R_ROWMAX) + zoff / 768, la.row_max = nullptr;
-            int r = launch_layer_auto(la, 1, F32(R_WPACK), ms);
+            int r = pixel_gemm_persistent_eligible(la) ? launch_pixel_gemm_persistent(la, F32(R_WPACK), ms) : launch_layer_auto(la, 1, F32(R_WPACK), ms);
             if (r) return r;
             zoff += (size_t)px * 768;
         }

@@ -575,6 +575,179 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
     }
 }
 
+// =====================================================================================================================
+// Persistent per-pixel GEMM of the pixel-first fcn1 (Z_l = F_l W1_l^T, plain: no bias / ReLU / statistics): both operands arrive
+// pre-packed (fp16 hi / lo shared-memory images: the FPN maps by pack_maps_f16_kernel, the weights by pack_weights_f16_kernel), so
+// there are no converters at all - a bulk-copy thread, an MMA thread and eight epilogue warps:
+//   warp 0      producer: per 32-k chunk one cp.async.bulk of the A tile (256 rows: [hi 16 KB | lo 16 KB]) and one of the weight
+//               chunk of the tile's 128-column block ([hi 8 KB | lo 8 KB]) into a 3-deep ring that keeps streaming ACROSS tiles
+//   warp 1      MMA issuer (+ TMEM allocation): per 16-k step and 128-row half D += A_lo B_hi + A_hi B_lo + A_hi B_hi, both
+//               operands from shared memory; two accumulator buffers of 2 x 128 TMEM columns (all 512)
+//   warps 2-9   epilogue, two groups of four (group = 128-row half, warp = TMEM lane quarter): tcgen05.ld of the finished buffer
+//               while the MMAs fill the other one, exact power-of-two rescale (row x column), 128 x 32 staging block, tensor store
+// The one-tile kernel it replaces (tc_layer_kernel<128, F16, -, TWO, APK>, two CTAs per SM) restarts its 2-stage ring for every
+// tile: ncu attributes 42 % of its samples to the epilogue warps idling through an ~6 us main loop that exposes one L2 round trip
+// per pair of chunks, then ~10 us of epilogue per CTA for 3.7 us of MMAs (profiles/r5v_pixel_gemm_stall_lines.txt).
+// Tile order: t = row tile x 6 + column block, striped over the CTAs, so the six tiles that share an A tile run at the same time
+// on neighbouring CTAs (one DRAM read of A, five L2 hits).
+// =====================================================================================================================
+constexpr int PG_TM = 256, PG_BN = 128, PG_KB = 32, PG_STAGES = 3;
+constexpr int PG_A_HALF = PG_TM * 64, PG_B_HALF = PG_BN * 64;        // 16 KB, 8 KB: one fp16 image of a chunk
+constexpr int PG_STAGE = 2 * PG_A_HALF + 2 * PG_B_HALF;             // 48 KB
+constexpr int PG_EPI_WARPS = 8, PG_THREADS = (2 + PG_EPI_WARPS) * 32;
+struct PgSmem {
+    static constexpr int kRing = 0;
+    static constexpr int kStg = kRing + PG_STAGES * PG_STAGE;        // [2 groups] 128 x 32 fp32 staging block
+    static constexpr int kColInv = kStg + 2 * T3_STG_BYTES;          // [Cout <= 768]
+    static constexpr int kBars = kColInv + 768 * 4;                  // full[3], empty[3], acc_full[2], acc_empty[2]
+    static constexpr int kTmemPtr = kBars + 8 * (2 * PG_STAGES + 4);
+    static constexpr int kTotal = kTmemPtr + 16 + 1024;
+};
+static_assert(PgSmem::kTotal <= 232448, "pixel GEMM: shared memory");
+
+struct PgArgs {
+    const uint8_t *a_pack;     // [row tiles][nk][hi 16 KB | lo 16 KB]
+    const float *a_rowinv;     // [R] inverse power-of-two row scales (or NULL)
+    const uint8_t *wpack;      // [column blocks][nk][hi 8 KB | lo 8 KB], then Cout inverse column scales
+    long long R;               // rows (pixels of all frames of the level)
+    int Cin, Cout, row_tiles;
+};
+
+__global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_persistent_kernel(const __grid_constant__ PgArgs g, const __grid_constant__ CUtensorMap tmZ) {
+    using S = PgSmem;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    float *s_colinv = reinterpret_cast<float *>(smem + S::kColInv);
+    const uint32_t bars = sbase + S::kBars;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (PG_STAGES + s); };
+    auto acc_full = [&](int b) { return bars + 8u * (2 * PG_STAGES + b); };
+    auto acc_empty = [&](int b) { return bars + 8u * (2 * PG_STAGES + 2 + b); };
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(smem + S::kTmemPtr);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nk = g.Cin / PG_KB, ncb = g.Cout / PG_BN;
+    const int total = g.row_tiles * ncb;
+
+    if (tid == 0) {
+        for (int s = 0; s < PG_STAGES; ++s) mbar_init(full_bar(s), 1), mbar_init(empty_bar(s), 1);
+        for (int b = 0; b < 2; ++b) mbar_init(acc_full(b), 1), mbar_init(acc_empty(b), PG_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int c = tid; c < g.Cout; c += PG_THREADS) s_colinv[c] = reinterpret_cast<const float *>(g.wpack + (size_t)g.Cin * g.Cout * 4)[c];
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::kTmemPtr), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================= producer =====================================================================================
+        if (lane == 0) {
+            int gc = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int rt = t / ncb, cb = t - rt * ncb;
+                const uint8_t *asrc = g.a_pack + (size_t)rt * nk * (2 * PG_A_HALF);
+                const uint8_t *bsrc = g.wpack + (size_t)cb * nk * (2 * PG_B_HALF);
+                for (int kc = 0; kc < nk; ++kc, ++gc) {
+                    const int s = gc % PG_STAGES;
+                    mbar_wait(empty_bar(s), ((gc / PG_STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(full_bar(s), PG_STAGE);
+                    bulk_g2s(sbase + S::kRing + s * PG_STAGE, asrc + (size_t)kc * (2 * PG_A_HALF), 2 * PG_A_HALF, full_bar(s));
+                    bulk_g2s(sbase + S::kRing + s * PG_STAGE + 2 * PG_A_HALF, bsrc + (size_t)kc * (2 * PG_B_HALF), 2 * PG_B_HALF, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer ===================================================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(PG_BN >> 3) << 17) | ((128u >> 4) << 24);   // fp16 x fp16 -> fp32, N = 128, M = 128
+            int gc = 0, it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+                const int ab = it & 1;
+                mbar_wait(acc_empty(ab), ((it >> 1) & 1) ^ 1);   // the epilogue drained this buffer two tiles ago
+                tc_fence_after();
+                for (int kc = 0; kc < nk; ++kc, ++gc) {
+                    const int s = gc % PG_STAGES;
+                    mbar_wait(full_bar(s), (gc / PG_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t sA = sbase + S::kRing + s * PG_STAGE, sB = sA + 2 * PG_A_HALF;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t d = tmem_base + ab * (2 * PG_BN) + h * PG_BN;
+                        const uint32_t aoff = h * (128 * 64);
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint64_t a_hi = make_desc(sA + aoff + ks * 32), a_lo = make_desc(sA + PG_A_HALF + aoff + ks * 32);
+                            const uint64_t b_hi = make_desc(sB + ks * 32), b_lo = make_desc(sB + PG_B_HALF + ks * 32);
+                            mma_f16(d, a_lo, b_hi, idesc, (kc | ks) != 0);
+                            mma_f16(d, a_hi, b_lo, idesc, 1);
+                            mma_f16(d, a_hi, b_hi, idesc, 1);
+                        }
+                    }
+                    mma_commit(empty_bar(s));
+                }
+                mma_commit(acc_full(ab));
+            }
+        }
+    } else {
+        // ================= epilogue: group = 128-row half of the tile, warp = TMEM lane quarter ==========================
+        const int q = warp & 3, eg = (warp - 2) >> 2;
+        const int et = (tid - 64) & 127;
+        const int bar_id = 2 + eg;
+        uint8_t *stg = smem + S::kStg + eg * T3_STG_BYTES;
+        if (et == 0) prefetch_tmap(&tmZ);
+        int it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+            const int rt = t / ncb, cb = t - rt * ncb;
+            const int ab = it & 1;
+            const long long row0 = (long long)rt * PG_TM + eg * 128;
+            const int rloc = q * 32 + lane;
+            const float rinv = (g.a_rowinv && row0 + rloc < g.R) ? __ldg(g.a_rowinv + row0 + rloc) : 1.f;   // in flight during the wait below
+            mbar_wait(acc_full(ab), (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c32 = 0; c32 < 4; ++c32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * (2 * PG_BN) + eg * PG_BN + c32 * 32, v);
+                if (c32 == 3) {   // the accumulator half is in registers: the MMA warp may reuse the buffer once every warp has said so
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty(ab));
+                }
+                if (et == 0) tma_store_wait_read<0>();   // the previous tensor store is done reading the staging block
+                named_bar_sync(bar_id, 128);
+                uint8_t *rowp = stg + rloc * 128;
+                const float *ci = s_colinv + cb * PG_BN + c32 * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 c4 = *reinterpret_cast<const float4 *>(ci + j * 4);
+                    float4 o;
+                    o.x = v[j * 4 + 0] * (rinv * c4.x), o.y = v[j * 4 + 1] * (rinv * c4.y);
+                    o.z = v[j * 4 + 2] * (rinv * c4.z), o.w = v[j * 4 + 3] * (rinv * c4.w);
+                    *reinterpret_cast<float4 *>(rowp + ((j ^ (rloc & 7)) << 4)) = o;   // SWIZZLE_128B like the store's tensor map
+                }
+                fence_async_smem();
+                named_bar_sync(bar_id, 128);
+                if (et == 0) {
+                    tma_store_2d(&tmZ, cb * PG_BN + c32 * 32, (int)row0, smem_u32(stg));   // rows beyond R are clipped by the tensor map
+                    tma_store_commit();
+                }
+            }
+        }
+        if (et == 0) tma_store_wait_all();
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -668,6 +841,37 @@ int launch_layer_tc3(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     if (a.X2) return launch_tc3_t<true, true, 0>(g, tmX, tmY, tmX2, grid, st);
     if (resident) return launch_tc3_t<true, false, 0>(g, tmX, tmY, tmX2, grid, st);
     return launch_tc3_t<false, false, 0>(g, tmX, tmY, tmX2, grid, st);
+}
+
+// defined in tc_layer.cu
+static int g_pixel_persistent = 1;   // 0: the one-tile two-CTAs-per-SM kernel of tc_layer.cu for the pixel GEMM (mvx_set_gemm_mode(12), A/B timing)
+void set_pixel_persistent(int on) { g_pixel_persistent = on; }
+
+bool pixel_gemm_persistent_eligible(const LayerArgs &a) {
+    return g_pixel_persistent && a.plain && a.a_pack && a.Y && !a.y_bf16 && !a.counts && a.rows_fixed > 0 && a.Cin % PG_KB == 0 && a.Cout % PG_BN == 0 &&
+           a.Cout <= 768 && a.ldy % 4 == 0 && !a.w_per_frame && !tc_bf16_enabled();
+}
+
+int launch_pixel_gemm_persistent(const LayerArgs &a, float *wpack, cudaStream_t st) {
+    MVX_REQUIRE(pixel_gemm_persistent_eligible(a) && wpack, MVX_EINVAL, "layer not eligible for the persistent pixel GEMM");
+    int rc = pack_weights_f16_128(a.Wt, a.Cin, a.Cout, wpack, st, false);
+    if (rc) return rc;
+    PgArgs g{};
+    g.a_pack = static_cast<const uint8_t *>(a.a_pack), g.a_rowinv = a.a_rowinv, g.wpack = reinterpret_cast<const uint8_t *>(wpack);
+    g.R = a.rows_fixed, g.Cin = a.Cin, g.Cout = a.Cout, g.row_tiles = (int)ceil_div(a.rows_fixed, (long long)PG_TM);
+    CUtensorMap tmZ;
+    rc = make_tmap(&tmZ, a.Y, a.rows_fixed, a.Cout, a.ldy);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(pixel_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PgSmem::kTotal));
+        attr_set = true;
+    }
+    const long long tiles = (long long)g.row_tiles * (a.Cout / PG_BN);
+    const int grid = (int)(tiles < kSMs ? tiles : kSMs);
+    pixel_gemm_persistent_kernel<<<grid, PG_THREADS, PgSmem::kTotal, st>>>(g, tmZ);
+    MVX_LAUNCH_CHECK();
+    return MVX_OK;
 }
 
 }  // namespace mvx

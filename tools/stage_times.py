@@ -20,6 +20,11 @@ path = PointPath(synth.make_weights(0), synth.KITTI_GRID, device=dev)
 _lib.set_gemm_mode(mode)
 for _ in range(3): path.forward_device(pts, offsets, calib, maps)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(30): path.forward_device(pts, offsets, calib, maps)
+e1.record(); torch.cuda.synchronize()
+print(f'mode={mode} step (overlapped schedule, 30 steps): {e0.elapsed_time(e1) / 30:.3f} ms = {B * 30 / e0.elapsed_time(e1) * 1e3:.0f} frames/s')
 _lib.check(_lib.lib.mvx_timing_enable(steps), 'te')
 for _ in range(steps): path.forward_device(pts, offsets, calib, maps)
 torch.cuda.synchronize()
