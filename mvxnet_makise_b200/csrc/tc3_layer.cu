@@ -591,15 +591,19 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
 // Tile order: t = row tile x 6 + column block, striped over the CTAs, so the six tiles that share an A tile run at the same time
 // on neighbouring CTAs (one DRAM read of A, five L2 hits).
 // =====================================================================================================================
-constexpr int PG_TM = 256, PG_BN = 128, PG_KB = 32, PG_STAGES = 3;
+#ifndef MVX_PG_STAGES
+#define MVX_PG_STAGES 3
+#endif
+// 3 x 48 KB. A fourth stage makes the kernel itself faster (0.535 -> 0.484 ms next to the point branch) but the STEP slower (4.43 -> 4.46 ms,
+// three A/B pairs): at 228 KB the CTA leaves no shared memory for the point-branch kernels that share the SMs with it during the front
+constexpr int PG_TM = 256, PG_BN = 128, PG_KB = 32, PG_STAGES = MVX_PG_STAGES;
 constexpr int PG_A_HALF = PG_TM * 64, PG_B_HALF = PG_BN * 64;        // 16 KB, 8 KB: one fp16 image of a chunk
 constexpr int PG_STAGE = 2 * PG_A_HALF + 2 * PG_B_HALF;             // 48 KB
 constexpr int PG_EPI_WARPS = 8, PG_THREADS = (2 + PG_EPI_WARPS) * 32;
 struct PgSmem {
     static constexpr int kRing = 0;
     static constexpr int kStg = kRing + PG_STAGES * PG_STAGE;        // [2 groups] 128 x 32 fp32 staging block
-    static constexpr int kColInv = kStg + 2 * T3_STG_BYTES;          // [Cout <= 768]
-    static constexpr int kBars = kColInv + 768 * 4;                  // full[3], empty[3], acc_full[2], acc_empty[2]
+    static constexpr int kBars = kStg + 2 * T3_STG_BYTES;            // full[], empty[], acc_full[2], acc_empty[2] (the column scales are read from global memory: L1 hits, and the fourth stage needs their 3 KB)
     static constexpr int kTmemPtr = kBars + 8 * (2 * PG_STAGES + 4);
     static constexpr int kTotal = kTmemPtr + 16 + 1024;
 };
@@ -618,7 +622,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_persistent_kernel(co
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
-    float *s_colinv = reinterpret_cast<float *>(smem + S::kColInv);
+    const float *colinv = reinterpret_cast<const float *>(g.wpack + (size_t)g.Cin * g.Cout * 4);
     const uint32_t bars = sbase + S::kBars;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (PG_STAGES + s); };
@@ -634,7 +638,6 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_persistent_kernel(co
         for (int b = 0; b < 2; ++b) mbar_init(acc_full(b), 1), mbar_init(acc_empty(b), PG_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int c = tid; c < g.Cout; c += PG_THREADS) s_colinv[c] = reinterpret_cast<const float *>(g.wpack + (size_t)g.Cin * g.Cout * 4)[c];
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::kTmemPtr), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -721,10 +724,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_persistent_kernel(co
                 if (et == 0) tma_store_wait_read<0>();   // the previous tensor store is done reading the staging block
                 named_bar_sync(bar_id, 128);
                 uint8_t *rowp = stg + rloc * 128;
-                const float *ci = s_colinv + cb * PG_BN + c32 * 32;
+                const float4 *ci = reinterpret_cast<const float4 *>(colinv + cb * PG_BN + c32 * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 c4 = *reinterpret_cast<const float4 *>(ci + j * 4);
+                    const float4 c4 = __ldg(ci + j);
                     float4 o;
                     o.x = v[j * 4 + 0] * (rinv * c4.x), o.y = v[j * 4 + 1] * (rinv * c4.y);
                     o.z = v[j * 4 + 2] * (rinv * c4.z), o.w = v[j * 4 + 3] * (rinv * c4.w);
