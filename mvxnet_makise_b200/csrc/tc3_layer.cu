@@ -36,9 +36,11 @@ constexpr int T3_RAW_RES = 6, T3_RAW_STR = 7;   // raw A ring depth (weights res
                                                 // SM's share of the bandwidth (~1.5 us x 44 GB/s = 66 KB) on top of the stage being converted
 constexpr int T3_AST = 4;            // A stages in TMEM
 constexpr int T3_BRING = 3;          // streamed-weights ring depth
-constexpr int T3_CONV_WARPS = 8, T3_EPI_WARPS = 8;   // two groups of four each (one warp per TMEM lane quarter and group)
-constexpr int T3_W_PROD = 0, T3_W_MMA = 1, T3_W_CONV = 2, T3_W_EPI = T3_W_CONV + T3_CONV_WARPS, T3_W_BPROD = T3_W_EPI + T3_EPI_WARPS;
-constexpr int T3_THREADS = (3 + T3_CONV_WARPS + T3_EPI_WARPS) * 32;   // 608
+// Converter and epilogue warps come in groups of four (one warp per TMEM lane quarter). Weights resident (K = 128: fcn2, last FCN,
+// epilogue-bound): 2 converter groups + 2 epilogue groups. Weights streamed (conv1, K = 768, converter-bound: 24 chunks per tile
+// and an epilogue that idles most of the time): 3 converter groups + 1 epilogue group - the same 19 warps and 96 registers.
+constexpr int T3_W_PROD = 0, T3_W_MMA = 1, T3_W_CONV = 2;
+__host__ __device__ constexpr int t3_threads(int ncg, int neg) { return (3 + 4 * ncg + 4 * neg) * 32; }
 constexpr int T3_RAW_BYTES = T3_TM * T3_KB * 4;      // 16 KB
 constexpr int T3_B_STAGE = 2 * T3_BN * 64;           // 16 KB: [hi | lo] images of one 32-k chunk
 constexpr int T3_STG_BYTES = T3_TM * 32 * 4;         // 16 KB: one 128 x 32 fp32 output block
@@ -115,13 +117,17 @@ struct T3Args {
 // Only the one tile per frame that straddles the real-row / pad-row boundary needs two ranges: its pad rows read global memory.
 // PREC: 0 = fp32-accurate 3xFP16 from fp32 rows; 1 = bf16 mode (ONE bf16 product per k-step, reduced precision) from fp32 rows;
 //       2 = bf16 mode from bf16 rows (conv1 reading the bf16 Y1 of the combine kernel: half the bytes per stage)
-template <bool RESIDENT, bool CAT, int PREC>
-__global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_constant__ T3Args g, const __grid_constant__ CUtensorMap tmX,
+template <bool RESIDENT, bool CAT, int PREC, int NCG = RESIDENT ? 2 : 3, int NEG = RESIDENT ? 2 : 1>
+__global__ void __launch_bounds__(t3_threads(NCG, NEG), 1) tc3_layer_kernel(const __grid_constant__ T3Args g, const __grid_constant__ CUtensorMap tmX,
                                                                   const __grid_constant__ CUtensorMap tmY,
                                                                   const __grid_constant__ CUtensorMap tmX2) {
     using S = T3Smem<RESIDENT>;
     constexpr int T3_RAW = S::T3_RAW;
     constexpr bool BF = PREC != 0, RAWBF = PREC == 2;
+    constexpr int T3_CONV_WARPS = 4 * NCG, T3_EPI_WARPS = 4 * NEG, T3_THREADS = t3_threads(NCG, NEG);
+    constexpr int T3_W_EPI = T3_W_CONV + T3_CONV_WARPS, T3_W_BPROD = T3_W_EPI + T3_EPI_WARPS;
+    constexpr int CBG = (T3_BN / 32) / NEG;          // 32-column blocks per epilogue group
+    static_assert(NEG == 1 || NEG == 2, "epilogue groups");
     constexpr int RAW_TX = RAWBF ? T3_RAW_BYTES / 2 : T3_RAW_BYTES;     // bytes one raw stage receives
     constexpr int B_TX = BF ? T3_B_STAGE / 2 : T3_B_STAGE;              // bf16 weights: the hi image only
     static_assert(!(CAT && RAWBF), "the concat layer reads fp32 rows");
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(smem + S::kTmemPtr);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nk = a.Cin / T3_KB;                                 // even (Cin % 64 == 0): chunk kc of every tile goes to converter group kc & 1
+    const int nk = a.Cin / T3_KB;                                 // a multiple of NCG (checked by the launcher): chunk kc of every tile goes to converter group kc % NCG
     const int nk_x = CAT ? (a.Cin - a.x2_cols) / T3_KB : nk;     // chunks that come from X; the others from X2
     const int total = g.F * g.row_tiles;
 
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
                 fetch(cg, r);
                 primed = true;
             }
-            for (int kc = cg; kc < nk; kc += 2) {
+            for (int kc = cg; kc < nk; kc += NCG) {
                 const int gcur = gc + kc;
                 float4 x[8];
 #pragma unroll
@@ -366,8 +372,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
 #pragma unroll
                     for (int j = 0; j < 8; ++j) x[j] = __ldg(src + j);
                 }
-                // the group's next chunk: same tile (kc + 2) or the first one of the next tile (always an X chunk: row r)
-                if (gcur + 2 < n_chunks) fetch(gcur + 2, (CAT && kc + 2 < nk && kc + 2 >= nk_x) ? vrel : r);
+                // the group's next chunk: same tile (kc + NCG) or its first one of the next tile (always an X chunk: row r)
+                if (gcur + NCG < n_chunks) fetch(gcur + NCG, (CAT && kc + NCG < nk && kc + NCG >= nk_x) ? vrel : r);
                 const int k0 = kc * T3_KB;
                 uint32_t hi[16], lo[16];
 #pragma unroll
@@ -411,15 +417,15 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
         const int ecol = et & 31, egrp = et >> 5;           // statistics: thread = (column of a 32-column block, 32-row group)
         const int bar_id = 2 + eg;
         double *s_part = reinterpret_cast<double *>(smem + S::kPart) + eg * (4 * 32 * 2);
+        constexpr int SG = 2 * T3_BN / NEG;                  // this group's columns x {sum, sum of squares}
         uint8_t *stg = smem + S::kStg + eg * T3_STG_BYTES;
         if (et == 0 && g.store) prefetch_tmap(&tmY);
-        for (int i = et; i < 64 * 2; i += 128) s_stat[eg * 128 + i] = 0.0;   // this group's 64 columns x {sum, sum of squares}
+        for (int i = et; i < SG; i += 128) s_stat[eg * SG + i] = 0.0;
         named_bar_sync(bar_id, 128);
         int it = 0, cur_f = -1;
         auto flush_stats = [&](int f) {   // one fp64 atomic pair per column, CTA and frame
             named_bar_sync(bar_id, 128);
-            {
-                const int i = eg * 128 + et;
+            for (int i = eg * SG + et; i < (eg + 1) * SG; i += 128) {
                 const double v = s_stat[i];
                 if (v != 0.0) atomicAdd(a.out_stats + (size_t)f * a.Cout * 2 + i, v);
                 s_stat[i] = 0.0;
@@ -477,11 +483,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) tc3_layer_kernel(const __grid_c
             mbar_wait(acc_full(ab), (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int cbl = 0; cbl < 2; ++cbl) {
-                const int cb = eg * 2 + cbl;
+            for (int cbl = 0; cbl < CBG; ++cbl) {
+                const int cb = eg * CBG + cbl;
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + T3_ACC_COL + ab * T3_BN + cb * 32, v);
-                if (cbl == 1) {   // the accumulator is in registers: the MMA warp may start the tile after next
+                if (cbl == CBG - 1) {   // the accumulator is in registers: the MMA warp may start the tile after next
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(ab));
@@ -789,7 +795,7 @@ int launch_tc3_t(const T3Args &g, const CUtensorMap &tmX, const CUtensorMap &tmY
         MVX_CUDA_CHECK(cudaFuncSetAttribute(tc3_layer_kernel<RESIDENT, CAT, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         attr_set = true;
     }
-    tc3_layer_kernel<RESIDENT, CAT, PREC><<<grid, T3_THREADS, S::kTotal, st>>>(g, tmX, tmY, tmX2);
+    tc3_layer_kernel<RESIDENT, CAT, PREC><<<grid, t3_threads(RESIDENT ? 2 : 3, RESIDENT ? 2 : 1), S::kTotal, st>>>(g, tmX, tmY, tmX2);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }
@@ -798,7 +804,7 @@ int launch_tc3_t(const T3Args &g, const CUtensorMap &tmX, const CUtensorMap &tmY
 
 bool tc3_layer_eligible(const LayerArgs &a) {
     if (!(a.f16_ok && a.in_stats && a.counts && !a.row_max && !a.plain && !a.a_pack && !a.w_per_frame)) return false;
-    if (a.Cout != T3_BN || a.Cin % (2 * T3_KB) != 0 || a.Cin > 768 || (a.rows_mode != 1 && a.rows_mode != 2)) return false;
+    if (a.Cout != T3_BN || a.Cin % (2 * T3_KB) != 0 || (a.Cin != 128 && a.Cin % (3 * T3_KB) != 0) || a.Cin > 768 || (a.rows_mode != 1 && a.rows_mode != 2)) return false;
     if (a.rowcap % T3_TM != 0 || a.ldx % 4 != 0 || (a.Y && a.ldy % 4 != 0)) return false;
     if (a.vmax && !a.row_v) return false;
     if (a.y_bf16 || (a.x_bf16 && a.X2)) return false;
