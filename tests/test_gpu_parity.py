@@ -963,3 +963,29 @@ def test_vfe_inputs_built_in_the_loader_equal_materialised_inputs(mvx):
     assert np.array_equal(c1, c2)
     for f in range(len(frames)):
         assert rel_err(fused[f], mat[f]) < 1e-5, f
+
+
+def test_persistent_pixel_gemm_equals_one_tile_kernel(mvx):
+    """The persistent per-pixel GEMM of fcn1 (default) against the one-tile kernel it replaced (mvx_set_gemm_mode(12)): same
+    pre-packed operands, same sequence of tensor-core products per accumulator, same exact power-of-two rescale - the per-pixel
+    products Z are BIT-IDENTICAL, including the partial last row tile of every level and a level smaller than one tile."""
+    from mvxnet_makise_b200 import _lib
+    sd = synth.make_weights(14)
+    calib = synth.kitti_calib()
+    frames = [synth.make_points(170, 1800), synth.make_points(171, 900), synth.make_points(172, 1200)]
+    maps = small_maps(23, B=len(frames))
+    npix = sum(m.shape[0] * m.shape[2] * m.shape[3] for m in maps)
+    out = {}
+    for mode in (1, 12):
+        try:
+            _lib.set_gemm_mode(mode)
+            path = mvx.P.PointPath(sd, G)
+            path(frames, [calib] * len(frames), [torch.from_numpy(m) for m in maps], want_grid=False)
+            torch.cuda.synchronize()
+            out[mode] = (path.region('Z', torch.float32, (npix, 768)).clone(), [path.voxel_features(f)[0].clone() for f in range(len(frames))])
+        finally:
+            _lib.set_gemm_mode(1)
+    assert torch.isfinite(out[1][0]).all() and out[1][0].abs().max() > 0
+    assert torch.equal(out[1][0], out[12][0]), 'per-pixel products differ between the two kernels'
+    for a, b in zip(out[1][1], out[12][1]):
+        assert rel_err(a, b) < 1e-5
