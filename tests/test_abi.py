@@ -99,3 +99,20 @@ def test_synth_frame_invariants():
     sd = synth.make_weights(0)
     assert sum(v.size for v in sd.values()) == 726_880
     assert synth.fpn_shapes() == [(104, 336), (52, 168), (26, 84)]
+
+
+def test_occupancy_helper_of_the_gpu_tests():
+    """tests/_util.same_occupancy: cells where exactly one grid is zero may only hold rounding-level values."""
+    import torch
+    from _util import same_occupancy
+    a = torch.zeros(4, 5)
+    a[1, 2], a[3, 0] = 2.0, -1.5
+    b = a.clone()
+    assert same_occupancy(a, b)
+    b[0, 0] = 1e-7              # an exactly-zero feature in one evaluation, rounding noise in the other
+    assert same_occupancy(a, b)
+    b[0, 0] = 1e-3              # a voxel that only one side has
+    assert not same_occupancy(a, b)
+    b[0, 0] = 0.0
+    b[1, 2] = 0.0               # a voxel that only the other side has
+    assert not same_occupancy(a, b)
