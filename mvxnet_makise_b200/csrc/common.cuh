@@ -86,4 +86,33 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
     return base + inc - v;
 }
 
+// the same for one 64-bit value per thread (two packed 32-bit counters scan in one pass: they do not carry into each other
+// as long as each total stays below 2^32)
+__device__ __forceinline__ unsigned long long block_exclusive_scan_u64(unsigned long long v, unsigned long long *total) {
+    __shared__ unsigned long long warp_sums64[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    __syncthreads();  // protect warp_sums64 reuse across calls
+    if (lane == 31) warp_sums64[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long winc = lane < nw ? warp_sums64[lane] : 0ull;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += t;
+        }
+        warp_sums64[lane] = winc;  // inclusive over warps
+    }
+    __syncthreads();
+    const unsigned long long base = wid == 0 ? 0ull : warp_sums64[wid - 1];
+    *total = warp_sums64[nw - 1];
+    return base + inc - v;
+}
+
 }  // namespace mvx

@@ -331,24 +331,26 @@ __global__ void __launch_bounds__(256) combine_hist_kernel(CombineArgs a) {
     atomicAdd(a.bin_count + (size_t)f * (a.nbins + 1) + combine_key(a, f, r, K), 1);
 }
 
-__global__ void __launch_bounds__(1024) combine_scan_kernel(CombineArgs a) {  // one CTA per frame
+__global__ void __launch_bounds__(1024) combine_scan_kernel(CombineArgs a) {  // one CTA per frame, four bins per thread and round
     const int f = blockIdx.x, nb = a.nbins + 1;
     int *cnt = a.bin_count + (size_t)f * nb, *start = a.bin_start + (size_t)f * (nb + 1);
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < nb; b0 += 1024) {
-        const int b = b0 + threadIdx.x;
-        const int v = b < nb ? cnt[b] : 0;
+    int carry = 0;
+    for (int b0 = 0; b0 < nb; b0 += 4096) {
+        const int b = b0 + threadIdx.x * 4;
+        int v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = b + q < nb ? cnt[b + q] : 0;
         int total;
-        const int ex = block_exclusive_scan(v, &total);
-        if (b < nb) {
-            start[b] = carry + ex;
-            cnt[b] = 0;  // becomes the scatter cursor
+        int ex = carry + block_exclusive_scan(v[0] + v[1] + v[2] + v[3], &total);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (b + q < nb) {
+                start[b + q] = ex;
+                cnt[b + q] = 0;  // becomes the scatter cursor
+            }
+            ex += v[q];
         }
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
+        carry += total;
     }
     if (threadIdx.x == 0) start[nb] = carry;
 }
