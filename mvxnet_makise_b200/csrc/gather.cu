@@ -85,6 +85,10 @@ __device__ __forceinline__ void pk_split(float x0, float x1, uint32_t &hi, uint3
     const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
     lo = pk_half2(x0 - hf.x, x1 - hf.y);
 }
+#ifndef MVX_PACK_UNROLL
+#define MVX_PACK_UNROLL 16
+#endif
+constexpr int kPackUnroll = MVX_PACK_UNROLL;   // channel rows in flight per thread (A/B on the serialised stage: 4: 0.147-0.167 ms, 8: 0.181, 16: 0.133-0.147, 32: 0.167)
 __global__ void __launch_bounds__(256) pack_maps_f16_kernel(const float *__restrict__ in, int C, int HW, uint8_t *__restrict__ apack,
                                                             float *__restrict__ rowinv) {
     __shared__ float tile[256][33];
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(256) pack_maps_f16_kernel(const float *__restr
     const int f = blockIdx.y, p0 = blockIdx.x * 32, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const float *src = in + (size_t)f * C * HW;
     float mx = 0.f;
-#pragma unroll 4
+#pragma unroll kPackUnroll
     for (int k = 0; k < 32; ++k) {
         const int c = ty + 8 * k;
         const float v = (p0 + tx < HW) ? __ldg(src + (size_t)c * HW + p0 + tx) : 0.f;
