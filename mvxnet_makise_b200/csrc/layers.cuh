@@ -95,6 +95,7 @@ int launch_layer_tc3(const LayerArgs &a, int F, float *wpack, cudaStream_t st);
 bool pixel_gemm_persistent_eligible(const LayerArgs &a);
 int launch_pixel_gemm_persistent(const LayerArgs &a, float *wpack, cudaStream_t st);
 void set_pixel_persistent(int on);
+bool pixel_persistent_enabled();
 void set_tc3(int on);
 bool tc_persistent_enabled();
 bool tc_f16_enabled();

@@ -240,7 +240,10 @@ int pointpath_forward(const mvx_pointpath_args_t *a, bool train) {
         MVX_CUDA_CHECK(cudaStreamWaitEvent(ms, side->fork, 0));
     }
     // pixel-first with 3xFP16: the maps are written directly as the pre-packed A operand of the pixel GEMM (no NHWC copy)
-    const bool apack = pixel_first && tc_f16_enabled() && !tc_bf16_enabled() && g_apack;
+    // bf16 mode too: its per-pixel GEMM keeps the 3xFP16 products of the pre-packed operands (the persistent kernel is bound by its
+    // loads and stores, not by the MMAs) and only writes Z as bf16; without the persistent kernel (gemm mode 12) the bf16 mode keeps its
+    // channels-last copy + one-product kernel
+    const bool apack = pixel_first && tc_f16_enabled() && g_apack && (!tc_bf16_enabled() || pixel_persistent_enabled());
     const bool fold = apack && g_fold;
     // bf16 mode (mvx_set_gemm_mode(6)): the two largest intermediates - the per-pixel products Z and the raw fcn1 rows Y1 - are
     // stored as bf16 (half the bytes written and read back); every sum in between stays fp32

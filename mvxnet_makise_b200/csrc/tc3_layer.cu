@@ -623,6 +623,8 @@ struct PgArgs {
     int Cin, Cout, row_tiles;
 };
 
+// ZB: Z is written as bf16 (the bf16 mode stores its two largest intermediates, Z and Y1, as bf16; the products stay 3xFP16)
+template <bool ZB>
 __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_persistent_kernel(const __grid_constant__ PgArgs g, const __grid_constant__ CUtensorMap tmZ) {
     using S = PgSmem;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -729,8 +731,21 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_persistent_kernel(co
                 }
                 if (et == 0) tma_store_wait_read<0>();   // the previous tensor store is done reading the staging block
                 named_bar_sync(bar_id, 128);
-                uint8_t *rowp = stg + rloc * 128;
                 const float4 *ci = reinterpret_cast<const float4 *>(colinv + cb * PG_BN + c32 * 32);
+                if constexpr (ZB) {   // 64-byte rows, SWIZZLE_64B: 16-byte piece j of row i at position j ^ ((i >> 1) & 3)
+                    uint8_t *rowp = stg + rloc * 64;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 ca = __ldg(ci + 2 * j), cb4 = __ldg(ci + 2 * j + 1);
+                        uint4 o;
+                        o.x = pack_bf16x2(v[j * 8 + 0] * (rinv * ca.x), v[j * 8 + 1] * (rinv * ca.y));
+                        o.y = pack_bf16x2(v[j * 8 + 2] * (rinv * ca.z), v[j * 8 + 3] * (rinv * ca.w));
+                        o.z = pack_bf16x2(v[j * 8 + 4] * (rinv * cb4.x), v[j * 8 + 5] * (rinv * cb4.y));
+                        o.w = pack_bf16x2(v[j * 8 + 6] * (rinv * cb4.z), v[j * 8 + 7] * (rinv * cb4.w));
+                        *reinterpret_cast<uint4 *>(rowp + ((j ^ ((rloc >> 1) & 3)) << 4)) = o;
+                    }
+                } else {
+                uint8_t *rowp = stg + rloc * 128;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 c4 = __ldg(ci + j);
@@ -738,6 +753,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_persistent_kernel(co
                     o.x = v[j * 4 + 0] * (rinv * c4.x), o.y = v[j * 4 + 1] * (rinv * c4.y);
                     o.z = v[j * 4 + 2] * (rinv * c4.z), o.w = v[j * 4 + 3] * (rinv * c4.w);
                     *reinterpret_cast<float4 *>(rowp + ((j ^ (rloc & 7)) << 4)) = o;   // SWIZZLE_128B like the store's tensor map
+                }
                 }
                 fence_async_smem();
                 named_bar_sync(bar_id, 128);
@@ -855,10 +871,11 @@ int launch_layer_tc3(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
 // defined in tc_layer.cu
 static int g_pixel_persistent = 1;   // 0: the one-tile two-CTAs-per-SM kernel of tc_layer.cu for the pixel GEMM (mvx_set_gemm_mode(12), A/B timing)
 void set_pixel_persistent(int on) { g_pixel_persistent = on; }
+bool pixel_persistent_enabled() { return g_pixel_persistent != 0; }
 
 bool pixel_gemm_persistent_eligible(const LayerArgs &a) {
-    return g_pixel_persistent && a.plain && a.a_pack && a.Y && !a.y_bf16 && !a.counts && a.rows_fixed > 0 && a.Cin % PG_KB == 0 && a.Cout % PG_BN == 0 &&
-           a.Cout <= 768 && a.ldy % 4 == 0 && !a.w_per_frame && !tc_bf16_enabled();
+    return g_pixel_persistent && a.plain && a.a_pack && a.Y && !a.counts && a.rows_fixed > 0 && a.Cin % PG_KB == 0 && a.Cout % PG_BN == 0 &&
+           a.Cout <= 768 && a.ldy % 8 == 0 && !a.w_per_frame;
 }
 
 int launch_pixel_gemm_persistent(const LayerArgs &a, float *wpack, cudaStream_t st) {
@@ -869,16 +886,18 @@ int launch_pixel_gemm_persistent(const LayerArgs &a, float *wpack, cudaStream_t 
     g.a_pack = static_cast<const uint8_t *>(a.a_pack), g.a_rowinv = a.a_rowinv, g.wpack = reinterpret_cast<const uint8_t *>(wpack);
     g.R = a.rows_fixed, g.Cin = a.Cin, g.Cout = a.Cout, g.row_tiles = (int)ceil_div(a.rows_fixed, (long long)PG_TM);
     CUtensorMap tmZ;
-    rc = make_tmap(&tmZ, a.Y, a.rows_fixed, a.Cout, a.ldy);
+    rc = make_tmap(&tmZ, a.Y, a.rows_fixed, a.Cout, a.ldy, a.y_bf16 != 0);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        MVX_CUDA_CHECK(cudaFuncSetAttribute(pixel_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PgSmem::kTotal));
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(pixel_gemm_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PgSmem::kTotal));
+        MVX_CUDA_CHECK(cudaFuncSetAttribute(pixel_gemm_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PgSmem::kTotal));
         attr_set = true;
     }
     const long long tiles = (long long)g.row_tiles * (a.Cout / PG_BN);
     const int grid = (int)(tiles < kSMs ? tiles : kSMs);
-    pixel_gemm_persistent_kernel<<<grid, PG_THREADS, PgSmem::kTotal, st>>>(g, tmZ);
+    if (a.y_bf16) pixel_gemm_persistent_kernel<true><<<grid, PG_THREADS, PgSmem::kTotal, st>>>(g, tmZ);
+    else pixel_gemm_persistent_kernel<false><<<grid, PG_THREADS, PgSmem::kTotal, st>>>(g, tmZ);
     MVX_LAUNCH_CHECK();
     return MVX_OK;
 }
