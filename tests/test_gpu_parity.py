@@ -364,7 +364,7 @@ def test_fused_path_matches_reference_golden(mvx, golden_dir, tag, fusion_mode):
     cnt = path.region('vox_cnt', torch.int32, (1, cap))[0, :N].cpu().numpy()
     assert row0[N] == K and np.array_equal(cnt, (ref['voxels9'][..., :3] != 0).any(-1).sum(1).numpy())
     # the concat [voxel columns | image features] of MVXNet.py:26: the default inference path builds it inside VFE1's loader
-    # (csrc/row_layer.cu); gemm mode 10 materialises it as X6 (prep_vfe1_kernel, what training uses), which is what is read here
+    # (fcn_layer_kernel<16, 1> in csrc/layers.cu); gemm mode 10 materialises it as X6 (prep_vfe1_kernel, what training uses), which is what is read here
     from mvxnet_makise_b200 import _lib
     try:
         _lib.set_gemm_mode(10)
