@@ -414,16 +414,29 @@ __global__ void __launch_bounds__(t3_threads(NCG, NEG), 1) tc3_layer_kernel(cons
         // blocks 2 eg and 2 eg + 1 of every tile, with its own staging blocks, partials and named barrier ==================
         const int q = warp & 3, eg = (warp - T3_W_EPI) >> 2;
         const int et = (tid - T3_W_EPI * 32) & 127;         // thread inside the group
-        const int ecol = et & 31, egrp = et >> 5;           // statistics: thread = (column of a 32-column block, 32-row group)
+        const int ecol = lane;                              // statistics / maxima: lane = column of a 32-column block ...
+        const int erow = q * 32 + lane;                     // ... over the warp's OWN 32 rows (its TMEM lane quarter); metadata: lane = row
         const int bar_id = 2 + eg;
-        double *s_part = reinterpret_cast<double *>(smem + S::kPart) + eg * (4 * 32 * 2);
+        // Every warp is self-contained inside the tile loop: it stages, stores (its own 32-row tensor store) and walks only the 32 rows
+        // it drained from tensor memory, and keeps its BatchNorm sums in registers until the frame changes - no named barrier between
+        // the four warps of a group per block (there were three; with K = 128 the epilogue bounds the kernel and its warps spent their
+        // time waiting for each other).
         constexpr int SG = 2 * T3_BN / NEG;                  // this group's columns x {sum, sum of squares}
         uint8_t *stg = smem + S::kStg + eg * T3_STG_BYTES;
         if (et == 0 && g.store) prefetch_tmap(&tmY);
         for (int i = et; i < SG; i += 128) s_stat[eg * SG + i] = 0.0;
         named_bar_sync(bar_id, 128);
         int it = 0, cur_f = -1;
-        auto flush_stats = [&](int f) {   // one fp64 atomic pair per column, CTA and frame
+        double acc_sy[CBG], acc_syy[CBG];                  // this lane's column of every block of the group, this warp's rows
+#pragma unroll
+        for (int c = 0; c < CBG; ++c) acc_sy[c] = acc_syy[c] = 0.0;
+        auto flush_stats = [&](int f) {   // warps -> CTA (shared fp64 atomics), then one fp64 atomic pair per column, CTA and frame
+#pragma unroll
+            for (int c = 0; c < CBG; ++c) {
+                atomicAdd(&s_stat[((eg * CBG + c) * 32 + lane) * 2], acc_sy[c]);
+                atomicAdd(&s_stat[((eg * CBG + c) * 32 + lane) * 2 + 1], acc_syy[c]);
+                acc_sy[c] = acc_syy[c] = 0.0;
+            }
             named_bar_sync(bar_id, 128);
             for (int i = eg * SG + et; i < (eg + 1) * SG; i += 128) {
                 const double v = s_stat[i];
@@ -440,7 +453,7 @@ __global__ void __launch_bounds__(t3_threads(NCG, NEG), 1) tc3_layer_kernel(cons
             return tn;
         };
         auto load_meta = [&](int f, long long row0, long long n_rows, int Kf, float &w, int &v) {
-            const long long rr = row0 + et;
+            const long long rr = row0 + erow;
             const bool has_v = a.vmax && rr < n_rows && !(a.rows_mode == 1 && rr >= Kf);
             // both loads are issued back to back (the voxel id does not wait for the multiplicity to arrive)
             const int vl = has_v ? a.row_v[(size_t)f * a.rowv_cap + rr] : -1;
@@ -468,9 +481,9 @@ __global__ void __launch_bounds__(t3_threads(NCG, NEG), 1) tc3_layer_kernel(cons
             long long row0n = 0, n_rowsn = 0;
             const int tn = next_valid(t + gridDim.x, fn, row0n, n_rowsn, Kfn);
             if (tn < total) load_meta(fn, row0n, n_rowsn, Kfn, pw, pv);     // in flight during this tile
-            roww[et] = w_own;
-            rowv[et] = v_own;
-            // This warp's lanes hold the rows egrp * 32 + lane - exactly the rows its threads walk below. Run structure of the voxel
+            roww[erow] = w_own;
+            rowv[erow] = v_own;
+            // This warp's lanes hold the rows q * 32 + lane - exactly the rows its threads walk below. Run structure of the voxel
             // ids as bit masks (a row starts / ends a run of equal ids), rows of multiplicity 1, and whether any row is weighted
             // (neither 0 nor 1: the pad rows; the fp64 side path is skipped by whole warps on ordinary tiles): the walk tests
             // register bits instead of chasing shared-memory loads with compares and branches row by row.
@@ -479,10 +492,10 @@ __global__ void __launch_bounds__(t3_threads(NCG, NEG), 1) tc3_layer_kernel(cons
             const unsigned endmask = __ballot_sync(0xffffffffu, v_own >= 0 && (lane == 31 || v_own != v_next));
             const unsigned onesmask = __ballot_sync(0xffffffffu, w_own == 1.f);
             const bool heavy = __any_sync(0xffffffffu, w_own != 1.f && w_own != 0.f);
-            named_bar_sync(bar_id, 128);
+            __syncwarp();                                    // roww / rowv of this warp's rows are read by its own lanes only
             mbar_wait(acc_full(ab), (it >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int cbl = 0; cbl < CBG; ++cbl) {
                 const int cb = eg * CBG + cbl;
                 float v[32];
@@ -492,8 +505,8 @@ __global__ void __launch_bounds__(t3_threads(NCG, NEG), 1) tc3_layer_kernel(cons
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(ab));
                 }
-                if (g.store && et == 0) tma_store_wait_read<0>();   // the tensor store of the previous block is done reading the staging block
-                named_bar_sync(bar_id, 128);                        // ... and everybody is done with the column walk of that block
+                if (g.store && lane == 0) tma_store_wait_read<0>();   // this warp's previous tensor store is done reading its staging rows
+                __syncwarp();                                         // ... and all its lanes are done with the column walk of that block
                 const int rloc = q * 32 + lane;
                 uint8_t *rowp = stg + rloc * 128;
 #pragma unroll
@@ -508,9 +521,9 @@ __global__ void __launch_bounds__(t3_threads(NCG, NEG), 1) tc3_layer_kernel(cons
                     *reinterpret_cast<float4 *>(rowp + ((j ^ (rloc & 7)) << 4)) = o;   // SWIZZLE_128B like the store's tensor map
                 }
                 fence_async_smem();
-                named_bar_sync(bar_id, 128);
-                if (g.store && et == 0) {
-                    tma_store_2d(&tmY, cb * 32, (int)((long long)f * a.rowcap + row0), smem_u32(stg));
+                __syncwarp();
+                if (g.store && lane == 0) {   // this warp's 32 rows x 32 columns (the tensor map's box)
+                    tma_store_2d(&tmY, cb * 32, (int)((long long)f * a.rowcap + row0 + q * 32), smem_u32(stg + q * 4096));
                     tma_store_commit();
                 }
                 // column walk over this thread's 32 rows: sums of the ordinary rows in fp32 over 16 rows, fp64 beyond; weighted
@@ -519,14 +532,14 @@ __global__ void __launch_bounds__(t3_threads(NCG, NEG), 1) tc3_layer_kernel(cons
                     double sy = 0.0, syy = 0.0;
                     int *vm = a.vmax ? a.vmax + (size_t)f * a.vcap * a.Cout + cb * 32 + ecol : nullptr;
                     float cm = 0.f;                       // running maximum of the current run (y >= 0 after the ReLU: 0 is neutral)
-                    const float *rw_ = roww + egrp * 32;
-                    const int *rv_ = rowv + egrp * 32;
+                    const float *rw_ = roww + q * 32;
+                    const int *rv_ = rowv + q * 32;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         float yv[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const int rw = egrp * 32 + h * 16 + j;
+                            const int rw = q * 32 + h * 16 + j;
                             yv[j] = *reinterpret_cast<const float *>(stg + rw * 128 + (((ecol >> 2) ^ (rw & 7)) << 4) + (ecol & 3) * 4);
                         }
                         float ps = 0.f, pss = 0.f;
@@ -557,21 +570,15 @@ __global__ void __launch_bounds__(t3_threads(NCG, NEG), 1) tc3_layer_kernel(cons
                             }
                         }
                     }
-                    s_part[(egrp * 32 + ecol) * 2] = sy;
-                    s_part[(egrp * 32 + ecol) * 2 + 1] = syy;
-                }
-                named_bar_sync(bar_id, 128);
-                if (et < 64) {   // 32 columns x {sum, sum of squares}: add the four row groups into the CTA's running sums
-                    const int c = et >> 1, k = et & 1;
-                    s_stat[(cb * 32 + c) * 2 + k] += s_part[(0 * 32 + c) * 2 + k] + s_part[(1 * 32 + c) * 2 + k] + s_part[(2 * 32 + c) * 2 + k] +
-                                                     s_part[(3 * 32 + c) * 2 + k];
+                    acc_sy[cbl] += sy;
+                    acc_syy[cbl] += syy;
                 }
             }
             ++it;
             t = tn, f = fn, row0 = row0n, n_rows = n_rowsn, Kf = Kfn;
         }
         if (cur_f >= 0) flush_stats(cur_f);
-        if (g.store && et == 0) tma_store_wait_all();
+        if (g.store && lane == 0) tma_store_wait_all();
     }
     __syncwarp();   // single-lane role warps: lanes 1-31 wait here for their looping lane 0
     tc_fence_before();
@@ -708,7 +715,6 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_persistent_kernel(co
         // ================= epilogue: group = 128-row half of the tile, warp = TMEM lane quarter ==========================
         const int q = warp & 3, eg = (warp - 2) >> 2;
         const int et = (tid - 64) & 127;
-        const int bar_id = 2 + eg;
         uint8_t *stg = smem + S::kStg + eg * T3_STG_BYTES;
         if (et == 0) prefetch_tmap(&tmZ);
         int it = 0;
@@ -729,8 +735,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_persistent_kernel(co
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(ab));
                 }
-                if (et == 0) tma_store_wait_read<0>();   // the previous tensor store is done reading the staging block
-                named_bar_sync(bar_id, 128);
+                if (lane == 0) tma_store_wait_read<0>();   // this warp's previous tensor store is done reading its 32 staging rows
+                __syncwarp();                              // (every warp stages and stores its own rows: no barrier between the warps)
                 const float4 *ci = reinterpret_cast<const float4 *>(colinv + cb * PG_BN + c32 * 32);
                 if constexpr (ZB) {   // 64-byte rows, SWIZZLE_64B: 16-byte piece j of row i at position j ^ ((i >> 1) & 3)
                     uint8_t *rowp = stg + rloc * 64;
@@ -756,14 +762,14 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_persistent_kernel(co
                 }
                 }
                 fence_async_smem();
-                named_bar_sync(bar_id, 128);
-                if (et == 0) {
-                    tma_store_2d(&tmZ, cb * PG_BN + c32 * 32, (int)row0, smem_u32(stg));   // rows beyond R are clipped by the tensor map
+                __syncwarp();
+                if (lane == 0) {   // 32 rows x 32 columns: rows beyond R are clipped by the tensor map
+                    tma_store_2d(&tmZ, cb * PG_BN + c32 * 32, (int)(row0 + q * 32), smem_u32(stg + q * (ZB ? 2048 : 4096)));
                     tma_store_commit();
                 }
             }
         }
-        if (et == 0) tma_store_wait_all();
+        if (lane == 0) tma_store_wait_all();
     }
     __syncwarp();
     tc_fence_before();
@@ -789,12 +795,12 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D tensor (rows, cols) of fp32 (or bf16) elements with row pitch ld elements; box = 128 rows x 32 columns: 128-byte rows with
 // SWIZZLE_128B (fp32), 64-byte rows with SWIZZLE_64B (bf16)
-static int make_tmap(CUtensorMap *m, const void *base, long long rows, int cols, int ld, bool bf16 = false) {
+static int make_tmap(CUtensorMap *m, const void *base, long long rows, int cols, int ld, bool bf16 = false, int box_rows = T3_TM) {
     EncodeTiledFn fn = encode_fn();
     MVX_REQUIRE(fn, MVX_ECUDA, "cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
-    const cuuint32_t box[2] = {32, (cuuint32_t)T3_TM};
+    const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -844,7 +850,7 @@ int launch_layer_tc3(const LayerArgs &a, int F, float *wpack, cudaStream_t st) {
     rc = make_tmap(&tmX, a.X, (long long)F * a.rowcap, xcols, a.ldx, a.x_bf16 != 0);
     if (rc) return rc;
     if (a.Y) {
-        rc = make_tmap(&tmY, a.Y, (long long)F * a.rowcap, a.Cout, a.ldy);
+        rc = make_tmap(&tmY, a.Y, (long long)F * a.rowcap, a.Cout, a.ldy, false, 32);   // one box per epilogue warp
         if (rc) return rc;
     } else {
         tmY = tmX;
@@ -886,7 +892,7 @@ int launch_pixel_gemm_persistent(const LayerArgs &a, float *wpack, cudaStream_t 
     g.a_pack = static_cast<const uint8_t *>(a.a_pack), g.a_rowinv = a.a_rowinv, g.wpack = reinterpret_cast<const uint8_t *>(wpack);
     g.R = a.rows_fixed, g.Cin = a.Cin, g.Cout = a.Cout, g.row_tiles = (int)ceil_div(a.rows_fixed, (long long)PG_TM);
     CUtensorMap tmZ;
-    rc = make_tmap(&tmZ, a.Y, a.rows_fixed, a.Cout, a.ldy, a.y_bf16 != 0);
+    rc = make_tmap(&tmZ, a.Y, a.rows_fixed, a.Cout, a.ldy, a.y_bf16 != 0, 32);   // one 32-row box per epilogue warp
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
